@@ -1,0 +1,181 @@
+/*
+ * sga_b200.h -- C ABI of libsga_b200.so: the B200 (sm_100a) kernels behind the SGAligner
+ * node-embedding / matching / contrastive-loss hot path.
+ *
+ * The reference (sayands/sgaligner) is pure Python/PyTorch: its "FFI" for this path is the
+ * nn.Module call surface (src/aligner/sg_aligner.py:71 MultiModalEncoder.forward,
+ * src/aligner/losses.py:114 OverallLoss.forward, src/inference/sgaligner/inference_align_reg.py:125
+ * matching head).  Each entry point below replaces the ATen / cuDNN / cuBLAS / PyG call sequence of
+ * one reference function (cited per function); the Python mirror of the reference modules
+ * (sgaligner_b200/sg_aligner.py, losses.py, matching.py) binds them with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller (PyTorch) allocates every buffer, including workspaces; the library never
+ *     allocates or frees device memory and keeps no state besides the last error string and
+ *     cached function attributes;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - return value: 0 on success, SGA_E* (< 0) for argument errors, a positive cudaError_t for
+ *     launch errors; sga_last_error() gives the text;
+ *   - row-major contiguous tensors; "N" is the number of objects (graph nodes) in the batch.
+ */
+#ifndef SGA_B200_H
+#define SGA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGA_OK 0
+#define SGA_EINVAL (-1)      /* bad argument / unsupported shape */
+#define SGA_EWORKSPACE (-2)  /* workspace too small */
+#define SGA_EARCH (-3)       /* not running on an sm_100 device */
+
+/* kernel selection for sga_pointnet_fwd */
+#define SGA_POINTNET_SIMT 0  /* fp32 FMA reference path (any shape) */
+#define SGA_POINTNET_TC 1    /* tcgen05 bf16x3 split-operand tensor-core path */
+
+const char* sga_last_error(void);
+int sga_version(void);
+/* device query used by the host side to size persistent grids */
+int sga_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- a3: PointNetfeat.forward (src/aligner/networks/pointnet.py:120-175; conv1..3 + ReLU + max)
+ * pts [N,P,3] f32 (data_dict['tot_obj_pts'] as collated, NOT permuted); W1 [64,3] b1 [64];
+ * W2 [128,64] b2 [128]; W3 [C3,128] b3 [C3]; out [N,C3]; argmax [N,C3] int32 (point index that
+ * attains the max, lowest index on ties) or NULL.  mode: SGA_POINTNET_*. */
+int sga_pointnet_fwd(const float* pts, int64_t N, int P,
+                     const float* W1, const float* b1, const float* W2, const float* b2,
+                     const float* W3, const float* b3, int C3,
+                     float* out, int32_t* argmax, int mode, void* stream);
+
+/* backward of the above (autograd of pointnet.py:140-163 through the max-pool): accumulates (+=)
+ * into gW1 [64,3] gb1 gW2 [128,64] gb2 gW3 [C3,128] gb3.  `out`/`argmax` are the forward results. */
+int sga_pointnet_bwd(const float* pts, int64_t N, int P,
+                     const float* W1, const float* b1, const float* W2, const float* b2,
+                     const float* W3, const float* b3, int C3,
+                     const float* out, const int32_t* argmax, const float* grad_out,
+                     float* gW1, float* gb1, float* gW2, float* gb2, float* gW3, float* gb3,
+                     void* stream);
+
+/* train-mode side effect of the discarded BatchNorm1d calls (pointnet.py:141-142,154-155,158-159):
+ * per-channel sum and sum of squares of the three pre-ReLU conv outputs over all N*P points.
+ * moments: f64 [2*(64+128+C3)] = {sum1[64], sq1[64], sum2[128], sq2[128], sum3[C3], sq3[C3]}, zeroed
+ * by the caller. */
+int sga_pointnet_bn_moments(const float* pts, int64_t N, int P,
+                            const float* W1, const float* b1, const float* W2, const float* b2,
+                            const float* W3, const float* b3, int C3, double* moments, void* stream);
+
+/* ---- a2/a7: block-diagonal CSR (by destination) for all 2B graphs of the batch, replacing the
+ * per-graph Python slicing of sg_aligner.py:86-104 plus PyG's remove_self_loops/add_self_loops.
+ * edges [E,2] int64 graph-local (src,dst) rows as collated (scan3r.py:201); node_off [G+1] int32 and
+ * edge_off [G+1] int64 are exclusive prefix sums of graph_per_obj_count / graph_per_edge_count.
+ * Outputs: row_beg [N] / row_cnt [N] int32 and col [E+N] int32 (GLOBAL source node ids; the slots of
+ * graph g start at edge_off[g]+node_off[g]; within a row: surviving edges in input order, then the
+ * added self loop). */
+int sga_csr_build(const int64_t* edges, const int32_t* node_off, const int64_t* edge_off, int G,
+                  int max_graph_nodes, int32_t* row_beg, int32_t* row_cnt, int32_t* col, void* stream);
+
+/* ---- a7 (first half): GATConv linear + attention logits.  x [N,in_dim] (f32, or f64 when
+ * x_is_f64 -- data_dict['tot_rel_pose'] arrives as f64); W [H*C,in_dim]; att_src/att_dst [H*C].
+ * xs [H][N][C] (head-major so that one graph's tile of one head is contiguous); a_src/a_dst [N,H]. */
+int sga_gat_linear(const void* x, int x_is_f64, int64_t N, int in_dim, const float* W,
+                   const float* att_src, const float* att_dst, int H, int C,
+                   float* xs, float* a_src, float* a_dst, void* stream);
+
+/* ---- a7 (second half): leaky-ReLU(0.2) edge logits, softmax over incoming edges (+1e-16),
+ * weighted aggregation, + bias, optional ELU (gat.py:45-46).  out [N,H*C]. */
+int sga_gat_aggregate(const float* xs, const float* a_src, const float* a_dst,
+                      const int32_t* row_beg, const int32_t* row_cnt, const int32_t* col,
+                      const int32_t* node_off, int G, int max_graph_nodes, int64_t N, int H, int C,
+                      const float* bias, int apply_elu, float* out, void* stream);
+
+/* backward of sga_gat_aggregate: given grad_out [N,H*C] (and `out` for the ELU derivative) produces
+ * g_xs [H][N][C] (zeroed by the caller; accumulated with atomics), g_a_src/g_a_dst [N,H] (zeroed by
+ * the caller) and accumulates g_bias [H*C]. */
+int sga_gat_aggregate_bwd(const float* xs, const float* a_src, const float* a_dst,
+                          const int32_t* row_beg, const int32_t* row_cnt, const int32_t* col,
+                          int64_t N, int H, int C, int apply_elu, const float* out,
+                          const float* grad_out, float* g_xs, float* g_a_src, float* g_a_dst,
+                          float* g_bias, void* stream);
+
+/* backward of sga_gat_linear: folds g_a_src/g_a_dst into g_xs, then gW += g_xs^T x, g_att_* +=,
+ * and (if gx != NULL) gx [N,in_dim] = g_xs W.  g_xs is modified in place. */
+int sga_gat_linear_bwd(const void* x, int x_is_f64, int64_t N, int in_dim, const float* W,
+                       const float* att_src, const float* att_dst, int H, int C,
+                       const float* xs, float* g_xs, const float* g_a_src, const float* g_a_dst,
+                       float* gW, float* g_att_src, float* g_att_dst, float* gx, void* stream);
+
+/* ---- a5 + a8: one modality's nn.Linear (sg_aligner.py:112-122) fused with its slice of
+ * MultiModalFusion (sg_aligner.py:30-35).  x [N,in_dim] f32/f64; W [out_dim,in_dim]; b [out_dim];
+ * emb [N,out_dim].  When joint != NULL: joint[n, joint_col : joint_col+out_dim] =
+ * softmax(fusion_w)[m] * emb[n] / max(||emb[n]||, 1e-12), joint row stride joint_ld floats. */
+int sga_project_fuse_fwd(const void* x, int x_is_f64, int64_t N, int in_dim, const float* W,
+                         const float* b, int out_dim, float* emb, float* joint, int joint_ld,
+                         int joint_col, const float* fusion_w, int M, int m, void* stream);
+
+/* backward: g_emb [N,out_dim] (direct gradient on the modality embedding, may be NULL) and
+ * g_joint (gradient on the joint embedding, may be NULL) -> gW +=, gb +=, g_fusion_w [M] +=, and
+ * gx [N,in_dim] (may be NULL). */
+int sga_project_fuse_bwd(const void* x, int x_is_f64, int64_t N, int in_dim, const float* W,
+                         int out_dim, const float* emb, const float* g_emb, const float* g_joint,
+                         int joint_ld, int joint_col, const float* fusion_w, int M, int m,
+                         float* gW, float* gb, float* g_fusion_w, float* gx, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* ---- a9: matching head (inference_align_reg.py:125-128) for all pairs of the batch at once.
+ * emb [N,D]; pair_off [B+1] int32 node offsets; sim_off [B+1] int64 = prefix sum of n_b^2 (n_b =
+ * nodes of pair b, source + reference).  Per pair: rows L2-normalised (division by the norm, no
+ * eps), sim = 1 - E E^T over source+reference nodes.  norms [N] is scratch, sim is packed per pair
+ * at sim_off[b] as [n_b, n_b]. */
+int sga_match_sim(const float* emb, int64_t N, int D, const int32_t* pair_off, const int64_t* sim_off,
+                  int B, int max_pair_nodes, float* norms, float* sim, void* stream);
+
+/* rank_list = argsort(sim, dim=1) made deterministic: ascending by (sim, column).  node_pair [N]
+ * int32 maps a node to its pair.  topk_idx/topk_dist [N,K] (pair-local columns, the node itself
+ * included exactly as in the reference's rank_list; -1 / +inf padding when n_b < K) may be NULL;
+ * rank_full (int32, packed like sim) may be NULL. */
+int sga_match_rank(const float* sim, int64_t N, const int32_t* pair_off, const int64_t* sim_off,
+                   const int32_t* node_pair, int max_pair_nodes, int K, int32_t* topk_idx,
+                   float* topk_dist, int32_t* rank_full, void* stream);
+
+/* ---- a10: utils/alignment.py:3-25 on the device: for anchor t, the 0-based position of e2i[t] in
+ * row e1i[t] of the ranking once the node itself is removed (Hits@k <=> pos < k, RR = 1/(pos+1)).
+ * e1i/e2i [A] are GLOBAL node ids as collated. */
+int sga_match_anchor_pos(const float* sim, const int32_t* pair_off, const int64_t* sim_off,
+                         const int32_t* node_pair, const int32_t* e1i, const int32_t* e2i, int A,
+                         int32_t* anchor_pos, void* stream);
+
+/* ---- a12-a16: OverallLoss.forward (losses.py:114-152) and its gradient w.r.t. every embedding.
+ * embs_host: host array of M+1 device pointers (M modal embeddings in module order, then the joint;
+ * for M == 1 pass only the single embedding and n_emb = 1); dims_host [n_emb] feature widths.
+ * e1i/e2i [A], e1j [J1], e2j [J2] int32 global row ids.  log_vars_ial/icl [M] (device).
+ * losses_out [4] = {loss, icl_unimodal, icl_multimodal, ial}.  When want_grad: g_embs_host gives
+ * n_emb device pointers [N,dim] that receive d loss / d emb (overwritten), g_log_vars_ial/icl [M].
+ * workspace >= sga_loss_workspace_bytes(). */
+size_t sga_loss_workspace_bytes(int n_emb, const int* dims_host, int64_t N, int A, int J1, int J2, int want_grad);
+int sga_loss_fwd_bwd(const float* const* embs_host, const int* dims_host, int n_emb, int64_t N,
+                     const int32_t* e1i, const int32_t* e2i, const int32_t* e1j, const int32_t* e2j,
+                     int A, int J1, int J2, const float* log_vars_ial, const float* log_vars_icl,
+                     float zoom, float* losses_out, int want_grad, float* const* g_embs_host,
+                     float* g_log_vars_ial, float* g_log_vars_icl, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* ---- a17: torch.optim.Adam step (L2 weight decay folded into the gradient, bias-corrected) over
+ * a flat parameter buffer; grad is multiplied by grad_scale first (1/world_size after allreduce). */
+int sga_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                  float grad_scale, void* stream);
+
+/* ---- bring-up / self-test kernels (tests only): one 128xN tile D = A B^T through tcgen05 with
+ * split operands.  kind 0: bf16x3, kind 1: tf32x3.  A [128,K], B [Ncols,K] f32 row-major,
+ * D [128,Ncols] f32. */
+int sga_selftest_umma(const float* A, const float* B, float* D, int Ncols, int K, int kind, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGA_B200_H */

@@ -1,0 +1,88 @@
+"""ctypes binding of ``libsga_b200.so`` (C ABI declared in ``include/sga_b200.h``).
+
+There is no CPU fallback anywhere in the package: if the shared object is missing it is built
+with nvcc (``sgaligner_b200.build``), and if that is impossible a ``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+_LIB = None
+
+c_f = c_float
+c_i = c_int
+c_p = c_void_p
+c_l = c_int64
+
+
+def _declare(lib):
+    def sig(name, res, *args):
+        fn = getattr(lib, name, None)
+        if fn is None:      # caught by tests/test_abi.py, which checks every declared symbol
+            return
+        fn.restype = res
+        fn.argtypes = list(args)
+
+    sig('sga_last_error', c_char_p)
+    sig('sga_version', c_i)
+    sig('sga_device_info', c_i, POINTER(c_i), POINTER(c_i), POINTER(c_i))
+    sig('sga_pointnet_fwd', c_i, c_p, c_l, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_p)
+    sig('sga_pointnet_bwd', c_i, c_p, c_l, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p,
+        c_p, c_p, c_p, c_p, c_p, c_p, c_p)
+    sig('sga_pointnet_bn_moments', c_i, c_p, c_l, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p)
+    sig('sga_csr_build', c_i, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p)
+    sig('sga_gat_linear', c_i, c_p, c_i, c_l, c_i, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p)
+    sig('sga_gat_aggregate', c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_l, c_i, c_i, c_p, c_i, c_p, c_p)
+    sig('sga_gat_aggregate_bwd', c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p)
+    sig('sga_gat_linear_bwd', c_i, c_p, c_i, c_l, c_i, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p)
+    sig('sga_project_fuse_fwd', c_i, c_p, c_i, c_l, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_i, c_i, c_p)
+    sig('sga_project_fuse_bwd', c_i, c_p, c_i, c_l, c_i, c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_p, c_i, c_i,
+        c_p, c_p, c_p, c_p, c_p, c_size_t, c_p)
+    sig('sga_match_sim', c_i, c_p, c_l, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p)
+    sig('sga_match_rank', c_i, c_p, c_l, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p)
+    sig('sga_match_anchor_pos', c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p)
+    sig('sga_loss_workspace_bytes', c_size_t, c_i, POINTER(c_i), c_l, c_i, c_i, c_i, c_i)
+    sig('sga_loss_fwd_bwd', c_i, POINTER(c_p), POINTER(c_i), c_i, c_l, c_p, c_p, c_p, c_p, c_i, c_i, c_i,
+        c_p, c_p, c_f, c_p, c_i, POINTER(c_p), c_p, c_p, c_p, c_size_t, c_p)
+    sig('sga_adam_step', c_i, c_p, c_p, c_p, c_p, c_l, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_p)
+    sig('sga_selftest_umma', c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_p)
+
+
+EXPORTS = ['sga_last_error', 'sga_version', 'sga_device_info', 'sga_pointnet_fwd', 'sga_pointnet_bwd',
+           'sga_pointnet_bn_moments', 'sga_csr_build', 'sga_gat_linear', 'sga_gat_aggregate',
+           'sga_gat_aggregate_bwd', 'sga_gat_linear_bwd', 'sga_project_fuse_fwd', 'sga_project_fuse_bwd',
+           'sga_match_sim', 'sga_match_rank', 'sga_match_anchor_pos', 'sga_loss_workspace_bytes',
+           'sga_loss_fwd_bwd', 'sga_adam_step', 'sga_selftest_umma']
+
+
+def lib_path() -> str:
+    from . import build
+    return build.LIB
+
+
+def get_lib():
+    """Load (building first if needed) the CUDA library.  Never falls back to anything else."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    from . import build
+    path = build.LIB
+    if not os.path.exists(path):
+        try:
+            build.build()
+        except Exception as e:  # noqa: BLE001
+            raise RuntimeError(
+                'sgaligner_b200: libsga_b200.so is missing and could not be built with nvcc; '
+                'there is no CPU or PyTorch fallback for the hot path') from e
+    lib = ctypes.CDLL(path)
+    _declare(lib)
+    _LIB = lib
+    return lib
+
+
+def check(rc: int, what: str = ''):
+    if rc != 0:
+        msg = get_lib().sga_last_error().decode(errors='replace')
+        raise RuntimeError(f'libsga_b200 {what} failed (code {rc}): {msg}')

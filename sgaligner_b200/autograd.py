@@ -1,0 +1,116 @@
+"""``torch.autograd.Function`` glue: forward and backward of every stage are CUDA kernels of
+``libsga_b200.so``; autograd only routes the tensors between them."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class PointNetFeat(torch.autograd.Function):
+    """PointNetfeat.forward (pointnet.py:140-163) as one fused kernel; the backward goes through
+    the saved per-channel argmax of the max-pool."""
+
+    @staticmethod
+    def forward(ctx, pts, W1, b1, W2, b2, W3, b3, mode):
+        need = any(t.requires_grad for t in (W1, b1, W2, b2, W3, b3))
+        out, arg = ops.pointnet_forward(pts, W1, b1, W2, b2, W3, b3, want_argmax=need, mode=mode)
+        if need:
+            ctx.save_for_backward(pts, W1, b1, W2, b2, W3, b3, out, arg)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        pts, W1, b1, W2, b2, W3, b3, out, arg = ctx.saved_tensors
+        gW1, gb1, gW2, gb2, gW3, gb3 = ops.pointnet_backward(pts, W1, b1, W2, b2, W3, b3, out, arg, gout.contiguous())
+        return None, gW1.view_as(W1), gb1, gW2.view_as(W2), gb2, gW3.view_as(W3), gb3, None
+
+
+class GATLayer(torch.autograd.Function):
+    """One GATConv layer (+ optional ELU) over the block-diagonal batch graph."""
+
+    @staticmethod
+    def forward(ctx, x, W, att_src, att_dst, bias, graph, H, C, apply_elu):
+        xs, a_s, a_d = ops.gat_linear(x, W, att_src, att_dst, H, C)
+        out = ops.gat_aggregate(xs, a_s, a_d, graph, bias, apply_elu)
+        ctx.graph, ctx.H, ctx.C, ctx.apply_elu = graph, H, C, apply_elu
+        ctx.need_gx = x.requires_grad
+        ctx.save_for_backward(x, W, att_src, att_dst, xs, a_s, a_d, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, W, att_src, att_dst, xs, a_s, a_d, out = ctx.saved_tensors
+        g_xs, g_as, g_ad, g_bias = ops.gat_aggregate_backward(xs, a_s, a_d, ctx.graph, ctx.apply_elu, out, gout.contiguous())
+        gW, g_att_s, g_att_d, gx = ops.gat_linear_backward(x, W, att_src, att_dst, ctx.H, ctx.C, xs, g_xs, g_as, g_ad, ctx.need_gx)
+        return gx, gW, g_att_s.view_as(att_src), g_att_d.view_as(att_dst), g_bias, None, None, None, None
+
+
+class ProjectFuse(torch.autograd.Function):
+    """All modality projections + the fusion in one autograd node.
+
+    forward(fusion_w, M, *[x_m, W_m, b_m]*M) -> (emb_0, ..., emb_{M-1}, joint)  (joint omitted if M == 1)
+    """
+
+    @staticmethod
+    def forward(ctx, fusion_w, M, *args):
+        xs, Ws, bs = args[0::3], args[1::3], args[2::3]
+        N = xs[0].shape[0]
+        out_dims = [W.shape[0] for W in Ws]
+        dev = xs[0].device
+        joint = torch.empty((N, sum(out_dims)), device=dev, dtype=torch.float32) if M > 1 else None
+        embs, col = [], 0
+        for m in range(M):
+            embs.append(ops.project_fuse(xs[m], Ws[m], bs[m], joint, col, fusion_w, M, m))
+            col += out_dims[m]
+        ctx.M, ctx.out_dims = M, out_dims
+        ctx.need_gx = [x.requires_grad for x in xs]
+        ctx.save_for_backward(fusion_w, *xs, *Ws, *embs)
+        return (*embs, joint) if M > 1 else (embs[0],)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        M = ctx.M
+        saved = ctx.saved_tensors
+        fusion_w, xs, Ws, embs = saved[0], saved[1:1 + M], saved[1 + M:1 + 2 * M], saved[1 + 2 * M:1 + 3 * M]
+        g_joint = gouts[M] if M > 1 else None
+        if g_joint is not None:
+            g_joint = g_joint.contiguous()
+        g_fw = torch.zeros(M, device=fusion_w.device, dtype=torch.float32)
+        grads, col = [], 0
+        for m in range(M):
+            g_emb = gouts[m]
+            gW, gb, gfw, gx = ops.project_fuse_backward(xs[m], Ws[m], embs[m], None if g_emb is None else g_emb.contiguous(),
+                                                        g_joint, col, fusion_w, M, m, ctx.need_gx[m])
+            g_fw += gfw
+            grads += [gx, gW, gb]
+            col += ctx.out_dims[m]
+        return (g_fw.view_as(fusion_w), None, *grads)
+
+
+class OverallLossFn(torch.autograd.Function):
+    """OverallLoss.forward (losses.py:114-152): value and gradient come out of one fused pass."""
+
+    @staticmethod
+    def forward(ctx, idx, zoom, lv_ial, lv_icl, *embs):
+        want_grad = any(e.requires_grad for e in embs) or (lv_ial is not None and lv_ial.requires_grad)
+        losses, grads, g_ial, g_icl = ops.loss_forward_backward(embs, idx, lv_ial, lv_icl, zoom, want_grad)
+        ctx.n = len(embs)
+        ctx.has_lv = lv_ial is not None
+        if want_grad:
+            saved = list(grads) + ([g_ial, g_icl] if ctx.has_lv else [])
+            ctx.save_for_backward(*saved)
+        ctx.mark_non_differentiable()
+        return losses
+
+    @staticmethod
+    def backward(ctx, g):
+        # only losses[0] (= 'loss') carries gradient; the other three entries are reporting values
+        s = g[0]
+        saved = ctx.saved_tensors
+        grads = [t * s for t in saved[:ctx.n]]
+        if ctx.has_lv:
+            g_ial, g_icl = saved[ctx.n] * s, saved[ctx.n + 1] * s
+        else:
+            g_ial = g_icl = None
+        return (None, None, g_ial, g_icl, *grads)

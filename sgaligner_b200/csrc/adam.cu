@@ -1,0 +1,40 @@
+// Fused Adam step over one flat parameter buffer (torch.optim.Adam semantics as configured at
+// src/trainers/trainval_sgaligner.py:53: L2 weight decay added to the gradient, bias-corrected
+// first/second moments, eps added after the square root of the corrected second moment).
+#include "common.cuh"
+
+namespace sga {
+namespace {
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            int64_t n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    float gi = g[i] * gscale;
+    float pi = p[i];
+    gi = fmaf(wd, pi, gi);
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+}  // namespace
+}  // namespace sga
+
+extern "C" int sga_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                             float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                             float grad_scale, void* stream) {
+  if (n <= 0) return SGA_OK;
+  SGA_REQUIRE(step >= 1, "sga_adam_step: step=%d must be >= 1", step);
+  double bc1 = 1.0 - pow((double)beta1, (double)step);
+  double bc2 = 1.0 - pow((double)beta2, (double)step);
+  int64_t blocks = (n + 255) / 256;
+  int64_t cap = (int64_t)sga::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  sga::adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                                      weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}

@@ -1,0 +1,305 @@
+"""Thin torch-side launch wrappers over the C ABI (``include/sga_b200.h``).
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; every arithmetic step
+of the hot path runs in ``libsga_b200.so``.  All wrappers launch on the caller's current CUDA
+stream and never synchronise.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ._lib import check, get_lib
+
+POINTNET_SIMT = 0
+POINTNET_TC = 1
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('sgaligner_b200: the hot path runs on a CUDA device only (no CPU fallback); '
+                               'got a CPU tensor')
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# --------------------------------------------------------------------------------- PointNet
+def pointnet_forward(pts, W1, b1, W2, b2, W3, b3, want_argmax: bool, mode: int = POINTNET_TC):
+    _need_cuda(pts, W1, W3)
+    pts = _f32c(pts)
+    N, P, _ = pts.shape
+    C3 = W3.shape[0]
+    W1c, W2c, W3c = _f32c(W1.reshape(64, 3)), _f32c(W2.reshape(128, 64)), _f32c(W3.reshape(C3, 128))
+    if mode == POINTNET_TC and (W2c.data_ptr() % 16 or W3c.data_ptr() % 16):
+        W2c, W3c = W2c.clone(), W3c.clone()
+    out = torch.empty((N, C3), device=pts.device, dtype=torch.float32)
+    arg = torch.empty((N, C3), device=pts.device, dtype=torch.int32) if want_argmax else None
+    check(get_lib().sga_pointnet_fwd(_ptr(pts), N, P, _ptr(W1c), _ptr(_f32c(b1)), _ptr(W2c), _ptr(_f32c(b2)),
+                                     _ptr(W3c), _ptr(_f32c(b3)), C3, _ptr(out), _ptr(arg), mode, _stream()),
+          'sga_pointnet_fwd')
+    return out, arg
+
+
+def pointnet_backward(pts, W1, b1, W2, b2, W3, b3, out, arg, gout):
+    pts = _f32c(pts)
+    N, P, _ = pts.shape
+    C3 = W3.shape[0]
+    dev = pts.device
+    g = [torch.zeros(s, device=dev, dtype=torch.float32) for s in ((64, 3), (64,), (128, 64), (128,), (C3, 128), (C3,))]
+    check(get_lib().sga_pointnet_bwd(_ptr(pts), N, P, _ptr(_f32c(W1.reshape(64, 3))), _ptr(_f32c(b1)),
+                                     _ptr(_f32c(W2.reshape(128, 64))), _ptr(_f32c(b2)), _ptr(_f32c(W3.reshape(C3, 128))),
+                                     _ptr(_f32c(b3)), C3, _ptr(out), _ptr(arg), _ptr(_f32c(gout)),
+                                     *[_ptr(t) for t in g], _stream()), 'sga_pointnet_bwd')
+    return g
+
+
+def pointnet_bn_moments(pts, W1, b1, W2, b2, W3, b3):
+    pts = _f32c(pts)
+    N, P, _ = pts.shape
+    C3 = W3.shape[0]
+    mom = torch.zeros(2 * (64 + 128 + C3), device=pts.device, dtype=torch.float64)
+    check(get_lib().sga_pointnet_bn_moments(_ptr(pts), N, P, _ptr(_f32c(W1.reshape(64, 3))), _ptr(_f32c(b1)),
+                                            _ptr(_f32c(W2.reshape(128, 64))), _ptr(_f32c(b2)),
+                                            _ptr(_f32c(W3.reshape(C3, 128))), _ptr(_f32c(b3)), C3, _ptr(mom), _stream()),
+          'sga_pointnet_bn_moments')
+    return mom
+
+
+# --------------------------------------------------------------------------------- graphs
+class BatchGraph:
+    """Device-side block-diagonal CSR (by destination) of all 2B graphs of a collated batch."""
+
+    def __init__(self, edges: torch.Tensor, obj_count: np.ndarray, edge_count: np.ndarray):
+        _need_cuda(edges)
+        dev = edges.device
+        oc = np.asarray(obj_count, dtype=np.int64).reshape(-1)
+        ec = np.asarray(edge_count, dtype=np.int64).reshape(-1)
+        self.G = int(oc.shape[0])
+        self.N = int(oc.sum())
+        self.E = int(ec.sum())
+        self.max_nodes = int(oc.max()) if self.G else 0
+        node_off = np.concatenate([[0], np.cumsum(oc)]).astype(np.int32)
+        edge_off = np.concatenate([[0], np.cumsum(ec)]).astype(np.int64)
+        self.node_off = torch.from_numpy(node_off).to(dev, non_blocking=True)
+        self.edge_off = torch.from_numpy(edge_off).to(dev, non_blocking=True)
+        edges = edges.to(torch.int64).contiguous()
+        assert edges.shape[0] == self.E, 'edge tensor does not match graph_per_edge_count'
+        self.row_beg = torch.empty(self.N, device=dev, dtype=torch.int32)
+        self.row_cnt = torch.empty(self.N, device=dev, dtype=torch.int32)
+        self.col = torch.empty(self.E + self.N, device=dev, dtype=torch.int32)
+        check(get_lib().sga_csr_build(_ptr(edges), _ptr(self.node_off), _ptr(self.edge_off), self.G, self.max_nodes,
+                                      _ptr(self.row_beg), _ptr(self.row_cnt), _ptr(self.col), _stream()), 'sga_csr_build')
+
+
+def gat_linear(x: torch.Tensor, W, att_src, att_dst, H: int, C: int):
+    _need_cuda(x, W)
+    is64 = 1 if x.dtype == torch.float64 else 0
+    if not is64:
+        x = _f32c(x)
+    x = x.contiguous()
+    N, in_dim = x.shape
+    dev = x.device
+    xs = torch.empty((H, N, C), device=dev, dtype=torch.float32)
+    a_s = torch.empty((N, H), device=dev, dtype=torch.float32)
+    a_d = torch.empty((N, H), device=dev, dtype=torch.float32)
+    check(get_lib().sga_gat_linear(_ptr(x), is64, N, in_dim, _ptr(_f32c(W)), _ptr(_f32c(att_src).reshape(-1)),
+                                   _ptr(_f32c(att_dst).reshape(-1)), H, C, _ptr(xs), _ptr(a_s), _ptr(a_d), _stream()),
+          'sga_gat_linear')
+    return xs, a_s, a_d
+
+
+def gat_aggregate(xs, a_s, a_d, graph: BatchGraph, bias, apply_elu: bool):
+    H, N, C = xs.shape
+    out = torch.empty((N, H * C), device=xs.device, dtype=torch.float32)
+    check(get_lib().sga_gat_aggregate(_ptr(xs), _ptr(a_s), _ptr(a_d), _ptr(graph.row_beg), _ptr(graph.row_cnt),
+                                      _ptr(graph.col), _ptr(graph.node_off), graph.G, graph.max_nodes, N, H, C,
+                                      _ptr(_f32c(bias)), 1 if apply_elu else 0, _ptr(out), _stream()), 'sga_gat_aggregate')
+    return out
+
+
+def gat_aggregate_backward(xs, a_s, a_d, graph: BatchGraph, apply_elu: bool, out, gout):
+    H, N, C = xs.shape
+    dev = xs.device
+    g_xs = torch.zeros_like(xs)
+    g_as = torch.zeros((N, H), device=dev, dtype=torch.float32)
+    g_ad = torch.zeros((N, H), device=dev, dtype=torch.float32)
+    g_bias = torch.zeros(H * C, device=dev, dtype=torch.float32)
+    check(get_lib().sga_gat_aggregate_bwd(_ptr(xs), _ptr(a_s), _ptr(a_d), _ptr(graph.row_beg), _ptr(graph.row_cnt),
+                                          _ptr(graph.col), N, H, C, 1 if apply_elu else 0, _ptr(out), _ptr(_f32c(gout)),
+                                          _ptr(g_xs), _ptr(g_as), _ptr(g_ad), _ptr(g_bias), _stream()),
+          'sga_gat_aggregate_bwd')
+    return g_xs, g_as, g_ad, g_bias
+
+
+def gat_linear_backward(x, W, att_src, att_dst, H, C, xs, g_xs, g_as, g_ad, need_gx: bool):
+    is64 = 1 if x.dtype == torch.float64 else 0
+    if not is64:
+        x = _f32c(x)
+    x = x.contiguous()
+    N, in_dim = x.shape
+    dev = x.device
+    gW = torch.zeros((H * C, in_dim), device=dev, dtype=torch.float32)
+    g_att_s = torch.zeros(H * C, device=dev, dtype=torch.float32)
+    g_att_d = torch.zeros(H * C, device=dev, dtype=torch.float32)
+    gx = torch.empty((N, in_dim), device=dev, dtype=torch.float32) if need_gx else None
+    check(get_lib().sga_gat_linear_bwd(_ptr(x), is64, N, in_dim, _ptr(_f32c(W)), _ptr(_f32c(att_src).reshape(-1)),
+                                       _ptr(_f32c(att_dst).reshape(-1)), H, C, _ptr(xs), _ptr(g_xs), _ptr(g_as), _ptr(g_ad),
+                                       _ptr(gW), _ptr(g_att_s), _ptr(g_att_d), _ptr(gx), _stream()), 'sga_gat_linear_bwd')
+    return gW, g_att_s, g_att_d, gx
+
+
+# --------------------------------------------------------------------------------- projection + fusion
+def project_fuse(x, W, b, joint: Optional[torch.Tensor], joint_col: int, fusion_w, M: int, m: int):
+    _need_cuda(x, W)
+    is64 = 1 if x.dtype == torch.float64 else 0
+    if not is64:
+        x = _f32c(x)
+    x = x.contiguous()
+    N, in_dim = x.shape
+    out_dim = W.shape[0]
+    emb = torch.empty((N, out_dim), device=x.device, dtype=torch.float32)
+    fw = None if joint is None else _f32c(fusion_w).reshape(-1)
+    check(get_lib().sga_project_fuse_fwd(_ptr(x), is64, N, in_dim, _ptr(_f32c(W)), _ptr(_f32c(b)), out_dim, _ptr(emb),
+                                         _ptr(joint), 0 if joint is None else joint.shape[1], joint_col, _ptr(fw), M, m,
+                                         _stream()), 'sga_project_fuse_fwd')
+    return emb
+
+
+def project_fuse_backward(x, W, emb, g_emb, g_joint, joint_col: int, fusion_w, M: int, m: int, need_gx: bool):
+    is64 = 1 if x.dtype == torch.float64 else 0
+    if not is64:
+        x = _f32c(x)
+    x = x.contiguous()
+    N, in_dim = x.shape
+    out_dim = W.shape[0]
+    dev = x.device
+    gW = torch.zeros((out_dim, in_dim), device=dev, dtype=torch.float32)
+    gb = torch.zeros(out_dim, device=dev, dtype=torch.float32)
+    gfw = torch.zeros(M, device=dev, dtype=torch.float32)
+    gx = torch.empty((N, in_dim), device=dev, dtype=torch.float32) if need_gx else None
+    ws = torch.empty((N, out_dim), device=dev, dtype=torch.float32)
+    fw = None if g_joint is None else _f32c(fusion_w).reshape(-1)
+    check(get_lib().sga_project_fuse_bwd(_ptr(x), is64, N, in_dim, _ptr(_f32c(W)), out_dim, _ptr(emb),
+                                         _ptr(None if g_emb is None else _f32c(g_emb)),
+                                         _ptr(None if g_joint is None else _f32c(g_joint)),
+                                         0 if g_joint is None else g_joint.shape[1], joint_col, _ptr(fw), M, m,
+                                         _ptr(gW), _ptr(gb), _ptr(gfw), _ptr(gx), _ptr(ws), ws.numel() * 4, _stream()),
+          'sga_project_fuse_bwd')
+    return gW, gb, gfw, gx
+
+
+# --------------------------------------------------------------------------------- matching
+class PairLayout:
+    """Per-pair node offsets of a collated batch, resident on the device."""
+
+    def __init__(self, obj_count: np.ndarray, device):
+        n = np.asarray(obj_count, dtype=np.int64).reshape(-1, 2).sum(1)
+        self.B = int(n.shape[0])
+        self.n = n
+        self.N = int(n.sum())
+        self.max_n = int(n.max()) if self.B else 0
+        self.pair_off_host = np.concatenate([[0], np.cumsum(n)]).astype(np.int32)
+        self.sim_off_host = np.concatenate([[0], np.cumsum(n * n)]).astype(np.int64)
+        node_pair = np.repeat(np.arange(self.B, dtype=np.int32), n)
+        self.pair_off = torch.from_numpy(self.pair_off_host).to(device, non_blocking=True)
+        self.sim_off = torch.from_numpy(self.sim_off_host).to(device, non_blocking=True)
+        self.node_pair = torch.from_numpy(node_pair).to(device, non_blocking=True)
+
+
+def match_sim(emb: torch.Tensor, lay: PairLayout):
+    _need_cuda(emb)
+    emb = _f32c(emb)
+    N, D = emb.shape
+    norms = torch.empty(N, device=emb.device, dtype=torch.float32)
+    sim = torch.empty(int(lay.sim_off_host[-1]), device=emb.device, dtype=torch.float32)
+    check(get_lib().sga_match_sim(_ptr(emb), N, D, _ptr(lay.pair_off), _ptr(lay.sim_off), lay.B, lay.max_n, _ptr(norms),
+                                  _ptr(sim), _stream()), 'sga_match_sim')
+    return sim
+
+
+def match_rank(sim: torch.Tensor, lay: PairLayout, K: int, full: bool):
+    dev = sim.device
+    topk_idx = torch.empty((lay.N, K), device=dev, dtype=torch.int32) if K > 0 else None
+    topk_dist = torch.empty((lay.N, K), device=dev, dtype=torch.float32) if K > 0 else None
+    rank = torch.empty(sim.numel(), device=dev, dtype=torch.int32) if full else None
+    check(get_lib().sga_match_rank(_ptr(sim), lay.N, _ptr(lay.pair_off), _ptr(lay.sim_off), _ptr(lay.node_pair), lay.max_n, K,
+                                   _ptr(topk_idx), _ptr(topk_dist), _ptr(rank), _stream()), 'sga_match_rank')
+    return topk_idx, topk_dist, rank
+
+
+def match_anchor_pos(sim: torch.Tensor, lay: PairLayout, e1i: torch.Tensor, e2i: torch.Tensor):
+    A = int(e1i.numel())
+    pos = torch.empty(A, device=sim.device, dtype=torch.int32)
+    check(get_lib().sga_match_anchor_pos(_ptr(sim), _ptr(lay.pair_off), _ptr(lay.sim_off), _ptr(lay.node_pair), _ptr(e1i),
+                                         _ptr(e2i), A, _ptr(pos), _stream()), 'sga_match_anchor_pos')
+    return pos
+
+
+# --------------------------------------------------------------------------------- loss
+_WS_CACHE = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes * 1.25) + 256, device=device, dtype=torch.uint8)
+        _WS_CACHE[key] = ws
+    return ws
+
+
+def loss_forward_backward(embs: Sequence[torch.Tensor], idx: Sequence[torch.Tensor], lv_ial, lv_icl, zoom: float,
+                          want_grad: bool):
+    """embs: M modal embeddings then the joint (or a single embedding).  idx: e1i,e2i,e1j,e2j int32
+    device tensors.  Returns (losses[4], grads or None, g_lv_ial, g_lv_icl)."""
+    lib = get_lib()
+    embs = [_f32c(e) for e in embs]
+    _need_cuda(*embs)
+    n_emb = len(embs)
+    dev = embs[0].device
+    N = embs[0].shape[0]
+    dims = (ctypes.c_int * n_emb)(*[int(e.shape[1]) for e in embs])
+    A, J1, J2 = int(idx[0].numel()), int(idx[2].numel()), int(idx[3].numel())
+    nbytes = lib.sga_loss_workspace_bytes(n_emb, dims, N, A, J1, J2, 1 if want_grad else 0)
+    ws = _workspace(nbytes, dev)
+    losses = torch.empty(4, device=dev, dtype=torch.float32)
+    grads = [torch.empty_like(e) for e in embs] if want_grad else None
+    M = 1 if n_emb == 1 else n_emb - 1
+    g_ial = torch.zeros(M, device=dev, dtype=torch.float32) if want_grad else None
+    g_icl = torch.zeros(M, device=dev, dtype=torch.float32) if want_grad else None
+    e_ptrs = (ctypes.c_void_p * n_emb)(*[e.data_ptr() for e in embs])
+    g_ptrs = (ctypes.c_void_p * n_emb)(*[(g.data_ptr() if want_grad else 0) for g in (grads or embs)])
+    check(lib.sga_loss_fwd_bwd(e_ptrs, dims, n_emb, N, _ptr(idx[0]), _ptr(idx[1]), _ptr(idx[2]), _ptr(idx[3]), A, J1, J2,
+                               _ptr(None if lv_ial is None else _f32c(lv_ial)), _ptr(None if lv_icl is None else _f32c(lv_icl)),
+                               float(zoom), _ptr(losses), 1 if want_grad else 0, g_ptrs, _ptr(g_ial), _ptr(g_icl),
+                               _ptr(ws), ws.numel(), _stream()), 'sga_loss_fwd_bwd')
+    return losses, grads, g_ial, g_icl
+
+
+# --------------------------------------------------------------------------------- optimiser
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    check(get_lib().sga_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), lr, beta1, beta2,
+                                  eps, weight_decay, int(step), float(grad_scale), _stream()), 'sga_adam_step')
+
+
+def selftest_umma(A: torch.Tensor, B: torch.Tensor, kind: int) -> torch.Tensor:
+    D = torch.empty((128, B.shape[0]), device=A.device, dtype=torch.float32)
+    check(get_lib().sga_selftest_umma(_ptr(_f32c(A)), _ptr(_f32c(B)), _ptr(D), B.shape[0], A.shape[1], kind, _stream()),
+          'sga_selftest_umma')
+    return D

@@ -1,0 +1,219 @@
+"""B200-native mirror of ``src/aligner/sg_aligner.py`` of the reference.
+
+Same class names, constructor signatures, ``forward(data_dict)`` dict contract and ``state_dict``
+keys, so ``from aligner.sg_aligner import *`` in the reference's trainers / testers can resolve to
+this module.  The arithmetic runs in the CUDA kernels of ``libsga_b200.so``;
+the ``nn.Linear`` / ``nn.Conv1d`` / ``nn.BatchNorm1d`` objects below are parameter containers that
+reproduce the reference's key names, shapes and initialisation -- their own ``forward`` is never
+called.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F   # noqa: F401  (re-exported: the reference scripts rely on `import *`)
+
+from . import autograd as ag
+from . import ops
+
+__all__ = ['torch', 'nn', 'F', 'ProjectionHead', 'MultiModalFusion', 'MultiModalEncoder', 'PointNetfeat', 'MultiGAT', 'GATConv']
+
+
+class ProjectionHead(nn.Module):
+    """``sg_aligner.py:9-21`` (not used by the trainer; kept for API completeness).  Small MLP on
+    top of an embedding -- plain PyTorch, it is not on the hot path."""
+
+    def __init__(self, in_dim, hidden_dim, out_dim, dropout):
+        super().__init__()
+        self.l1 = nn.Linear(in_dim, hidden_dim, bias=False)
+        self.l2 = nn.Linear(hidden_dim, out_dim, bias=False)
+        self.dropout = dropout
+
+    def forward(self, x):
+        return self.l2(F.dropout(F.relu(self.l1(x)), self.dropout, training=self.training))
+
+
+class MultiModalFusion(nn.Module):
+    """``sg_aligner.py:23-35``: holds the modality weights; the fused kernel applies them."""
+
+    def __init__(self, modal_num, with_weight=1):
+        super().__init__()
+        self.modal_num = modal_num
+        self.requires_grad = True if with_weight > 0 else False
+        self.weight = nn.Parameter(torch.ones((self.modal_num, 1)), requires_grad=self.requires_grad)
+
+    def forward(self, embs):
+        # stand-alone use on already-projected embeddings: identity projections are not worth a
+        # kernel of their own -- route through the fused node with explicit identity weights
+        assert len(embs) == self.modal_num
+        args = []
+        for e in embs:
+            d = e.shape[1]
+            args += [e, torch.eye(d, device=e.device, dtype=torch.float32), torch.zeros(d, device=e.device)]
+        return ag.ProjectFuse.apply(self.weight, self.modal_num, *args)[-1]
+
+
+class PointNetfeat(nn.Module):
+    """Parameter container + launcher for ``networks/pointnet.py:87-175`` in the configuration the
+    aligner uses (no STN, global feature, batch_norm=True whose outputs are discarded)."""
+
+    def __init__(self, global_feat=True, input_transform=False, feature_transform=False, point_size=3, out_size=1024,
+                 batch_norm=True, init_weights=True, pointnet_str=None):
+        super().__init__()
+        if input_transform or feature_transform or not global_feat or point_size != 3:
+            raise NotImplementedError('only the configuration used by MultiModalEncoder is implemented')
+        self.name = 'pnetenc'
+        self.use_batch_norm = batch_norm
+        self.point_size = point_size
+        self.out_size = out_size
+        self.conv1 = nn.Conv1d(point_size, 64, 1)
+        self.conv2 = nn.Conv1d(64, 128, 1)
+        self.conv3 = nn.Conv1d(128, out_size, 1)
+        if batch_norm:
+            self.bn1 = nn.BatchNorm1d(64)
+            self.bn2 = nn.BatchNorm1d(128)
+            self.bn3 = nn.BatchNorm1d(out_size)
+        self.track_bn_stats = True
+        self.kernel_mode = ops.POINTNET_TC if out_size % 128 == 0 else ops.POINTNET_SIMT
+        if init_weights:
+            # networks/base.py:5-56 as called at pointnet.py:116-118: xavier_normal(gain 1), zero bias,
+            # BatchNorm weight 1 / bias 0
+            for conv in (self.conv1, self.conv2, self.conv3):
+                nn.init.xavier_normal_(conv.weight.data, gain=1)
+                nn.init.constant_(conv.bias.data, 0.0)
+
+    def forward(self, pts_npc: torch.Tensor) -> torch.Tensor:
+        """``pts_npc``: [N, P, 3] (the collated layout; the reference permutes to [N,3,P] first)."""
+        if self.use_batch_norm and self.training and self.track_bn_stats:
+            self._update_bn_running_stats(pts_npc)
+        return ag.PointNetFeat.apply(pts_npc, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
+                                     self.conv3.weight, self.conv3.bias, self.kernel_mode)
+
+    @torch.no_grad()
+    def _update_bn_running_stats(self, pts):
+        """Train-mode side effect of the discarded BatchNorm calls (pointnet.py:141-142,154-155,
+        158-159): running_mean/var <- momentum update with the batch statistics of the pre-ReLU
+        conv outputs; outputs are unaffected."""
+        mom = ops.pointnet_bn_moments(pts, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
+                                      self.conv3.weight, self.conv3.bias)
+        cnt = float(pts.shape[0] * pts.shape[1])
+        o = 0
+        for bn, c in ((self.bn1, 64), (self.bn2, 128), (self.bn3, self.out_size)):
+            s, sq = mom[o:o + c], mom[o + c:o + 2 * c]
+            o += 2 * c
+            mean = s / cnt
+            var_unbiased = (sq - s * mean) / max(cnt - 1.0, 1.0)
+            m = bn.momentum
+            bn.running_mean.mul_(1 - m).add_(mean.float(), alpha=m)
+            bn.running_var.mul_(1 - m).add_(var_unbiased.float(), alpha=m)
+            bn.num_batches_tracked += 1
+
+
+class _SharedLinear(nn.Module):
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels))
+
+
+class GATConv(nn.Module):
+    """Parameter container with torch_geometric 2.2.0 ``GATConv`` names: ``lin_src`` / ``lin_dst``
+    (one shared module), ``att_src``, ``att_dst`` [1,H,C], ``bias`` [H*C]; glorot init."""
+
+    def __init__(self, in_channels, out_channels, heads=1):
+        super().__init__()
+        self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
+        self.lin_src = _SharedLinear(in_channels, heads * out_channels)
+        self.lin_dst = self.lin_src
+        self.att_src = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.att_dst = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.bias = nn.Parameter(torch.zeros(heads * out_channels))
+        for t in (self.lin_src.weight, self.att_src, self.att_dst):
+            a = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
+            with torch.no_grad():
+                t.uniform_(-a, a)
+
+
+class MultiGAT(nn.Module):
+    """``networks/gat.py:27-48`` over a whole batch of graphs at once."""
+
+    def __init__(self, n_units=(17, 128, 100), n_heads=(2, 2), dropout=0.0):
+        super().__init__()
+        self.num_layers = len(n_units) - 1
+        self.dropout = dropout
+        if dropout != 0.0:
+            raise NotImplementedError('dropout > 0 is not used by the reference configs')
+        layers = []
+        for i in range(self.num_layers):
+            in_channels = n_units[i] * n_heads[i - 1] if i else n_units[i]
+            layers.append(GATConv(in_channels=in_channels, out_channels=n_units[i + 1], heads=n_heads[i]))
+        self.layer_stack = nn.ModuleList(layers)
+
+    def forward(self, x: torch.Tensor, graph: 'ops.BatchGraph') -> torch.Tensor:
+        for idx, layer in enumerate(self.layer_stack):
+            x = ag.GATLayer.apply(x, layer.lin_src.weight, layer.att_src, layer.att_dst, layer.bias, graph, layer.heads,
+                                  layer.out_channels, idx + 1 < self.num_layers)
+        return x
+
+
+class MultiModalEncoder(nn.Module):
+    """``sg_aligner.py:37-137``."""
+
+    def __init__(self, modules, rel_dim, attr_dim, hidden_units=[3, 128, 128], heads=[2, 2], emb_dim=100, pt_out_dim=256,
+                 dropout=0.0, attn_dropout=0.0, instance_norm=False):
+        super().__init__()
+        self.modules = modules            # a plain list attribute, exactly as in the reference (:42)
+        self.pt_out_dim = pt_out_dim
+        self.rel_dim = rel_dim
+        self.emb_dim = emb_dim
+        self.attr_dim = attr_dim
+        self.hidden_units = hidden_units
+        self.heads = heads
+        self.dropout = dropout
+        self.attn_dropout = attn_dropout
+        self.instance_norm = instance_norm
+        self.inner_view_num = len(self.modules)
+
+        self.meta_embedding_rel = nn.Linear(self.rel_dim, self.emb_dim)
+        self.meta_embedding_attr = nn.Linear(self.attr_dim, self.emb_dim)
+        if 'point' in self.modules:
+            self.object_encoder = PointNetfeat(global_feat=True, batch_norm=True, point_size=3, input_transform=False,
+                                               feature_transform=False, out_size=self.pt_out_dim)
+        elif 'pct' in self.modules:
+            raise NotImplementedError("the 'pct' object encoder is outside the B200 hot path (SURVEY.md 8(f))")
+        else:
+            raise NotImplementedError
+        self.object_embedding = nn.Linear(self.pt_out_dim, self.emb_dim)
+        self.structure_encoder = MultiGAT(n_units=self.hidden_units, n_heads=self.heads, dropout=self.dropout)
+        self.structure_embedding = nn.Linear(256, self.emb_dim)
+        self.fusion = MultiModalFusion(modal_num=self.inner_view_num, with_weight=1)
+
+    def forward(self, data_dict):
+        pts = data_dict['tot_obj_pts']
+        if not (torch.is_tensor(pts) and pts.is_cuda):
+            raise RuntimeError('sgaligner_b200.MultiModalEncoder needs the batch on a CUDA device (no CPU fallback)')
+        args = []
+        for module in self.modules:
+            if module == 'gat':
+                graph = data_dict.get('_sga_graph')
+                if graph is None:
+                    graph = ops.BatchGraph(data_dict['edges'], np.asarray(data_dict['graph_per_obj_count']),
+                                           np.asarray(data_dict['graph_per_edge_count']))
+                x = self.structure_encoder(data_dict['tot_rel_pose'], graph)
+                args += [x, self.structure_embedding.weight, self.structure_embedding.bias]
+            elif module == 'point':
+                x = self.object_encoder(pts)
+                args += [x, self.object_embedding.weight, self.object_embedding.bias]
+            elif module == 'rel':
+                args += [data_dict['tot_bow_vec_object_edge_feats'], self.meta_embedding_rel.weight, self.meta_embedding_rel.bias]
+            elif module == 'attr':
+                args += [data_dict['tot_bow_vec_object_attr_feats'], self.meta_embedding_attr.weight, self.meta_embedding_attr.bias]
+            else:
+                raise NotImplementedError
+        outs = ag.ProjectFuse.apply(self.fusion.weight, len(self.modules), *args)
+        embs = {module: outs[i] for i, module in enumerate(self.modules)}
+        if len(self.modules) > 1:
+            embs['joint'] = outs[len(self.modules)]
+        return embs

@@ -1,0 +1,67 @@
+"""tcgen05 bring-up and the tensor-core PointNet kernel vs the oracle and vs the fp32 FMA kernel."""
+import pytest
+import torch
+
+from oracle import sgaligner_oracle as O
+from tests.util import CASES, load_case, rel_inf
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device('cuda:0')
+
+
+@pytest.mark.parametrize('kind,K,ncols', [(0, 64, 128), (0, 128, 128), (0, 128, 64), (1, 32, 128), (1, 64, 128), (1, 64, 48)])
+def test_umma_selftest(kind, K, ncols, dev):
+    """One split-operand UMMA tile (bf16x3 / tf32x3) against an fp64 matmul: validates the
+    shared-memory descriptors, the swizzled operand layout, the instruction descriptor and the
+    TMEM load shape that every tensor-core kernel of the library shares."""
+    from sgaligner_b200 import ops
+    g = torch.Generator().manual_seed(kind * 100 + K + ncols)
+    A = torch.randn(128, K, generator=g)
+    B = torch.randn(ncols, K, generator=g)
+    D = ops.selftest_umma(A.to(dev), B.to(dev), kind)
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().t()
+    err = rel_inf(D, ref)
+    assert err < (3e-5 if kind == 0 else 3e-6), err
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_pointnet_tc_vs_oracle(name, dev):
+    from sgaligner_b200 import ops
+    c = load_case(name)
+    p = c['params']
+    pts = c['data']['tot_obj_pts']
+    ref64 = O.pointnet_feat(pts.double(), {k: v.double() for k, v in p.items() if v.is_floating_point()})
+    w = [p[f'object_encoder.conv{i}.{k}'].to(dev) for i in (1, 2, 3) for k in ('weight', 'bias')]
+    out, arg = ops.pointnet_forward(pts.to(dev), *w, want_argmax=True, mode=ops.POINTNET_TC)
+    out2, _ = ops.pointnet_forward(pts.to(dev), *w, want_argmax=False, mode=ops.POINTNET_TC)
+    simt, arg_s = ops.pointnet_forward(pts.to(dev), *w, want_argmax=True, mode=ops.POINTNET_SIMT)
+    torch.cuda.synchronize()
+    assert rel_inf(out, ref64) < 3e-5
+    assert torch.equal(out, out2)
+    assert rel_inf(out, simt) < 3e-5
+    live = (simt > 1e-3 * simt.max()).cpu()
+    assert int(arg.min()) >= 0 and int(arg.max()) < pts.shape[1]
+    # same argmax as the fp32 kernel wherever the channel is alive (ties / near-ties may differ)
+    agree = (arg.cpu() == arg_s.cpu())[live].float().mean()
+    assert float(agree) > 0.97
+
+
+def test_pointnet_tc_ragged_sizes(dev):
+    """P not a multiple of the 128-point tile, N not a multiple of the SM count, C3 = 128 / 512."""
+    from sgaligner_b200 import ops
+    for (N, P, C3, seed) in [(5, 100, 256, 0), (301, 130, 128, 1), (17, 1, 256, 2), (40, 513, 512, 3)]:
+        p = O.init_params(['point'], 41, 164, pt_out_dim=C3, seed=seed)
+        for i in (1, 2, 3):
+            p[f'object_encoder.conv{i}.bias'] = 0.1 * torch.randn(p[f'object_encoder.conv{i}.bias'].shape)
+        pts = torch.randn(N, P, 3) + torch.rand(N, 1, 3) * 4 - 2
+        ref = O.pointnet_feat(pts, p)
+        w = [p[f'object_encoder.conv{i}.{k}'].to(dev) for i in (1, 2, 3) for k in ('weight', 'bias')]
+        out, _ = ops.pointnet_forward(pts.to(dev), *w, want_argmax=False, mode=ops.POINTNET_TC)
+        torch.cuda.synchronize()
+        assert rel_inf(out, ref) < 3e-5, (N, P, C3)
