@@ -94,20 +94,23 @@ int sga_gat_aggregate(const float* xs, const float* a_src, const float* a_dst,
                       const float* bias, int apply_elu, float* out, void* stream);
 
 /* backward of sga_gat_aggregate: given grad_out [N,H*C] (and `out` for the ELU derivative) produces
- * g_xs [H][N][C] (zeroed by the caller; accumulated with atomics), g_a_src/g_a_dst [N,H] (zeroed by
- * the caller) and accumulates g_bias [H*C]. */
+ * g_xs [H][N][C], g_a_src / g_a_dst [N,H] (all three zeroed by the caller) and accumulates g_bias [H*C]. */
 int sga_gat_aggregate_bwd(const float* xs, const float* a_src, const float* a_dst,
                           const int32_t* row_beg, const int32_t* row_cnt, const int32_t* col,
-                          int64_t N, int H, int C, int apply_elu, const float* out,
-                          const float* grad_out, float* g_xs, float* g_a_src, float* g_a_dst,
-                          float* g_bias, void* stream);
+                          const int32_t* node_off, int G, int max_graph_nodes, int64_t N, int H, int C,
+                          int apply_elu, const float* out, const float* grad_out, float* g_xs,
+                          float* g_a_src, float* g_a_dst, float* g_bias, void* stream);
 
-/* backward of sga_gat_linear: folds g_a_src/g_a_dst into g_xs, then gW += g_xs^T x, g_att_* +=,
- * and (if gx != NULL) gx [N,in_dim] = g_xs W.  g_xs is modified in place. */
-int sga_gat_linear_bwd(const void* x, int x_is_f64, int64_t N, int in_dim, const float* W,
-                       const float* att_src, const float* att_dst, int H, int C,
-                       const float* xs, float* g_xs, const float* g_a_src, const float* g_a_dst,
-                       float* gW, float* g_att_src, float* g_att_dst, float* gx, void* stream);
+/* backward of sga_gat_linear (x must be f32 here -- see sga_cast_f64_f32): folds g_a_src/g_a_dst into
+ * g_xs (in place), then gW += g_xs^T x, g_att_* +=, and (if gx != NULL) gx [N,in_dim] = g_xs W. */
+int sga_gat_linear_bwd(const float* x, int64_t N, int in_dim, const float* W, const float* att_src,
+                       const float* att_dst, int H, int C, const float* xs, float* g_xs,
+                       const float* g_a_src, const float* g_a_dst, float* gW, float* g_att_src,
+                       float* g_att_dst, float* gx, void* stream);
+
+/* the reference's `.float()` on the f64 dataloader tensors (sg_aligner.py:73-75) for the backward
+ * kernels, which take f32 inputs only */
+int sga_cast_f64_f32(const double* in, float* out, int64_t n, void* stream);
 
 /* ---- a5 + a8: one modality's nn.Linear (sg_aligner.py:112-122) fused with its slice of
  * MultiModalFusion (sg_aligner.py:30-35).  x [N,in_dim] f32/f64; W [out_dim,in_dim]; b [out_dim];
@@ -119,12 +122,12 @@ int sga_project_fuse_fwd(const void* x, int x_is_f64, int64_t N, int in_dim, con
 
 /* backward: g_emb [N,out_dim] (direct gradient on the modality embedding, may be NULL) and
  * g_joint (gradient on the joint embedding, may be NULL) -> gW +=, gb +=, g_fusion_w [M] +=, and
- * gx [N,in_dim] (may be NULL). */
-int sga_project_fuse_bwd(const void* x, int x_is_f64, int64_t N, int in_dim, const float* W,
-                         int out_dim, const float* emb, const float* g_emb, const float* g_joint,
-                         int joint_ld, int joint_col, const float* fusion_w, int M, int m,
-                         float* gW, float* gb, float* g_fusion_w, float* gx, void* workspace,
-                         size_t workspace_bytes, void* stream);
+ * gx [N,in_dim] (may be NULL).  x must be f32.  workspace >= (N*out_dim + 64) floats. */
+int sga_project_fuse_bwd(const float* x, int64_t N, int in_dim, const float* W, int out_dim,
+                         const float* emb, const float* g_emb, const float* g_joint, int joint_ld,
+                         int joint_col, const float* fusion_w, int M, int m, float* gW, float* gb,
+                         float* g_fusion_w, float* gx, void* workspace, size_t workspace_bytes,
+                         void* stream);
 
 /* ---- a9: matching head (inference_align_reg.py:125-128) for all pairs of the batch at once.
  * emb [N,D]; pair_off [B+1] int32 node offsets; sim_off [B+1] int64 = prefix sum of n_b^2 (n_b =

@@ -35,10 +35,12 @@ def _declare(lib):
     sig('sga_csr_build', c_i, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p)
     sig('sga_gat_linear', c_i, c_p, c_i, c_l, c_i, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p)
     sig('sga_gat_aggregate', c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_l, c_i, c_i, c_p, c_i, c_p, c_p)
-    sig('sga_gat_aggregate_bwd', c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p)
-    sig('sga_gat_linear_bwd', c_i, c_p, c_i, c_l, c_i, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p)
+    sig('sga_gat_aggregate_bwd', c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_l, c_i, c_i, c_i, c_p, c_p, c_p, c_p,
+        c_p, c_p, c_p)
+    sig('sga_gat_linear_bwd', c_i, c_p, c_l, c_i, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p)
+    sig('sga_cast_f64_f32', c_i, c_p, c_p, c_l, c_p)
     sig('sga_project_fuse_fwd', c_i, c_p, c_i, c_l, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_i, c_i, c_p)
-    sig('sga_project_fuse_bwd', c_i, c_p, c_i, c_l, c_i, c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_p, c_i, c_i,
+    sig('sga_project_fuse_bwd', c_i, c_p, c_l, c_i, c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_p, c_i, c_i,
         c_p, c_p, c_p, c_p, c_p, c_size_t, c_p)
     sig('sga_match_sim', c_i, c_p, c_l, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p)
     sig('sga_match_rank', c_i, c_p, c_l, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p)
@@ -52,7 +54,7 @@ def _declare(lib):
 
 EXPORTS = ['sga_last_error', 'sga_version', 'sga_device_info', 'sga_pointnet_fwd', 'sga_pointnet_bwd',
            'sga_pointnet_bn_moments', 'sga_csr_build', 'sga_gat_linear', 'sga_gat_aggregate',
-           'sga_gat_aggregate_bwd', 'sga_gat_linear_bwd', 'sga_project_fuse_fwd', 'sga_project_fuse_bwd',
+           'sga_gat_aggregate_bwd', 'sga_gat_linear_bwd', 'sga_cast_f64_f32', 'sga_project_fuse_fwd', 'sga_project_fuse_bwd',
            'sga_match_sim', 'sga_match_rank', 'sga_match_anchor_pos', 'sga_loss_workspace_bytes',
            'sga_loss_fwd_bwd', 'sga_adam_step', 'sga_selftest_umma']
 

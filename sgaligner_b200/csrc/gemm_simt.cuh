@@ -12,7 +12,7 @@ constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
 
 static __global__ void __launch_bounds__(NT)
 gemm_kernel(const float* __restrict__ A, int64_t sai, int64_t sak, const float* __restrict__ B, int64_t sbk,
-            int64_t sbj, float* __restrict__ C, int64_t ldc, int M, int N, int K, int accumulate) {
+            int64_t sbj, float* __restrict__ C, int64_t ldc, int M, int N, int K, int accumulate, int kchunk) {
   __shared__ float As[BK][BM + 1];
   __shared__ float Bs[BK][BN + 1];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -23,7 +23,10 @@ gemm_kernel(const float* __restrict__ A, int64_t sai, int64_t sak, const float* 
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const bool a_kfast = (sak == 1), b_kfast = (sbk == 1);
-  for (int k0 = 0; k0 < K; k0 += BK) {
+  // split-K: slice blockIdx.z covers [kbeg, kend) and adds its partial product atomically
+  const int kbeg = blockIdx.z * kchunk;
+  if (gridDim.z > 1) K = min(K, kbeg + kchunk);
+  for (int k0 = kbeg; k0 < K; k0 += BK) {
     __syncthreads();
     for (int t = tid; t < BM * BK; t += NT) {
       int i, k;
@@ -58,19 +61,36 @@ gemm_kernel(const float* __restrict__ A, int64_t sai, int64_t sak, const float* 
       int c = j0 + tx + 16 * j;
       if (c < N) {
         float* p = C + (int64_t)r * ldc + c;
-        *p = accumulate ? *p + acc[i][j] : acc[i][j];
+        if (gridDim.z > 1) atomicAdd(p, acc[i][j]);
+        else *p = accumulate ? *p + acc[i][j] : acc[i][j];
       }
     }
   }
 }
 }  // namespace gemm_detail
 
+// splitk > 1 requires accumulate semantics (C already holds the value to add to, e.g. zeros).
 static inline cudaError_t launch_gemm(const float* A, int64_t sai, int64_t sak, const float* B, int64_t sbk, int64_t sbj,
-                               float* C, int64_t ldc, int M, int N, int K, int accumulate, cudaStream_t st) {
+                               float* C, int64_t ldc, int M, int N, int K, int accumulate, cudaStream_t st,
+                               int splitk = 1) {
   if (M <= 0 || N <= 0) return cudaSuccess;
-  dim3 grid((N + gemm_detail::BN - 1) / gemm_detail::BN, (M + gemm_detail::BM - 1) / gemm_detail::BM);
-  gemm_detail::gemm_kernel<<<grid, gemm_detail::NT, 0, st>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K, accumulate);
+  if (!accumulate || splitk < 1) splitk = 1;
+  int kchunk = ((K + splitk - 1) / splitk + gemm_detail::BK - 1) / gemm_detail::BK * gemm_detail::BK;
+  if (kchunk < gemm_detail::BK) kchunk = gemm_detail::BK;
+  splitk = (K + kchunk - 1) / kchunk;
+  if (splitk < 1) splitk = 1;
+  dim3 grid((N + gemm_detail::BN - 1) / gemm_detail::BN, (M + gemm_detail::BM - 1) / gemm_detail::BM, splitk);
+  gemm_detail::gemm_kernel<<<grid, gemm_detail::NT, 0, st>>>(A, sai, sak, B, sbk, sbj, C, ldc, M, N, K, accumulate, kchunk);
   return cudaGetLastError();
+}
+
+// number of K slices that fills the machine for a small-output / long-K product
+static inline int splitk_for(int M, int N, int K) {
+  int tiles = ((M + gemm_detail::BM - 1) / gemm_detail::BM) * ((N + gemm_detail::BN - 1) / gemm_detail::BN);
+  int want = (2 * sm_count() + tiles - 1) / tiles;
+  int maxs = (K + 4 * gemm_detail::BK - 1) / (4 * gemm_detail::BK);
+  if (want > maxs) want = maxs;
+  return want < 1 ? 1 : want;
 }
 
 }  // namespace sga

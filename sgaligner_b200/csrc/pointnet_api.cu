@@ -3,7 +3,7 @@
 
 namespace sga {
 int pointnet_fwd_simt(const float*, int64_t, int, const float*, const float*, const float*, const float*, const float*,
-                      const float*, int, float*, int32_t*, cudaStream_t);
+                      const float*, int, float*, int32_t*, double*, cudaStream_t);
 int pointnet_fwd_tc(const float*, int64_t, int, const float*, const float*, const float*, const float*, const float*,
                     const float*, int, float*, int32_t*, cudaStream_t);
 }  // namespace sga
@@ -14,11 +14,19 @@ extern "C" int sga_pointnet_fwd(const float* pts, int64_t N, int P, const float*
   if (N <= 0) return SGA_OK;
   SGA_REQUIRE(P >= 1 && C3 >= 1, "sga_pointnet_fwd: P=%d C3=%d", P, C3);
   SGA_REQUIRE(pts && W1 && b1 && W2 && b2 && W3 && b3 && out, "sga_pointnet_fwd: null pointer");
-  if (mode == SGA_POINTNET_SIMT) return sga::pointnet_fwd_simt(pts, N, P, W1, b1, W2, b2, W3, b3, C3, out, argmax, (cudaStream_t)stream);
+  if (mode == SGA_POINTNET_SIMT) return sga::pointnet_fwd_simt(pts, N, P, W1, b1, W2, b2, W3, b3, C3, out, argmax, nullptr, (cudaStream_t)stream);
   if (mode == SGA_POINTNET_TC) {
     SGA_REQUIRE(((uintptr_t)W2 & 15) == 0 && ((uintptr_t)W3 & 15) == 0, "sga_pointnet_fwd(TC): W2/W3 must be 16-byte aligned");
     return sga::pointnet_fwd_tc(pts, N, P, W1, b1, W2, b2, W3, b3, C3, out, argmax, (cudaStream_t)stream);
   }
   sga::set_error("sga_pointnet_fwd: unknown mode %d", mode);
   return SGA_EINVAL;
+}
+
+extern "C" int sga_pointnet_bn_moments(const float* pts, int64_t N, int P, const float* W1, const float* b1,
+                                       const float* W2, const float* b2, const float* W3, const float* b3, int C3,
+                                       double* moments, void* stream) {
+  if (N <= 0) return SGA_OK;
+  SGA_REQUIRE(P >= 1 && C3 >= 1 && moments, "sga_pointnet_bn_moments: bad arguments");
+  return sga::pointnet_fwd_simt(pts, N, P, W1, b1, W2, b2, W3, b3, C3, nullptr, nullptr, moments, (cudaStream_t)stream);
 }

@@ -133,6 +133,17 @@ def gat_aggregate(xs, a_s, a_d, graph: BatchGraph, bias, apply_elu: bool):
     return out
 
 
+def as_f32(x: torch.Tensor) -> torch.Tensor:
+    """f32 contiguous view/copy of a dataloader tensor; f64 inputs go through the library's cast
+    kernel (the reference's `.float()`, sg_aligner.py:73-75)."""
+    if x.dtype == torch.float64:
+        x = x.contiguous()
+        out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+        check(get_lib().sga_cast_f64_f32(_ptr(x), _ptr(out), x.numel(), _stream()), 'sga_cast_f64_f32')
+        return out
+    return _f32c(x)
+
+
 def gat_aggregate_backward(xs, a_s, a_d, graph: BatchGraph, apply_elu: bool, out, gout):
     H, N, C = xs.shape
     dev = xs.device
@@ -141,24 +152,22 @@ def gat_aggregate_backward(xs, a_s, a_d, graph: BatchGraph, apply_elu: bool, out
     g_ad = torch.zeros((N, H), device=dev, dtype=torch.float32)
     g_bias = torch.zeros(H * C, device=dev, dtype=torch.float32)
     check(get_lib().sga_gat_aggregate_bwd(_ptr(xs), _ptr(a_s), _ptr(a_d), _ptr(graph.row_beg), _ptr(graph.row_cnt),
-                                          _ptr(graph.col), N, H, C, 1 if apply_elu else 0, _ptr(out), _ptr(_f32c(gout)),
+                                          _ptr(graph.col), _ptr(graph.node_off), graph.G, graph.max_nodes, N, H, C,
+                                          1 if apply_elu else 0, _ptr(out), _ptr(_f32c(gout)),
                                           _ptr(g_xs), _ptr(g_as), _ptr(g_ad), _ptr(g_bias), _stream()),
           'sga_gat_aggregate_bwd')
     return g_xs, g_as, g_ad, g_bias
 
 
 def gat_linear_backward(x, W, att_src, att_dst, H, C, xs, g_xs, g_as, g_ad, need_gx: bool):
-    is64 = 1 if x.dtype == torch.float64 else 0
-    if not is64:
-        x = _f32c(x)
-    x = x.contiguous()
+    x = as_f32(x)
     N, in_dim = x.shape
     dev = x.device
     gW = torch.zeros((H * C, in_dim), device=dev, dtype=torch.float32)
     g_att_s = torch.zeros(H * C, device=dev, dtype=torch.float32)
     g_att_d = torch.zeros(H * C, device=dev, dtype=torch.float32)
     gx = torch.empty((N, in_dim), device=dev, dtype=torch.float32) if need_gx else None
-    check(get_lib().sga_gat_linear_bwd(_ptr(x), is64, N, in_dim, _ptr(_f32c(W)), _ptr(_f32c(att_src).reshape(-1)),
+    check(get_lib().sga_gat_linear_bwd(_ptr(x), N, in_dim, _ptr(_f32c(W)), _ptr(_f32c(att_src).reshape(-1)),
                                        _ptr(_f32c(att_dst).reshape(-1)), H, C, _ptr(xs), _ptr(g_xs), _ptr(g_as), _ptr(g_ad),
                                        _ptr(gW), _ptr(g_att_s), _ptr(g_att_d), _ptr(gx), _stream()), 'sga_gat_linear_bwd')
     return gW, g_att_s, g_att_d, gx
@@ -182,10 +191,7 @@ def project_fuse(x, W, b, joint: Optional[torch.Tensor], joint_col: int, fusion_
 
 
 def project_fuse_backward(x, W, emb, g_emb, g_joint, joint_col: int, fusion_w, M: int, m: int, need_gx: bool):
-    is64 = 1 if x.dtype == torch.float64 else 0
-    if not is64:
-        x = _f32c(x)
-    x = x.contiguous()
+    x = as_f32(x)
     N, in_dim = x.shape
     out_dim = W.shape[0]
     dev = x.device
@@ -193,9 +199,9 @@ def project_fuse_backward(x, W, emb, g_emb, g_joint, joint_col: int, fusion_w, M
     gb = torch.zeros(out_dim, device=dev, dtype=torch.float32)
     gfw = torch.zeros(M, device=dev, dtype=torch.float32)
     gx = torch.empty((N, in_dim), device=dev, dtype=torch.float32) if need_gx else None
-    ws = torch.empty((N, out_dim), device=dev, dtype=torch.float32)
+    ws = torch.empty(N * out_dim + 64, device=dev, dtype=torch.float32)
     fw = None if g_joint is None else _f32c(fusion_w).reshape(-1)
-    check(get_lib().sga_project_fuse_bwd(_ptr(x), is64, N, in_dim, _ptr(_f32c(W)), out_dim, _ptr(emb),
+    check(get_lib().sga_project_fuse_bwd(_ptr(x), N, in_dim, _ptr(_f32c(W)), out_dim, _ptr(emb),
                                          _ptr(None if g_emb is None else _f32c(g_emb)),
                                          _ptr(None if g_joint is None else _f32c(g_joint)),
                                          0 if g_joint is None else g_joint.shape[1], joint_col, _ptr(fw), M, m,
