@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Headline benchmark: subscan-pairs/sec of the SGAligner hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload = BASELINE.json configs[1] ("C2"): synthetic sub-scan pairs, 64 objects/scene, 512
+points/object, ~6 edges/node, batch = 32 pairs per GPU, modules PointNet + GAT, joint embedding ->
+cosine-similarity matching head.  One *step* = one pass of the serving hot
+path over one batch: CSR build, encoder forward (tcgen05 PointNet, batched GAT, fused
+projection/fusion), per-pair similarity + ranking (top-6) + anchor positions (Hits@k / MRR inputs).
+Weak scaling: every rank gets its own 32 pairs, there is no data-path collective in serving.
+The same JSON line also carries the *training* step (forward + OverallLoss + backward + one
+gradient all-reduce + Adam) as ``train``.
+
+Timing: per-step CUDA events on the launching stream, a 512 MiB L2 flush (untimed) between steps,
+barrier + synchronize on both sides of the K timed steps, MAX over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+MODULES = ['point', 'gat']
+PAIRS_PER_GPU = 32
+N_OBJ, N_PTS = 64, 512
+METRIC = 'subscan-pairs/sec (64obj x 512pt, 256-d), encoder forward + matching head'
+UNIT = 'pairs/s'
+FLOP_PER_OBJECT = 2.0 * N_PTS * (3 * 64 + 64 * 128 + 128 * 256)     # 42.14 MFLOP
+BYTES_PER_OBJECT = 12.0 * N_PTS + 4.0 * 256                          # 7168 B algorithmic HBM traffic
+
+
+def workload_name():
+    return (f'C2: {PAIRS_PER_GPU} synthetic sub-scan pairs/GPU, {N_OBJ}+{N_OBJ} objects, {N_PTS} pts/object, 6 out-edges/node, '
+            f'modules {"+".join(MODULES)}, joint 200-d, top-6 matching')
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d['bf16_tflops']), float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json, burst)'
+        except Exception:   # noqa: BLE001
+            pass
+    return 1590.0, 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ------------------------------------------------------------------------------------ CPU reference arm
+def oracle_step(params, data):
+    """The reference's CPU path for the same step (oracle restatement; torch CPU fp32, all host
+    threads): encoder forward + per-pair normalise / Gram / argsort + rank metrics."""
+    from oracle import sgaligner_oracle as O
+    with torch.no_grad():
+        out = O.encoder_forward(params, data, MODULES)
+        return O.evaluate_batch(out['joint'], data)
+
+
+def cpu_sample(n_pairs: int, seed: int = 100):
+    """Same weights (torch.manual_seed(0) construction of the module tree, used as a parameter
+    container only) and the same synthetic pairs (rank-0 seed) as the GPU arm, so Hits@1 of the two
+    arms is comparable."""
+    from sgaligner_b200 import synthetic
+    from sgaligner_b200.sg_aligner import MultiModalEncoder
+    data = synthetic.config_c2(batch=PAIRS_PER_GPU, seed=seed, n_obj=N_OBJ, n_points=N_PTS)
+    if n_pairs < PAIRS_PER_GPU:
+        data = synthetic.slice_pairs(data, 0, n_pairs)
+    torch.manual_seed(0)
+    params = {k: v.detach().clone() for k, v in MultiModalEncoder(modules=MODULES, rel_dim=41, attr_dim=164).state_dict().items()}
+    return params, data
+
+
+def time_cpu_baseline(budget_s: float = 20.0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params, data = cpu_sample(2)
+    t0 = time.perf_counter()
+    oracle_step(params, data)
+    t_pair = (time.perf_counter() - t0) / 2
+    n = int(max(1, min(PAIRS_PER_GPU, budget_s / 3 / max(t_pair, 1e-3))))
+    params, data = cpu_sample(n)
+    ts = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        oracle_step(params, data)
+        ts.append(time.perf_counter() - t0)
+    return {'value': n / min(ts), 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': f'{n} pairs of the C2 workload (encoder forward + matching), best of 2 after 1 warm-up, '
+                      f'torch {torch.__version__} CPU fp32, {torch.get_num_threads()} threads'}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # bounded sample per step so that warmup+steps end within a few minutes
+    params, data = cpu_sample(1)
+    t0 = time.perf_counter()
+    oracle_step(params, data)
+    t_pair = time.perf_counter() - t0
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    n = int(max(1, min(PAIRS_PER_GPU, budget / max(t_pair, 1e-3))))
+    params, data = cpu_sample(n)
+    for _ in range(args.warmup):
+        oracle_step(params, data)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ev = oracle_step(params, data)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    value = n / dt
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload_name(), 'sample_pairs_per_step': n,
+                   'note': 'reference CPU path (PyTorch fp32 restatement of src/aligner + matching head), host cores only'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': f'{n} pairs/step of the C2 workload, {torch.get_num_threads()} threads'},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'hits_at_1': ev['hits'][1] / max(1, ev['total']),
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '50', '-i', str(self.gpu)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:   # noqa: BLE001
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.06)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:   # noqa: BLE001
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(',') for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+                for nme, v in zip(names, r[4:8]):
+                    if v.strip().lower() == 'active':
+                        reasons.add(nme)
+            except Exception:   # noqa: BLE001
+                continue
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        hi = [s for s, pw in zip(sm, power) if pw >= 0.5 * max(power)] or sm
+        return {'sm_mhz': float(np.median(hi)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm),
+                'power_w_max': float(max(power))}
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch.distributed as dist
+    from sgaligner_b200 import matching, ops, synthetic, to_cuda
+    from sgaligner_b200.data import h2d_bytes, pin
+    from sgaligner_b200.losses import CustomMultiLossLayer, OverallLoss
+    from sgaligner_b200.sg_aligner import MultiModalEncoder
+    from sgaligner_b200.trainer import FlatAdam, train_step
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py (impl=ours) needs a CUDA device: the hot path has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- model + data (each rank: its own 32 pairs; weights identical on every rank)
+    torch.manual_seed(0)
+    model = MultiModalEncoder(modules=MODULES, rel_dim=41, attr_dim=164).to(dev)
+    M = len(MODULES)
+    li, lc = CustomMultiLossLayer(M).to(dev), CustomMultiLossLayer(M).to(dev)
+    loss_fn = OverallLoss(li, lc, dev, {'zoom': 0.1, 'wt_align_loss': 1.0, 'wt_contrastive_loss': 1.0, 'modules': MODULES})
+    host = synthetic.config_c2(batch=PAIRS_PER_GPU, seed=100 + rank, n_obj=N_OBJ, n_points=N_PTS)
+    host_pinned = pin(host)
+    data = to_cuda(dict(host_pinned), dev)
+    e1 = torch.as_tensor(host['e1i']).to(dev)
+    e2 = torch.as_tensor(host['e2i']).to(dev)
+    N = int(data['tot_obj_pts'].shape[0])
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def serve_step(d):
+        with torch.no_grad():
+            out = model(d)
+            res = matching.match_batch(out['joint'], d, k=6, full_rank=False)
+            pos = ops.match_anchor_pos(res['sim'], res['layout'], e1, e2)
+        return res['topk_idx'], pos
+
+    def timed(fn, steps, warmup, collect_kernel_events=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = []
+        ops.KERNEL_EVENTS = [] if collect_kernel_events else None
+        l0 = ops.LAUNCHES
+        for _ in range(steps):
+            flush.zero_()                       # L2 flush, outside the timed region
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        launches = ops.LAUNCHES - l0
+        kev = ops.KERNEL_EVENTS
+        ops.KERNEL_EVENTS = None
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        kms = None
+        if kev:
+            kms = float(np.mean([a.elapsed_time(b) for nme, a, b in kev if nme == 'pointnet_fwd']))
+        return float(t.item()), launches, kms
+
+    model.eval()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- (1) device-resident serving step: the headline `value`
+    tot_ms, launches, k_ms = timed(lambda: serve_step(data), args.steps, args.warmup, collect_kernel_events=True)
+    ms_step = tot_ms / args.steps
+    value = world * PAIRS_PER_GPU / (ms_step * 1e-3)
+
+    # ---- (2) end to end through the public API with HOST buffers (pinned): H2D + step + D2H
+    def e2e_step():
+        d = to_cuda(dict(host_pinned), dev)
+        tk, pos = serve_step(d)
+        return tk.cpu(), pos.cpu()
+
+    e2e_ms, _, _ = timed(e2e_step, args.steps, args.warmup)
+    e2e_ms /= args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    tk, pos = serve_step(data)
+    d2h = tk.numel() * 4 + pos.numel() * 4
+    hits1 = float((pos < 1).float().mean().item())
+
+    # ---- (3) training step (forward + loss + backward + gradient all-reduce + Adam)
+    model.train()
+    opt = FlatAdam(list(model.parameters()) + list(li.parameters()) + list(lc.parameters()), lr=1e-3, weight_decay=1e-6)
+    tr_ms, tr_launches, _ = timed(lambda: train_step(model, loss_fn, opt, data), args.steps, args.warmup)
+    tr_ms /= args.steps
+    model.object_encoder.track_bn_stats = False
+    tr2_ms, _, _ = timed(lambda: train_step(model, loss_fn, opt, data), args.steps, max(1, args.warmup // 2))
+    tr2_ms /= args.steps
+
+    if rank == 0:
+        tf_peak, hbm_peak, peak_src = measured_peaks()
+        flops = FLOP_PER_OBJECT * N
+        achieved = flops / (k_ms * 1e-3) / 1e12 if k_ms else None
+        cpu = time_cpu_baseline()
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 (PointNet convs: bf16x3 split-operand tcgen05, fp32 accumulate)', 'data': 'synthetic',
+            'config': {'workload': workload_name(), 'pairs_per_gpu': PAIRS_PER_GPU, 'objects': N,
+                       'l2': 'flushed between timed steps (512 MiB memset, untimed)', 'timing': 'per-step CUDA events, max over ranks'},
+            'roofline': {'kernel': 'pointnet_fwd_tc_kernel', 'bound': 'tensor', 'achieved': achieved, 'peak': tf_peak, 'unit': 'TFLOP/s',
+                         'frac': (achieved / tf_peak) if achieved else None, 'traffic': None, 'peak_source': peak_src,
+                         'kernel_ms': k_ms, 'algorithmic_flops_per_launch': flops,
+                         'hbm': {'achieved_gbs': BYTES_PER_OBJECT * N / (k_ms * 1e-3) / 1e9 if k_ms else None, 'peak_gbs': hbm_peak,
+                                 'algorithmic_bytes_per_launch': BYTES_PER_OBJECT * N},
+                         'executed_flops_factor': 3},
+            'cpu_baseline': cpu,
+            'e2e': {'value': world * PAIRS_PER_GPU / (e2e_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_ms,
+                    'h2d_bytes_per_step': h2d_bytes(host), 'd2h_bytes_per_step': int(d2h)},
+            'gpu_launches': int(launches),
+            'clocks': clocks,
+            'hits_at_1': hits1,
+            'train': {'pairs_per_s': world * PAIRS_PER_GPU / (tr_ms * 1e-3), 'ms_per_step': tr_ms, 'gpu_launches': int(tr_launches),
+                      'pairs_per_s_without_bn_running_stats': world * PAIRS_PER_GPU / (tr2_ms * 1e-3),
+                      'what': 'forward + OverallLoss + backward + flat-gradient all-reduce + fused Adam, same workload'},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -17,6 +17,34 @@ from ._lib import check, get_lib
 POINTNET_SIMT = 0
 POINTNET_TC = 1
 
+# ---- instrumentation used by bench.py (never changes what is launched)
+LAUNCHES = 0            # kernels of libsga_b200 launched so far (counted per C-ABI call)
+KERNEL_EVENTS = None    # when a list: (name, start_event, end_event) of the dominant kernels
+
+
+def _count(n: int):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+class _timed:
+    """Brackets one C-ABI call with CUDA events on the launching stream when bench.py asks for it."""
+
+    def __init__(self, name):
+        self.name = name
+        self.on = KERNEL_EVENTS is not None
+
+    def __enter__(self):
+        if self.on:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream())
+
+    def __exit__(self, *a):
+        if self.on:
+            self.e1.record(torch.cuda.current_stream())
+            KERNEL_EVENTS.append((self.name, self.e0, self.e1))
+
 
 def _ptr(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(0 if t is None else t.data_ptr())
@@ -50,9 +78,12 @@ def pointnet_forward(pts, W1, b1, W2, b2, W3, b3, want_argmax: bool, mode: int =
         W2c, W3c = W2c.clone(), W3c.clone()
     out = torch.empty((N, C3), device=pts.device, dtype=torch.float32)
     arg = torch.empty((N, C3), device=pts.device, dtype=torch.int32) if want_argmax else None
-    check(get_lib().sga_pointnet_fwd(_ptr(pts), N, P, _ptr(W1c), _ptr(_f32c(b1)), _ptr(W2c), _ptr(_f32c(b2)),
-                                     _ptr(W3c), _ptr(_f32c(b3)), C3, _ptr(out), _ptr(arg), mode, _stream()),
-          'sga_pointnet_fwd')
+    b1c, b2c, b3c = _f32c(b1), _f32c(b2), _f32c(b3)
+    with _timed('pointnet_fwd'):
+        check(get_lib().sga_pointnet_fwd(_ptr(pts), N, P, _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c),
+                                         _ptr(W3c), _ptr(b3c), C3, _ptr(out), _ptr(arg), mode, _stream()),
+              'sga_pointnet_fwd')
+    _count(1)
     return out, arg
 
 
@@ -66,6 +97,7 @@ def pointnet_backward(pts, W1, b1, W2, b2, W3, b3, out, arg, gout):
                                      _ptr(_f32c(W2.reshape(128, 64))), _ptr(_f32c(b2)), _ptr(_f32c(W3.reshape(C3, 128))),
                                      _ptr(_f32c(b3)), C3, _ptr(out), _ptr(arg), _ptr(_f32c(gout)),
                                      *[_ptr(t) for t in g], _stream()), 'sga_pointnet_bwd')
+    _count(1)
     return g
 
 
@@ -78,6 +110,7 @@ def pointnet_bn_moments(pts, W1, b1, W2, b2, W3, b3):
                                             _ptr(_f32c(W2.reshape(128, 64))), _ptr(_f32c(b2)),
                                             _ptr(_f32c(W3.reshape(C3, 128))), _ptr(_f32c(b3)), C3, _ptr(mom), _stream()),
           'sga_pointnet_bn_moments')
+    _count(1)
     return mom
 
 
@@ -105,6 +138,7 @@ class BatchGraph:
         self.col = torch.empty(self.E + self.N, device=dev, dtype=torch.int32)
         check(get_lib().sga_csr_build(_ptr(edges), _ptr(self.node_off), _ptr(self.edge_off), self.G, self.max_nodes,
                                       _ptr(self.row_beg), _ptr(self.row_cnt), _ptr(self.col), _stream()), 'sga_csr_build')
+        _count(1)
 
 
 def gat_linear(x: torch.Tensor, W, att_src, att_dst, H: int, C: int):
@@ -121,6 +155,7 @@ def gat_linear(x: torch.Tensor, W, att_src, att_dst, H: int, C: int):
     check(get_lib().sga_gat_linear(_ptr(x), is64, N, in_dim, _ptr(_f32c(W)), _ptr(_f32c(att_src).reshape(-1)),
                                    _ptr(_f32c(att_dst).reshape(-1)), H, C, _ptr(xs), _ptr(a_s), _ptr(a_d), _stream()),
           'sga_gat_linear')
+    _count(1)
     return xs, a_s, a_d
 
 
@@ -130,6 +165,7 @@ def gat_aggregate(xs, a_s, a_d, graph: BatchGraph, bias, apply_elu: bool):
     check(get_lib().sga_gat_aggregate(_ptr(xs), _ptr(a_s), _ptr(a_d), _ptr(graph.row_beg), _ptr(graph.row_cnt),
                                       _ptr(graph.col), _ptr(graph.node_off), graph.G, graph.max_nodes, N, H, C,
                                       _ptr(_f32c(bias)), 1 if apply_elu else 0, _ptr(out), _stream()), 'sga_gat_aggregate')
+    _count(1)
     return out
 
 
@@ -140,6 +176,7 @@ def as_f32(x: torch.Tensor) -> torch.Tensor:
         x = x.contiguous()
         out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
         check(get_lib().sga_cast_f64_f32(_ptr(x), _ptr(out), x.numel(), _stream()), 'sga_cast_f64_f32')
+        _count(1)
         return out
     return _f32c(x)
 
@@ -156,6 +193,7 @@ def gat_aggregate_backward(xs, a_s, a_d, graph: BatchGraph, apply_elu: bool, out
                                           1 if apply_elu else 0, _ptr(out), _ptr(_f32c(gout)),
                                           _ptr(g_xs), _ptr(g_as), _ptr(g_ad), _ptr(g_bias), _stream()),
           'sga_gat_aggregate_bwd')
+    _count(1)
     return g_xs, g_as, g_ad, g_bias
 
 
@@ -170,6 +208,7 @@ def gat_linear_backward(x, W, att_src, att_dst, H, C, xs, g_xs, g_as, g_ad, need
     check(get_lib().sga_gat_linear_bwd(_ptr(x), N, in_dim, _ptr(_f32c(W)), _ptr(_f32c(att_src).reshape(-1)),
                                        _ptr(_f32c(att_dst).reshape(-1)), H, C, _ptr(xs), _ptr(g_xs), _ptr(g_as), _ptr(g_ad),
                                        _ptr(gW), _ptr(g_att_s), _ptr(g_att_d), _ptr(gx), _stream()), 'sga_gat_linear_bwd')
+    _count(1 + H * (2 if need_gx else 1))
     return gW, g_att_s, g_att_d, gx
 
 
@@ -187,6 +226,7 @@ def project_fuse(x, W, b, joint: Optional[torch.Tensor], joint_col: int, fusion_
     check(get_lib().sga_project_fuse_fwd(_ptr(x), is64, N, in_dim, _ptr(_f32c(W)), _ptr(_f32c(b)), out_dim, _ptr(emb),
                                          _ptr(joint), 0 if joint is None else joint.shape[1], joint_col, _ptr(fw), M, m,
                                          _stream()), 'sga_project_fuse_fwd')
+    _count(1)
     return emb
 
 
@@ -207,6 +247,7 @@ def project_fuse_backward(x, W, emb, g_emb, g_joint, joint_col: int, fusion_w, M
                                          0 if g_joint is None else g_joint.shape[1], joint_col, _ptr(fw), M, m,
                                          _ptr(gW), _ptr(gb), _ptr(gfw), _ptr(gx), _ptr(ws), ws.numel() * 4, _stream()),
           'sga_project_fuse_bwd')
+    _count(3 + (1 if g_joint is not None else 0) + (1 if need_gx else 0))
     return gW, gb, gfw, gx
 
 
@@ -236,6 +277,7 @@ def match_sim(emb: torch.Tensor, lay: PairLayout):
     sim = torch.empty(int(lay.sim_off_host[-1]), device=emb.device, dtype=torch.float32)
     check(get_lib().sga_match_sim(_ptr(emb), N, D, _ptr(lay.pair_off), _ptr(lay.sim_off), lay.B, lay.max_n, _ptr(norms),
                                   _ptr(sim), _stream()), 'sga_match_sim')
+    _count(2)
     return sim
 
 
@@ -246,6 +288,7 @@ def match_rank(sim: torch.Tensor, lay: PairLayout, K: int, full: bool):
     rank = torch.empty(sim.numel(), device=dev, dtype=torch.int32) if full else None
     check(get_lib().sga_match_rank(_ptr(sim), lay.N, _ptr(lay.pair_off), _ptr(lay.sim_off), _ptr(lay.node_pair), lay.max_n, K,
                                    _ptr(topk_idx), _ptr(topk_dist), _ptr(rank), _stream()), 'sga_match_rank')
+    _count(1)
     return topk_idx, topk_dist, rank
 
 
@@ -254,6 +297,7 @@ def match_anchor_pos(sim: torch.Tensor, lay: PairLayout, e1i: torch.Tensor, e2i:
     pos = torch.empty(A, device=sim.device, dtype=torch.int32)
     check(get_lib().sga_match_anchor_pos(_ptr(sim), _ptr(lay.pair_off), _ptr(lay.sim_off), _ptr(lay.node_pair), _ptr(e1i),
                                          _ptr(e2i), A, _ptr(pos), _stream()), 'sga_match_anchor_pos')
+    _count(1)
     return pos
 
 
@@ -295,6 +339,8 @@ def loss_forward_backward(embs: Sequence[torch.Tensor], idx: Sequence[torch.Tens
                                _ptr(None if lv_ial is None else _f32c(lv_ial)), _ptr(None if lv_icl is None else _f32c(lv_icl)),
                                float(zoom), _ptr(losses), 1 if want_grad else 0, g_ptrs, _ptr(g_ial), _ptr(g_icl),
                                _ptr(ws), ws.numel(), _stream()), 'sga_loss_fwd_bwd')
+    # per embedding: norm, gather, 2 GEMMs, <=4 exp-sums, pair kernel; + finalize; backward: 2 coef, 4 GEMMs, scatter, normalize
+    _count(n_emb * 9 + 1 + (n_emb * 8 if want_grad else 0))
     return losses, grads, g_ial, g_icl
 
 
@@ -302,6 +348,7 @@ def loss_forward_backward(embs: Sequence[torch.Tensor], idx: Sequence[torch.Tens
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
     check(get_lib().sga_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), lr, beta1, beta2,
                                   eps, weight_decay, int(step), float(grad_scale), _stream()), 'sga_adam_step')
+    _count(1)
 
 
 def selftest_umma(A: torch.Tensor, B: torch.Tensor, kind: int) -> torch.Tensor:
