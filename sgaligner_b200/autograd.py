@@ -13,7 +13,7 @@ class PointNetFeat(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, pts, W1, b1, W2, b2, W3, b3, mode):
-        need = any(t.requires_grad for t in (W1, b1, W2, b2, W3, b3))
+        need = any(ctx.needs_input_grad[1:7])
         out, arg = ops.pointnet_forward(pts, W1, b1, W2, b2, W3, b3, want_argmax=need, mode=mode)
         if need:
             ctx.save_for_backward(pts, W1, b1, W2, b2, W3, b3, out, arg)
@@ -93,7 +93,7 @@ class OverallLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, idx, zoom, lv_ial, lv_icl, *embs):
-        want_grad = any(e.requires_grad for e in embs) or (lv_ial is not None and lv_ial.requires_grad)
+        want_grad = any(ctx.needs_input_grad[2:])
         losses, grads, g_ial, g_icl = ops.loss_forward_backward(embs, idx, lv_ial, lv_icl, zoom, want_grad)
         ctx.n = len(embs)
         ctx.has_lv = lv_ial is not None

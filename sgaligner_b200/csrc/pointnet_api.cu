@@ -6,6 +6,7 @@ int pointnet_fwd_simt(const float*, int64_t, int, const float*, const float*, co
                       const float*, int, float*, int32_t*, double*, cudaStream_t);
 int pointnet_fwd_tc(const float*, int64_t, int, const float*, const float*, const float*, const float*, const float*,
                     const float*, int, float*, int32_t*, cudaStream_t);
+int debug_set_trace(long long* ptr);
 }  // namespace sga
 
 extern "C" int sga_pointnet_fwd(const float* pts, int64_t N, int P, const float* W1, const float* b1,
@@ -30,3 +31,7 @@ extern "C" int sga_pointnet_bn_moments(const float* pts, int64_t N, int P, const
   SGA_REQUIRE(P >= 1 && C3 >= 1 && moments, "sga_pointnet_bn_moments: bad arguments");
   return sga::pointnet_fwd_simt(pts, N, P, W1, b1, W2, b2, W3, b3, C3, nullptr, nullptr, moments, (cudaStream_t)stream);
 }
+
+/* diagnostics only: device buffer of >= 2048 int64 that CTA 0 of the tensor-core PointNet kernel
+ * fills with clock64() stamps of its pipeline events (NULL switches tracing off) */
+extern "C" int sga_debug_set_trace(long long* trace) { return sga::debug_set_trace(trace); }

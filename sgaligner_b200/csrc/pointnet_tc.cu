@@ -18,13 +18,24 @@
 //   E3  TMEM->regs, running max over columns (= points): channels sit on TMEM lanes, so the
 //       max-pool is thread-local; bias + ReLU are applied once per object after the max
 //       (max_p relu(z_p + b) == relu(max_p z_p + b)).
-// S1 of the next tile and MMA2 of the next tile overlap E3 of the current one.
+// Overlap: the H2 half that doubles as the A1 buffer is released by a tcgen05.commit right after
+// conv3 has consumed it (half-way through MMA3), so conv1 of tile g+1 runs under MMA3(g), MMA2(g+1)
+// is queued directly behind MMA3(g) and runs under E3(g); the tensor pipe only idles for the first
+// quarter of E2.  Points of the next tile are prefetched into registers one stage ahead.
 // W2 / W3 (hi and lo) stay resident in shared memory for the life of the CTA (160 KiB).
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace sga {
 namespace {
+
+// test/diagnostic hook: when set (sga_debug_set_trace), CTA 0 stamps clock64() at every pipeline
+// event of its first 64 tiles: trace[g*16 + k] (compute thread 0), trace[1024 + g*16 + k] (MMA lane)
+__device__ long long* g_trace = nullptr;
+#define SGA_TRACE(base, g, k)                                                            \
+  do {                                                                                   \
+    if (trace && (g) < 64) trace[(base) + (g) * 16 + (k)] = clock64();                   \
+  } while (0)
 
 constexpr int kComputeThreads = 256;
 constexpr int kThreads = kComputeThreads + 32;
@@ -41,8 +52,8 @@ constexpr uint32_t H2LO = H2HI + 2 * kBlk;    // 2 blocks;      block 0 doubles 
 constexpr uint32_t SMALL = H2LO + 2 * kBlk;   // 229376
 constexpr uint32_t W1B1 = SMALL;              // float4[64] = {w0,w1,w2,b}
 constexpr uint32_t B2 = W1B1 + 1024;          // float[128]
-constexpr uint32_t BARS = B2 + 512;           // 8 mbarriers
-constexpr uint32_t TMEMPTR = BARS + 64;
+constexpr uint32_t BARS = B2 + 512;           // 9 mbarriers
+constexpr uint32_t TMEMPTR = BARS + 80;
 constexpr uint32_t SMEM_USED = TMEMPTR + 16;
 constexpr uint32_t SMEM_BYTES = SMEM_USED + 1024;   // + alignment slack
 
@@ -50,7 +61,7 @@ constexpr uint32_t D2_COL = 0;
 constexpr uint32_t D3_COL = 128;              // + mt*128
 constexpr int kTmemCols = 512;
 
-enum { BAR_A1_FULL = 0, BAR_D2_FULL = 1, BAR_H2_FULL = 2 /*..5*/, BAR_D3_FULL = 6, BAR_D3_FREE = 7 };
+enum { BAR_A1_FULL = 0, BAR_D2_FULL = 1, BAR_H2_FULL = 2 /*..5*/, BAR_D3_FULL = 6, BAR_D3_FREE = 7, BAR_BLK0_FREE = 8 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {   // a -> low half (lower address)
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -126,6 +137,7 @@ pointnet_fwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
     for (int c = 0; c < 4; ++c) ptx::mbar_init(&bars[BAR_H2_FULL + c], kComputeThreads);
     ptx::mbar_init(&bars[BAR_D3_FULL], 1);
     ptx::mbar_init(&bars[BAR_D3_FREE], kComputeThreads);
+    ptx::mbar_init(&bars[BAR_BLK0_FREE], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 8) ptx::tmem_alloc<kTmemCols>(tmem_slot);
@@ -139,56 +151,71 @@ pointnet_fwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
   // objects owned by this CTA: blockIdx.x, +gridDim.x, ...
   const int64_t nobj = (N > (int64_t)blockIdx.x) ? (N - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const int64_t G = nobj * ntile;     // tiles this CTA processes, as one stream
+  long long* trace = (blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0 || tid == 256)) ? g_trace : nullptr;
 
   if (warp == 8) {
-    // =============================== MMA issuer (one lane) ===============================
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc(1, 128, 128);
-      for (int64_t g = 0; g < G; ++g) {
-        const uint32_t ph = (uint32_t)(g & 1);
-        // ---- conv2: D2[pts x 128] = A1 * W2^T
-        ptx::mbar_wait(&bars[BAR_A1_FULL], ph);
-        ptx::tc_fence_after();
+    // =============================== MMA issuer ===============================
+    // The whole warp runs the (warp-uniform) control flow; one lane chosen by elect.sync issues.
+    // Written this way ptxas keeps descriptors in uniform registers; a plain `if (lane == 0)` makes
+    // it wrap every UTCHMMA in an ELECT/R2UR waterfall loop (~100 cycles per MMA).
+    const uint32_t idesc = ptx::make_idesc(1, 128, 128);
+    // descriptors differ only in the start-address field: base + (byte offset >> 4)
+    const uint64_t dA1hi = ptx::smem_desc_sw128(sm_base + H2HI), dA1lo = ptx::smem_desc_sw128(sm_base + H2LO);
+    const uint64_t dW2hi = ptx::smem_desc_sw128(sm_base + W2HI), dW2lo = ptx::smem_desc_sw128(sm_base + W2LO);
+    const uint64_t dW3hi = ptx::smem_desc_sw128(sm_base + W3HI), dW3lo = ptx::smem_desc_sw128(sm_base + W3LO);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    for (int64_t g = 0; g < G; ++g) {
+      const uint32_t ph = (uint32_t)(g & 1);
+      // ---- conv2: D2[pts x 128] = A1 * W2^T
+      ptx::mbar_wait(&bars[BAR_A1_FULL], ph);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        SGA_TRACE(1024, g, 0);
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a_off = (pass == 1) ? H2LO : H2HI;   // A1 aliases block 0 of H2
-          const uint32_t b_off = (pass == 2) ? W2LO : W2HI;
+          const uint64_t ab = (pass == 1) ? dA1lo : dA1hi;   // A1 aliases block 0 of H2
+          const uint64_t bb = (pass == 2) ? dW2lo : dW2hi;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            uint64_t ad = ptx::smem_desc_sw128(sm_base + a_off + ks * 32);
-            uint64_t bd = ptx::smem_desc_sw128(sm_base + b_off + ks * 32);
-            ptx::umma_bf16(tmem + D2_COL, ad, bd, idesc, (pass | ks) != 0);
-          }
+          for (int ks = 0; ks < 4; ++ks)
+            ptx::umma_bf16(tmem_u + D2_COL, ab + (uint64_t)(ks * 2), bb + (uint64_t)(ks * 2), idesc, (pass | ks) != 0);
         }
         ptx::umma_commit(&bars[BAR_D2_FULL]);
-        // ---- conv3: D3[mt][ch x pts] = W3[mt] * H2^T, released chunk by chunk (32 channels of K)
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          ptx::mbar_wait(&bars[BAR_H2_FULL + c], ph);
-          ptx::tc_fence_after();
-          if (c == 0 && g > 0) {
-            ptx::mbar_wait(&bars[BAR_D3_FREE], (uint32_t)((g - 1) & 1));
-            ptx::tc_fence_after();
-          }
-          const uint32_t koff = (uint32_t)(c >> 1) * kBlk + (uint32_t)(c & 1) * 64;
-          for (int mt = 0; mt < nmt; ++mt) {
+        SGA_TRACE(1024, g, 1);
+      }
+      __syncwarp();
+      // ---- conv3: D3[mt][ch x pts] = W3[mt] * H2^T, released chunk by chunk (32 channels of K)
 #pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-              const uint32_t a_off = ((pass == 2) ? W3LO : W3HI) + (uint32_t)mt * 2 * kBlk;
-              const uint32_t b_off = (pass == 1) ? H2LO : H2HI;
+      for (int c = 0; c < 4; ++c) {
+        ptx::mbar_wait(&bars[BAR_H2_FULL + c], ph);
+        if (c == 0 && g > 0) ptx::mbar_wait(&bars[BAR_D3_FREE], (uint32_t)((g - 1) & 1));
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          SGA_TRACE(1024, g, 2 + c);
+          constexpr uint32_t kBlk16 = kBlk >> 4;
+          const uint64_t koff = (uint64_t)((c >> 1) * kBlk16 + (c & 1) * 4);
 #pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                uint64_t ad = ptx::smem_desc_sw128(sm_base + a_off + koff + ks * 32);
-                uint64_t bd = ptx::smem_desc_sw128(sm_base + b_off + koff + ks * 32);
-                ptx::umma_bf16(tmem + D3_COL + mt * 128, ad, bd, idesc, (c | pass | ks) != 0);
+          for (int mt = 0; mt < 2; ++mt) {
+            if (mt < nmt) {
+#pragma unroll
+              for (int pass = 0; pass < 3; ++pass) {
+                const uint64_t ab = ((pass == 2) ? dW3lo : dW3hi) + (uint64_t)(mt * 2 * kBlk16) + koff;
+                const uint64_t bb = ((pass == 1) ? dA1lo : dA1hi) + koff;   // H2{hi,lo} base == A1 base
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+                  ptx::umma_bf16(tmem_u + D3_COL + mt * 128, ab + (uint64_t)(ks * 2), bb + (uint64_t)(ks * 2), idesc, (c | pass | ks) != 0);
               }
             }
           }
+          // chunks 0,1 live in H2 block 0, which doubles as the next tile's A1 buffer
+          if (c == 1) ptx::umma_commit(&bars[BAR_BLK0_FREE]);
+          if (c == 3) {
+            ptx::umma_commit(&bars[BAR_D3_FULL]);
+            SGA_TRACE(1024, g, 6);
+          }
         }
-        ptx::umma_commit(&bars[BAR_D3_FULL]);
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else {
     // =============================== compute warps ===============================
     const int q = warp & 3;            // TMEM lane quarter
@@ -196,25 +223,36 @@ pointnet_fwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
     const int row = 32 * q + lane;     // TMEM lane = point (E2) or channel-in-tile (E3)
     const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
 
-    auto stage1 = [&](int64_t g) {
+    // conv1 mapping: thread -> 8 channels (warp-uniform group cg) x 4 points (pg + 32 i).  The 8
+    // channels' weights live in registers for the whole kernel, so conv1 issues no shared-memory
+    // loads (the tensor pipe saturates shared-memory bandwidth while conv3 runs).
+    const int pg = tid & 31, cg = tid >> 5;
+    float4 wreg[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) wreg[e] = w1b1[8 * cg + e];
+    float px[4], py[4], pz[4];               // this thread's points of the NEXT tile to encode
+    auto prefetch = [&](int64_t g) {
       const int64_t n = blockIdx.x + (g / ntile) * (int64_t)gridDim.x;
       const int t = (int)(g % ntile);
-      const int pl = tid & 127, hh = tid >> 7;
-      const int pg = min(t * kTile + pl, P - 1);
-      const float* pp = pts + (n * P + pg) * 3;
-      const float x = pp[0], y = pp[1], z = pp[2];
 #pragma unroll
-      for (int jc = 0; jc < 4; ++jc) {
+      for (int i = 0; i < 4; ++i) {
+        const int pi = min(t * kTile + pg + 32 * i, P - 1);
+        const float* pp = pts + (n * P + pi) * 3;
+        px[i] = __ldg(pp); py[i] = __ldg(pp + 1); pz[i] = __ldg(pp + 2);
+      }
+    };
+    auto stage1 = [&]() {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
         float f[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          float4 w = w1b1[32 * hh + 8 * jc + e];
-          float v = fmaf(w.x, x, fmaf(w.y, y, fmaf(w.z, z, w.w)));
+          float v = fmaf(wreg[e].x, px[i], fmaf(wreg[e].y, py[i], fmaf(wreg[e].z, pz[i], wreg[e].w)));
           f[e] = v > 0.f ? v : 0.f;
         }
         uint4 hi, lo;
         split8(f, hi, lo);
-        uint32_t off = ptx::sw128_offset(pl, 4 * hh + jc);
+        uint32_t off = ptx::sw128_offset(pg + 32 * i, cg);
         st_chunk(sm, H2HI + off, hi);
         st_chunk(sm, H2LO + off, lo);
       }
@@ -225,13 +263,18 @@ pointnet_fwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
 
     float rmax = -INFINITY;
     int ridx = 0;
-    if (G > 0) stage1(0);
+    if (G > 0) {
+      prefetch(0);
+      stage1();
+    }
     for (int64_t g = 0; g < G; ++g) {
       const uint32_t ph = (uint32_t)(g & 1);
       const int t = (int)(g % ntile);
+      if (g + 1 < G) prefetch(g + 1);
       // ---- E2: conv2 epilogue, 4 chunks of 32 channels; this warp converts 16 of each
       ptx::mbar_wait(&bars[BAR_D2_FULL], ph);
       ptx::tc_fence_after();
+      SGA_TRACE(0, g, 0);
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         const int k0 = 32 * c + 16 * wh;
@@ -239,12 +282,17 @@ pointnet_fwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
         ptx::tmem_ld16(tmem + lane_addr + D2_COL + k0, v);
         ptx::tmem_ld_wait();
         float f0[8], f1[8];
+        {
+          const float4* bq = reinterpret_cast<const float4*>(b2s + k0);
+          const float4 q0 = bq[0], q1 = bq[1], q2 = bq[2], q3 = bq[3];
+          const float bb[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float a = __uint_as_float(v[e]) + b2s[k0 + e];
-          float b = __uint_as_float(v[8 + e]) + b2s[k0 + 8 + e];
-          f0[e] = a > 0.f ? a : 0.f;
-          f1[e] = b > 0.f ? b : 0.f;
+          for (int e = 0; e < 8; ++e) {
+            float a = __uint_as_float(v[e]) + bb[e];
+            float b = __uint_as_float(v[8 + e]) + bb[8 + e];
+            f0[e] = a > 0.f ? a : 0.f;
+            f1[e] = b > 0.f ? b : 0.f;
+          }
         }
         uint4 h0, l0, h1, l1;
         split8(f0, h0, l0);
@@ -259,11 +307,20 @@ pointnet_fwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&bars[BAR_H2_FULL + c]);
+        SGA_TRACE(0, g, 1 + c);
       }
-      // ---- conv3 done: H2/A1 buffers and D3 are ours
+      // ---- conv1 of the next tile as soon as conv3 has consumed H2 block 0 (= the A1 buffer);
+      //      its conv2 is then queued on the tensor pipe directly behind this tile's conv3
+      if (g + 1 < G) {
+        ptx::mbar_wait(&bars[BAR_BLK0_FREE], ph);
+        SGA_TRACE(0, g, 5);
+        stage1();
+        SGA_TRACE(0, g, 6);
+      }
+      // ---- conv3 done: D3 is ours
       ptx::mbar_wait(&bars[BAR_D3_FULL], ph);
       ptx::tc_fence_after();
-      if (g + 1 < G) stage1(g + 1);      // next tile's conv1 (+ its conv2 on the tensor pipe) overlaps E3
+      SGA_TRACE(0, g, 7);
       // ---- E3: running max over the 128 points (columns) of this tile
       if (wh < nmt) {
         const uint32_t base = tmem + lane_addr + D3_COL + (uint32_t)wh * 128;
@@ -296,6 +353,7 @@ pointnet_fwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bars[BAR_D3_FREE]);
+      SGA_TRACE(0, g, 8);
       if (t == ntile - 1) {
         if (wh < nmt) {
           const int64_t n = blockIdx.x + (g / ntile) * (int64_t)gridDim.x;
@@ -316,6 +374,11 @@ pointnet_fwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
 }
 
 }  // namespace
+
+int debug_set_trace(long long* ptr) {
+  SGA_CUDA(cudaMemcpyToSymbol(g_trace, &ptr, sizeof(ptr)));
+  return SGA_OK;
+}
 
 int pointnet_fwd_tc(const float* pts, int64_t N, int P, const float* W1, const float* b1, const float* W2,
                     const float* b2, const float* W3, const float* b3, int C3, float* out, int32_t* argmax,
