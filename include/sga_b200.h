@@ -173,6 +173,10 @@ int sga_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                   float grad_scale, void* stream);
 
+/* diagnostics only: device buffer of >= 2048 int64 that CTA 0 of the tensor-core PointNet kernel fills
+ * with clock64() stamps of its pipeline events (profiles/trace_pointnet.py); NULL switches it off. */
+int sga_debug_set_trace(long long* trace);
+
 /* ---- bring-up / self-test kernels (tests only): one 128xN tile D = A B^T through tcgen05 with
  * split operands.  kind 0: bf16x3, kind 1: tf32x3.  A [128,K], B [Ncols,K] f32 row-major,
  * D [128,Ncols] f32. */
