@@ -12,9 +12,9 @@ class PointNetFeat(torch.autograd.Function):
     the saved per-channel argmax of the max-pool."""
 
     @staticmethod
-    def forward(ctx, pts, W1, b1, W2, b2, W3, b3, mode):
+    def forward(ctx, pts, W1, b1, W2, b2, W3, b3, mode, chunks=None):
         need = any(ctx.needs_input_grad[1:7])
-        out, arg = ops.pointnet_forward(pts, W1, b1, W2, b2, W3, b3, want_argmax=need, mode=mode)
+        out, arg = ops.pointnet_forward(pts, W1, b1, W2, b2, W3, b3, want_argmax=need, mode=mode, chunks=chunks)
         if need:
             ctx.save_for_backward(pts, W1, b1, W2, b2, W3, b3, out, arg)
         return out
@@ -23,7 +23,7 @@ class PointNetFeat(torch.autograd.Function):
     def backward(ctx, gout):
         pts, W1, b1, W2, b2, W3, b3, out, arg = ctx.saved_tensors
         gW1, gb1, gW2, gb2, gW3, gb3 = ops.pointnet_backward(pts, W1, b1, W2, b2, W3, b3, out, arg, gout.contiguous())
-        return None, gW1.view_as(W1), gb1, gW2.view_as(W2), gb2, gW3.view_as(W3), gb3, None
+        return None, gW1.view_as(W1), gb1, gW2.view_as(W2), gb2, gW3.view_as(W3), gb3, None, None
 
 
 class GATLayer(torch.autograd.Function):

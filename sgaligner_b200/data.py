@@ -36,3 +36,53 @@ def h2d_bytes(data: dict) -> int:
         if k in data:
             n += np.asarray(data[k]).size * 4
     return int(n)
+
+
+def to_cuda_streamed(data: dict, device, n_chunks: int = 4, copy_stream=None) -> dict:
+    """``to_cuda`` for serving: the copies run on a side stream so that they overlap the kernels of the
+    same step.  The small tensors (edges, BoW, poses) go first, then ``tot_obj_pts`` in ``n_chunks``
+    object ranges, each with its own event; ``MultiModalEncoder.forward`` waits for the small tensors,
+    runs the graph branch, and launches the point encoder chunk by chunk as the copies land.
+    Host tensors should be pinned (:func:`pin`), otherwise the copies are synchronous."""
+    import torch
+    dev = torch.device(device) if not isinstance(device, torch.device) else device
+    cs = copy_stream if copy_stream is not None else _copy_stream(dev)
+    cur = torch.cuda.current_stream(dev)
+    cs.wait_stream(cur)          # do not overwrite buffers a previous step may still be reading
+    out = {}
+    with torch.cuda.stream(cs):
+        for k, v in data.items():
+            if torch.is_tensor(v) and k != 'tot_obj_pts':
+                out[k] = v.to(dev, non_blocking=True)
+            elif not torch.is_tensor(v):
+                out[k] = v
+        ev_small = torch.cuda.Event()
+        ev_small.record(cs)
+        pts = data['tot_obj_pts']
+        N = pts.shape[0]
+        dpts = torch.empty(pts.shape, dtype=pts.dtype, device=dev)
+        chunks = []
+        per = (N + n_chunks - 1) // n_chunks
+        for s in range(0, N, per):
+            e = min(N, s + per)
+            dpts[s:e].copy_(pts[s:e], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            chunks.append((s, e, ev))
+    out['tot_obj_pts'] = dpts
+    for v in out.values():       # allocated on the copy stream, consumed on the compute stream
+        if torch.is_tensor(v) and v.is_cuda:
+            v.record_stream(cur)
+    out['_sga_ready'] = {'small': ev_small, 'pts': chunks, 'stream': cs}
+    return out
+
+
+_COPY_STREAMS = {}
+
+
+def _copy_stream(dev):
+    import torch
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _COPY_STREAMS[key]

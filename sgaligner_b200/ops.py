@@ -68,7 +68,9 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------- PointNet
-def pointnet_forward(pts, W1, b1, W2, b2, W3, b3, want_argmax: bool, mode: int = POINTNET_TC):
+def pointnet_forward(pts, W1, b1, W2, b2, W3, b3, want_argmax: bool, mode: int = POINTNET_TC, chunks=None):
+    """chunks: optional [(obj_start, obj_end, cuda_event)] -- the object ranges of ``pts`` become valid
+    when their event fires (streamed H2D copy, ``data.to_cuda_streamed``); one launch per range."""
     _need_cuda(pts, W1, W3)
     pts = _f32c(pts)
     N, P, _ = pts.shape
@@ -79,6 +81,17 @@ def pointnet_forward(pts, W1, b1, W2, b2, W3, b3, want_argmax: bool, mode: int =
     out = torch.empty((N, C3), device=pts.device, dtype=torch.float32)
     arg = torch.empty((N, C3), device=pts.device, dtype=torch.int32) if want_argmax else None
     b1c, b2c, b3c = _f32c(b1), _f32c(b2), _f32c(b3)
+    if chunks:
+        cur = torch.cuda.current_stream()
+        lib = get_lib()
+        for (s, e, ev) in chunks:
+            cur.wait_event(ev)
+            check(lib.sga_pointnet_fwd(ctypes.c_void_p(pts.data_ptr() + s * P * 12), e - s, P, _ptr(W1c), _ptr(b1c), _ptr(W2c),
+                                       _ptr(b2c), _ptr(W3c), _ptr(b3c), C3, ctypes.c_void_p(out.data_ptr() + s * C3 * 4),
+                                       ctypes.c_void_p(0 if arg is None else arg.data_ptr() + s * C3 * 4), mode, _stream()),
+                  'sga_pointnet_fwd')
+            _count(1)
+        return out, arg
     with _timed('pointnet_fwd'):
         check(get_lib().sga_pointnet_fwd(_ptr(pts), N, P, _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c),
                                          _ptr(W3c), _ptr(b3c), C3, _ptr(out), _ptr(arg), mode, _stream()),

@@ -85,12 +85,16 @@ class PointNetfeat(nn.Module):
                 nn.init.xavier_normal_(conv.weight.data, gain=1)
                 nn.init.constant_(conv.bias.data, 0.0)
 
-    def forward(self, pts_npc: torch.Tensor) -> torch.Tensor:
-        """``pts_npc``: [N, P, 3] (the collated layout; the reference permutes to [N,3,P] first)."""
+    def forward(self, pts_npc: torch.Tensor, chunks=None) -> torch.Tensor:
+        """``pts_npc``: [N, P, 3] (the collated layout; the reference permutes to [N,3,P] first).
+        ``chunks``: readiness events of a streamed host-to-device copy (``data.to_cuda_streamed``)."""
         if self.use_batch_norm and self.training and self.track_bn_stats:
+            if chunks:
+                for (_, _, ev) in chunks:
+                    torch.cuda.current_stream().wait_event(ev)
             self._update_bn_running_stats(pts_npc)
         return ag.PointNetFeat.apply(pts_npc, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
-                                     self.conv3.weight, self.conv3.bias, self.kernel_mode)
+                                     self.conv3.weight, self.conv3.bias, self.kernel_mode, chunks)
 
     @torch.no_grad()
     def _update_bn_running_stats(self, pts):
@@ -194,17 +198,23 @@ class MultiModalEncoder(nn.Module):
         pts = data_dict['tot_obj_pts']
         if not (torch.is_tensor(pts) and pts.is_cuda):
             raise RuntimeError('sgaligner_b200.MultiModalEncoder needs the batch on a CUDA device (no CPU fallback)')
+        ready = data_dict.get('_sga_ready')          # streamed H2D copy in flight (data.to_cuda_streamed)
+        if ready is not None:
+            torch.cuda.current_stream().wait_event(ready['small'])
+        # the graph branch only needs the small tensors: run it first so that it overlaps the point copy
+        gat_out = None
+        if 'gat' in self.modules:
+            graph = data_dict.get('_sga_graph')
+            if graph is None:
+                graph = ops.BatchGraph(data_dict['edges'], np.asarray(data_dict['graph_per_obj_count']),
+                                       np.asarray(data_dict['graph_per_edge_count']))
+            gat_out = self.structure_encoder(data_dict['tot_rel_pose'], graph)
         args = []
         for module in self.modules:
             if module == 'gat':
-                graph = data_dict.get('_sga_graph')
-                if graph is None:
-                    graph = ops.BatchGraph(data_dict['edges'], np.asarray(data_dict['graph_per_obj_count']),
-                                           np.asarray(data_dict['graph_per_edge_count']))
-                x = self.structure_encoder(data_dict['tot_rel_pose'], graph)
-                args += [x, self.structure_embedding.weight, self.structure_embedding.bias]
+                args += [gat_out, self.structure_embedding.weight, self.structure_embedding.bias]
             elif module == 'point':
-                x = self.object_encoder(pts)
+                x = self.object_encoder(pts, None if ready is None else ready['pts'])
                 args += [x, self.object_embedding.weight, self.object_embedding.bias]
             elif module == 'rel':
                 args += [data_dict['tot_bow_vec_object_edge_feats'], self.meta_embedding_rel.weight, self.meta_embedding_rel.bias]

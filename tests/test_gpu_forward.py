@@ -178,3 +178,18 @@ def test_no_cpu_fallback(dev):
     model = _model(c, dev)
     with pytest.raises(RuntimeError):
         model(dict(c['data']))
+
+
+def test_streamed_h2d_matches_plain(dev):
+    """data.to_cuda_streamed (chunked, overlapped point copy) gives bit-identical embeddings."""
+    from sgaligner_b200 import to_cuda
+    from sgaligner_b200.data import pin, to_cuda_streamed
+    c = load_case('mid4')
+    model = _model(c, dev).eval()
+    host = pin(dict(c['data']))
+    with torch.no_grad():
+        a = model(to_cuda(dict(host), dev))
+        b = model(to_cuda_streamed(host, dev, n_chunks=3))
+    torch.cuda.synchronize()
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
