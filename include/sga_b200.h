@@ -137,6 +137,14 @@ int sga_project_fuse_bwd(const float* x, int64_t N, int in_dim, const float* W, 
 int sga_match_sim(const float* emb, int64_t N, int D, const int32_t* pair_off, const int64_t* sim_off,
                   int B, int max_pair_nodes, float* norms, float* sim, void* stream);
 
+/* Tensor-core matching head: the same sim = 1 - E E^T as a tcgen05 tf32x3 Gram (fp32-faithful,
+ * ~1e-6) fused with the per-row top-K (K <= 8) of the ranking, one CTA per (pair, 128-row block).
+ * topk_idx/topk_dist [N,K] as in sga_match_rank; sim_out (packed like sga_match_sim) may be NULL, in
+ * which case the similarity matrix never reaches HBM.  norms [N] is scratch. */
+int sga_match_topk_tc(const float* emb, int64_t N, int D, const int32_t* pair_off, const int64_t* sim_off,
+                      int B, int max_pair_nodes, int K, float* norms, int32_t* topk_idx, float* topk_dist,
+                      float* sim_out, void* stream);
+
 /* rank_list = argsort(sim, dim=1) made deterministic: ascending by (sim, column).  node_pair [N]
  * int32 maps a node to its pair.  topk_idx/topk_dist [N,K] (pair-local columns, the node itself
  * included exactly as in the reference's rank_list; -1 / +inf padding when n_b < K) may be NULL;

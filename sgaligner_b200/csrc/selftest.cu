@@ -3,6 +3,7 @@
 // operand tiles, shared-memory matrix descriptors, instruction descriptor, TMEM load shapes).
 #include "common.cuh"
 #include "ptx.cuh"
+#include "umma_tf32.cuh"
 
 namespace sga {
 namespace {
@@ -54,8 +55,8 @@ selftest_umma_kernel(const float* __restrict__ A, const float* __restrict__ B, f
           uint32_t h[4], l[4];
           for (int e = 0; e < 4; ++e) {
             float a = p[e];
-            h[e] = __float_as_uint(a) & 0xFFFFE000u;
-            l[e] = __float_as_uint(a - __uint_as_float(h[e]));
+            h[e] = tf32x3::rn_tf32(a);
+            l[e] = tf32x3::rn_tf32(a - __uint_as_float(h[e]));
           }
           hi = make_uint4(h[0], h[1], h[2], h[3]);
           lo = make_uint4(l[0], l[1], l[2], l[3]);

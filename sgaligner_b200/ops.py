@@ -294,6 +294,23 @@ def match_sim(emb: torch.Tensor, lay: PairLayout):
     return sim
 
 
+def match_topk_tc(emb: torch.Tensor, lay: PairLayout, K: int, want_sim: bool):
+    """Fused tcgen05 Gram + per-row top-K (K <= 8); returns (topk_idx, topk_dist, sim or None)."""
+    _need_cuda(emb)
+    emb = _f32c(emb)
+    N, D = emb.shape
+    dev = emb.device
+    norms = torch.empty(N, device=dev, dtype=torch.float32)
+    topk_idx = torch.empty((N, K), device=dev, dtype=torch.int32) if K > 0 else None
+    topk_dist = torch.empty((N, K), device=dev, dtype=torch.float32) if K > 0 else None
+    sim = torch.empty(int(lay.sim_off_host[-1]), device=dev, dtype=torch.float32) if want_sim else None
+    with _timed('match_topk_tc'):
+        check(get_lib().sga_match_topk_tc(_ptr(emb), N, D, _ptr(lay.pair_off), _ptr(lay.sim_off), lay.B, lay.max_n, K, _ptr(norms),
+                                          _ptr(topk_idx), _ptr(topk_dist), _ptr(sim), _stream()), 'sga_match_topk_tc')
+    _count(2)
+    return topk_idx, topk_dist, sim
+
+
 def match_rank(sim: torch.Tensor, lay: PairLayout, K: int, full: bool):
     dev = sim.device
     topk_idx = torch.empty((lay.N, K), device=dev, dtype=torch.int32) if K > 0 else None

@@ -149,7 +149,7 @@ def test_matching_vs_golden(name, dev):
         kk = min(6, n)
         assert (tk[:, :kk] == r[:, :kk]).all()
         sim_dev = res['sim'][int(lay.sim_off_host[b]):int(lay.sim_off_host[b]) + n * n].view(n, n).cpu().numpy()
-        assert np.abs(sim_dev - ref_sim).max() < 2e-6
+        assert np.abs(sim_dev - ref_sim).max() < 1e-5   # tensor-core fp32 accumulation truncates: ~-2^-24 per accumulate step, one-signed
 
 
 @pytest.mark.parametrize('name', CASES)
