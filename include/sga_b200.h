@@ -175,6 +175,16 @@ int sga_loss_fwd_bwd(const float* const* embs_host, const int* dims_host, int n_
                      float* g_log_vars_ial, float* g_log_vars_icl, void* workspace,
                      size_t workspace_bytes, void* stream);
 
+/* Generic fp32-faithful tensor-core GEMM (tcgen05, tf32x3 split operands) used by the loss and its
+ * backward:  C[M,N] = sum_k A(m,k) B(n,k).  An operand is K-major (X(r,k) = P[row(r)*ld + k]) or
+ * MN-major (X(r,k) = P[row(k)*ld + r]); row(i) = idx ? idx[i] : i; values are divided by div[row] when
+ * div != NULL.  c_idx == NULL: C is stored; otherwise rows are scatter-added (atomicAdd) into
+ * C[c_idx[m]*ldc + n] and the K range may be cut into `ksplit` slices.  Supported layout pairs:
+ * (K,K), (K,MN), (MN,MN). */
+int sga_gemm_tf32x3(const float* A, int64_t lda, int a_mn_major, const int32_t* a_idx, const float* a_div,
+                    const float* B, int64_t ldb, int b_mn_major, const int32_t* b_idx, const float* b_div,
+                    int M, int N, int K, float* C, int64_t ldc, const int32_t* c_idx, int ksplit, void* stream);
+
 /* ---- a17: torch.optim.Adam step (L2 weight decay folded into the gradient, bias-corrected) over
  * a flat parameter buffer; grad is multiplied by grad_scale first (1/world_size after allreduce). */
 int sga_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,

@@ -1,0 +1,322 @@
+// Persistent tcgen05 GEMM with fp32-faithful tf32x3 split operands (umma_tf32.cuh) for the loss
+// Grams and their backward (src/aligner/losses.py:5-15 -- the matmuls inside calculate_prob_dist --
+// and the autograd of them).
+//
+//   C[M,N] (op)= sum_k A(m,k) * B(n,k)
+// Each operand is read straight from a row-major fp32 matrix, either
+//   K-major : X(r,k) = P[row(r)*ld + k]          (row gather through idx, division by div[row])
+//   MN-major: X(r,k) = P[row(k)*ld + r]          (the CONTRACTION index is the gathered row)
+// so that  F = Zn[e1i] Zn[R]^T  (forward),  dZn[e1i] += dF Zn[R]  and  dZn[R] += dF^T Zn[e1i]
+// (backward) are all one launch each without gather / transpose passes: L2-normalisation and the
+// e1i/e2i/e1j/e2j gathers happen in the operand loader, the scatter-add in the epilogue.
+//
+// 128x128 output tiles, K chunks of 32, 3-stage shared-memory ring (4 x 16 KiB per stage), two TMEM
+// accumulators so the epilogue of tile i overlaps the main loop of tile i+1.  9 warps: 4 operand
+// loaders, 1 MMA issuer (elect.sync), 4 epilogue warps (one TMEM lane quarter each).
+#include "common.cuh"
+#include "umma_tf32.cuh"
+
+namespace sga {
+
+struct GemmOperand {
+  const float* p;
+  int64_t ld;
+  const int32_t* idx;   // optional row gather
+  const float* div;     // optional per-(source)-row divisor (L2 norm, clamped by the caller)
+  int mn_major;
+};
+
+struct GemmParams {
+  GemmOperand A, B;
+  int M, N, K;
+  float* C;
+  int64_t ldc;
+  int mode;               // 0 store, 1 store + exp-sums, 2 scatter-add rows (atomicAdd C[c_idx[m]][n])
+  const int32_t* c_idx;   // mode 2
+  int es_c0, es_split;    // mode 1: columns >= es_c0 feed the sums; < es_split -> S_lo else S_hi
+  double* s01_lo; double* s01_hi; double* s1_lo; double* s1_hi;   // sum exp(x/0.1), sum exp(x)
+  int ksplit;             // mode 2 only: the K range is cut into ksplit slices, each adds its partial product
+};
+
+namespace {
+
+constexpr int kStages = 3;
+constexpr int kLoaders = 128;
+constexpr int kThreads = 288;
+constexpr uint32_t BAR_OFF = kStages * tf32x3::kStageBytes;
+constexpr uint32_t SMEM_BYTES = BAR_OFF + 256 + 1024;
+
+// MN-major [128 mn x 32 k] tile.  For 32-bit operands the only MN-major shared-memory layout tcgen05
+// accepts is SWIZZLE_128B_BASE32B (descriptor layout type 1): atoms of [4 k-rows x 128 B], the
+// 32-byte chunk index XORed with (k & 3).  Here: the 32 k-rows of one 32-wide MN atom are contiguous
+// (128 B apart; 4-row atoms 512 B apart = SBO), MN atoms 4096 B apart (= LBO).
+__device__ __forceinline__ void load_mn_major(unsigned char* hi, unsigned char* lo, const GemmOperand& X, int mn0, int MN, int k0,
+                                              int K, int t, bool vec_ok) {
+  const int kk = (t & 7) + 8 * ((t >> 3) & 3);   // k row inside the chunk
+  const int qd = t >> 5;                          // which 32-wide MN atom
+  const int krow = k0 + kk;
+  const bool kvalid = krow < K;
+  int64_t sr = 0;
+  float d = 1.f;
+  if (kvalid) {
+    sr = X.idx ? (int64_t)X.idx[krow] : (int64_t)krow;
+    if (X.div) d = X.div[sr];
+  }
+  const int c0 = mn0 + 32 * qd;
+  const float* p = X.p + sr * X.ld + c0;
+  const uint32_t base = (uint32_t)qd * 4096u + (uint32_t)kk * 128u;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (kvalid) {
+      if (vec_ok && c0 + 4 * j + 3 < MN) {
+        float4 q = *reinterpret_cast<const float4*>(p + 4 * j);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (c0 + 4 * j + e < MN) v[e] = p[4 * j + e];
+      }
+    }
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float x = X.div ? v[e] / d : v[e];
+      h[e] = tf32x3::rn_tf32(x);
+      l[e] = tf32x3::rn_tf32(x - __uint_as_float(h[e]));
+    }
+    const uint32_t off = base + (uint32_t)((((j >> 1) ^ (kk & 3)) << 5) + ((j & 1) << 4));
+    *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+__device__ __forceinline__ uint64_t desc_mn_major(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(4096u >> 4) << 16;      // LBO: next 32-element atom along MN
+  d |= (uint64_t)(512u >> 4) << 32;       // SBO: next group of 4 k rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                 // SWIZZLE_128B_BASE32B
+  return d;
+}
+
+template <bool A_MN, bool B_MN>
+__device__ __forceinline__ void issue_stage_any(uint32_t d_tmem, uint32_t stage_addr, uint32_t idesc, bool first) {
+  using namespace tf32x3;
+  const uint64_t dAhi = A_MN ? desc_mn_major(stage_addr) : ptx::smem_desc_sw128(stage_addr);
+  const uint64_t dAlo = A_MN ? desc_mn_major(stage_addr + kTileBytes) : ptx::smem_desc_sw128(stage_addr + kTileBytes);
+  const uint64_t dBhi = B_MN ? desc_mn_major(stage_addr + 2 * kTileBytes) : ptx::smem_desc_sw128(stage_addr + 2 * kTileBytes);
+  const uint64_t dBlo = B_MN ? desc_mn_major(stage_addr + 3 * kTileBytes) : ptx::smem_desc_sw128(stage_addr + 3 * kTileBytes);
+  constexpr uint64_t aStep = A_MN ? (1024 >> 4) : 2;   // one k-step = 8 k: 8 rows of 128 B / +32 bytes
+  constexpr uint64_t bStep = B_MN ? (1024 >> 4) : 2;
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint64_t a = (pass == 1) ? dAlo : dAhi;
+    const uint64_t b = (pass == 2) ? dBlo : dBhi;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      ptx::umma_tf32(d_tmem, a + aStep * ks, b + bStep * ks, idesc, (first && pass == 0 && ks == 0) ? 0u : 1u);
+  }
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32x3_kernel(const GemmParams P) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sm_base = ptx::smem_u32(sm);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + BAR_OFF);
+  uint64_t* empty = full + kStages;
+  uint64_t* acc_full = empty + kStages;    // [2]
+  uint64_t* acc_free = acc_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&full[s], kLoaders);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&acc_full[i], 1);
+      ptx::mbar_init(&acc_free[i], 128);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 4) ptx::tmem_alloc<256>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int ntm = (P.M + 127) / 128, ntn = (P.N + 127) / 128;
+  const int ksplit = P.ksplit > 1 ? P.ksplit : 1;
+  const int ntiles = ntm * ntn * ksplit;          // work items: (output tile, K slice)
+  const int nkc_all = (P.K + 31) / 32;
+  const int kc_per = (nkc_all + ksplit - 1) / ksplit;
+
+  if (warp < 4) {
+    // ------------------------------- operand loaders
+    const bool a_vec = (P.A.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.A.p) & 15) == 0);
+    const bool b_vec = (P.B.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.B.p) & 15) == 0);
+    int it = 0;
+    for (int work = blockIdx.x; work < ntiles; work += gridDim.x) {
+      const int tile = work / ksplit, ksl = work % ksplit;
+      const int m0 = (tile / ntn) * 128, n0 = (tile % ntn) * 128;
+      const int kc_beg = ksl * kc_per, kc_end = min(nkc_all, kc_beg + kc_per);
+      for (int kc = kc_beg; kc < kc_end; ++kc, ++it) {
+        const int s = it % kStages;
+        if (it >= kStages) ptx::mbar_wait(&empty[s], (uint32_t)(((it / kStages) - 1) & 1));
+        unsigned char* st = sm + s * tf32x3::kStageBytes;
+        if (A_MN) load_mn_major(st, st + tf32x3::kTileBytes, P.A, m0, P.M, kc * 32, P.K, tid, a_vec);
+        else tf32x3::load_rows(st, st + tf32x3::kTileBytes, P.A.p, P.A.ld, P.A.idx, P.A.div, m0, P.M - m0, kc * 32, P.K, tid, a_vec);
+        if (B_MN) load_mn_major(st + 2 * tf32x3::kTileBytes, st + 3 * tf32x3::kTileBytes, P.B, n0, P.N, kc * 32, P.K, tid, b_vec);
+        else tf32x3::load_rows(st + 2 * tf32x3::kTileBytes, st + 3 * tf32x3::kTileBytes, P.B.p, P.B.ld, P.B.idx, P.B.div, n0, P.N - n0,
+                               kc * 32, P.K, tid, b_vec);
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&full[s]);
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------- MMA issuer
+    const uint32_t idesc = ptx::make_idesc(2, 128, 128) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    int it = 0, ti = 0;
+    for (int work = blockIdx.x; work < ntiles; work += gridDim.x, ++ti) {
+      const int ksl = work % ksplit;
+      const int kc_beg = ksl * kc_per, kc_end = min(nkc_all, kc_beg + kc_per);
+      const int ab = ti & 1;
+      if (ti >= 2) {
+        ptx::mbar_wait(&acc_free[ab], (uint32_t)(((ti >> 1) - 1) & 1));
+        ptx::tc_fence_after();
+      }
+      for (int kc = kc_beg; kc < kc_end; ++kc, ++it) {
+        const int s = it % kStages;
+        ptx::mbar_wait(&full[s], (uint32_t)((it / kStages) & 1));
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          issue_stage_any<A_MN, B_MN>(tmem_u + ab * 128, sm_base + s * tf32x3::kStageBytes, idesc, kc == kc_beg);
+          ptx::umma_commit(&empty[s]);
+          if (kc == kc_end - 1) ptx::umma_commit(&acc_full[ab]);
+        }
+        __syncwarp();
+      }
+      if (kc_end <= kc_beg && ptx::elect_one()) ptx::umma_commit(&acc_full[ab]);   // empty slice: nothing to add
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------- epilogue
+    const int q = warp & 3;
+    const int r = 32 * q + lane;
+    float s_acc[4] = {0.f, 0.f, 0.f, 0.f};   // {s01_lo, s01_hi, s1_lo, s1_hi}
+    int ti = 0;
+    for (int work = blockIdx.x; work < ntiles; work += gridDim.x, ++ti) {
+      const int tile = work / ksplit, ksl = work % ksplit;
+      const int m0 = (tile / ntn) * 128, n0 = (tile % ntn) * 128;
+      const int ab = ti & 1;
+      ptx::mbar_wait(&acc_full[ab], (uint32_t)((ti >> 1) & 1));
+      ptx::tc_fence_after();
+      const int row = m0 + r;
+      const bool row_ok = row < P.M && (ksl * kc_per < nkc_all);
+      float* crow = nullptr;
+      if (row_ok) crow = P.C + (P.mode == 2 ? (int64_t)P.c_idx[row] : (int64_t)row) * P.ldc;
+      const uint32_t base = tmem + ((uint32_t)(32 * q) << 16) + ab * 128;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t v[32];
+        ptx::tmem_ld32(base + cc * 32, v);
+        ptx::tmem_ld_wait();
+        if (row_ok) {
+          const int c0 = n0 + cc * 32;
+          if (P.mode == 2) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (c0 + e < P.N) atomicAdd(crow + c0 + e, __uint_as_float(v[e]));
+          } else {
+            if (c0 + 31 < P.N && (P.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0)) {
+#pragma unroll
+              for (int e = 0; e < 32; e += 4)
+                *reinterpret_cast<uint4*>(crow + c0 + e) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                if (c0 + e < P.N) crow[c0 + e] = __uint_as_float(v[e]);
+            }
+            if (P.mode == 1 && c0 + 31 >= P.es_c0) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                const int c = c0 + e;
+                if (c >= P.es_c0 && c < P.N) {
+                  const float x = __uint_as_float(v[e]);
+                  const float e01 = expf(x / 0.1f), e1 = expf(x);
+                  if (c < P.es_split) { s_acc[0] += e01; s_acc[2] += e1; }
+                  else { s_acc[1] += e01; s_acc[3] += e1; }
+                }
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&acc_free[ab]);
+    }
+    if (P.mode == 1) {
+      double* dst[4] = {P.s01_lo, P.s01_hi, P.s1_lo, P.s1_hi};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float s = warp_sum(s_acc[i]);
+        if (lane == 0 && dst[i] && s != 0.f) atomicAdd(dst[i], (double)s);
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) ptx::tmem_dealloc<256>(tmem);
+}
+
+}  // namespace
+
+int launch_gemm_tc(const GemmParams& P, cudaStream_t st) {
+  if (P.M <= 0 || P.N <= 0 || P.K <= 0) return SGA_OK;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SGA_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    SGA_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    SGA_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    attr_done = true;
+  }
+  if (P.ksplit > 1 && P.mode != 2) {
+    set_error("gemm_tc: split-K needs the scatter-add epilogue");
+    return SGA_EINVAL;
+  }
+  const int ntiles = ((P.M + 127) / 128) * ((P.N + 127) / 128) * (P.ksplit > 1 ? P.ksplit : 1);
+  int grid = ntiles < sm_count() ? ntiles : sm_count();
+  if (!P.A.mn_major && !P.B.mn_major) gemm_tf32x3_kernel<false, false><<<grid, kThreads, SMEM_BYTES, st>>>(P);
+  else if (!P.A.mn_major && P.B.mn_major) gemm_tf32x3_kernel<false, true><<<grid, kThreads, SMEM_BYTES, st>>>(P);
+  else if (P.A.mn_major && P.B.mn_major) gemm_tf32x3_kernel<true, true><<<grid, kThreads, SMEM_BYTES, st>>>(P);
+  else {
+    set_error("gemm_tc: (A MN-major, B K-major) is not instantiated");
+    return SGA_EINVAL;
+  }
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+}  // namespace sga
+
+// Test / generic entry: C (mode 0: =, mode 2: scatter-add through c_idx) A B^T with optional gathers.
+extern "C" int sga_gemm_tf32x3(const float* A, int64_t lda, int a_mn_major, const int32_t* a_idx, const float* a_div,
+                               const float* B, int64_t ldb, int b_mn_major, const int32_t* b_idx, const float* b_div,
+                               int M, int N, int K, float* C, int64_t ldc, const int32_t* c_idx, int ksplit, void* stream) {
+  sga::GemmParams P;
+  memset(&P, 0, sizeof(P));
+  P.A = {A, lda, a_idx, a_div, a_mn_major};
+  P.B = {B, ldb, b_idx, b_div, b_mn_major};
+  P.M = M; P.N = N; P.K = K;
+  P.C = C; P.ldc = ldc;
+  P.mode = c_idx ? 2 : 0;
+  P.c_idx = c_idx;
+  P.ksplit = c_idx ? ksplit : 1;
+  return sga::launch_gemm_tc(P, (cudaStream_t)stream);
+}

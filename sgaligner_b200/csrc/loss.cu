@@ -11,11 +11,34 @@
 // and by all M IAL terms that reuse the joint embedding.  The backward is 4 more GEMMs per
 // embedding on the in-place gradient of F1/F2.
 //
-// This file is the fp32 FMA path (materialised F1/F2 in HBM).
+// The GEMMs run on the tensor cores (gemm_tc.cu, tcgen05 tf32x3): L2-normalisation and the index
+// gathers are fused into the operand loader, the normaliser sums into the forward epilogue, and the
+// backward GEMMs scatter-add straight into d(normalised embedding); F1/F2 are materialised in HBM
+// (A x T fp32 each) because the element-wise loss terms need the global normalisers first.
 #include "common.cuh"
-#include "gemm_simt.cuh"
 
 namespace sga {
+
+struct GemmOperand {
+  const float* p;
+  int64_t ld;
+  const int32_t* idx;
+  const float* div;
+  int mn_major;
+};
+struct GemmParams {
+  GemmOperand A, B;
+  int M, N, K;
+  float* C;
+  int64_t ldc;
+  int mode;
+  const int32_t* c_idx;
+  int es_c0, es_split;
+  double* s01_lo; double* s01_hi; double* s1_lo; double* s1_hi;
+  int ksplit;
+};
+int launch_gemm_tc(const GemmParams& P, cudaStream_t st);   // gemm_tc.cu
+
 namespace {
 
 constexpr int NT = 256;
@@ -24,9 +47,11 @@ constexpr float kEps = 1e-9f;
 struct Layout {
   // byte offsets into the workspace
   size_t scal;                // doubles: S[n_emb][2][4], dS[n_emb][2][4], icl_raw[n_emb], ial_raw[n_emb]
-  size_t norms[17], P1[17], P2[17], R[17], R2[17], F1[17], F2[17], dP1[17], dP2[17], dR[17], dR2[17], dXh[17];
+  size_t ridx, r2idx;         // int32 [T]: rows [e2i;e1j;e2j] and [e1i;e2j;e1j]
+  size_t norms[17], den[17], F1[17], F2[17], dXh[17];
   size_t acc1, acc2;
   size_t total;
+  int ldF;
 };
 
 inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -36,24 +61,18 @@ Layout make_layout(int n_emb, const int* dims, int64_t N, int A, int J1, int J2,
   memset(&L, 0, sizeof(L));
   size_t o = 0;
   const size_t T = (size_t)A + J1 + J2;
+  L.ldF = (int)((T + 3) & ~(size_t)3);     // 16-byte aligned rows for the vectorised operand loads
   L.scal = o;
   o = al256(o + sizeof(double) * (size_t)n_emb * 18);
+  L.ridx = o; o = al256(o + 4 * T);
+  L.r2idx = o; o = al256(o + 4 * T);
   for (int x = 0; x < n_emb; ++x) {
     const size_t d = dims[x];
     L.norms[x] = o; o = al256(o + 4 * (size_t)N);
-    L.P1[x] = o; o = al256(o + 4 * (size_t)A * d);
-    L.P2[x] = o; o = al256(o + 4 * (size_t)A * d);
-    L.R[x] = o; o = al256(o + 4 * T * d);
-    L.R2[x] = o; o = al256(o + 4 * T * d);
-    L.F1[x] = o; o = al256(o + 4 * (size_t)A * T);
-    L.F2[x] = o; o = al256(o + 4 * (size_t)A * T);
-    if (want_grad) {
-      L.dP1[x] = o; o = al256(o + 4 * (size_t)A * d);
-      L.dP2[x] = o; o = al256(o + 4 * (size_t)A * d);
-      L.dR[x] = o; o = al256(o + 4 * T * d);
-      L.dR2[x] = o; o = al256(o + 4 * T * d);
-      L.dXh[x] = o; o = al256(o + 4 * (size_t)N * d);
-    }
+    L.den[x] = o; o = al256(o + 4 * (size_t)N);
+    L.F1[x] = o; o = al256(o + 4 * (size_t)A * L.ldF);
+    L.F2[x] = o; o = al256(o + 4 * (size_t)A * L.ldF);
+    if (want_grad) { L.dXh[x] = o; o = al256(o + 4 * (size_t)N * d); }
   }
   if (want_grad && n_emb > 1) {
     L.acc1 = o; o = al256(o + 4 * (size_t)A * A);
@@ -65,7 +84,7 @@ Layout make_layout(int n_emb, const int* dims, int64_t N, int A, int J1, int J2,
 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT)
-row_norm_kernel(const float* __restrict__ X, int64_t N, int D, float* __restrict__ norms) {
+row_norm_kernel(const float* __restrict__ X, int64_t N, int D, float* __restrict__ norms, float* __restrict__ den) {
   int64_t row = (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
   if (row >= N) return;
   int lane = threadIdx.x & 31;
@@ -75,35 +94,22 @@ row_norm_kernel(const float* __restrict__ X, int64_t N, int D, float* __restrict
     s = fmaf(v, v, s);
   }
   s = warp_sum(s);
-  if (lane == 0) norms[row] = sqrtf(s);
+  if (lane == 0) {
+    norms[row] = sqrtf(s);
+    den[row] = fmaxf(sqrtf(s), 1e-12f);    // F.normalize: x / max(||x||, eps)
+  }
 }
 
-// rows of P1 | P2 | R=[e2i;e1j;e2j] | R2=[e1i;e2j;e1j], each = X[idx] / max(||X[idx]||, 1e-12)
+// ridx = [e2i; e1j; e2j], r2idx = [e1i; e2j; e1j]
 __global__ void __launch_bounds__(NT)
-gather_norm_kernel(const float* __restrict__ X, const float* __restrict__ norms, int D,
-                   const int32_t* __restrict__ e1i, const int32_t* __restrict__ e2i,
-                   const int32_t* __restrict__ e1j, const int32_t* __restrict__ e2j, int A, int J1, int J2,
-                   float* __restrict__ P1, float* __restrict__ P2, float* __restrict__ R, float* __restrict__ R2) {
+build_ridx_kernel(const int32_t* __restrict__ e1i, const int32_t* __restrict__ e2i, const int32_t* __restrict__ e1j,
+                  const int32_t* __restrict__ e2j, int A, int J1, int J2, int32_t* __restrict__ ridx,
+                  int32_t* __restrict__ r2idx) {
   const int T = A + J1 + J2;
-  int64_t row = (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
-  if (row >= 2 * (int64_t)A + 2 * (int64_t)T) return;
-  int lane = threadIdx.x & 31;
-  int idx;
-  float* dst;
-  int r = (int)row;
-  if (r < A) { idx = e1i[r]; dst = P1 + (int64_t)r * D; }
-  else if (r < 2 * A) { r -= A; idx = e2i[r]; dst = P2 + (int64_t)r * D; }
-  else if (r < 2 * A + T) {
-    r -= 2 * A;
-    idx = r < A ? e2i[r] : (r < A + J1 ? e1j[r - A] : e2j[r - A - J1]);
-    dst = R + (int64_t)r * D;
-  } else {
-    r -= 2 * A + T;
-    idx = r < A ? e1i[r] : (r < A + J2 ? e2j[r - A] : e1j[r - A - J2]);
-    dst = R2 + (int64_t)r * D;
+  for (int r = blockIdx.x * NT + threadIdx.x; r < T; r += gridDim.x * NT) {
+    ridx[r] = r < A ? e2i[r] : (r < A + J1 ? e1j[r - A] : e2j[r - A - J1]);
+    r2idx[r] = r < A ? e1i[r] : (r < A + J2 ? e2j[r - A] : e1j[r - A - J2]);
   }
-  const float den = fmaxf(norms[idx], 1e-12f);
-  for (int k = lane; k < D; k += 32) dst[k] = X[(int64_t)idx * D + k] / den;
 }
 
 template <int NV>
@@ -121,24 +127,6 @@ __device__ __forceinline__ void block_reduce_add(float (&v)[NV], double* const* 
     for (int w = 0; w < NT / 32; ++w) s += (double)red[w][threadIdx.x];
     if (dst[threadIdx.x]) atomicAdd(dst[threadIdx.x], s);
   }
-}
-
-// S[tau][seg] += sum exp(F[a, c0:c1] / tau) for tau in {0.1, 1.0}
-__global__ void __launch_bounds__(NT)
-expsum_kernel(const float* __restrict__ F, int A, int T, int c0, int c1, double* __restrict__ S01,
-              double* __restrict__ S1) {
-  const int64_t w = c1 - c0, total = (int64_t)A * w;
-  float acc[2] = {0.f, 0.f};
-  for (int64_t t = (int64_t)blockIdx.x * NT + threadIdx.x; t < total; t += (int64_t)gridDim.x * NT) {
-    int64_t a = t / w, c = c0 + t % w;
-    float u = F[a * T + c];
-    acc[0] += expf(u / 0.1f);
-    acc[1] += expf(u);
-  }
-  __shared__ double* dst[2];
-  if (threadIdx.x == 0) { dst[0] = S01; dst[1] = S1; }
-  __syncthreads();
-  block_reduce_add<2>(acc, dst);
 }
 
 struct QD { float q, dg, dsa, dsb; };
@@ -255,43 +243,15 @@ pair_kernel(PairArgs p) {
 
 // in place over the U blocks of F1 / F2: u -> sum_tau dS[tau][seg] / tau * exp(u / tau)
 __global__ void __launch_bounds__(NT)
-coef_kernel(float* __restrict__ F, int A, int T, int c_split, const double* __restrict__ dS, int seg_lo, int seg_hi) {
+coef_kernel(float* __restrict__ F, int A, int T, int ld, int c_split, const double* __restrict__ dS, int seg_lo, int seg_hi) {
   const int64_t w = T - A, total = (int64_t)A * w;
   const float lo01 = (float)dS[seg_lo] * 10.f, lo1 = (float)dS[4 + seg_lo];
   const float hi01 = (float)dS[seg_hi] * 10.f, hi1 = (float)dS[4 + seg_hi];
   for (int64_t t = (int64_t)blockIdx.x * NT + threadIdx.x; t < total; t += (int64_t)gridDim.x * NT) {
     int64_t a = t / w, c = A + t % w;
-    float u = F[a * T + c];
+    float u = F[a * ld + c];
     float e01 = expf(u / 0.1f), e1 = expf(u);
-    F[a * T + c] = (c < c_split) ? lo01 * e01 + lo1 * e1 : hi01 * e01 + hi1 * e1;
-  }
-}
-
-// dXh[idx] += gradient rows of the gathered operands
-__global__ void __launch_bounds__(NT)
-scatter_kernel(const float* __restrict__ dP1, const float* __restrict__ dP2, const float* __restrict__ dR,
-               const float* __restrict__ dR2, int D, const int32_t* __restrict__ e1i,
-               const int32_t* __restrict__ e2i, const int32_t* __restrict__ e1j,
-               const int32_t* __restrict__ e2j, int A, int J1, int J2, float* __restrict__ dXh) {
-  const int T = A + J1 + J2;
-  const int64_t rows = 2 * (int64_t)A + 2 * (int64_t)T;
-  const int64_t total = rows * D;
-  for (int64_t t = (int64_t)blockIdx.x * NT + threadIdx.x; t < total; t += (int64_t)gridDim.x * NT) {
-    int r = (int)(t / D), k = (int)(t % D);
-    int idx;
-    float v;
-    if (r < A) { idx = e1i[r]; v = dP1[(int64_t)r * D + k]; }
-    else if (r < 2 * A) { r -= A; idx = e2i[r]; v = dP2[(int64_t)r * D + k]; }
-    else if (r < 2 * A + T) {
-      r -= 2 * A;
-      idx = r < A ? e2i[r] : (r < A + J1 ? e1j[r - A] : e2j[r - A - J1]);
-      v = dR[(int64_t)r * D + k];
-    } else {
-      r -= 2 * A + T;
-      idx = r < A ? e1i[r] : (r < A + J2 ? e2j[r - A] : e1j[r - A - J2]);
-      v = dR2[(int64_t)r * D + k];
-    }
-    atomicAdd(&dXh[(int64_t)idx * D + k], v);
+    F[a * ld + c] = (c < c_split) ? lo01 * e01 + lo1 * e1 : hi01 * e01 + hi1 * e1;
   }
 }
 
@@ -378,6 +338,7 @@ extern "C" int sga_loss_fwd_bwd(const float* const* embs_host, const int* dims_h
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char* ws = (unsigned char*)workspace;
   const int T = A + J1 + J2;
+  const int ldF = L.ldF;
   double* scal = (double*)(ws + L.scal);
   double* S = scal;                       // [n_emb][2][4]
   double* dS = scal + (size_t)n_emb * 8;  // [n_emb][2][4]
@@ -385,29 +346,33 @@ extern "C" int sga_loss_fwd_bwd(const float* const* embs_host, const int* dims_h
   double* ial_raw = icl_raw + n_emb;
   SGA_CUDA(cudaMemsetAsync(scal, 0, sizeof(double) * (size_t)n_emb * 18, st));
   auto F = [&](size_t off) { return (float*)(ws + off); };
+  int32_t* ridx = (int32_t*)(ws + L.ridx);
+  int32_t* r2idx = (int32_t*)(ws + L.r2idx);
+  build_ridx_kernel<<<(T + NT - 1) / NT, NT, 0, st>>>(e1i, e2i, e1j, e2j, A, J1, J2, ridx, r2idx);
+  SGA_LAUNCH_CHECK();
 
-  // ---- forward Grams + normaliser sums
+  // ---- forward Grams on the tensor cores; normalise + gather in the loader, exp-sums in the epilogue
   for (int x = 0; x < n_emb; ++x) {
     const int d = dims_host[x];
     const float* X = embs_host[x];
-    row_norm_kernel<<<(unsigned)((N + 7) / 8), NT, 0, st>>>(X, N, d, F(L.norms[x]));
+    row_norm_kernel<<<(unsigned)((N + 7) / 8), NT, 0, st>>>(X, N, d, F(L.norms[x]), F(L.den[x]));
     SGA_LAUNCH_CHECK();
-    int64_t rows = 2 * (int64_t)A + 2 * (int64_t)T;
-    gather_norm_kernel<<<(unsigned)((rows + 7) / 8), NT, 0, st>>>(X, F(L.norms[x]), d, e1i, e2i, e1j, e2j, A, J1, J2, F(L.P1[x]), F(L.P2[x]),
-                                                                  F(L.R[x]), F(L.R2[x]));
-    SGA_LAUNCH_CHECK();
-    SGA_CUDA(launch_gemm(F(L.P1[x]), d, 1, F(L.R[x]), 1, d, F(L.F1[x]), T, A, T, d, 0, st));
-    SGA_CUDA(launch_gemm(F(L.P2[x]), d, 1, F(L.R2[x]), 1, d, F(L.F2[x]), T, A, T, d, 0, st));
     double* Sx = S + (size_t)x * 8;
-    if (J1 > 0) {
-      expsum_kernel<<<grid_for((int64_t)A * J1), NT, 0, st>>>(F(L.F1[x]), A, T, A, A + J1, Sx + 0, Sx + 4 + 0);
-      expsum_kernel<<<grid_for((int64_t)A * J1), NT, 0, st>>>(F(L.F2[x]), A, T, A + J2, T, Sx + 3, Sx + 4 + 3);
+    for (int dir = 0; dir < 2; ++dir) {
+      GemmParams P;
+      memset(&P, 0, sizeof(P));
+      P.A = {X, d, dir == 0 ? e1i : e2i, F(L.den[x]), 0};
+      P.B = {X, d, dir == 0 ? ridx : r2idx, F(L.den[x]), 0};
+      P.M = A; P.N = T; P.K = d;
+      P.C = F(dir == 0 ? L.F1[x] : L.F2[x]); P.ldc = ldF;
+      P.mode = 1;
+      P.es_c0 = A;
+      P.es_split = A + (dir == 0 ? J1 : J2);
+      const int lo = dir == 0 ? 0 : 2, hi = dir == 0 ? 1 : 3;   // {S11,S12} / {S22,S21}
+      P.s01_lo = Sx + lo; P.s01_hi = Sx + hi; P.s1_lo = Sx + 4 + lo; P.s1_hi = Sx + 4 + hi;
+      int rc = launch_gemm_tc(P, st);
+      if (rc != SGA_OK) return rc;
     }
-    if (J2 > 0) {
-      expsum_kernel<<<grid_for((int64_t)A * J2), NT, 0, st>>>(F(L.F1[x]), A, T, A + J1, T, Sx + 1, Sx + 4 + 1);
-      expsum_kernel<<<grid_for((int64_t)A * J2), NT, 0, st>>>(F(L.F2[x]), A, T, A, A + J2, Sx + 2, Sx + 4 + 2);
-    }
-    SGA_LAUNCH_CHECK();
   }
   // ---- element-wise loss terms (+ in-place gradient of the G blocks)
   const int xj = n_emb - 1;   // joint (or the single modality)
@@ -423,7 +388,7 @@ extern "C" int sga_loss_fwd_bwd(const float* const* embs_host, const int* dims_h
     p.F1j = F(L.F1[xj]); p.F2j = F(L.F2[xj]);
     p.acc1 = (want_grad && n_emb > 1) ? F(L.acc1) : nullptr;
     p.acc2 = (want_grad && n_emb > 1) ? F(L.acc2) : nullptr;
-    p.A = A; p.T = T;
+    p.A = A; p.T = ldF;
     p.Sm = S + (size_t)x * 8; p.Sj = S + (size_t)xj * 8;
     p.dSm = dS + (size_t)x * 8; p.dSj = dS + (size_t)xj * 8;
     p.icl_raw = icl_raw + x; p.ial_raw = ial_raw + x;
@@ -440,23 +405,50 @@ extern "C" int sga_loss_fwd_bwd(const float* const* embs_host, const int* dims_h
   SGA_LAUNCH_CHECK();
   if (!want_grad) return SGA_OK;
 
-  // ---- backward: coefficient blocks, 4 GEMMs per embedding, scatter, normalize backward
+  // ---- backward: coefficient blocks in place, then 4 scatter-add GEMMs per embedding:
+  //   dXh[e1i]  += dF1   Xh[R]      dXh[R]  += dF1^T Xh[e1i]
+  //   dXh[e2i]  += dF2   Xh[R']     dXh[R'] += dF2^T Xh[e2i]
+  auto ksplit_for = [&](int Mr, int Nc, int Kc) {
+    int tiles = ((Mr + 127) / 128) * ((Nc + 127) / 128);
+    int chunks = (Kc + 31) / 32;
+    int want = (2 * sm_count() + tiles - 1) / tiles;
+    int cap = chunks / 4;
+    if (want > cap) want = cap;
+    return want < 1 ? 1 : want;
+  };
   for (int x = 0; x < n_emb; ++x) {
     const int d = dims_host[x];
+    const float* X = embs_host[x];
     double* dSx = dS + (size_t)x * 8;
     if (T > A) {
-      coef_kernel<<<grid_for((int64_t)A * (T - A)), NT, 0, st>>>(F(L.F1[x]), A, T, A + J1, dSx, 0, 1);
-      coef_kernel<<<grid_for((int64_t)A * (T - A)), NT, 0, st>>>(F(L.F2[x]), A, T, A + J2, dSx, 2, 3);
+      coef_kernel<<<grid_for((int64_t)A * (T - A)), NT, 0, st>>>(F(L.F1[x]), A, T, ldF, A + J1, dSx, 0, 1);
+      coef_kernel<<<grid_for((int64_t)A * (T - A)), NT, 0, st>>>(F(L.F2[x]), A, T, ldF, A + J2, dSx, 2, 3);
       SGA_LAUNCH_CHECK();
     }
-    SGA_CUDA(launch_gemm(F(L.F1[x]), T, 1, F(L.R[x]), d, 1, F(L.dP1[x]), d, A, d, T, 0, st));
-    SGA_CUDA(launch_gemm(F(L.F1[x]), 1, T, F(L.P1[x]), d, 1, F(L.dR[x]), d, T, d, A, 0, st));
-    SGA_CUDA(launch_gemm(F(L.F2[x]), T, 1, F(L.R2[x]), d, 1, F(L.dP2[x]), d, A, d, T, 0, st));
-    SGA_CUDA(launch_gemm(F(L.F2[x]), 1, T, F(L.P2[x]), d, 1, F(L.dR2[x]), d, T, d, A, 0, st));
     SGA_CUDA(cudaMemsetAsync(ws + L.dXh[x], 0, 4 * (size_t)N * d, st));
-    int64_t tot = (2 * (int64_t)A + 2 * (int64_t)T) * d;
-    scatter_kernel<<<grid_for(tot), NT, 0, st>>>(F(L.dP1[x]), F(L.dP2[x]), F(L.dR[x]), F(L.dR2[x]), d, e1i, e2i, e1j, e2j, A, J1, J2, F(L.dXh[x]));
-    SGA_LAUNCH_CHECK();
+    for (int dir = 0; dir < 2; ++dir) {
+      const float* Fd = F(dir == 0 ? L.F1[x] : L.F2[x]);
+      const int32_t* rows_i = dir == 0 ? e1i : e2i;
+      const int32_t* rows_r = dir == 0 ? ridx : r2idx;
+      GemmParams P;
+      memset(&P, 0, sizeof(P));
+      // dXh[rows_i[a]] += sum_t Fd[a,t] Xh[rows_r[t]]
+      P.A = {Fd, ldF, nullptr, nullptr, 0};
+      P.B = {X, d, rows_r, F(L.den[x]), 1};
+      P.M = A; P.N = d; P.K = T;
+      P.C = F(L.dXh[x]); P.ldc = d; P.mode = 2; P.c_idx = rows_i;
+      P.ksplit = ksplit_for(A, d, T);
+      int rc = launch_gemm_tc(P, st);
+      if (rc != SGA_OK) return rc;
+      // dXh[rows_r[t]] += sum_a Fd[a,t] Xh[rows_i[a]]
+      P.A = {Fd, ldF, nullptr, nullptr, 1};
+      P.B = {X, d, rows_i, F(L.den[x]), 1};
+      P.M = T; P.N = d; P.K = A;
+      P.c_idx = rows_r;
+      P.ksplit = ksplit_for(T, d, A);
+      rc = launch_gemm_tc(P, st);
+      if (rc != SGA_OK) return rc;
+    }
     normalize_bwd_kernel<<<(unsigned)((N + 7) / 8), NT, 0, st>>>(embs_host[x], F(L.norms[x]), F(L.dXh[x]), N, d, g_embs_host[x]);
     SGA_LAUNCH_CHECK();
   }

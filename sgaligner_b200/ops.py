@@ -369,9 +369,22 @@ def loss_forward_backward(embs: Sequence[torch.Tensor], idx: Sequence[torch.Tens
                                _ptr(None if lv_ial is None else _f32c(lv_ial)), _ptr(None if lv_icl is None else _f32c(lv_icl)),
                                float(zoom), _ptr(losses), 1 if want_grad else 0, g_ptrs, _ptr(g_ial), _ptr(g_icl),
                                _ptr(ws), ws.numel(), _stream()), 'sga_loss_fwd_bwd')
-    # per embedding: norm, gather, 2 GEMMs, <=4 exp-sums, pair kernel; + finalize; backward: 2 coef, 4 GEMMs, scatter, normalize
-    _count(n_emb * 9 + 1 + (n_emb * 8 if want_grad else 0))
+    # index build + finalize; per embedding: norm, 2 GEMMs, pair kernel; backward: 2 coef, 4 GEMMs, normalize
+    _count(2 + n_emb * 4 + (n_emb * 7 if want_grad else 0))
     return losses, grads, g_ial, g_icl
+
+
+def gemm_tf32x3(A, B, M, N, K, a_mn=False, b_mn=False, a_idx=None, b_idx=None, a_div=None, b_div=None, out=None, c_idx=None,
+                ksplit=1):
+    """C[M,N] = sum_k A(m,k) B(n,k) on the tensor cores (see sga_gemm_tf32x3 in the header)."""
+    _need_cuda(A, B)
+    if out is None:
+        out = torch.zeros((M, N), device=A.device, dtype=torch.float32)
+    check(get_lib().sga_gemm_tf32x3(_ptr(A), A.stride(0), 1 if a_mn else 0, _ptr(a_idx), _ptr(a_div), _ptr(B), B.stride(0),
+                                    1 if b_mn else 0, _ptr(b_idx), _ptr(b_div), M, N, K, _ptr(out), out.stride(0), _ptr(c_idx),
+                                    int(ksplit), _stream()), 'sga_gemm_tf32x3')
+    _count(1)
+    return out
 
 
 # --------------------------------------------------------------------------------- optimiser

@@ -117,3 +117,42 @@ def test_match_topk_tc_large_pairs(dev):
     agree = (a['topk_idx'] == b['topk_idx']).float().mean()
     assert float(agree) > 0.999
     assert float((a['topk_dist'] - b['topk_dist']).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize('layout', ['kk', 'kmn', 'mnmn'])
+@pytest.mark.parametrize('shape', [(128, 128, 32), (200, 300, 100), (1024, 700, 400), (77, 130, 33)])
+def test_gemm_tf32x3_layouts(layout, shape, dev):
+    """The generic tcgen05 GEMM in all three operand-layout pairs, with row gathers, divisors, ragged
+    sizes; plus the scatter-add / split-K epilogue -- against an fp64 matmul."""
+    from sgaligner_b200 import ops
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N + K)
+    nsrc = 1500
+    Z = torch.randn(nsrc, max(M, N, K) + 8, generator=g)
+    div = torch.rand(nsrc, generator=g) + 0.5
+    Zd = Z.double() / div.double()[:, None]
+    if layout == 'kk':        # A(m,k) = Z[ia[m], k]/div ; B(n,k) = Z[ib[n], k]/div
+        ia = torch.randint(0, nsrc, (M,), generator=g)
+        ib = torch.randint(0, nsrc, (N,), generator=g)
+        ref = Zd[ia][:, :K] @ Zd[ib][:, :K].t()
+        out = ops.gemm_tf32x3(Z.to(dev), Z.to(dev), M, N, K, a_idx=ia.int().to(dev), b_idx=ib.int().to(dev), a_div=div.to(dev), b_div=div.to(dev))
+    elif layout == 'kmn':     # A(m,k) = D[m,k] ; B(n,k) = Z[ib[k], n]/div
+        D = torch.randn(M, K, generator=g)
+        ib = torch.randint(0, nsrc, (K,), generator=g)
+        ref = D.double() @ Zd[ib][:, :N]
+        out = ops.gemm_tf32x3(D.to(dev), Z.to(dev), M, N, K, b_mn=True, b_idx=ib.int().to(dev), b_div=div.to(dev))
+    else:                     # A(m,k) = D[k,m] ; B(n,k) = Z[ib[k], n]/div
+        D = torch.randn(K, M, generator=g)
+        ib = torch.randint(0, nsrc, (K,), generator=g)
+        ref = D.double().t() @ Zd[ib][:, :N]
+        out = ops.gemm_tf32x3(D.to(dev), Z.to(dev), M, N, K, a_mn=True, b_mn=True, b_idx=ib.int().to(dev), b_div=div.to(dev))
+    torch.cuda.synchronize()
+    assert rel_inf(out, ref) < 5e-6, rel_inf(out, ref)
+    if layout == 'mnmn':      # scatter-add rows + split-K
+        ci = torch.randint(0, 50, (M,), generator=g)
+        acc = torch.zeros(50, N, device=dev)
+        ops.gemm_tf32x3(D.to(dev), Z.to(dev), M, N, K, a_mn=True, b_mn=True, b_idx=ib.int().to(dev), b_div=div.to(dev), out=acc,
+                        c_idx=ci.int().to(dev), ksplit=3)
+        torch.cuda.synchronize()
+        want = torch.zeros(50, N, dtype=torch.float64).index_add_(0, ci, ref)
+        assert rel_inf(acc, want) < 1e-5
