@@ -64,8 +64,10 @@ pointnet_bwd_kernel(const float* __restrict__ pts, int64_t N, int P,
   for (int i = tid; i < 128; i += NT) s.b2s[i] = b2[i];
 
   // persistent register accumulators
-  // dW2 tile: rows k2 = 4*(tid/8) .. +3, cols k1 = 8*(tid%8) .. +7
-  const int r2 = 4 * (tid >> 3), c1 = 8 * (tid & 7);
+  // Column ownership is float4-interleaved everywhere (thread t7 = tid%8 owns columns t7*4 + 32*h + e):
+  // 8 consecutive threads then read/write 128 contiguous bytes -> no shared-memory bank conflicts.
+  // dW2 tile: rows k2 = 4*(tid/8) .. +3, cols k1 = 4*(tid%8) + 32*h + e  (h < 2, e < 4)
+  const int r2 = 4 * (tid >> 3), t7 = tid & 7;
   float aW2[4][8];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -101,18 +103,20 @@ pointnet_bwd_kernel(const float* __restrict__ pts, int64_t N, int P,
         s.h1[r][k] = v > 0.f ? v : 0.f;
       }
       __syncthreads();
-      // ---- h2 = relu(h1 W2^T + b2): thread -> instance r = tid/8, k2 in [16*(tid%8), +16)
+      // ---- h2 = relu(h1 W2^T + b2): thread -> instance r = tid/8, k2 = 4*t7 + 32*j4 + e
       {
-        const int r = tid >> 3, k20 = 16 * (tid & 7);
+        const int r = tid >> 3;
         float acc[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = s.b2s[k20 + j];
+        for (int j4 = 0; j4 < 4; ++j4) {
+          float4 bv = *reinterpret_cast<const float4*>(&s.b2s[4 * t7 + 32 * j4]);
+          acc[4 * j4 + 0] = bv.x; acc[4 * j4 + 1] = bv.y; acc[4 * j4 + 2] = bv.z; acc[4 * j4 + 3] = bv.w;
+        }
         for (int k1 = 0; k1 < 64; ++k1) {
           float a = s.h1[r][k1];
-          const float4* w = reinterpret_cast<const float4*>(&s.W2t[k1][k20]);
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            float4 wv = w[j4];
+            float4 wv = *reinterpret_cast<const float4*>(&s.W2t[k1][4 * t7 + 32 * j4]);
             acc[4 * j4 + 0] = fmaf(a, wv.x, acc[4 * j4 + 0]);
             acc[4 * j4 + 1] = fmaf(a, wv.y, acc[4 * j4 + 1]);
             acc[4 * j4 + 2] = fmaf(a, wv.z, acc[4 * j4 + 2]);
@@ -121,12 +125,22 @@ pointnet_bwd_kernel(const float* __restrict__ pts, int64_t N, int P,
         }
         const float g = s.g[r];
         const int c = ch0 + r;
-        const float* w3 = W3 + (int64_t)(cb0 + (c < ncb ? c : 0)) * 128 + k20;
+        const bool live = c < ncb;
+        const float* w3 = W3 + (int64_t)(cb0 + (live ? c : 0)) * 128;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float h = acc[j] > 0.f ? acc[j] : 0.f;
-          s.h2[r][k20 + j] = h;
-          s.dz2[r][k20 + j] = (h > 0.f && c < ncb) ? g * w3[j] : 0.f;
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const int k2 = 4 * t7 + 32 * j4;
+          float4 wv = *reinterpret_cast<const float4*>(w3 + k2);
+          float h[4] = {acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]};
+          const float wq[4] = {wv.x, wv.y, wv.z, wv.w};
+          float dz[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            h[e] = h[e] > 0.f ? h[e] : 0.f;
+            dz[e] = (h[e] > 0.f && live) ? g * wq[e] : 0.f;
+          }
+          *reinterpret_cast<float4*>(&s.h2[r][k2]) = make_float4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<float4*>(&s.dz2[r][k2]) = make_float4(dz[0], dz[1], dz[2], dz[3]);
         }
       }
       __syncthreads();
@@ -140,8 +154,8 @@ pointnet_bwd_kernel(const float* __restrict__ pts, int64_t N, int P,
 #pragma unroll 4
       for (int r = 0; r < IC; ++r) {
         float4 a = *reinterpret_cast<const float4*>(&s.dz2[r][r2]);
-        float4 b0 = *reinterpret_cast<const float4*>(&s.h1[r][c1]);
-        float4 b1v = *reinterpret_cast<const float4*>(&s.h1[r][c1 + 4]);
+        float4 b0 = *reinterpret_cast<const float4*>(&s.h1[r][4 * t7]);
+        float4 b1v = *reinterpret_cast<const float4*>(&s.h1[r][4 * t7 + 32]);
         const float av[4] = {a.x, a.y, a.z, a.w};
         const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1v.x, b1v.y, b1v.z, b1v.w};
 #pragma unroll
@@ -154,21 +168,26 @@ pointnet_bwd_kernel(const float* __restrict__ pts, int64_t N, int P,
         for (int r = 0; r < IC; ++r) t += s.dz2[r][tid];
         ab2 += t;
       }
-      // ---- dz1 = (h1 > 0) . (dz2 W2): thread -> instance r = tid/8, k1 in [8*(tid%8), +8)
+      // ---- dz1 = (h1 > 0) . (dz2 W2): thread -> instance r = tid/8, k1 = 4*t7 + 32*h + e
       {
-        const int r = tid >> 3, k10 = 8 * (tid & 7);
+        const int r = tid >> 3;
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int k2 = 0; k2 < 128; ++k2) {
           float a = s.dz2[r][k2];
-          float4 w0 = *reinterpret_cast<const float4*>(&s.W2s[k2][k10]);
-          float4 w1 = *reinterpret_cast<const float4*>(&s.W2s[k2][k10 + 4]);
+          float4 w0 = *reinterpret_cast<const float4*>(&s.W2s[k2][4 * t7]);
+          float4 w1 = *reinterpret_cast<const float4*>(&s.W2s[k2][4 * t7 + 32]);
           acc[0] = fmaf(a, w0.x, acc[0]); acc[1] = fmaf(a, w0.y, acc[1]);
           acc[2] = fmaf(a, w0.z, acc[2]); acc[3] = fmaf(a, w0.w, acc[3]);
           acc[4] = fmaf(a, w1.x, acc[4]); acc[5] = fmaf(a, w1.y, acc[5]);
           acc[6] = fmaf(a, w1.z, acc[6]); acc[7] = fmaf(a, w1.w, acc[7]);
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s.dz1[r][k10 + j] = s.h1[r][k10 + j] > 0.f ? acc[j] : 0.f;
+        for (int h = 0; h < 2; ++h) {
+          float4 hv = *reinterpret_cast<const float4*>(&s.h1[r][4 * t7 + 32 * h]);
+          *reinterpret_cast<float4*>(&s.dz1[r][4 * t7 + 32 * h]) =
+              make_float4(hv.x > 0.f ? acc[4 * h] : 0.f, hv.y > 0.f ? acc[4 * h + 1] : 0.f, hv.z > 0.f ? acc[4 * h + 2] : 0.f,
+                          hv.w > 0.f ? acc[4 * h + 3] : 0.f);
+        }
       }
       __syncthreads();
       // ---- dW1, db1
@@ -195,7 +214,7 @@ pointnet_bwd_kernel(const float* __restrict__ pts, int64_t N, int P,
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&gW2[(r2 + i) * 64 + c1 + j], aW2[i][j]);
+    for (int j = 0; j < 8; ++j) atomicAdd(&gW2[(r2 + i) * 64 + 4 * t7 + 32 * (j >> 2) + (j & 3)], aW2[i][j]);
   if (tid < 128) atomicAdd(&gb2[tid], ab2);
   if (tid < 192) atomicAdd(&gW1[tid], aW1);
   if (tid < 64) atomicAdd(&gb1[tid], ab1);
