@@ -69,6 +69,19 @@ int sga_pointnet_bn_moments(const float* pts, int64_t N, int P,
                             const float* W1, const float* b1, const float* W2, const float* b2,
                             const float* W3, const float* b3, int C3, double* moments, void* stream);
 
+/* Training-mode forward on the tensor cores: sga_pointnet_fwd(mode = SGA_POINTNET_TC) that ALSO accumulates
+ * the statistics of sga_pointnet_bn_moments in the same pass (conv3 thread-locally in the max-pool
+ * epilogue, conv2 by a warp transpose-reduce, conv1 analytically from the point moments), i.e. the whole
+ * train-mode PointNetfeat.forward (pointnet.py:140-163 incl. the BatchNorm side effect) in one launch + a
+ * finalize launch.  moments as in sga_pointnet_bn_moments (added into; zeroed by the caller); scratch:
+ * zeroed device buffer of >= sga_pointnet_stats_scratch_bytes(C3) bytes.  C3 must be a multiple of 128. */
+size_t sga_pointnet_stats_scratch_bytes(int C3);
+int sga_pointnet_fwd_stats(const float* pts, int64_t N, int P,
+                           const float* W1, const float* b1, const float* W2, const float* b2,
+                           const float* W3, const float* b3, int C3,
+                           float* out, int32_t* argmax, double* moments, void* scratch, size_t scratch_bytes,
+                           void* stream);
+
 /* ---- a2/a7: block-diagonal CSR (by destination) for all 2B graphs of the batch, replacing the
  * per-graph Python slicing of sg_aligner.py:86-104 plus PyG's remove_self_loops/add_self_loops.
  * edges [E,2] int64 graph-local (src,dst) rows as collated (scan3r.py:201); node_off [G+1] int32 and

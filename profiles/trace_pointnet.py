@@ -23,10 +23,10 @@ with torch.no_grad():
 t = trace.cpu().numpy()
 c, m = t[:1024].reshape(64, 16), t[1024:].reshape(64, 16)
 base = c[8, 0]
-names_c = ['d2_full', 'E2c0', 'E2c1', 'E2c2', 'E2c3', 'blk0_free', 'S1done', 'd3_full', 'E3done']
-names_m = ['a1_full', 'MMA2iss', 'h2c0', 'h2c1', 'h2c2', 'h2c3', 'MMA3iss']
+names_c = ['d2_full', 'D2inregs', 'converted', 'S1next', 'H2stored', '-', '-', 'd3_full', 'E3done']
+names_m = ['MMA2beg', 'MMA2iss', 'h2c0', 'h2c1', 'h2c2', 'h2c3', 'MMA3iss']
 for g in range(8, 16):
-    print(f'tile {g}: compute ' + ' '.join(f'{n}={c[g, k] - base}' for k, n in enumerate(names_c)))
+    print(f'tile {g}: compute ' + ' '.join(f'{n}={c[g, k] - base}' for k, n in enumerate(names_c) if n != '-'))
     print(f'          mma     ' + ' '.join(f'{n}={m[g, k] - base}' for k, n in enumerate(names_m)))
 per = np.diff(c[8:60, 0])
 print('period (cycles/tile): mean', per.mean(), 'min', per.min(), 'max', per.max())

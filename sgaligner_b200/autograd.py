@@ -12,18 +12,28 @@ class PointNetFeat(torch.autograd.Function):
     the saved per-channel argmax of the max-pool."""
 
     @staticmethod
-    def forward(ctx, pts, W1, b1, W2, b2, W3, b3, mode, chunks=None):
+    def forward(ctx, pts, W1, b1, W2, b2, W3, b3, mode, chunks=None, want_stats=False):
+        """Returns (pooled feature, moments); moments (f64, non-differentiable) is None unless want_stats."""
         need = any(ctx.needs_input_grad[1:7])
-        out, arg = ops.pointnet_forward(pts, W1, b1, W2, b2, W3, b3, want_argmax=need, mode=mode, chunks=chunks)
+        mom = None
+        if want_stats:
+            if chunks:      # statistics span the whole batch: one launch once every chunk has landed
+                for (_, _, ev) in chunks:
+                    torch.cuda.current_stream().wait_event(ev)
+            out, arg, mom = ops.pointnet_forward_stats(pts, W1, b1, W2, b2, W3, b3, want_argmax=need)
+        else:
+            out, arg = ops.pointnet_forward(pts, W1, b1, W2, b2, W3, b3, want_argmax=need, mode=mode, chunks=chunks)
         if need:
             ctx.save_for_backward(pts, W1, b1, W2, b2, W3, b3, out, arg)
-        return out
+        if mom is not None:
+            ctx.mark_non_differentiable(mom)
+        return out, mom
 
     @staticmethod
-    def backward(ctx, gout):
+    def backward(ctx, gout, _gmom=None):
         pts, W1, b1, W2, b2, W3, b3, out, arg = ctx.saved_tensors
         gW1, gb1, gW2, gb2, gW3, gb3 = ops.pointnet_backward(pts, W1, b1, W2, b2, W3, b3, out, arg, gout.contiguous())
-        return None, gW1.view_as(W1), gb1, gW2.view_as(W2), gb2, gW3.view_as(W3), gb3, None, None
+        return None, gW1.view_as(W1), gb1, gW2.view_as(W2), gb2, gW3.view_as(W3), gb3, None, None, None
 
 
 class GATLayer(torch.autograd.Function):

@@ -5,7 +5,8 @@ namespace sga {
 int pointnet_fwd_simt(const float*, int64_t, int, const float*, const float*, const float*, const float*, const float*,
                       const float*, int, float*, int32_t*, double*, cudaStream_t);
 int pointnet_fwd_tc(const float*, int64_t, int, const float*, const float*, const float*, const float*, const float*,
-                    const float*, int, float*, int32_t*, cudaStream_t);
+                    const float*, int, float*, int32_t*, double*, double*, cudaStream_t);
+size_t pointnet_tc_raw_doubles(int C3);
 int debug_set_trace(long long* ptr);
 }  // namespace sga
 
@@ -18,10 +19,28 @@ extern "C" int sga_pointnet_fwd(const float* pts, int64_t N, int P, const float*
   if (mode == SGA_POINTNET_SIMT) return sga::pointnet_fwd_simt(pts, N, P, W1, b1, W2, b2, W3, b3, C3, out, argmax, nullptr, (cudaStream_t)stream);
   if (mode == SGA_POINTNET_TC) {
     SGA_REQUIRE(((uintptr_t)W2 & 15) == 0 && ((uintptr_t)W3 & 15) == 0, "sga_pointnet_fwd(TC): W2/W3 must be 16-byte aligned");
-    return sga::pointnet_fwd_tc(pts, N, P, W1, b1, W2, b2, W3, b3, C3, out, argmax, (cudaStream_t)stream);
+    return sga::pointnet_fwd_tc(pts, N, P, W1, b1, W2, b2, W3, b3, C3, out, argmax, nullptr, nullptr, (cudaStream_t)stream);
   }
   sga::set_error("sga_pointnet_fwd: unknown mode %d", mode);
   return SGA_EINVAL;
+}
+
+extern "C" size_t sga_pointnet_stats_scratch_bytes(int C3) { return sga::pointnet_tc_raw_doubles(C3) * sizeof(double); }
+
+extern "C" int sga_pointnet_fwd_stats(const float* pts, int64_t N, int P, const float* W1, const float* b1,
+                                      const float* W2, const float* b2, const float* W3, const float* b3, int C3,
+                                      float* out, int32_t* argmax, double* moments, void* scratch, size_t scratch_bytes,
+                                      void* stream) {
+  if (N <= 0) return SGA_OK;
+  SGA_REQUIRE(P >= 1 && C3 >= 1, "sga_pointnet_fwd_stats: P=%d C3=%d", P, C3);
+  SGA_REQUIRE(pts && W1 && b1 && W2 && b2 && W3 && b3 && out && moments && scratch, "sga_pointnet_fwd_stats: null pointer");
+  SGA_REQUIRE(((uintptr_t)W2 & 15) == 0 && ((uintptr_t)W3 & 15) == 0, "sga_pointnet_fwd_stats: W2/W3 must be 16-byte aligned");
+  SGA_REQUIRE(((uintptr_t)scratch & 7) == 0, "sga_pointnet_fwd_stats: scratch must be 8-byte aligned");
+  if (scratch_bytes < sga_pointnet_stats_scratch_bytes(C3)) {
+    sga::set_error("sga_pointnet_fwd_stats: scratch of %zu bytes, need %zu", scratch_bytes, sga_pointnet_stats_scratch_bytes(C3));
+    return SGA_EWORKSPACE;
+  }
+  return sga::pointnet_fwd_tc(pts, N, P, W1, b1, W2, b2, W3, b3, C3, out, argmax, (double*)scratch, moments, (cudaStream_t)stream);
 }
 
 extern "C" int sga_pointnet_bn_moments(const float* pts, int64_t N, int P, const float* W1, const float* b1,

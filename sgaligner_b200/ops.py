@@ -68,36 +68,59 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------- PointNet
-def pointnet_forward(pts, W1, b1, W2, b2, W3, b3, want_argmax: bool, mode: int = POINTNET_TC, chunks=None):
-    """chunks: optional [(obj_start, obj_end, cuda_event)] -- the object ranges of ``pts`` become valid
-    when their event fires (streamed H2D copy, ``data.to_cuda_streamed``); one launch per range."""
+def _pointnet_args(pts, W1, b1, W2, b2, W3, b3, mode):
     _need_cuda(pts, W1, W3)
     pts = _f32c(pts)
-    N, P, _ = pts.shape
     C3 = W3.shape[0]
     W1c, W2c, W3c = _f32c(W1.reshape(64, 3)), _f32c(W2.reshape(128, 64)), _f32c(W3.reshape(C3, 128))
     if mode == POINTNET_TC and (W2c.data_ptr() % 16 or W3c.data_ptr() % 16):
         W2c, W3c = W2c.clone(), W3c.clone()
+    return pts, (W1c, _f32c(b1), W2c, _f32c(b2), W3c, _f32c(b3))
+
+
+def pointnet_forward(pts, W1, b1, W2, b2, W3, b3, want_argmax: bool, mode: int = POINTNET_TC, chunks=None):
+    """chunks: optional [(obj_start, obj_end, cuda_event)] -- the object ranges of ``pts`` become valid
+    when their event fires (streamed H2D copy, ``data.to_cuda_streamed``); one launch per range."""
+    pts, w = _pointnet_args(pts, W1, b1, W2, b2, W3, b3, mode)
+    N, P, _ = pts.shape
+    C3 = W3.shape[0]
     out = torch.empty((N, C3), device=pts.device, dtype=torch.float32)
     arg = torch.empty((N, C3), device=pts.device, dtype=torch.int32) if want_argmax else None
-    b1c, b2c, b3c = _f32c(b1), _f32c(b2), _f32c(b3)
+    lib = get_lib()
     if chunks:
         cur = torch.cuda.current_stream()
-        lib = get_lib()
         for (s, e, ev) in chunks:
             cur.wait_event(ev)
-            check(lib.sga_pointnet_fwd(ctypes.c_void_p(pts.data_ptr() + s * P * 12), e - s, P, _ptr(W1c), _ptr(b1c), _ptr(W2c),
-                                       _ptr(b2c), _ptr(W3c), _ptr(b3c), C3, ctypes.c_void_p(out.data_ptr() + s * C3 * 4),
+            check(lib.sga_pointnet_fwd(ctypes.c_void_p(pts.data_ptr() + s * P * 12), e - s, P, *[_ptr(t) for t in w], C3,
+                                       ctypes.c_void_p(out.data_ptr() + s * C3 * 4),
                                        ctypes.c_void_p(0 if arg is None else arg.data_ptr() + s * C3 * 4), mode, _stream()),
                   'sga_pointnet_fwd')
             _count(1)
         return out, arg
     with _timed('pointnet_fwd'):
-        check(get_lib().sga_pointnet_fwd(_ptr(pts), N, P, _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c),
-                                         _ptr(W3c), _ptr(b3c), C3, _ptr(out), _ptr(arg), mode, _stream()),
+        check(lib.sga_pointnet_fwd(_ptr(pts), N, P, *[_ptr(t) for t in w], C3, _ptr(out), _ptr(arg), mode, _stream()),
               'sga_pointnet_fwd')
     _count(1)
     return out, arg
+
+
+def pointnet_forward_stats(pts, W1, b1, W2, b2, W3, b3, want_argmax: bool):
+    """Train-mode forward on the tensor cores: pooled feature, argmax AND the f64 moments of
+    ``pointnet_bn_moments`` out of one launch (+ a finalize launch).  Returns (out, argmax, moments)."""
+    pts, w = _pointnet_args(pts, W1, b1, W2, b2, W3, b3, POINTNET_TC)
+    N, P, _ = pts.shape
+    C3 = W3.shape[0]
+    out = torch.empty((N, C3), device=pts.device, dtype=torch.float32)
+    arg = torch.empty((N, C3), device=pts.device, dtype=torch.int32) if want_argmax else None
+    lib = get_lib()
+    n_mom = 2 * (64 + 128 + C3)
+    sbytes = int(lib.sga_pointnet_stats_scratch_bytes(C3))
+    buf = torch.zeros(n_mom + sbytes // 8, device=pts.device, dtype=torch.float64)
+    with _timed('pointnet_fwd_stats'):
+        check(lib.sga_pointnet_fwd_stats(_ptr(pts), N, P, *[_ptr(t) for t in w], C3, _ptr(out), _ptr(arg), _ptr(buf),
+                                         ctypes.c_void_p(buf.data_ptr() + n_mom * 8), sbytes, _stream()), 'sga_pointnet_fwd_stats')
+    _count(2)
+    return out, arg, buf[:n_mom]
 
 
 def pointnet_backward(pts, W1, b1, W2, b2, W3, b3, out, arg, gout):

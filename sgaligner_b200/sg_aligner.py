@@ -88,22 +88,26 @@ class PointNetfeat(nn.Module):
     def forward(self, pts_npc: torch.Tensor, chunks=None) -> torch.Tensor:
         """``pts_npc``: [N, P, 3] (the collated layout; the reference permutes to [N,3,P] first).
         ``chunks``: readiness events of a streamed host-to-device copy (``data.to_cuda_streamed``)."""
-        if self.use_batch_norm and self.training and self.track_bn_stats:
+        want_stats = self.use_batch_norm and self.training and self.track_bn_stats
+        fused = want_stats and self.kernel_mode == ops.POINTNET_TC
+        if want_stats and not fused:        # fp32 FMA kernel (pt_out_dim not a multiple of 128): separate statistics pass
             if chunks:
                 for (_, _, ev) in chunks:
                     torch.cuda.current_stream().wait_event(ev)
-            self._update_bn_running_stats(pts_npc)
-        return ag.PointNetFeat.apply(pts_npc, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
-                                     self.conv3.weight, self.conv3.bias, self.kernel_mode, chunks)
+            mom = ops.pointnet_bn_moments(pts_npc, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
+                                          self.conv3.weight, self.conv3.bias)
+            self._update_bn_running_stats(mom, float(pts_npc.shape[0] * pts_npc.shape[1]))
+        out, mom = ag.PointNetFeat.apply(pts_npc, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
+                                         self.conv3.weight, self.conv3.bias, self.kernel_mode, chunks, fused)
+        if fused:                           # statistics came out of the forward launch itself
+            self._update_bn_running_stats(mom, float(pts_npc.shape[0] * pts_npc.shape[1]))
+        return out
 
     @torch.no_grad()
-    def _update_bn_running_stats(self, pts):
+    def _update_bn_running_stats(self, mom, cnt):
         """Train-mode side effect of the discarded BatchNorm calls (pointnet.py:141-142,154-155,
         158-159): running_mean/var <- momentum update with the batch statistics of the pre-ReLU
-        conv outputs; outputs are unaffected."""
-        mom = ops.pointnet_bn_moments(pts, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
-                                      self.conv3.weight, self.conv3.bias)
-        cnt = float(pts.shape[0] * pts.shape[1])
+        conv outputs; outputs are unaffected.  ``mom``: f64 {sum1,sq1,sum2,sq2,sum3,sq3}."""
         o = 0
         for bn, c in ((self.bn1, 64), (self.bn2, 128), (self.bn3, self.out_size)):
             s, sq = mom[o:o + c], mom[o + c:o + 2 * c]

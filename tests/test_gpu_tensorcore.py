@@ -67,6 +67,38 @@ def test_pointnet_tc_ragged_sizes(dev):
         assert rel_inf(out, ref) < 3e-5, (N, P, C3)
 
 
+def test_pointnet_tc_fused_bn_statistics(dev):
+    """Train-mode forward: the statistics accumulated inside the tensor-core launch (conv3 thread-local,
+    conv2 warp transpose-reduce, conv1 analytic from the point moments) against the oracle's fp64 batch
+    statistics and the stand-alone fp32 statistics kernel; pooled feature / argmax identical to the
+    launch without statistics.  Includes ragged P (padded tile columns must not be counted) and C3 = 512
+    (two channel-block CTAs per SM column: conv1/conv2 statistics counted once)."""
+    from sgaligner_b200 import ops
+    for (N, P, C3, seed) in [(64, 512, 256, 0), (301, 130, 128, 1), (9, 100, 512, 2), (200, 257, 256, 3)]:
+        p = O.init_params(['point'], 41, 164, pt_out_dim=C3, seed=seed)
+        for i in (1, 2, 3):
+            p[f'object_encoder.conv{i}.bias'] = 0.1 * torch.randn(p[f'object_encoder.conv{i}.bias'].shape)
+        pts = torch.randn(N, P, 3) + torch.rand(N, 1, 3) * 4 - 2
+        w = [p[f'object_encoder.conv{i}.{k}'].to(dev) for i in (1, 2, 3) for k in ('weight', 'bias')]
+        out, arg, mom = ops.pointnet_forward_stats(pts.to(dev), *w, want_argmax=True)
+        out0, arg0 = ops.pointnet_forward(pts.to(dev), *w, want_argmax=True, mode=ops.POINTNET_TC)
+        mom_simt = ops.pointnet_bn_moments(pts.to(dev), *w)
+        torch.cuda.synchronize()
+        assert torch.equal(out, out0) and torch.equal(arg, arg0)
+        stats = O.pointnet_bn_batch_stats(pts.double(), {k: v.double() for k, v in p.items() if v.is_floating_point()})
+        cnt = float(N * P)
+        o = 0
+        for i, c in ((1, 64), (2, 128), (3, C3)):
+            for m in (mom, mom_simt):
+                s, sq = m[o:o + c].cpu(), m[o + c:o + 2 * c].cpu()
+                mean = s / cnt
+                var = (sq - s * mean) / (cnt - 1.0)
+                rmean, rvar = stats[i - 1]
+                assert rel_inf(mean, rmean) < 2e-5, (N, P, C3, i)
+                assert rel_inf(var, rvar) < 2e-5, (N, P, C3, i)
+            o += 2 * c
+
+
 @pytest.mark.parametrize('name', CASES)
 def test_match_topk_tc_vs_fma_path(name, dev):
     """Fused tcgen05 Gram + top-k vs the fp32 FMA kernels on the golden embedding: similarity within

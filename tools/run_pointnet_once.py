@@ -1,0 +1,31 @@
+"""A few launches of the tensor-core PointNet kernel at the C2 shape (for ncu; tools only)."""
+import os, sys
+sys.path.insert(0, os.getcwd())
+import torch
+from sgaligner_b200 import ops
+from sgaligner_b200.sg_aligner import PointNetfeat
+dev = torch.device('cuda:0')
+torch.manual_seed(0)
+net = PointNetfeat(out_size=256).to(dev)
+pts = torch.randn(4096, 512, 3, device=dev)
+w = [net.conv1.weight, net.conv1.bias, net.conv2.weight, net.conv2.bias, net.conv3.weight, net.conv3.bias]
+stats = len(sys.argv) > 1 and sys.argv[1] == 'stats'
+with torch.no_grad():
+    for _ in range(3):
+        if stats:
+            ops.pointnet_forward_stats(pts, *w, want_argmax=True)
+        else:
+            ops.pointnet_forward(pts, *w, want_argmax=False)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        if stats:
+            ops.pointnet_forward_stats(pts, *w, want_argmax=True)
+        else:
+            ops.pointnet_forward(pts, *w, want_argmax=False)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+print('pointnet_fwd', 'stats' if stats else 'plain', 'ms:', min(ts), sorted(ts)[len(ts) // 2])
