@@ -133,6 +133,13 @@ int sga_project_fuse_fwd(const void* x, int x_is_f64, int64_t N, int in_dim, con
                          const float* b, int out_dim, float* emb, float* joint, int joint_ld,
                          int joint_col, const float* fusion_w, int M, int m, void* stream);
 
+/* The same for ALL M modalities in one launch (MultiModalEncoder.forward, sg_aligner.py:112-135): host arrays
+ * of M device pointers / sizes; every modality projects to out_dim (= emb_dim, <= 128) columns and modality m
+ * writes joint[:, m*out_dim : (m+1)*out_dim].  joint may be NULL (M == 1: no fusion). */
+int sga_project_fuse_fwd_multi(const void* const* x_host, const int* x_is_f64_host, const int* in_dim_host,
+                               const float* const* W_host, const float* const* b_host, float* const* emb_host, int M,
+                               int64_t N, int out_dim, float* joint, int joint_ld, const float* fusion_w, void* stream);
+
 /* backward: g_emb [N,out_dim] (direct gradient on the modality embedding, may be NULL) and
  * g_joint (gradient on the joint embedding, may be NULL) -> gW +=, gb +=, g_fusion_w [M] +=, and
  * gx [N,in_dim] (may be NULL).  x must be f32.  workspace >= (N*out_dim + 64) floats. */

@@ -68,11 +68,14 @@ class ProjectFuse(torch.autograd.Function):
         N = xs[0].shape[0]
         out_dims = [W.shape[0] for W in Ws]
         dev = xs[0].device
-        joint = torch.empty((N, sum(out_dims)), device=dev, dtype=torch.float32) if M > 1 else None
-        embs, col = [], 0
-        for m in range(M):
-            embs.append(ops.project_fuse(xs[m], Ws[m], bs[m], joint, col, fusion_w, M, m))
-            col += out_dims[m]
+        if len(set(out_dims)) == 1 and out_dims[0] <= 128 and M <= 8:
+            embs, joint = ops.project_fuse_multi(xs, Ws, bs, fusion_w, want_joint=M > 1)      # one launch
+        else:
+            joint = torch.empty((N, sum(out_dims)), device=dev, dtype=torch.float32) if M > 1 else None
+            embs, col = [], 0
+            for m in range(M):
+                embs.append(ops.project_fuse(xs[m], Ws[m], bs[m], joint, col, fusion_w, M, m))
+                col += out_dims[m]
         ctx.M, ctx.out_dims = M, out_dims
         ctx.need_gx = [x.requires_grad for x in xs]
         ctx.save_for_backward(fusion_w, *xs, *Ws, *embs)

@@ -3,6 +3,7 @@
 // src/aligner/sg_aligner.py:86-110 (per-graph Python loop this batching replaces); arithmetic of
 // torch_geometric 2.2.0 nn/conv/gat_conv.py + utils/softmax.py (see oracle/sgaligner_oracle.py).
 #include "common.cuh"
+#include "linear.cuh"
 #include "ptx.cuh"
 
 namespace sga {
@@ -78,6 +79,47 @@ gat_linear_kernel(const void* __restrict__ x, int x_is_f64, int64_t N, int in_di
   for (int i = 0; i < 4; ++i) {
     float s = warp_sum(as_acc[i]), d = warp_sum(ad_acc[i]);
     int64_t n = n0 + ty * 4 + i;
+    if (tx == 0 && n < N) {
+      a_src[n * H + h] = s;
+      a_dst[n * H + h] = d;
+    }
+  }
+}
+
+// Same contract for C <= 128 (every reference configuration) on the shared double-buffered tile
+// (linear.cuh): grid (ceil(N/32), H), one CTA = 32 nodes x one head.
+__global__ void __launch_bounds__(linear::NT)
+gat_linear_tile_kernel(const void* __restrict__ x, int x_is_f64, int64_t N, int in_dim,
+                       const float* __restrict__ W, const float* __restrict__ att_src,
+                       const float* __restrict__ att_dst, int H, int C, float* __restrict__ xs,
+                       float* __restrict__ a_src, float* __restrict__ a_dst) {
+  __shared__ linear::Smem sm;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int h = blockIdx.y;
+  const int64_t n0 = (int64_t)blockIdx.x * linear::BM;
+  float acc[2][8];
+  linear::tile_mma(sm, x, x_is_f64, N, in_dim, W + (int64_t)h * C * in_dim, C, n0, 0, acc);
+  float as_acc[2] = {0.f, 0.f}, ad_acc[2] = {0.f, 0.f};
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int c0 = linear::col_of(tx, 4 * g);
+    if (c0 < C) {     // C % 4 == 0 (checked by the launcher): the 4-column group is all in or all out
+      const float4 ws = *reinterpret_cast<const float4*>(att_src + h * C + c0);
+      const float4 wd = *reinterpret_cast<const float4*>(att_dst + h * C + c0);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float* a = &acc[i][4 * g];
+        as_acc[i] += a[0] * ws.x + a[1] * ws.y + a[2] * ws.z + a[3] * ws.w;
+        ad_acc[i] += a[0] * wd.x + a[1] * wd.y + a[2] * wd.z + a[3] * wd.w;
+        const int64_t n = n0 + ty * 2 + i;
+        if (n < N) *reinterpret_cast<float4*>(xs + ((int64_t)h * N + n) * C + c0) = make_float4(a[0], a[1], a[2], a[3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float s = linear::row_sum16(as_acc[i]), d = linear::row_sum16(ad_acc[i]);
+    const int64_t n = n0 + ty * 2 + i;
     if (tx == 0 && n < N) {
       a_src[n * H + h] = s;
       a_dst[n * H + h] = d;
@@ -193,6 +235,14 @@ extern "C" int sga_gat_linear(const void* x, int x_is_f64, int64_t N, int in_dim
                               float* a_src, float* a_dst, void* stream) {
   if (N <= 0) return SGA_OK;
   SGA_REQUIRE(in_dim > 0 && H > 0 && C > 0, "sga_gat_linear: bad dims in=%d H=%d C=%d", in_dim, H, C);
+  if (C <= sga::linear::BN && C % 4 == 0 && ((reinterpret_cast<uintptr_t>(att_src) | reinterpret_cast<uintptr_t>(att_dst) |
+                                               reinterpret_cast<uintptr_t>(xs)) & 15) == 0) {
+    dim3 grid((unsigned)((N + sga::linear::BM - 1) / sga::linear::BM), H);
+    sga::gat_linear_tile_kernel<<<grid, sga::linear::NT, 0, (cudaStream_t)stream>>>(x, x_is_f64, N, in_dim, W, att_src, att_dst, H, C, xs,
+                                                                                  a_src, a_dst);
+    SGA_LAUNCH_CHECK();
+    return SGA_OK;
+  }
   dim3 grid((unsigned)((N + sga::LN - 1) / sga::LN), H);
   sga::gat_linear_kernel<<<grid, sga::NT, 0, (cudaStream_t)stream>>>(x, x_is_f64, N, in_dim, W, att_src, att_dst, H, C, xs, a_src, a_dst);
   SGA_LAUNCH_CHECK();

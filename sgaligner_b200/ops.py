@@ -266,6 +266,31 @@ def project_fuse(x, W, b, joint: Optional[torch.Tensor], joint_col: int, fusion_
     return emb
 
 
+def project_fuse_multi(xs, Ws, bs, fusion_w, want_joint: bool):
+    """Every modality's Linear + its slice of the fusion in ONE launch.  All modalities project to the same
+    width (emb_dim).  Returns ([emb_m], joint or None)."""
+    M = len(xs)
+    _need_cuda(*xs, *Ws)
+    N = xs[0].shape[0]
+    out_dim = Ws[0].shape[0]
+    dev = xs[0].device
+    xs = [(x if x.dtype == torch.float64 else _f32c(x)).contiguous() for x in xs]
+    Wc = [_f32c(W) for W in Ws]
+    bc = [_f32c(b) for b in bs]
+    embs = [torch.empty((N, out_dim), device=dev, dtype=torch.float32) for _ in range(M)]
+    joint = torch.empty((N, M * out_dim), device=dev, dtype=torch.float32) if want_joint else None
+    fw = _f32c(fusion_w).reshape(-1) if want_joint else None
+    arr_p = ctypes.c_void_p * M
+    arr_i = ctypes.c_int * M
+    check(get_lib().sga_project_fuse_fwd_multi(arr_p(*[x.data_ptr() for x in xs]), arr_i(*[1 if x.dtype == torch.float64 else 0 for x in xs]),
+                                               arr_i(*[int(x.shape[1]) for x in xs]), arr_p(*[w.data_ptr() for w in Wc]),
+                                               arr_p(*[b.data_ptr() for b in bc]), arr_p(*[e.data_ptr() for e in embs]), M, N, out_dim,
+                                               _ptr(joint), 0 if joint is None else joint.shape[1], _ptr(fw), _stream()),
+          'sga_project_fuse_fwd_multi')
+    _count(1)
+    return embs, joint
+
+
 def project_fuse_backward(x, W, emb, g_emb, g_joint, joint_col: int, fusion_w, M: int, m: int, need_gx: bool):
     x = as_f32(x)
     N, in_dim = x.shape
