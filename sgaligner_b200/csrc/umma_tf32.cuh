@@ -81,5 +81,22 @@ __device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint32_t stage_addr
   }
 }
 
+// Same with independent A / B stage addresses ({hi, lo} tiles each): a Gram block on the diagonal passes the
+// same tiles for both operands.
+__device__ __forceinline__ void issue_stage_ab(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool first) {
+  const uint64_t dAhi = ptx::smem_desc_sw128(a_addr);
+  const uint64_t dAlo = ptx::smem_desc_sw128(a_addr + kTileBytes);
+  const uint64_t dBhi = ptx::smem_desc_sw128(b_addr);
+  const uint64_t dBlo = ptx::smem_desc_sw128(b_addr + kTileBytes);
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint64_t a = (pass == 1) ? dAlo : dAhi;
+    const uint64_t b = (pass == 2) ? dBlo : dBhi;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      ptx::umma_tf32(d_tmem, a + (uint64_t)(ks * 2), b + (uint64_t)(ks * 2), idesc, (first && pass == 0 && ks == 0) ? 0u : 1u);
+  }
+}
+
 }  // namespace tf32x3
 }  // namespace sga

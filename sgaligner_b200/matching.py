@@ -17,13 +17,13 @@ from . import ops
 
 # ------------------------------------------------------------------------------ device path
 def match_batch(embedding: torch.Tensor, data_dict: dict, k: int = 6, full_rank: bool = False, want_sim: bool = True,
-                tensor_cores: bool = True) -> dict:
+                tensor_cores: bool = True, layout: 'ops.PairLayout' = None) -> dict:
     """For every node: its ``k`` best matches among the source+reference nodes of its own pair
     (pair-local indices, the node itself included, exactly like ``rank_list[:, :k]`` of the
     reference).  ``full_rank`` additionally returns the whole ``rank_list`` of every pair.
     Default path: one fused tcgen05 kernel (Gram + top-k, ``k <= 8``); ``tensor_cores=False`` selects
     the fp32 FMA kernels (any k)."""
-    lay = ops.PairLayout(np.asarray(data_dict['graph_per_obj_count']), embedding.device)
+    lay = layout if layout is not None else ops.PairLayout(np.asarray(data_dict['graph_per_obj_count']), embedding.device)
     if tensor_cores and k <= 8:
         topk_idx, topk_dist, sim = ops.match_topk_tc(embedding.detach(), lay, k, want_sim or full_rank)
         rank = ops.match_rank(sim, lay, 0, True)[2] if full_rank else None

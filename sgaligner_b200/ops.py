@@ -151,12 +151,11 @@ def pointnet_bn_moments(pts, W1, b1, W2, b2, W3, b3):
 
 
 # --------------------------------------------------------------------------------- graphs
-class BatchGraph:
-    """Device-side block-diagonal CSR (by destination) of all 2B graphs of a collated batch."""
+class GraphLayout:
+    """Per-graph node / edge offsets of a collated batch (host prefix sums of ``graph_per_obj_count`` /
+    ``graph_per_edge_count``, copied to the device once); depends on the counts only, not on the edges."""
 
-    def __init__(self, edges: torch.Tensor, obj_count: np.ndarray, edge_count: np.ndarray):
-        _need_cuda(edges)
-        dev = edges.device
+    def __init__(self, obj_count: np.ndarray, edge_count: np.ndarray, device):
         oc = np.asarray(obj_count, dtype=np.int64).reshape(-1)
         ec = np.asarray(edge_count, dtype=np.int64).reshape(-1)
         self.G = int(oc.shape[0])
@@ -165,8 +164,20 @@ class BatchGraph:
         self.max_nodes = int(oc.max()) if self.G else 0
         node_off = np.concatenate([[0], np.cumsum(oc)]).astype(np.int32)
         edge_off = np.concatenate([[0], np.cumsum(ec)]).astype(np.int64)
-        self.node_off = torch.from_numpy(node_off).to(dev, non_blocking=True)
-        self.edge_off = torch.from_numpy(edge_off).to(dev, non_blocking=True)
+        self.node_off = torch.from_numpy(node_off).to(device, non_blocking=True)
+        self.edge_off = torch.from_numpy(edge_off).to(device, non_blocking=True)
+
+
+class BatchGraph:
+    """Device-side block-diagonal CSR (by destination) of all 2B graphs of a collated batch."""
+
+    def __init__(self, edges: torch.Tensor, obj_count: np.ndarray = None, edge_count: np.ndarray = None, layout: GraphLayout = None):
+        _need_cuda(edges)
+        dev = edges.device
+        lay = layout if layout is not None else GraphLayout(obj_count, edge_count, dev)
+        self.layout = lay
+        self.G, self.N, self.E, self.max_nodes = lay.G, lay.N, lay.E, lay.max_nodes
+        self.node_off, self.edge_off = lay.node_off, lay.edge_off
         edges = edges.to(torch.int64).contiguous()
         assert edges.shape[0] == self.E, 'edge tensor does not match graph_per_edge_count'
         self.row_beg = torch.empty(self.N, device=dev, dtype=torch.int32)

@@ -1,0 +1,100 @@
+"""Serving step captured into one CUDA graph.
+
+The serving hot path (``MultiModalEncoder.forward`` + matching head + anchor positions) is a dozen
+short launches around one long one; issued eagerly from Python the GPU idles between them.  For a fixed
+batch *layout* (object / edge / anchor counts per pair -- what a bucketed serving loop sees) the whole
+step is captured once into a CUDA graph and replayed per batch: inputs are copied into static device
+buffers (H2D from pinned host memory or D2D), one graph launch runs every kernel, outputs live in
+static buffers.  Nothing here changes what is computed: the captured region is exactly
+``trainer.infer_step`` + ``ops.match_anchor_pos``.
+
+Reference call sites this replaces: ``src/inference/sgaligner/inference_align_reg.py:98-145`` (per-batch
+model call, per-pair matching loop, metric accumulation).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import matching, ops
+
+_COUNT_KEYS = ('graph_per_obj_count', 'graph_per_edge_count', 'e1i', 'e2i')
+
+
+class CapturedInference:
+    def __init__(self, model, example: Dict, k: int = 6, want_sim: bool = True):
+        pts = example['tot_obj_pts']
+        if not (torch.is_tensor(pts) and pts.is_cuda):
+            raise RuntimeError('CapturedInference needs a device-resident example batch (no CPU fallback)')
+        self.model, self.k, self.want_sim = model, k, want_sim
+        self.dev = pts.device
+        self.modules = list(model.modules)
+        self.static = {}
+        for key, v in example.items():
+            if key.startswith('_sga'):
+                continue
+            self.static[key] = v.clone() if torch.is_tensor(v) else v
+        self.oc = np.asarray(example['graph_per_obj_count']).copy()
+        self.ec = np.asarray(example['graph_per_edge_count']).copy()
+        self.graph_layout = ops.GraphLayout(self.oc, self.ec, self.dev) if 'gat' in self.modules else None
+        self.pair_layout = ops.PairLayout(self.oc, self.dev)
+        self.n_anchor = int(np.asarray(example['e1i']).size)
+        self.e1 = torch.as_tensor(np.asarray(example['e1i']).astype(np.int32)).to(self.dev)
+        self.e2 = torch.as_tensor(np.asarray(example['e2i']).astype(np.int32)).to(self.dev)
+        was_training = model.training
+        model.eval()
+        cur = torch.cuda.current_stream(self.dev)
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):            # warm-up outside the capture (lazy attribute / workspace initialisation)
+                self._step()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        l0 = ops.LAUNCHES
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self._step()
+        self.launches_per_replay = ops.LAUNCHES - l0
+        if was_training:
+            model.train()
+
+    def _step(self):
+        with torch.no_grad():
+            d = dict(self.static)
+            if self.graph_layout is not None:
+                d['_sga_graph_layout'] = self.graph_layout
+            out = self.model(d)
+            emb = out['joint'] if len(self.modules) > 1 else out[self.modules[0]]
+            res = matching.match_batch(emb, d, k=self.k, full_rank=False, want_sim=True, layout=self.pair_layout)
+            pos = ops.match_anchor_pos(res['sim'], self.pair_layout, self.e1, self.e2) if self.n_anchor else None
+        return {'embeddings': out, 'topk_idx': res['topk_idx'], 'topk_dist': res['topk_dist'], 'sim': res['sim'],
+                'anchor_pos': pos, 'layout': self.pair_layout}
+
+    def check_layout(self, batch: Dict):
+        if not (np.array_equal(np.asarray(batch['graph_per_obj_count']), self.oc)
+                and np.array_equal(np.asarray(batch['graph_per_edge_count']), self.ec)
+                and int(np.asarray(batch['e1i']).size) == self.n_anchor):
+            raise ValueError('batch layout differs from the captured one: capture a new CapturedInference for it')
+
+    def load(self, batch: Dict, e1i: Optional[torch.Tensor] = None, e2i: Optional[torch.Tensor] = None):
+        """Copy a batch with the captured layout into the static buffers (async on the current stream;
+        pinned host tensors give true asynchronous H2D copies).  ``e1i`` / ``e2i``: int32 tensors (host,
+        pinned, or device); default: taken from the batch dict."""
+        self.check_layout(batch)
+        for key, dst in self.static.items():
+            if torch.is_tensor(dst):
+                dst.copy_(batch[key], non_blocking=True)
+        if self.n_anchor:
+            self.e1.copy_(e1i if e1i is not None else torch.as_tensor(np.asarray(batch['e1i']).astype(np.int32)), non_blocking=True)
+            self.e2.copy_(e2i if e2i is not None else torch.as_tensor(np.asarray(batch['e2i']).astype(np.int32)), non_blocking=True)
+
+    def replay(self) -> Dict:
+        self.graph.replay()
+        return self.out
+
+    def __call__(self, batch: Dict, **kw) -> Dict:
+        self.load(batch, **kw)
+        return self.replay()

@@ -9,7 +9,8 @@ torch.manual_seed(0)
 net = PointNetfeat(out_size=256).to(dev)
 pts = torch.randn(4096, 512, 3, device=dev)
 w = [net.conv1.weight, net.conv1.bias, net.conv2.weight, net.conv2.bias, net.conv3.weight, net.conv3.bias]
-stats = len(sys.argv) > 1 and sys.argv[1] == 'stats'
+stats = 'stats' in sys.argv[1:]
+flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev) if 'flush' in sys.argv[1:] else None
 with torch.no_grad():
     for _ in range(3):
         if stats:
@@ -19,6 +20,8 @@ with torch.no_grad():
     torch.cuda.synchronize()
     ts = []
     for _ in range(10):
+        if flush is not None:
+            flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         if stats:
@@ -28,4 +31,4 @@ with torch.no_grad():
         b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
-print('pointnet_fwd', 'stats' if stats else 'plain', 'ms:', min(ts), sorted(ts)[len(ts) // 2])
+print('pointnet_fwd', 'stats' if stats else 'plain', 'flushed' if flush is not None else 'warm', 'ms:', min(ts), sorted(ts)[len(ts) // 2])
