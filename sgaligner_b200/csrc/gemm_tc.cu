@@ -11,8 +11,10 @@
 // e1i/e2i/e1j/e2j gathers happen in the operand loader, the scatter-add in the epilogue.
 //
 // 128x128 output tiles, K chunks of 32, 3-stage shared-memory ring (4 x 16 KiB per stage), two TMEM
-// accumulators so the epilogue of tile i overlaps the main loop of tile i+1.  9 warps: 4 operand
-// loaders, 1 MMA issuer (elect.sync), 4 epilogue warps (one TMEM lane quarter each).
+// accumulators so the epilogue of tile i overlaps the main loop of tile i+1.  13 warps: 8 operand
+// loaders (half an operand row / half an MN atom each, the global loads of chunk c+1 in flight while
+// chunk c is normalised, split and stored), 1 MMA issuer (elect.sync), 4 epilogue warps (one TMEM lane
+// quarter each).
 #include "common.cuh"
 #include "umma_tf32.cuh"
 
@@ -41,53 +43,118 @@ struct GemmParams {
 namespace {
 
 constexpr int kStages = 3;
-constexpr int kLoaders = 128;
-constexpr int kThreads = 288;
+constexpr int kLoaders = 256;
+constexpr int kThreads = kLoaders + 32 + 128;
 constexpr uint32_t BAR_OFF = kStages * tf32x3::kStageBytes;
 constexpr uint32_t SMEM_BYTES = BAR_OFF + 256 + 1024;
+
+// One loader thread's share of a [128 x 32] operand tile for one K chunk: 16 fp32 values held in registers
+// between the global load and the conversion (so that the next chunk's loads overlap this chunk's work).
+struct Piece {
+  float4 v[4];
+  float d;        // divisor of these values (1 when the operand is not normalised)
+};
+
+// K-major operand: thread t -> tile row t/2, features [16*(t&1), +16) of the chunk.
+__device__ __forceinline__ void fetch_k(Piece& f, const GemmOperand& X, int row0, int nrows, int k0, int K, int t, bool vec_ok) {
+  const int r = t >> 1, kb = k0 + 16 * (t & 1);
+  const bool valid = r < nrows;
+  int64_t sr = 0;
+  f.d = 1.f;
+  if (valid) {
+    sr = X.idx ? (int64_t)X.idx[row0 + r] : (int64_t)(row0 + r);
+    if (X.div) f.d = X.div[sr];
+  }
+  const float* p = X.p + sr * X.ld + kb;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int k = kb + 4 * j;
+    if (valid) {
+      if (vec_ok && k + 3 < K) {
+        q = *reinterpret_cast<const float4*>(p + 4 * j);
+      } else {
+        if (k < K) q.x = p[4 * j];
+        if (k + 1 < K) q.y = p[4 * j + 1];
+        if (k + 2 < K) q.z = p[4 * j + 2];
+        if (k + 3 < K) q.w = p[4 * j + 3];
+      }
+    }
+    f.v[j] = q;
+  }
+}
+
+__device__ __forceinline__ void split4(const float4& q, float d, bool use_div, uint32_t (&h)[4], uint32_t (&l)[4]) {
+  const float x[4] = {use_div ? q.x / d : q.x, use_div ? q.y / d : q.y, use_div ? q.z / d : q.z, use_div ? q.w / d : q.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    h[e] = tf32x3::rn_tf32(x[e]);
+    l[e] = tf32x3::rn_tf32(x[e] - __uint_as_float(h[e]));
+  }
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, const uint32_t (&w)[4]) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+}
+
+__device__ __forceinline__ void store_k(uint32_t hi, uint32_t lo, const Piece& f, bool use_div, int t) {
+  const int r = t >> 1, half = t & 1;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t h[4], l[4];
+    split4(f.v[j], f.d, use_div, h, l);
+    const uint32_t off = ptx::sw128_offset(r, 4 * half + j);
+    sts128(hi + off, h);
+    sts128(lo + off, l);
+  }
+}
 
 // MN-major [128 mn x 32 k] tile.  For 32-bit operands the only MN-major shared-memory layout tcgen05
 // accepts is SWIZZLE_128B_BASE32B (descriptor layout type 1): atoms of [4 k-rows x 128 B], the
 // 32-byte chunk index XORed with (k & 3).  Here: the 32 k-rows of one 32-wide MN atom are contiguous
 // (128 B apart; 4-row atoms 512 B apart = SBO), MN atoms 4096 B apart (= LBO).
-__device__ __forceinline__ void load_mn_major(unsigned char* hi, unsigned char* lo, const GemmOperand& X, int mn0, int MN, int k0,
-                                              int K, int t, bool vec_ok) {
-  const int kk = (t & 7) + 8 * ((t >> 3) & 3);   // k row inside the chunk
-  const int qd = t >> 5;                          // which 32-wide MN atom
+// Thread t -> k row (t & 31), MN atom (t >> 5) & 3, half (16 mn values) t >> 7.
+__device__ __forceinline__ void fetch_mn(Piece& f, const GemmOperand& X, int mn0, int MN, int k0, int K, int t, bool vec_ok) {
+  const int kk = t & 31, qd = (t >> 5) & 3, half = t >> 7;
   const int krow = k0 + kk;
   const bool kvalid = krow < K;
   int64_t sr = 0;
-  float d = 1.f;
+  f.d = 1.f;
   if (kvalid) {
     sr = X.idx ? (int64_t)X.idx[krow] : (int64_t)krow;
-    if (X.div) d = X.div[sr];
+    if (X.div) f.d = X.div[sr];
   }
-  const int c0 = mn0 + 32 * qd;
+  const int c0 = mn0 + 32 * qd + 16 * half;
   const float* p = X.p + sr * X.ld + c0;
-  const uint32_t base = (uint32_t)qd * 4096u + (uint32_t)kk * 128u;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j = 0; j < 4; ++j) {
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c = c0 + 4 * j;
     if (kvalid) {
-      if (vec_ok && c0 + 4 * j + 3 < MN) {
-        float4 q = *reinterpret_cast<const float4*>(p + 4 * j);
-        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+      if (vec_ok && c + 3 < MN) {
+        q = *reinterpret_cast<const float4*>(p + 4 * j);
       } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (c0 + 4 * j + e < MN) v[e] = p[4 * j + e];
+        if (c < MN) q.x = p[4 * j];
+        if (c + 1 < MN) q.y = p[4 * j + 1];
+        if (c + 2 < MN) q.z = p[4 * j + 2];
+        if (c + 3 < MN) q.w = p[4 * j + 3];
       }
     }
-    uint32_t h[4], l[4];
+    f.v[j] = q;
+  }
+}
+
+__device__ __forceinline__ void store_mn(uint32_t hi, uint32_t lo, const Piece& f, bool use_div, int t) {
+  const int kk = t & 31, qd = (t >> 5) & 3, half = t >> 7;
+  const uint32_t base = (uint32_t)qd * 4096u + (uint32_t)kk * 128u;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float x = X.div ? v[e] / d : v[e];
-      h[e] = tf32x3::rn_tf32(x);
-      l[e] = tf32x3::rn_tf32(x - __uint_as_float(h[e]));
-    }
-    const uint32_t off = base + (uint32_t)((((j >> 1) ^ (kk & 3)) << 5) + ((j & 1) << 4));
-    *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  for (int j = 0; j < 4; ++j) {
+    uint32_t h[4], l[4];
+    split4(f.v[j], f.d, use_div, h, l);
+    const int jj = 4 * half + j;      // 16-byte chunk of the 128-byte k row
+    const uint32_t off = base + (uint32_t)((((jj >> 1) ^ (kk & 3)) << 5) + ((jj & 1) << 4));
+    sts128(hi + off, h);
+    sts128(lo + off, l);
   }
 }
 
@@ -144,7 +211,7 @@ gemm_tf32x3_kernel(const GemmParams P) {
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 4) ptx::tmem_alloc<256>(tmem_slot);
+  if (warp == 8) ptx::tmem_alloc<256>(tmem_slot);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -156,29 +223,39 @@ gemm_tf32x3_kernel(const GemmParams P) {
   const int nkc_all = (P.K + 31) / 32;
   const int kc_per = (nkc_all + ksplit - 1) / ksplit;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ------------------------------- operand loaders
     const bool a_vec = (P.A.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.A.p) & 15) == 0);
     const bool b_vec = (P.B.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.B.p) & 15) == 0);
+    const bool a_div = P.A.div != nullptr, b_div = P.B.div != nullptr;
     int it = 0;
     for (int work = blockIdx.x; work < ntiles; work += gridDim.x) {
       const int tile = work / ksplit, ksl = work % ksplit;
       const int m0 = (tile / ntn) * 128, n0 = (tile % ntn) * 128;
       const int kc_beg = ksl * kc_per, kc_end = min(nkc_all, kc_beg + kc_per);
+      auto fetch = [&](Piece& fa, Piece& fb, int kc) {
+        if (A_MN) fetch_mn(fa, P.A, m0, P.M, kc * 32, P.K, tid, a_vec);
+        else fetch_k(fa, P.A, m0, P.M - m0, kc * 32, P.K, tid, a_vec);
+        if (B_MN) fetch_mn(fb, P.B, n0, P.N, kc * 32, P.K, tid, b_vec);
+        else fetch_k(fb, P.B, n0, P.N - n0, kc * 32, P.K, tid, b_vec);
+      };
+      Piece fa, fb;
+      if (kc_beg < kc_end) fetch(fa, fb, kc_beg);
       for (int kc = kc_beg; kc < kc_end; ++kc, ++it) {
         const int s = it % kStages;
+        const Piece ca = fa, cb = fb;
+        if (kc + 1 < kc_end) fetch(fa, fb, kc + 1);      // in flight during the conversion below
         if (it >= kStages) ptx::mbar_wait(&empty[s], (uint32_t)(((it / kStages) - 1) & 1));
-        unsigned char* st = sm + s * tf32x3::kStageBytes;
-        if (A_MN) load_mn_major(st, st + tf32x3::kTileBytes, P.A, m0, P.M, kc * 32, P.K, tid, a_vec);
-        else tf32x3::load_rows(st, st + tf32x3::kTileBytes, P.A.p, P.A.ld, P.A.idx, P.A.div, m0, P.M - m0, kc * 32, P.K, tid, a_vec);
-        if (B_MN) load_mn_major(st + 2 * tf32x3::kTileBytes, st + 3 * tf32x3::kTileBytes, P.B, n0, P.N, kc * 32, P.K, tid, b_vec);
-        else tf32x3::load_rows(st + 2 * tf32x3::kTileBytes, st + 3 * tf32x3::kTileBytes, P.B.p, P.B.ld, P.B.idx, P.B.div, n0, P.N - n0,
-                               kc * 32, P.K, tid, b_vec);
+        const uint32_t st = sm_base + s * tf32x3::kStageBytes;
+        if (A_MN) store_mn(st, st + tf32x3::kTileBytes, ca, a_div, tid);
+        else store_k(st, st + tf32x3::kTileBytes, ca, a_div, tid);
+        if (B_MN) store_mn(st + 2 * tf32x3::kTileBytes, st + 3 * tf32x3::kTileBytes, cb, b_div, tid);
+        else store_k(st + 2 * tf32x3::kTileBytes, st + 3 * tf32x3::kTileBytes, cb, b_div, tid);
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&full[s]);
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ------------------------------- MMA issuer
     const uint32_t idesc = ptx::make_idesc(2, 128, 128) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
@@ -249,7 +326,9 @@ gemm_tf32x3_kernel(const GemmParams P) {
                 const int c = c0 + e;
                 if (c >= P.es_c0 && c < P.N) {
                   const float x = __uint_as_float(v[e]);
-                  const float e01 = expf(x / 0.1f), e1 = expf(x);
+                  // cosines: |x| <= 1, so the fast exponential (ex2.approx, ~2 ulp) is exact enough for sums of
+                  // 1e6 positive terms; 1/0.1f rounds to 10.f
+                  const float e01 = __expf(x * 10.f), e1 = __expf(x);
                   if (c < P.es_split) { s_acc[0] += e01; s_acc[2] += e1; }
                   else { s_acc[1] += e01; s_acc[3] += e1; }
                 }
@@ -272,7 +351,7 @@ gemm_tf32x3_kernel(const GemmParams P) {
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 4) ptx::tmem_dealloc<256>(tmem);
+  if (warp == 8) ptx::tmem_dealloc<256>(tmem);
 }
 
 }  // namespace

@@ -8,6 +8,11 @@ dev = torch.device('cuda:0')
 torch.manual_seed(0)
 net = PointNetfeat(out_size=256).to(dev)
 pts = torch.randn(4096, 512, 3, device=dev)
+if 'c2' in sys.argv[1:]:
+    from sgaligner_b200 import synthetic
+    pts = synthetic.config_c2(batch=32, seed=100)['tot_obj_pts'].to(dev)
+if 'offset' in sys.argv[1:]:
+    pts = pts + (torch.rand(4096, 1, 3, device=dev) * 4 - 2)
 w = [net.conv1.weight, net.conv1.bias, net.conv2.weight, net.conv2.bias, net.conv3.weight, net.conv3.bias]
 stats = 'stats' in sys.argv[1:]
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev) if 'flush' in sys.argv[1:] else None
@@ -31,4 +36,4 @@ with torch.no_grad():
         b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
-print('pointnet_fwd', 'stats' if stats else 'plain', 'flushed' if flush is not None else 'warm', 'ms:', min(ts), sorted(ts)[len(ts) // 2])
+print('pointnet_fwd', 'stats' if stats else 'plain', 'flushed' if flush is not None else 'warm', ' '.join(sys.argv[1:]), 'ms:', min(ts), sorted(ts)[len(ts) // 2])
