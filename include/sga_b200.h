@@ -61,6 +61,16 @@ int sga_pointnet_bwd(const float* pts, int64_t N, int P,
                      float* gW1, float* gb1, float* gW2, float* gb2, float* gW3, float* gb3,
                      void* stream);
 
+/* the same with kernel selection: SGA_POINTNET_TC runs the backward as tcgen05 GEMMs over tiles of 128
+ * (object, channel) instances (conv2 recomputed for the argmax points, dW2 = dz2^T h1 and dh1 = dz2 W2 on the
+ * tensor cores, bf16x3 split operands); needs C3 % 128 == 0 and 16-byte aligned W2 / W3. */
+int sga_pointnet_bwd_mode(const float* pts, int64_t N, int P,
+                          const float* W1, const float* b1, const float* W2, const float* b2,
+                          const float* W3, const float* b3, int C3,
+                          const float* out, const int32_t* argmax, const float* grad_out,
+                          float* gW1, float* gb1, float* gW2, float* gb2, float* gW3, float* gb3,
+                          int mode, void* stream);
+
 /* train-mode side effect of the discarded BatchNorm1d calls (pointnet.py:141-142,154-155,158-159):
  * per-channel sum and sum of squares of the three pre-ReLU conv outputs over all N*P points.
  * moments: f64 [2*(64+128+C3)] = {sum1[64], sq1[64], sum2[128], sq2[128], sum3[C3], sq3[C3]}, zeroed

@@ -33,6 +33,8 @@ def _declare(lib):
     sig('sga_pointnet_fwd_stats', c_i, c_p, c_l, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_size_t, c_p)
     sig('sga_pointnet_bwd', c_i, c_p, c_l, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p,
         c_p, c_p, c_p, c_p, c_p, c_p, c_p)
+    sig('sga_pointnet_bwd_mode', c_i, c_p, c_l, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p,
+        c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p)
     sig('sga_pointnet_bn_moments', c_i, c_p, c_l, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p)
     sig('sga_csr_build', c_i, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p)
     sig('sga_gat_linear', c_i, c_p, c_i, c_l, c_i, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p)
@@ -59,7 +61,7 @@ def _declare(lib):
     sig('sga_debug_set_trace', c_i, c_p)
 
 
-EXPORTS = ['sga_last_error', 'sga_version', 'sga_device_info', 'sga_pointnet_fwd', 'sga_pointnet_bwd',
+EXPORTS = ['sga_last_error', 'sga_version', 'sga_device_info', 'sga_pointnet_fwd', 'sga_pointnet_bwd', 'sga_pointnet_bwd_mode',
            'sga_pointnet_bn_moments', 'sga_pointnet_stats_scratch_bytes', 'sga_pointnet_fwd_stats', 'sga_csr_build', 'sga_gat_linear', 'sga_gat_aggregate',
            'sga_gat_aggregate_bwd', 'sga_gat_linear_bwd', 'sga_cast_f64_f32', 'sga_project_fuse_fwd', 'sga_project_fuse_fwd_multi', 'sga_project_fuse_bwd',
            'sga_match_sim', 'sga_match_topk_tc', 'sga_match_rank', 'sga_match_anchor_pos', 'sga_loss_workspace_bytes',

@@ -25,6 +25,7 @@ class PointNetFeat(torch.autograd.Function):
             out, arg = ops.pointnet_forward(pts, W1, b1, W2, b2, W3, b3, want_argmax=need, mode=mode, chunks=chunks)
         if need:
             ctx.save_for_backward(pts, W1, b1, W2, b2, W3, b3, out, arg)
+            ctx.mode = mode if W3.shape[0] % 128 == 0 else ops.POINTNET_SIMT
         if mom is not None:
             ctx.mark_non_differentiable(mom)
         return out, mom
@@ -32,7 +33,7 @@ class PointNetFeat(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout, _gmom=None):
         pts, W1, b1, W2, b2, W3, b3, out, arg = ctx.saved_tensors
-        gW1, gb1, gW2, gb2, gW3, gb3 = ops.pointnet_backward(pts, W1, b1, W2, b2, W3, b3, out, arg, gout.contiguous())
+        gW1, gb1, gW2, gb2, gW3, gb3 = ops.pointnet_backward(pts, W1, b1, W2, b2, W3, b3, out, arg, gout.contiguous(), mode=ctx.mode)
         return None, gW1.view_as(W1), gb1, gW2.view_as(W2), gb2, gW3.view_as(W3), gb3, None, None, None
 
 

@@ -223,6 +223,28 @@ pointnet_bwd_kernel(const float* __restrict__ pts, int64_t N, int P,
 }  // namespace
 }  // namespace sga
 
+namespace sga {
+int pointnet_bwd_tc(const float* pts, int64_t N, int P, const float* W1, const float* b1, const float* W2, const float* b2,
+                    const float* W3, int C3, const float* out, const int32_t* argmax, const float* gout, float* gW1, float* gb1,
+                    float* gW2, float* gb2, float* gW3, float* gb3, cudaStream_t st);
+}
+
+// mode: SGA_POINTNET_TC (tensor cores; C3 % 128 == 0) or SGA_POINTNET_SIMT (fp32 FMA, any shape)
+extern "C" int sga_pointnet_bwd_mode(const float* pts, int64_t N, int P, const float* W1, const float* b1,
+                                     const float* W2, const float* b2, const float* W3, const float* b3, int C3,
+                                     const float* out, const int32_t* argmax, const float* grad_out, float* gW1,
+                                     float* gb1, float* gW2, float* gb2, float* gW3, float* gb3, int mode, void* stream) {
+  if (N <= 0) return SGA_OK;
+  if (mode == SGA_POINTNET_TC) {
+    SGA_REQUIRE(P >= 1 && C3 >= 128 && C3 % 128 == 0, "sga_pointnet_bwd(TC): P=%d C3=%d (C3 must be a multiple of 128)", P, C3);
+    SGA_REQUIRE(out && argmax && grad_out, "sga_pointnet_bwd: forward results / grad_out missing");
+    SGA_REQUIRE(((uintptr_t)W2 & 15) == 0 && ((uintptr_t)W3 & 15) == 0, "sga_pointnet_bwd(TC): W2/W3 must be 16-byte aligned");
+    return sga::pointnet_bwd_tc(pts, N, P, W1, b1, W2, b2, W3, C3, out, argmax, grad_out, gW1, gb1, gW2, gb2, gW3, gb3,
+                                (cudaStream_t)stream);
+  }
+  return sga_pointnet_bwd(pts, N, P, W1, b1, W2, b2, W3, b3, C3, out, argmax, grad_out, gW1, gb1, gW2, gb2, gW3, gb3, stream);
+}
+
 extern "C" int sga_pointnet_bwd(const float* pts, int64_t N, int P, const float* W1, const float* b1,
                                 const float* W2, const float* b2, const float* W3, const float* b3, int C3,
                                 const float* out, const int32_t* argmax, const float* grad_out, float* gW1,

@@ -123,16 +123,15 @@ def pointnet_forward_stats(pts, W1, b1, W2, b2, W3, b3, want_argmax: bool):
     return out, arg, buf[:n_mom]
 
 
-def pointnet_backward(pts, W1, b1, W2, b2, W3, b3, out, arg, gout):
-    pts = _f32c(pts)
+def pointnet_backward(pts, W1, b1, W2, b2, W3, b3, out, arg, gout, mode: int = POINTNET_SIMT):
+    pts, w = _pointnet_args(pts, W1, b1, W2, b2, W3, b3, mode)
     N, P, _ = pts.shape
     C3 = W3.shape[0]
     dev = pts.device
     g = [torch.zeros(s, device=dev, dtype=torch.float32) for s in ((64, 3), (64,), (128, 64), (128,), (C3, 128), (C3,))]
-    check(get_lib().sga_pointnet_bwd(_ptr(pts), N, P, _ptr(_f32c(W1.reshape(64, 3))), _ptr(_f32c(b1)),
-                                     _ptr(_f32c(W2.reshape(128, 64))), _ptr(_f32c(b2)), _ptr(_f32c(W3.reshape(C3, 128))),
-                                     _ptr(_f32c(b3)), C3, _ptr(out), _ptr(arg), _ptr(_f32c(gout)),
-                                     *[_ptr(t) for t in g], _stream()), 'sga_pointnet_bwd')
+    with _timed('pointnet_bwd'):
+        check(get_lib().sga_pointnet_bwd_mode(_ptr(pts), N, P, *[_ptr(t) for t in w], C3, _ptr(out), _ptr(arg), _ptr(_f32c(gout)),
+                                              *[_ptr(t) for t in g], mode, _stream()), 'sga_pointnet_bwd')
     _count(1)
     return g
 

@@ -99,6 +99,26 @@ def test_pointnet_tc_fused_bn_statistics(dev):
             o += 2 * c
 
 
+def test_pointnet_bwd_tc_vs_fma_kernel(dev):
+    """Tensor-core backward (tcgen05 GEMMs over 128-instance tiles) against the fp32 FMA backward on the SAME
+    forward results (same argmax), so the two differ by bf16x3 rounding only."""
+    from sgaligner_b200 import ops
+    for (N, P, C3, seed) in [(7, 64, 128, 0), (301, 130, 256, 1), (600, 512, 256, 2), (40, 257, 512, 3)]:
+        p = O.init_params(['point'], 41, 164, pt_out_dim=C3, seed=seed)
+        g = torch.Generator().manual_seed(seed)
+        for i in (1, 2, 3):
+            p[f'object_encoder.conv{i}.bias'] = 0.1 * torch.randn(p[f'object_encoder.conv{i}.bias'].shape, generator=g)
+        pts = (torch.randn(N, P, 3, generator=g) + torch.rand(N, 1, 3, generator=g) * 4 - 2).to(dev)
+        w = [p[f'object_encoder.conv{i}.{k}'].to(dev) for i in (1, 2, 3) for k in ('weight', 'bias')]
+        out, arg = ops.pointnet_forward(pts, *w, want_argmax=True, mode=ops.POINTNET_TC)
+        gout = torch.randn(N, C3, generator=g).to(dev)
+        a = ops.pointnet_backward(pts, *w, out, arg, gout, mode=ops.POINTNET_TC)
+        b = ops.pointnet_backward(pts, *w, out, arg, gout, mode=ops.POINTNET_SIMT)
+        torch.cuda.synchronize()
+        for name, x, y in zip(('gW1', 'gb1', 'gW2', 'gb2', 'gW3', 'gb3'), a, b):
+            assert rel_inf(x, y) < 5e-5, (N, P, C3, name, rel_inf(x, y))
+
+
 @pytest.mark.parametrize('name', CASES)
 def test_match_topk_tc_vs_fma_path(name, dev):
     """Fused tcgen05 Gram + top-k vs the fp32 FMA kernels on the golden embedding: similarity within
