@@ -314,9 +314,10 @@ def run_ours(args, out=sys.stdout):
 
     if rank == 0:
         pk = measured_peaks()
-        # the kernel is timed inside back-to-back steps (no idle gaps: the chip sits at its sustained, power-capped
-        # clock), so the denominator is the SUSTAINED cuBLAS bf16 figure; the burst figure is given beside it
-        tf_peak, hbm_peak, peak_src = pk['sustained'], pk['hbm'], pk['src'] + ', bf16 sustained (kernel timed inside a long step)'
+        # Denominator: the BURST cuBLAS bf16 figure.  The kernel runs ~0.35 ms inside a ~0.5 ms step whose other
+        # kernels are light, so the chip is nearer its burst than its sustained (power-capped, seconds-long GEMM loop)
+        # state; against the sustained figure the executed-FLOP fraction reads slightly above 1.0 (given beside it).
+        tf_peak, hbm_peak, peak_src = pk['burst'], pk['hbm'], pk['src'] + ', bf16 burst'
         flops = FLOP_PER_OBJECT * N
         achieved = flops / (k_ms * 1e-3) / 1e12 if k_ms else None
         cpu = time_cpu_baseline()
@@ -335,7 +336,7 @@ def run_ours(args, out=sys.stdout):
                          'note': 'algorithmic fp32 FLOPs; the kernel executes 3 bf16 passes per FLOP (fp32-faithful split operands), '
                                  'so frac tops out at 1/3; executed_frac = 3 x frac',
                          'executed_frac': (3 * achieved / tf_peak) if achieved else None,
-                         'frac_vs_burst_peak': (achieved / pk['burst']) if achieved else None, 'burst_peak': pk['burst'],
+                         'frac_vs_sustained_peak': (achieved / pk['sustained']) if achieved else None, 'sustained_peak': pk['sustained'],
                          'traffic_source': 'ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r1_ncu_pointnet_fwd_tc_v2_summary.txt)',
                          'hbm': {'achieved_gbs': BYTES_PER_OBJECT * N / (k_ms * 1e-3) / 1e9 if k_ms else None, 'peak_gbs': hbm_peak,
                                  'algorithmic_bytes_per_launch': BYTES_PER_OBJECT * N}},

@@ -12,9 +12,12 @@ class PointNetFeat(torch.autograd.Function):
     the saved per-channel argmax of the max-pool."""
 
     @staticmethod
-    def forward(ctx, pts, W1, b1, W2, b2, W3, b3, mode, chunks=None, want_stats=False):
-        """Returns (pooled feature, moments); moments (f64, non-differentiable) is None unless want_stats."""
-        need = any(ctx.needs_input_grad[1:7])
+    def forward(ctx, pts, W1, b1, W2, b2, W3, b3, mode, chunks=None, want_stats=False, grad_mode=True):
+        """Returns (pooled feature, moments); moments (f64, non-differentiable) is None unless want_stats.
+        ``grad_mode``: torch.is_grad_enabled() at the call site -- inside forward() autograd is always off and
+        needs_input_grad mirrors requires_grad of the parameters even under torch.no_grad(), so without it the
+        serving path would run the (slower) argmax-tracking variant of the kernel."""
+        need = grad_mode and any(ctx.needs_input_grad[1:7])
         mom = None
         if want_stats:
             if chunks:      # statistics span the whole batch: one launch once every chunk has landed
@@ -34,7 +37,7 @@ class PointNetFeat(torch.autograd.Function):
     def backward(ctx, gout, _gmom=None):
         pts, W1, b1, W2, b2, W3, b3, out, arg = ctx.saved_tensors
         gW1, gb1, gW2, gb2, gW3, gb3 = ops.pointnet_backward(pts, W1, b1, W2, b2, W3, b3, out, arg, gout.contiguous(), mode=ctx.mode)
-        return None, gW1.view_as(W1), gb1, gW2.view_as(W2), gb2, gW3.view_as(W3), gb3, None, None, None
+        return None, gW1.view_as(W1), gb1, gW2.view_as(W2), gb2, gW3.view_as(W3), gb3, None, None, None, None
 
 
 class GATLayer(torch.autograd.Function):

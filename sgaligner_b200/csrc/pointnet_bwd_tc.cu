@@ -39,7 +39,8 @@ constexpr uint32_t SMALL = DZLO + 2 * kBlk;    // 163840
 constexpr uint32_t W1B1 = SMALL;               // float4[64] = {w0,w1,w2,b}
 constexpr uint32_t B2 = W1B1 + 1024;           // float[128]
 constexpr uint32_t XS = B2 + 512;              // float4[128] = {x0,x1,x2,g} of the current tile
-constexpr uint32_t BARS = XS + 2048;
+constexpr uint32_t W2F = XS + 2048;             // float[128][64]: fp32 W2 for the exact recompute at the ReLU kink
+constexpr uint32_t BARS = W2F + 32768;
 constexpr uint32_t TMEMPTR = BARS + 64;
 constexpr uint32_t SMEM_USED = TMEMPTR + 16;
 constexpr uint32_t SMEM_BYTES = SMEM_USED + 1024;
@@ -146,6 +147,7 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
   for (int i = tid; i < 64; i += kThreads)
     reinterpret_cast<float4*>(sm + W1B1)[i] = make_float4(W1[i * 3], W1[i * 3 + 1], W1[i * 3 + 2], b1[i]);
   for (int i = tid; i < 128; i += kThreads) reinterpret_cast<float*>(sm + B2)[i] = b2[i];
+  for (int i = tid; i < 128 * 16; i += kThreads) reinterpret_cast<float4*>(sm + W2F)[i] = reinterpret_cast<const float4*>(W2)[i];
   if (tid == 0) {
     ptx::mbar_init(&bars[BAR_A1_FULL], kComputeThreads);
     ptx::mbar_init(&bars[BAR_D2_FULL], 1);
@@ -291,7 +293,7 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
       const float4 me = xs[row];
       const float g = me.w;
       if (wh == 0) accb3 += g;
-      const float tau = 4e-5f * (1.f + fabsf(me.x) + fabsf(me.y) + fabsf(me.z));
+      const float tau = 3e-5f * (1.f + fabsf(me.x) + fabsf(me.y) + fabsf(me.z));
       ptx::mbar_wait(&bars[BAR_D2_FULL], ph);
       ptx::tc_fence_after();
 #pragma unroll
@@ -315,11 +317,11 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
         for (int e = 0; e < 16; ++e) {      // unrolled: z / bb stay in registers; the branch is rarely taken
           if (__any_sync(0xffffffffu, fabsf(z[e]) < tau)) {
             const int k2 = 64 * wh + 16 * c + e;
-            const float4* wrow = reinterpret_cast<const float4*>(W2 + k2 * 64);
+            const float4* wrow = reinterpret_cast<const float4*>(sm + W2F) + k2 * 16;
             float zz = bb[e];
-#pragma unroll 1
+#pragma unroll 4
             for (int k4 = 0; k4 < 16; ++k4) {
-              const float4 wv = __ldg(wrow + k4);
+              const float4 wv = wrow[k4];
               const float wk[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
               for (int u = 0; u < 4; ++u) {

@@ -65,18 +65,28 @@ __global__ void fusion_w_bwd_kernel(const float* __restrict__ fusion_w, int M, i
   g_fw[i] += t_acc[0] * wm * ((i == m ? 1.f : 0.f) - wi);
 }
 
-// gb[c] += sum_n g[n,c]
+// gb[c] += sum_n g[n,c]: 64 rows per CTA (one wave of CTAs at N = 4096..9472), 4 row groups of 16 rows
+// combined through shared memory, one atomic per (CTA, column)
+constexpr int CS_ROWS = 64;
 __global__ void __launch_bounds__(NT)
 colsum_kernel(const float* __restrict__ g, int64_t N, int D, float* __restrict__ gb) {
-  const int64_t r0 = (int64_t)blockIdx.x * 256;
-  for (int c = threadIdx.x; c < D; c += NT) {
+  __shared__ float part[4][64];
+  const int64_t r0 = (int64_t)blockIdx.x * CS_ROWS;
+  const int cl = threadIdx.x & 63, rg = threadIdx.x >> 6;     // column within a 64-column slab, row group
+  for (int c0 = 0; c0 < D; c0 += 64) {
+    const int c = c0 + cl;
     float s = 0.f;
-    for (int r = 0; r < 256; ++r) {
-      int64_t n = r0 + r;
-      if (n >= N) break;
-      s += g[n * D + c];
+    if (c < D) {
+#pragma unroll 4
+      for (int r = rg * 16; r < rg * 16 + 16; ++r) {
+        const int64_t n = r0 + r;
+        if (n < N) s += g[n * D + c];
+      }
     }
-    atomicAdd(&gb[c], s);
+    part[rg][cl] = s;
+    __syncthreads();
+    if (rg == 0 && c < D) atomicAdd(&gb[c], part[0][cl] + part[1][cl] + part[2][cl] + part[3][cl]);
+    __syncthreads();
   }
 }
 
@@ -110,7 +120,7 @@ extern "C" int sga_project_fuse_bwd(const float* x, int64_t N, int in_dim, const
   // gW[c][k] += sum_n g[n][c] x[n][k]
   SGA_CUDA(sga::launch_gemm(g_total, 1, out_dim, x, in_dim, 1, gW, in_dim, out_dim, in_dim, (int)N, 1, st,
                             sga::splitk_for(out_dim, in_dim, (int)N)));
-  sga::colsum_kernel<<<(unsigned)((N + 255) / 256), sga::NT, 0, st>>>(g_total, N, out_dim, gb);
+  sga::colsum_kernel<<<(unsigned)((N + sga::CS_ROWS - 1) / sga::CS_ROWS), sga::NT, 0, st>>>(g_total, N, out_dim, gb);
   SGA_LAUNCH_CHECK();
   // gx[n][k] = sum_c g[n][c] W[c][k]
   if (gx) SGA_CUDA(sga::launch_gemm(g_total, out_dim, 1, W, in_dim, 1, gx, in_dim, (int)N, in_dim, out_dim, 0, st));

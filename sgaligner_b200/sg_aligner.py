@@ -98,7 +98,7 @@ class PointNetfeat(nn.Module):
                                           self.conv3.weight, self.conv3.bias)
             self._update_bn_running_stats(mom, float(pts_npc.shape[0] * pts_npc.shape[1]))
         out, mom = ag.PointNetFeat.apply(pts_npc, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
-                                         self.conv3.weight, self.conv3.bias, self.kernel_mode, chunks, fused)
+                                         self.conv3.weight, self.conv3.bias, self.kernel_mode, chunks, fused, torch.is_grad_enabled())
         if fused:                           # statistics came out of the forward launch itself
             self._update_bn_running_stats(mom, float(pts_npc.shape[0] * pts_npc.shape[1]))
         return out
