@@ -52,6 +52,10 @@ int sga_pointnet_fwd(const float* pts, int64_t N, int P,
                      const float* W3, const float* b3, int C3,
                      float* out, int32_t* argmax, int mode, void* stream);
 
+/* Cap on the SMs the persistent tensor-core forward occupies (0 = all of them): a serving step that runs the
+ * graph branch concurrently on a second stream leaves it a few SMs this way.  Process-wide setting. */
+int sga_pointnet_set_max_ctas(int n);
+
 /* backward of the above (autograd of pointnet.py:140-163 through the max-pool): accumulates (+=)
  * into gW1 [64,3] gb1 gW2 [128,64] gb2 gW3 [C3,128] gb3.  `out`/`argmax` are the forward results. */
 int sga_pointnet_bwd(const float* pts, int64_t N, int P,

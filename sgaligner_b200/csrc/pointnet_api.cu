@@ -7,6 +7,7 @@ int pointnet_fwd_simt(const float*, int64_t, int, const float*, const float*, co
 int pointnet_fwd_tc(const float*, int64_t, int, const float*, const float*, const float*, const float*, const float*,
                     const float*, int, float*, int32_t*, double*, double*, cudaStream_t);
 size_t pointnet_tc_raw_doubles(int C3);
+void pointnet_tc_set_max_ctas(int n);
 int debug_set_trace(long long* ptr);
 }  // namespace sga
 
@@ -23,6 +24,11 @@ extern "C" int sga_pointnet_fwd(const float* pts, int64_t N, int P, const float*
   }
   sga::set_error("sga_pointnet_fwd: unknown mode %d", mode);
   return SGA_EINVAL;
+}
+
+extern "C" int sga_pointnet_set_max_ctas(int n) {
+  sga::pointnet_tc_set_max_ctas(n);
+  return SGA_OK;
 }
 
 extern "C" size_t sga_pointnet_stats_scratch_bytes(int C3) { return sga::pointnet_tc_raw_doubles(C3) * sizeof(double); }

@@ -68,6 +68,17 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------- PointNet
+def pointnet_set_max_ctas(n: int):
+    """Cap on the SMs the persistent tensor-core PointNet forward occupies (0 = all)."""
+    check(get_lib().sga_pointnet_set_max_ctas(int(n)), 'sga_pointnet_set_max_ctas')
+
+
+def sm_count() -> int:
+    sm, maj, mnr = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    check(get_lib().sga_device_info(ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mnr)), 'sga_device_info')
+    return int(sm.value)
+
+
 def _pointnet_args(pts, W1, b1, W2, b2, W3, b3, mode):
     _need_cuda(pts, W1, W3)
     pts = _f32c(pts)

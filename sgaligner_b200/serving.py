@@ -24,13 +24,24 @@ _COUNT_KEYS = ('graph_per_obj_count', 'graph_per_edge_count', 'e1i', 'e2i')
 
 
 class CapturedInference:
-    def __init__(self, model, example: Dict, k: int = 6, want_sim: bool = True):
+    def __init__(self, model, example: Dict, k: int = 6, want_sim: bool = True, graph_branch_sms: int = 8):
+        """``graph_branch_sms`` > 0: the point encoder (one persistent CTA per SM) leaves that many SMs free and the
+        graph branch (CSR build + two GAT layers) is captured on a forked stream, so the two branches of the
+        encoder run concurrently inside the graph; 0: one stream, everything back to back."""
         pts = example['tot_obj_pts']
         if not (torch.is_tensor(pts) and pts.is_cuda):
             raise RuntimeError('CapturedInference needs a device-resident example batch (no CPU fallback)')
         self.model, self.k, self.want_sim = model, k, want_sim
         self.dev = pts.device
         self.modules = list(model.modules)
+        self.side = None
+        self.pointnet_ctas = 0
+        if graph_branch_sms > 0 and 'gat' in self.modules and 'point' in self.modules:
+            # balanced split: every point-encoder CTA gets the same number of objects (+-1)
+            sms, n_obj = ops.sm_count(), int(pts.shape[0])
+            per = -(-n_obj // max(1, sms - graph_branch_sms))
+            self.pointnet_ctas = min(sms - 1, -(-n_obj // per))
+            self.side = torch.cuda.Stream(device=self.dev)
         self.static = {}
         for key, v in example.items():
             if key.startswith('_sga'):
@@ -66,7 +77,14 @@ class CapturedInference:
             d = dict(self.static)
             if self.graph_layout is not None:
                 d['_sga_graph_layout'] = self.graph_layout
-            out = self.model(d)
+            if self.side is not None:
+                d['_sga_side_stream'] = self.side
+                ops.pointnet_set_max_ctas(self.pointnet_ctas)
+            try:
+                out = self.model(d)
+            finally:
+                if self.side is not None:
+                    ops.pointnet_set_max_ctas(0)
             emb = out['joint'] if len(self.modules) > 1 else out[self.modules[0]]
             res = matching.match_batch(emb, d, k=self.k, full_rank=False, want_sim=True, layout=self.pair_layout)
             pos = ops.match_anchor_pos(res['sim'], self.pair_layout, self.e1, self.e2) if self.n_anchor else None

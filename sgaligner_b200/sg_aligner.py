@@ -10,6 +10,7 @@ called.
 from __future__ import annotations
 
 import math
+from contextlib import nullcontext as _nullcontext
 
 import numpy as np
 import torch
@@ -214,11 +215,19 @@ class MultiModalEncoder(nn.Module):
             point_x = self.object_encoder(pts, None)
         gat_out = None
         if 'gat' in self.modules:
-            graph = data_dict.get('_sga_graph')
-            if graph is None:
-                graph = ops.BatchGraph(data_dict['edges'], np.asarray(data_dict['graph_per_obj_count']),
-                                       np.asarray(data_dict['graph_per_edge_count']), layout=data_dict.get('_sga_graph_layout'))
-            gat_out = self.structure_encoder(data_dict['tot_rel_pose'], graph)
+            # serving.CapturedInference: the graph branch on a forked stream, concurrent with the point encoder
+            side = data_dict.get('_sga_side_stream') if point_x is not None else None
+            cur = torch.cuda.current_stream()
+            if side is not None:
+                side.wait_stream(cur)
+            with torch.cuda.stream(side) if side is not None else _nullcontext():
+                graph = data_dict.get('_sga_graph')
+                if graph is None:
+                    graph = ops.BatchGraph(data_dict['edges'], np.asarray(data_dict['graph_per_obj_count']),
+                                           np.asarray(data_dict['graph_per_edge_count']), layout=data_dict.get('_sga_graph_layout'))
+                gat_out = self.structure_encoder(data_dict['tot_rel_pose'], graph)
+            if side is not None:
+                cur.wait_stream(side)
         args = []
         for module in self.modules:
             if module == 'gat':
