@@ -327,7 +327,7 @@ def run_ours(args, out=sys.stdout):
             'dtype': 'f32 (PointNet convs: bf16x3 split-operand tcgen05, fp32 accumulate)', 'data': 'synthetic',
             'config': {'workload': workload_name(), 'pairs_per_gpu': PAIRS_PER_GPU, 'objects': N,
                        'l2': 'flushed between timed steps (512 MiB memset, untimed)', 'timing': 'per-step CUDA events, max over ranks',
-                       'launch': 'one CUDA-graph replay per step (serving.CapturedInference); eager_ms_per_step = same kernels issued from Python'},
+                       'launch': 'one CUDA-graph replay per step (serving.CapturedInference: graph branch on a forked stream, 16 SMs left to it); eager_ms_per_step = same kernels issued from Python on one stream'},
             'eager_ms_per_step': eager_ms_step,
             'roofline': {'kernel': 'pointnet_fwd_tc_kernel', 'bound': 'tensor', 'achieved': achieved, 'peak': tf_peak, 'unit': 'TFLOP/s',
                          'frac': (achieved / tf_peak) if achieved else None, 'traffic': PROFILED_TRAFFIC_BYTES, 'peak_source': peak_src,

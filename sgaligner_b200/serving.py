@@ -24,7 +24,7 @@ _COUNT_KEYS = ('graph_per_obj_count', 'graph_per_edge_count', 'e1i', 'e2i')
 
 
 class CapturedInference:
-    def __init__(self, model, example: Dict, k: int = 6, want_sim: bool = True, graph_branch_sms: int = 8):
+    def __init__(self, model, example: Dict, k: int = 6, want_sim: bool = True, graph_branch_sms: int = 16):
         """``graph_branch_sms`` > 0: the point encoder (one persistent CTA per SM) leaves that many SMs free and the
         graph branch (CSR build + two GAT layers) is captured on a forked stream, so the two branches of the
         encoder run concurrently inside the graph; 0: one stream, everything back to back."""

@@ -211,15 +211,16 @@ class MultiModalEncoder(nn.Module):
         # first -- it is one long launch, and the host-side work of the graph branch (CSR offsets, four
         # short launches) is then enqueued while it runs instead of leaving the GPU idle.
         point_x = None
+        # serving.CapturedInference: the graph branch on a forked stream, concurrent with the point encoder; the
+        # fork has to precede the point-encoder launch, or the side stream would wait for it
+        side = data_dict.get('_sga_side_stream') if ('point' in self.modules and 'gat' in self.modules and ready is None) else None
+        cur = torch.cuda.current_stream()
+        if side is not None:
+            side.wait_stream(cur)
         if 'point' in self.modules and ready is None:
             point_x = self.object_encoder(pts, None)
         gat_out = None
         if 'gat' in self.modules:
-            # serving.CapturedInference: the graph branch on a forked stream, concurrent with the point encoder
-            side = data_dict.get('_sga_side_stream') if point_x is not None else None
-            cur = torch.cuda.current_stream()
-            if side is not None:
-                side.wait_stream(cur)
             with torch.cuda.stream(side) if side is not None else _nullcontext():
                 graph = data_dict.get('_sga_graph')
                 if graph is None:
