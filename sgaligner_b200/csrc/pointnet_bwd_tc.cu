@@ -226,9 +226,6 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
     const int row = 32 * q + lane;                       // TMEM lane = instance r
     const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
     const int pg = tid & 31, cg = tid >> 5;              // conv1 mapping: 8 channels (cg) x 4 rows (pg + 32 i)
-    float4 wreg[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) wreg[e] = w1b1[8 * cg + e];
 
     // persistent accumulators
     float acc3[64];                                      // dW3[cb0 + row][64*wh + j]
@@ -277,7 +274,8 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
         float f[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          float v = fmaf(wreg[e].x, xr.x, fmaf(wreg[e].y, xr.y, fmaf(wreg[e].z, xr.z, wreg[e].w)));
+          const float4 w = w1b1[8 * cg + e];     // broadcast LDS: registers are the scarce resource here (acc3)
+          float v = fmaf(w.x, xr.x, fmaf(w.y, xr.y, fmaf(w.z, xr.z, w.w)));
           f[e] = v > 0.f ? v : 0.f;
         }
         uint4 hi, lo;
@@ -313,24 +311,30 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
         // ReLU kink: a pre-activation within the bf16x3 error of zero could land on the other side of the
         // kink than in fp32, which would add / drop a whole gradient term.  Those (rare) elements are
         // recomputed on the FMA pipe in the reference summation order, so the mask is the fp32 mask.
+        uint32_t near = 0;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {      // unrolled: z / bb stay in registers; the branch is rarely taken
-          if (__any_sync(0xffffffffu, fabsf(z[e]) < tau)) {
-            const int k2 = 64 * wh + 16 * c + e;
-            const float4* wrow = reinterpret_cast<const float4*>(sm + W2F) + k2 * 16;
-            float zz = bb[e];
+        for (int e = 0; e < 16; ++e) near |= (fabsf(z[e]) < tau) ? (1u << e) : 0u;
+        if (__any_sync(0xffffffffu, near != 0)) {      // one vote per chunk; ~10 % of the chunks go on
+          const uint32_t wnear = __reduce_or_sync(0xffffffffu, near);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {                // unrolled: z / bb stay in registers
+            if (wnear & (1u << e)) {                    // warp-uniform
+              const int k2 = 64 * wh + 16 * c + e;
+              const float4* wrow = reinterpret_cast<const float4*>(sm + W2F) + k2 * 16;
+              float zz = bb[e];
 #pragma unroll 4
-            for (int k4 = 0; k4 < 16; ++k4) {
-              const float4 wv = wrow[k4];
-              const float wk[4] = {wv.x, wv.y, wv.z, wv.w};
+              for (int k4 = 0; k4 < 16; ++k4) {
+                const float4 wv = wrow[k4];
+                const float wk[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float4 w1 = w1b1[4 * k4 + u];
-                const float hv = fmaf(w1.x, me.x, fmaf(w1.y, me.y, fmaf(w1.z, me.z, w1.w)));
-                zz = fmaf(hv > 0.f ? hv : 0.f, wk[u], zz);
+                for (int u = 0; u < 4; ++u) {
+                  const float4 w1 = w1b1[4 * k4 + u];
+                  const float hv = fmaf(w1.x, me.x, fmaf(w1.y, me.y, fmaf(w1.z, me.z, w1.w)));
+                  zz = fmaf(hv > 0.f ? hv : 0.f, wk[u], zz);
+                }
               }
+              if (near & (1u << e)) z[e] = zz;
             }
-            if (fabsf(z[e]) < tau) z[e] = zz;
           }
         }
         float dz[16];
