@@ -190,7 +190,7 @@ class ClockSampler:
 def run_ours(args, out=sys.stdout):
     import torch.distributed as dist
     from sgaligner_b200 import matching, ops, synthetic, to_cuda
-    from sgaligner_b200.data import h2d_bytes, pin, to_cuda_streamed
+    from sgaligner_b200.data import h2d_bytes, needed_keys, pin, to_cuda_streamed
     from sgaligner_b200.losses import CustomMultiLossLayer, OverallLoss
     from sgaligner_b200.sg_aligner import MultiModalEncoder
     from sgaligner_b200.trainer import FlatAdam, train_step
@@ -283,17 +283,32 @@ def run_ours(args, out=sys.stdout):
     e1_host = torch.as_tensor(host['e1i']).pin_memory()
     e2_host = torch.as_tensor(host['e2i']).pin_memory()
 
+    KEYS = needed_keys(MODULES)      # the tensors this encoder configuration reads (points, poses, edges)
+
     def e2e_step():
         # everything the step consumes starts in (pinned) host memory; results end in host memory
-        d = to_cuda_streamed(host_pinned, dev, n_chunks=4)
+        d = to_cuda_streamed(host_pinned, dev, n_chunks=4, keys=KEYS)
         with torch.no_grad():
             out = model(d)
             res = matching.match_batch(out['joint'], d, k=6, full_rank=False)
             pos = ops.match_anchor_pos(res['sim'], res['layout'], e1_host.to(dev, non_blocking=True), e2_host.to(dev, non_blocking=True))
         return res['topk_idx'].cpu(), pos.cpu()
 
-    e2e_ms, _, _ = timed(e2e_step, args.steps, args.warmup)
-    e2e_ms /= args.steps
+    e2e_eager_ms, _, _ = timed(e2e_step, args.steps, args.warmup)
+    e2e_eager_ms /= args.steps
+    # the same host-to-host step as ONE graph: pinned staging buffers -> chunked H2D on a forked copy stream ->
+    # encoder (point encoder chunk by chunk as copies land) -> matching -> D2H into pinned result buffers
+    cap.capture_host_step(host, n_chunks=4)
+    e2e_graph_ms, _, _ = timed(cap.run_host, args.steps, args.warmup)
+    e2e_graph_ms /= args.steps
+    # both are public entry points for the same host-to-host step; report the faster one and say which
+    e2e_ms = min(e2e_graph_ms, e2e_eager_ms)
+    e2e_api = ('serving.CapturedInference.run_host(): one graph replay = H2D from pinned staging + step + D2H to pinned results, host sync included'
+               if e2e_graph_ms <= e2e_eager_ms else
+               'data.to_cuda_streamed + MultiModalEncoder.forward + matching.match_batch, eager launches, .cpu() of the results')
+    hres = cap.run_host()
+    tk_e, pos_e = e2e_step()
+    assert torch.equal(hres['topk_idx'], tk_e) and torch.equal(hres['anchor_pos'], pos_e), 'host-to-host graph differs from the eager e2e step'
     clocks = sampler.stop() if rank == 0 else None
     tk, pos = serve_step(data)
     d2h = tk.numel() * 4 + pos.numel() * 4
@@ -341,8 +356,10 @@ def run_ours(args, out=sys.stdout):
                          'hbm': {'achieved_gbs': BYTES_PER_OBJECT * N / (k_ms * 1e-3) / 1e9 if k_ms else None, 'peak_gbs': hbm_peak,
                                  'algorithmic_bytes_per_launch': BYTES_PER_OBJECT * N}},
             'cpu_baseline': cpu,
-            'e2e': {'value': world * PAIRS_PER_GPU / (e2e_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_ms,
-                    'h2d_bytes_per_step': h2d_bytes(host), 'd2h_bytes_per_step': int(d2h)},
+            'e2e': {'value': world * PAIRS_PER_GPU / (e2e_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_ms, 'eager_ms_per_step': e2e_eager_ms,
+                    'graph_ms_per_step': e2e_graph_ms, 'api': e2e_api,
+                    'h2d_bytes_per_step': h2d_bytes(host, KEYS), 'd2h_bytes_per_step': int(d2h),
+                    'h2d': 'pinned host batch; only the tensors the configured modalities read are copied (points, rel_pose, edges, anchors)'},
             'gpu_launches': int(launches),
             'clocks': clocks,
             'hits_at_1': hits1,

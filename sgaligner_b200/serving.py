@@ -113,6 +113,97 @@ class CapturedInference:
         self.graph.replay()
         return self.out
 
+    # ------------------------------------------------------------------ host-to-host step in one graph
+    def capture_host_step(self, host_batch: Dict, n_chunks: int = 8):
+        """Second graph for batches that start in HOST memory: pinned staging buffers (returned; a loader collates
+        into them in place) -> H2D copies on a forked copy stream (small tensors first, then the points in
+        ``n_chunks`` object ranges) -> graph branch as soon as the small tensors have landed, point encoder chunk by
+        chunk as the copies land -> matching head -> D2H of top-k / anchor positions into pinned result buffers.
+        Only the tensors the configured modalities read are staged (``data.needed_keys``)."""
+        from .data import needed_keys
+        self.check_layout(host_batch)
+        keys = [k for k in needed_keys(self.modules) if k in self.static and torch.is_tensor(self.static[k])]
+        self.host_in = {k: torch.empty(self.static[k].shape, dtype=self.static[k].dtype).pin_memory() for k in keys}
+        self.host_e1 = torch.empty(self.n_anchor, dtype=torch.int32).pin_memory()
+        self.host_e2 = torch.empty(self.n_anchor, dtype=torch.int32).pin_memory()
+        self.fill_host(host_batch)
+        N = int(self.static['tot_obj_pts'].shape[0])
+        per = -(-N // max(1, n_chunks))
+        ranges = [(s, min(N, s + per)) for s in range(0, N, per)]
+        cs = torch.cuda.Stream(device=self.dev)
+        self.host_out = {}
+
+        def body():
+            cur = torch.cuda.current_stream(self.dev)
+            cs.wait_stream(cur)
+            with torch.cuda.stream(cs):
+                for k in keys:
+                    if k != 'tot_obj_pts':
+                        self.static[k].copy_(self.host_in[k], non_blocking=True)
+                if self.n_anchor:
+                    self.e1.copy_(self.host_e1, non_blocking=True)
+                    self.e2.copy_(self.host_e2, non_blocking=True)
+                ev_small = torch.cuda.Event()
+                ev_small.record(cs)
+                chunks = []
+                if 'tot_obj_pts' in self.host_in:
+                    for (a, b) in ranges:
+                        self.static['tot_obj_pts'][a:b].copy_(self.host_in['tot_obj_pts'][a:b], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(cs)
+                        chunks.append((a, b, ev))
+            with torch.no_grad():
+                d = dict(self.static)
+                if self.graph_layout is not None:
+                    d['_sga_graph_layout'] = self.graph_layout
+                d['_sga_ready'] = {'small': ev_small, 'pts': chunks, 'stream': cs}
+                out = self.model(d)
+                emb = out['joint'] if len(self.modules) > 1 else out[self.modules[0]]
+                res = matching.match_batch(emb, d, k=self.k, full_rank=False, want_sim=True, layout=self.pair_layout)
+                pos = ops.match_anchor_pos(res['sim'], self.pair_layout, self.e1, self.e2) if self.n_anchor else None
+                if 'topk_idx' not in self.host_out:
+                    self.host_out['topk_idx'] = torch.empty(res['topk_idx'].shape, dtype=torch.int32).pin_memory()
+                    if pos is not None:
+                        self.host_out['anchor_pos'] = torch.empty(pos.shape, dtype=torch.int32).pin_memory()
+                self.host_out['topk_idx'].copy_(res['topk_idx'], non_blocking=True)
+                if pos is not None:
+                    self.host_out['anchor_pos'].copy_(pos, non_blocking=True)
+            cur.wait_stream(cs)
+            return {'embeddings': out, 'topk_idx': res['topk_idx'], 'anchor_pos': pos, 'sim': res['sim']}
+
+        was_training = self.model.training
+        self.model.eval()
+        cur = torch.cuda.current_stream(self.dev)
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            body()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        self.graph_host = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_host):
+            self.out_host = body()
+        if was_training:
+            self.model.train()
+        return self.host_in
+
+    def fill_host(self, host_batch: Dict):
+        """Slow path: copy a host batch into the pinned staging buffers (a production loader collates into
+        ``host_in`` directly)."""
+        self.check_layout(host_batch)
+        for k, dst in self.host_in.items():
+            dst.copy_(host_batch[k])
+        if self.n_anchor:
+            self.host_e1.copy_(torch.as_tensor(np.asarray(host_batch['e1i']).astype(np.int32)))
+            self.host_e2.copy_(torch.as_tensor(np.asarray(host_batch['e2i']).astype(np.int32)))
+
+    def run_host(self) -> Dict:
+        """One replay of the host-to-host graph on the staging buffers' current content; blocks until the pinned
+        results (``topk_idx``, ``anchor_pos``) are valid."""
+        self.graph_host.replay()
+        torch.cuda.current_stream(self.dev).synchronize()
+        return self.host_out
+
     def __call__(self, batch: Dict, **kw) -> Dict:
         self.load(batch, **kw)
         return self.replay()

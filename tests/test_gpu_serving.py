@@ -51,3 +51,26 @@ def test_captured_inference_matches_eager_and_replays(dev):
     other = to_cuda(dict(synthetic.make_batch([9, 12, 7, 31], nr, na, n_points=256, edge_mode='complete', seed=5)), dev)
     with pytest.raises(ValueError):
         cap(other)
+
+
+def test_captured_host_to_host_step(dev):
+    """H2D staging + encoder + matching + D2H in one graph: same top-k / anchor positions as the eager path, for
+    the captured batch and for another batch of the same layout written into the staging buffers."""
+    from sgaligner_b200 import synthetic, to_cuda
+    from sgaligner_b200.serving import CapturedInference
+    from sgaligner_b200.sg_aligner import MultiModalEncoder
+    torch.manual_seed(0)
+    for modules in (['point', 'gat'], ['point', 'gat', 'rel', 'attr']):
+        model = MultiModalEncoder(modules=modules, rel_dim=41, attr_dim=164).to(dev).eval()
+        ns, nr, na = [9, 12, 7, 30], [11, 8, 10, 25], [5, 6, 4, 12]
+        host_a = synthetic.make_batch(ns, nr, na, n_points=256, edge_mode='complete', seed=5)
+        host_b = synthetic.make_batch(ns, nr, na, n_points=256, edge_mode='complete', seed=6)
+        cap = CapturedInference(model, to_cuda(dict(host_a), dev), k=6)
+        cap.capture_host_step(host_a, n_chunks=3)
+        for host in (host_a, host_b, host_a):
+            cap.fill_host(host)
+            got = cap.run_host()
+            out, res, pos = _eager(model, to_cuda(dict(host), dev), 6)
+            torch.cuda.synchronize()
+            assert torch.equal(got['topk_idx'], res['topk_idx'].cpu())
+            assert torch.equal(got['anchor_pos'], pos.cpu())
