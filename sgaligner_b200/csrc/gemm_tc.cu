@@ -15,30 +15,10 @@
 // loaders (half an operand row / half an MN atom each, the global loads of chunk c+1 in flight while
 // chunk c is normalised, split and stored), 1 MMA issuer (elect.sync), 4 epilogue warps (one TMEM lane
 // quarter each).
-#include "common.cuh"
+#include "gemm_tc.cuh"
 #include "umma_tf32.cuh"
 
 namespace sga {
-
-struct GemmOperand {
-  const float* p;
-  int64_t ld;
-  const int32_t* idx;   // optional row gather
-  const float* div;     // optional per-(source)-row divisor (L2 norm, clamped by the caller)
-  int mn_major;
-};
-
-struct GemmParams {
-  GemmOperand A, B;
-  int M, N, K;
-  float* C;
-  int64_t ldc;
-  int mode;               // 0 store, 1 store + exp-sums, 2 scatter-add rows (atomicAdd C[c_idx[m]][n])
-  const int32_t* c_idx;   // mode 2
-  int es_c0, es_split;    // mode 1: columns >= es_c0 feed the sums; < es_split -> S_lo else S_hi
-  double* s01_lo; double* s01_hi; double* s1_lo; double* s1_hi;   // sum exp(x/0.1), sum exp(x)
-  int ksplit;             // mode 2 only: the K range is cut into ksplit slices, each adds its partial product
-};
 
 namespace {
 
@@ -46,7 +26,8 @@ constexpr int kStages = 3;
 constexpr int kLoaders = 256;
 constexpr int kThreads = kLoaders + 32 + 128;
 constexpr uint32_t BAR_OFF = kStages * tf32x3::kStageBytes;
-constexpr uint32_t SMEM_BYTES = BAR_OFF + 256 + 1024;
+constexpr uint32_t XPOSE_OFF = BAR_OFF + 256;                 // 4 epilogue warps x [32][33] fp32 transpose tiles
+constexpr uint32_t SMEM_BYTES = XPOSE_OFF + 4 * 32 * 33 * 4 + 1024;
 
 // One loader thread's share of a [128 x 32] operand tile for one K chunk: 16 fp32 values held in registers
 // between the global load and the conversion (so that the next chunk's loads overlap this chunk's work).
@@ -55,22 +36,39 @@ struct Piece {
   float d;        // divisor of these values (1 when the operand is not normalised)
 };
 
+// Where one loader thread's values come from: the (gathered) source row, resolved once per tile for a K-major
+// operand (the row does not change along K) and one chunk AHEAD for an MN-major operand (the gathered row is the
+// contraction index), so that the index -> divisor -> data dependency chain is never on the critical path.
+struct RowSrc {
+  const float* p;
+  float d;
+  bool valid;
+};
+
 // K-major operand: thread t -> tile row t/2, features [16*(t&1), +16) of the chunk.
-__device__ __forceinline__ void fetch_k(Piece& f, const GemmOperand& X, int row0, int nrows, int k0, int K, int t, bool vec_ok) {
-  const int r = t >> 1, kb = k0 + 16 * (t & 1);
-  const bool valid = r < nrows;
+__device__ __forceinline__ RowSrc src_k(const GemmOperand& X, int row0, int nrows, int t) {
+  const int r = t >> 1;
+  RowSrc s;
+  s.valid = r < nrows;
+  s.d = 1.f;
   int64_t sr = 0;
-  f.d = 1.f;
-  if (valid) {
+  if (s.valid) {
     sr = X.idx ? (int64_t)X.idx[row0 + r] : (int64_t)(row0 + r);
-    if (X.div) f.d = X.div[sr];
+    if (X.div) s.d = X.div[sr];
   }
-  const float* p = X.p + sr * X.ld + kb;
+  s.p = X.p + sr * X.ld + 16 * (t & 1);
+  return s;
+}
+
+__device__ __forceinline__ void fetch_k(Piece& f, const RowSrc& s, int k0, int K, int t, bool vec_ok) {
+  const int kb = k0 + 16 * (t & 1);
+  f.d = s.d;
+  const float* p = s.p + k0;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
     const int k = kb + 4 * j;
-    if (valid) {
+    if (s.valid) {
       if (vec_ok && k + 3 < K) {
         q = *reinterpret_cast<const float4*>(p + 4 * j);
       } else {
@@ -114,23 +112,30 @@ __device__ __forceinline__ void store_k(uint32_t hi, uint32_t lo, const Piece& f
 // 32-byte chunk index XORed with (k & 3).  Here: the 32 k-rows of one 32-wide MN atom are contiguous
 // (128 B apart; 4-row atoms 512 B apart = SBO), MN atoms 4096 B apart (= LBO).
 // Thread t -> k row (t & 31), MN atom (t >> 5) & 3, half (16 mn values) t >> 7.
-__device__ __forceinline__ void fetch_mn(Piece& f, const GemmOperand& X, int mn0, int MN, int k0, int K, int t, bool vec_ok) {
-  const int kk = t & 31, qd = (t >> 5) & 3, half = t >> 7;
-  const int krow = k0 + kk;
-  const bool kvalid = krow < K;
+__device__ __forceinline__ RowSrc src_mn(const GemmOperand& X, int k0, int K, int t) {
+  const int krow = k0 + (t & 31);
+  RowSrc s;
+  s.valid = krow < K;
+  s.d = 1.f;
   int64_t sr = 0;
-  f.d = 1.f;
-  if (kvalid) {
+  if (s.valid) {
     sr = X.idx ? (int64_t)X.idx[krow] : (int64_t)krow;
-    if (X.div) f.d = X.div[sr];
+    if (X.div) s.d = X.div[sr];
   }
+  s.p = X.p + sr * X.ld;
+  return s;
+}
+
+__device__ __forceinline__ void fetch_mn(Piece& f, const RowSrc& s, int mn0, int MN, int t, bool vec_ok) {
+  const int qd = (t >> 5) & 3, half = t >> 7;
+  f.d = s.d;
   const int c0 = mn0 + 32 * qd + 16 * half;
-  const float* p = X.p + sr * X.ld + c0;
+  const float* p = s.p + c0;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
     const int c = c0 + 4 * j;
-    if (kvalid) {
+    if (s.valid) {
       if (vec_ok && c + 3 < MN) {
         q = *reinterpret_cast<const float4*>(p + 4 * j);
       } else {
@@ -187,9 +192,22 @@ __device__ __forceinline__ void issue_stage_any(uint32_t d_tmem, uint32_t stage_
   }
 }
 
+// Work item `work` of the group -> (problem, item inside the problem)
+struct WorkItem {
+  int g, local;
+};
+__device__ __forceinline__ WorkItem find_work(const GemmGroup& G, int work) {
+  int g = 0, beg = 0;
+  while (g + 1 < G.n && work >= G.work_end[g]) {
+    beg = G.work_end[g];
+    ++g;
+  }
+  return {g, work - beg};
+}
+
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tf32x3_kernel(const GemmParams P) {
+gemm_tf32x3_kernel(const __grid_constant__ GemmGroup G) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sm_base = ptx::smem_u32(sm);
@@ -198,6 +216,7 @@ gemm_tf32x3_kernel(const GemmParams P) {
   uint64_t* acc_full = empty + kStages;    // [2]
   uint64_t* acc_free = acc_full + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
+  float* xpose = reinterpret_cast<float*>(sm + XPOSE_OFF);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
@@ -216,35 +235,49 @@ gemm_tf32x3_kernel(const GemmParams P) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-
-  const int ntm = (P.M + 127) / 128, ntn = (P.N + 127) / 128;
-  const int ksplit = P.ksplit > 1 ? P.ksplit : 1;
-  const int ntiles = ntm * ntn * ksplit;          // work items: (output tile, K slice)
-  const int nkc_all = (P.K + 31) / 32;
-  const int kc_per = (nkc_all + ksplit - 1) / ksplit;
+  const int nwork = G.work_end[G.n - 1];
 
   if (warp < 8) {
     // ------------------------------- operand loaders
-    const bool a_vec = (P.A.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.A.p) & 15) == 0);
-    const bool b_vec = (P.B.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.B.p) & 15) == 0);
-    const bool a_div = P.A.div != nullptr, b_div = P.B.div != nullptr;
     int it = 0;
-    for (int work = blockIdx.x; work < ntiles; work += gridDim.x) {
-      const int tile = work / ksplit, ksl = work % ksplit;
+    for (int work = blockIdx.x; work < nwork; work += gridDim.x) {
+      const WorkItem wi = find_work(G, work);
+      const GemmParams& P = G.p[wi.g];
+      const bool a_vec = (P.A.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.A.p) & 15) == 0);
+      const bool b_vec = (P.B.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.B.p) & 15) == 0);
+      const bool a_div = P.A.div != nullptr, b_div = P.B.div != nullptr;
+      const int ntn = (P.N + 127) / 128;
+      const int ksplit = P.ksplit > 1 ? P.ksplit : 1;
+      const int nkc_all = (P.K + 31) / 32;
+      const int kc_per = (nkc_all + ksplit - 1) / ksplit;
+      const int tile = wi.local / ksplit, ksl = wi.local % ksplit;
       const int m0 = (tile / ntn) * 128, n0 = (tile % ntn) * 128;
       const int kc_beg = ksl * kc_per, kc_end = min(nkc_all, kc_beg + kc_per);
+      if (kc_beg >= kc_end) continue;
+      RowSrc sa = A_MN ? src_mn(P.A, kc_beg * 32, P.K, tid) : src_k(P.A, m0, P.M - m0, tid);
+      RowSrc sb = B_MN ? src_mn(P.B, kc_beg * 32, P.K, tid) : src_k(P.B, n0, P.N - n0, tid);
       auto fetch = [&](Piece& fa, Piece& fb, int kc) {
-        if (A_MN) fetch_mn(fa, P.A, m0, P.M, kc * 32, P.K, tid, a_vec);
-        else fetch_k(fa, P.A, m0, P.M - m0, kc * 32, P.K, tid, a_vec);
-        if (B_MN) fetch_mn(fb, P.B, n0, P.N, kc * 32, P.K, tid, b_vec);
-        else fetch_k(fb, P.B, n0, P.N - n0, kc * 32, P.K, tid, b_vec);
+        if (A_MN) fetch_mn(fa, sa, m0, P.M, tid, a_vec);
+        else fetch_k(fa, sa, kc * 32, P.K, tid, a_vec);
+        if (B_MN) fetch_mn(fb, sb, n0, P.N, tid, b_vec);
+        else fetch_k(fb, sb, kc * 32, P.K, tid, b_vec);
+      };
+      auto advance_src = [&](int kc) {       // MN-major: resolve the gathered rows of chunk kc (one chunk ahead of its data)
+        if (kc < kc_end) {
+          if (A_MN) sa = src_mn(P.A, kc * 32, P.K, tid);
+          if (B_MN) sb = src_mn(P.B, kc * 32, P.K, tid);
+        }
       };
       Piece fa, fb;
-      if (kc_beg < kc_end) fetch(fa, fb, kc_beg);
+      fetch(fa, fb, kc_beg);
+      advance_src(kc_beg + 1);
       for (int kc = kc_beg; kc < kc_end; ++kc, ++it) {
         const int s = it % kStages;
         const Piece ca = fa, cb = fb;
-        if (kc + 1 < kc_end) fetch(fa, fb, kc + 1);      // in flight during the conversion below
+        if (kc + 1 < kc_end) {                // in flight during the conversion below
+          fetch(fa, fb, kc + 1);
+          advance_src(kc + 2);
+        }
         if (it >= kStages) ptx::mbar_wait(&empty[s], (uint32_t)(((it / kStages) - 1) & 1));
         const uint32_t st = sm_base + s * tf32x3::kStageBytes;
         if (A_MN) store_mn(st, st + tf32x3::kTileBytes, ca, a_div, tid);
@@ -260,8 +293,13 @@ gemm_tf32x3_kernel(const GemmParams P) {
     const uint32_t idesc = ptx::make_idesc(2, 128, 128) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
     int it = 0, ti = 0;
-    for (int work = blockIdx.x; work < ntiles; work += gridDim.x, ++ti) {
-      const int ksl = work % ksplit;
+    for (int work = blockIdx.x; work < nwork; work += gridDim.x, ++ti) {
+      const WorkItem wi = find_work(G, work);
+      const GemmParams& P = G.p[wi.g];
+      const int ksplit = P.ksplit > 1 ? P.ksplit : 1;
+      const int nkc_all = (P.K + 31) / 32;
+      const int kc_per = (nkc_all + ksplit - 1) / ksplit;
+      const int ksl = wi.local % ksplit;
       const int kc_beg = ksl * kc_per, kc_end = min(nkc_all, kc_beg + kc_per);
       const int ab = ti & 1;
       if (ti >= 2) {
@@ -286,10 +324,33 @@ gemm_tf32x3_kernel(const GemmParams P) {
     // ------------------------------- epilogue
     const int q = warp & 3;
     const int r = 32 * q + lane;
-    float s_acc[4] = {0.f, 0.f, 0.f, 0.f};   // {s01_lo, s01_hi, s1_lo, s1_hi}
+    float s_acc[4] = {0.f, 0.f, 0.f, 0.f};   // {s01_lo, s01_hi, s1_lo, s1_hi} of problem `cur_g`
+    int cur_g = -1;
+    auto flush_sums = [&]() {
+      if (cur_g < 0) return;
+      const GemmParams& Q = G.p[cur_g];
+      if (Q.mode != 1) return;
+      double* dst[4] = {Q.s01_lo, Q.s01_hi, Q.s1_lo, Q.s1_hi};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float s = warp_sum(s_acc[i]);
+        if (lane == 0 && dst[i] && s != 0.f) atomicAdd(dst[i], (double)s);
+        s_acc[i] = 0.f;
+      }
+    };
     int ti = 0;
-    for (int work = blockIdx.x; work < ntiles; work += gridDim.x, ++ti) {
-      const int tile = work / ksplit, ksl = work % ksplit;
+    for (int work = blockIdx.x; work < nwork; work += gridDim.x, ++ti) {
+      const WorkItem wi = find_work(G, work);
+      if (wi.g != cur_g) {
+        flush_sums();
+        cur_g = wi.g;
+      }
+      const GemmParams& P = G.p[wi.g];
+      const int ntn = (P.N + 127) / 128;
+      const int ksplit = P.ksplit > 1 ? P.ksplit : 1;
+      const int nkc_all = (P.K + 31) / 32;
+      const int kc_per = (nkc_all + ksplit - 1) / ksplit;
+      const int tile = wi.local / ksplit, ksl = wi.local % ksplit;
       const int m0 = (tile / ntn) * 128, n0 = (tile % ntn) * 128;
       const int ab = ti & 1;
       ptx::mbar_wait(&acc_full[ab], (uint32_t)((ti >> 1) & 1));
@@ -304,13 +365,24 @@ gemm_tf32x3_kernel(const GemmParams P) {
         uint32_t v[32];
         ptx::tmem_ld32(base + cc * 32, v);
         ptx::tmem_ld_wait();
-        if (row_ok) {
+        if (P.mode == 2) {
+          // scatter-add through a shared-memory transpose: lanes own consecutive COLUMNS of one output row, so each
+          // warp-level reduction is one contiguous <=128-byte request instead of 32 scattered ones
           const int c0 = n0 + cc * 32;
-          if (P.mode == 2) {
+          float* xt = xpose + (warp & 3) * (32 * 33);
 #pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (c0 + e < P.N) atomicAdd(crow + c0 + e, __uint_as_float(v[e]));
-          } else {
+          for (int e = 0; e < 32; ++e) xt[lane * 33 + e] = __uint_as_float(v[e]);
+          __syncwarp();
+          const unsigned long long cptr = reinterpret_cast<unsigned long long>(crow);   // 0 when this lane's row is out of range
+#pragma unroll 4
+          for (int rr = 0; rr < 32; ++rr) {
+            float* dst = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, cptr, rr));
+            if (dst && c0 + lane < P.N) atomicAdd(dst + c0 + lane, xt[rr * 33 + lane]);
+          }
+          __syncwarp();
+        } else if (row_ok) {
+          const int c0 = n0 + cc * 32;
+          {
             if (c0 + 31 < P.N && (P.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0)) {
 #pragma unroll
               for (int e = 0; e < 32; e += 4)
@@ -340,14 +412,7 @@ gemm_tf32x3_kernel(const GemmParams P) {
       ptx::tc_fence_before();
       ptx::mbar_arrive(&acc_free[ab]);
     }
-    if (P.mode == 1) {
-      double* dst[4] = {P.s01_lo, P.s01_hi, P.s1_lo, P.s1_hi};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float s = warp_sum(s_acc[i]);
-        if (lane == 0 && dst[i] && s != 0.f) atomicAdd(dst[i], (double)s);
-      }
-    }
+    flush_sums();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -356,8 +421,13 @@ gemm_tf32x3_kernel(const GemmParams P) {
 
 }  // namespace
 
-int launch_gemm_tc(const GemmParams& P, cudaStream_t st) {
-  if (P.M <= 0 || P.N <= 0 || P.K <= 0) return SGA_OK;
+namespace {
+inline int work_items(const GemmParams& P) {
+  return ((P.M + 127) / 128) * ((P.N + 127) / 128) * (P.ksplit > 1 ? P.ksplit : 1);
+}
+}  // namespace
+
+int launch_gemm_tc_group(const GemmParams* problems, int n, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
     SGA_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
@@ -365,22 +435,43 @@ int launch_gemm_tc(const GemmParams& P, cudaStream_t st) {
     SGA_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     attr_done = true;
   }
-  if (P.ksplit > 1 && P.mode != 2) {
-    set_error("gemm_tc: split-K needs the scatter-add epilogue");
-    return SGA_EINVAL;
+  int i = 0;
+  while (i < n) {
+    GemmGroup G;
+    memset(&G, 0, sizeof(G));
+    int total = 0;
+    const int a_mn = problems[i].A.mn_major, b_mn = problems[i].B.mn_major;
+    for (; i < n && G.n < kGemmMaxGroup; ++i) {
+      const GemmParams& P = problems[i];
+      if (P.M <= 0 || P.N <= 0 || P.K <= 0) continue;
+      if (P.A.mn_major != a_mn || P.B.mn_major != b_mn) {
+        set_error("gemm_tc: the problems of one group must share the operand layouts");
+        return SGA_EINVAL;
+      }
+      if (P.ksplit > 1 && P.mode != 2) {
+        set_error("gemm_tc: split-K needs the scatter-add epilogue");
+        return SGA_EINVAL;
+      }
+      total += work_items(P);
+      G.p[G.n] = P;
+      G.work_end[G.n] = total;
+      ++G.n;
+    }
+    if (G.n == 0) continue;
+    const int grid = total < sm_count() ? total : sm_count();
+    if (!a_mn && !b_mn) gemm_tf32x3_kernel<false, false><<<grid, kThreads, SMEM_BYTES, st>>>(G);
+    else if (!a_mn && b_mn) gemm_tf32x3_kernel<false, true><<<grid, kThreads, SMEM_BYTES, st>>>(G);
+    else if (a_mn && b_mn) gemm_tf32x3_kernel<true, true><<<grid, kThreads, SMEM_BYTES, st>>>(G);
+    else {
+      set_error("gemm_tc: (A MN-major, B K-major) is not instantiated");
+      return SGA_EINVAL;
+    }
+    SGA_LAUNCH_CHECK();
   }
-  const int ntiles = ((P.M + 127) / 128) * ((P.N + 127) / 128) * (P.ksplit > 1 ? P.ksplit : 1);
-  int grid = ntiles < sm_count() ? ntiles : sm_count();
-  if (!P.A.mn_major && !P.B.mn_major) gemm_tf32x3_kernel<false, false><<<grid, kThreads, SMEM_BYTES, st>>>(P);
-  else if (!P.A.mn_major && P.B.mn_major) gemm_tf32x3_kernel<false, true><<<grid, kThreads, SMEM_BYTES, st>>>(P);
-  else if (P.A.mn_major && P.B.mn_major) gemm_tf32x3_kernel<true, true><<<grid, kThreads, SMEM_BYTES, st>>>(P);
-  else {
-    set_error("gemm_tc: (A MN-major, B K-major) is not instantiated");
-    return SGA_EINVAL;
-  }
-  SGA_LAUNCH_CHECK();
   return SGA_OK;
 }
+
+int launch_gemm_tc(const GemmParams& P, cudaStream_t st) { return launch_gemm_tc_group(&P, 1, st); }
 
 }  // namespace sga
 

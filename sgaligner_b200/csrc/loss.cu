@@ -15,29 +15,9 @@
 // gathers are fused into the operand loader, the normaliser sums into the forward epilogue, and the
 // backward GEMMs scatter-add straight into d(normalised embedding); F1/F2 are materialised in HBM
 // (A x T fp32 each) because the element-wise loss terms need the global normalisers first.
-#include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace sga {
-
-struct GemmOperand {
-  const float* p;
-  int64_t ld;
-  const int32_t* idx;
-  const float* div;
-  int mn_major;
-};
-struct GemmParams {
-  GemmOperand A, B;
-  int M, N, K;
-  float* C;
-  int64_t ldc;
-  int mode;
-  const int32_t* c_idx;
-  int es_c0, es_split;
-  double* s01_lo; double* s01_hi; double* s1_lo; double* s1_hi;
-  int ksplit;
-};
-int launch_gemm_tc(const GemmParams& P, cudaStream_t st);   // gemm_tc.cu
 
 namespace {
 
@@ -48,7 +28,7 @@ struct Layout {
   // byte offsets into the workspace
   size_t scal;                // doubles: S[n_emb][2][4], dS[n_emb][2][4], icl_raw[n_emb], ial_raw[n_emb]
   size_t ridx, r2idx;         // int32 [T]: rows [e2i;e1j;e2j] and [e1i;e2j;e1j]
-  size_t norms[17], den[17], F1[17], F2[17], dXh[17];
+  size_t norms[17], Xh[17], F1[17], F2[17], dXh[17];
   size_t acc1, acc2;
   size_t total;
   int ldF;
@@ -69,7 +49,7 @@ Layout make_layout(int n_emb, const int* dims, int64_t N, int A, int J1, int J2,
   for (int x = 0; x < n_emb; ++x) {
     const size_t d = dims[x];
     L.norms[x] = o; o = al256(o + 4 * (size_t)N);
-    L.den[x] = o; o = al256(o + 4 * (size_t)N);
+    L.Xh[x] = o; o = al256(o + 4 * (size_t)N * d);
     L.F1[x] = o; o = al256(o + 4 * (size_t)A * L.ldF);
     L.F2[x] = o; o = al256(o + 4 * (size_t)A * L.ldF);
     if (want_grad) { L.dXh[x] = o; o = al256(o + 4 * (size_t)N * d); }
@@ -83,8 +63,10 @@ Layout make_layout(int n_emb, const int* dims, int64_t N, int A, int J1, int J2,
 }
 
 // ------------------------------------------------------------------------------------------
+// norms[row] = ||X[row]||, Xh[row] = F.normalize(X)[row] = X[row] / max(||X[row]||, 1e-12) (losses.py:44,69-70):
+// the normalised rows are written ONCE here, so the GEMM operand loaders only gather, split and store.
 __global__ void __launch_bounds__(NT)
-row_norm_kernel(const float* __restrict__ X, int64_t N, int D, float* __restrict__ norms, float* __restrict__ den) {
+row_norm_kernel(const float* __restrict__ X, int64_t N, int D, float* __restrict__ norms, float* __restrict__ Xh) {
   int64_t row = (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
   if (row >= N) return;
   int lane = threadIdx.x & 31;
@@ -94,10 +76,10 @@ row_norm_kernel(const float* __restrict__ X, int64_t N, int D, float* __restrict
     s = fmaf(v, v, s);
   }
   s = warp_sum(s);
-  if (lane == 0) {
-    norms[row] = sqrtf(s);
-    den[row] = fmaxf(sqrtf(s), 1e-12f);    // F.normalize: x / max(||x||, eps)
-  }
+  const float nrm = sqrtf(s);
+  const float den = fmaxf(nrm, 1e-12f);    // F.normalize: x / max(||x||, eps)
+  if (lane == 0) norms[row] = nrm;
+  for (int k = lane; k < D; k += 32) Xh[row * D + k] = X[row * D + k] / den;
 }
 
 // ridx = [e2i; e1j; e2j], r2idx = [e1i; e2j; e1j]
@@ -131,19 +113,21 @@ __device__ __forceinline__ void block_reduce_add(float (&v)[NV], double* const* 
 
 struct QD { float q, dg, dsa, dsb; };
 
-// calculate_prob_dist element (losses.py:5-15) and its partial derivatives
-__device__ __forceinline__ QD cpd(float g, float tau, float sa, float sb) {
+// calculate_prob_dist element (losses.py:5-15) and its partial derivatives.  `isa`, `isb` = 1 / (S + 1e-9) (one exact
+// division per launch); the per-element reciprocals use the SFU (MUFU.RCP / EX2, ~2 ulp): the element-wise pass is
+// ALU bound (6 of these per modal element) and feeds sums checked at 1e-3.
+__device__ __forceinline__ QD cpd(float g, float inv_tau, float isa, float isb) {
   QD r;
-  const float mx = expf(g / tau);
-  const float r1 = mx / sa, r2 = mx / sb;
-  const float u1 = r1 + kEps, u2 = r2 + kEps;
-  const float inv = 1.f + 1.f / u1 + 1.f / u2;
-  r.q = 1.f / (inv + kEps);
+  const float mx = __expf(g * inv_tau);
+  const float r1 = mx * isa, r2 = mx * isb;
+  const float iu1 = __fdividef(1.f, r1 + kEps), iu2 = __fdividef(1.f, r2 + kEps);
+  const float inv = 1.f + iu1 + iu2;
+  r.q = __fdividef(1.f, inv + kEps);
   const float q2 = r.q * r.q;
-  const float t1 = q2 / (u1 * u1) * r1, t2 = q2 / (u2 * u2) * r2;
-  r.dg = (t1 + t2) / tau;
-  r.dsa = -t1 / sa;
-  r.dsb = -t2 / sb;
+  const float t1 = q2 * iu1 * iu1 * r1, t2 = q2 * iu2 * iu2 * r2;
+  r.dg = (t1 + t2) * inv_tau;
+  r.dsa = -t1 * isa;
+  r.dsb = -t2 * isb;
   return r;
 }
 
@@ -167,30 +151,30 @@ pair_kernel(PairArgs p) {
   const float invA2 = 1.f / ((float)A * (float)A);
   const float c_icl = (p.lv_icl ? expf(-p.lv_icl[0]) : 1.f) * invA2;
   const float c_ial = p.modal ? p.zoom * expf(-p.lv_ial[0]) * 0.1f * 0.5f : 0.f;
-  float sm[2][4], sj[4];
+  float ism[2][4], isj[4];     // reciprocals of the normalisers (+1e-9, losses.py:12-13)
 #pragma unroll
   for (int t = 0; t < 2; ++t)
 #pragma unroll
-    for (int s = 0; s < 4; ++s) sm[t][s] = (float)p.Sm[t * 4 + s] + kEps;
+    for (int s = 0; s < 4; ++s) ism[t][s] = 1.f / ((float)p.Sm[t * 4 + s] + kEps);
 #pragma unroll
-  for (int s = 0; s < 4; ++s) sj[s] = p.modal ? (float)p.Sj[4 + s] + kEps : 1.f;
+  for (int s = 0; s < 4; ++s) isj[s] = p.modal ? 1.f / ((float)p.Sj[4 + s] + kEps) : 1.f;
   // accumulators: 0 icl, 1 ial, 2..5 dSm[0.1], 6..9 dSm[1.0], 10..13 dSj[1.0]
   float acc[14];
 #pragma unroll
   for (int i = 0; i < 14; ++i) acc[i] = 0.f;
-  const int64_t total = (int64_t)A * A;
-  for (int64_t t = (int64_t)blockIdx.x * NT + threadIdx.x; t < total; t += (int64_t)gridDim.x * NT) {
-    const int64_t a = t / A, b = t % A;
-    const int64_t off = a * T + b;
+  for (int a = blockIdx.x; a < A; a += gridDim.x) {
+   const int64_t rowF = (int64_t)a * T, rowA = (int64_t)a * A;
+   for (int b = threadIdx.x; b < A; b += NT) {
+    const int64_t off = rowF + b;
     const float g1 = p.F1m[off], g2 = p.F2m[off];
     // ---- ICL, tau = 0.1 (losses.py:43-58)
-    QD q12 = cpd(g1, 0.1f, sm[0][0], sm[0][1]);
-    QD q21 = cpd(g2, 0.1f, sm[0][2], sm[0][3]);
+    QD q12 = cpd(g1, 10.f, ism[0][0], ism[0][1]);
+    QD q21 = cpd(g2, 10.f, ism[0][2], ism[0][3]);
     const float w = 0.5f * q12.q + 0.5f * q21.q;
-    acc[0] += -logf(w);
+    acc[0] += -__logf(w);
     float d1 = 0.f, d2 = 0.f;
     if (p.want_grad) {
-      const float dq = -0.5f / w * c_icl;
+      const float dq = __fdividef(-0.5f * c_icl, w);
       d1 = dq * q12.dg;
       d2 = dq * q21.dg;
       acc[2] += dq * q12.dsa; acc[3] += dq * q12.dsb;
@@ -198,34 +182,35 @@ pair_kernel(PairArgs p) {
     }
     if (p.modal) {
       // ---- IAL, tau = 1.0 (losses.py:68-97): target = modal q, input = log(joint q)
-      QD o12 = cpd(g1, 1.f, sm[1][0], sm[1][1]);
-      QD o21 = cpd(g2, 1.f, sm[1][2], sm[1][3]);
+      QD o12 = cpd(g1, 1.f, ism[1][0], ism[1][1]);
+      QD o21 = cpd(g2, 1.f, ism[1][2], ism[1][3]);
       const float j1 = p.F1j[off], j2 = p.F2j[off];
-      QD m12 = cpd(j1, 1.f, sj[0], sj[1]);
-      QD m21 = cpd(j2, 1.f, sj[2], sj[3]);
-      const float ea = expf(o12.q), eb = expf(o21.q);
-      const float la = o12.q - logf(m12.q), lb = o21.q - logf(m21.q);
+      QD m12 = cpd(j1, 1.f, isj[0], isj[1]);
+      QD m21 = cpd(j2, 1.f, isj[2], isj[3]);
+      const float ea = __expf(o12.q), eb = __expf(o21.q);
+      const float la = o12.q - __logf(m12.q), lb = o21.q - __logf(m21.q);
       acc[1] += 0.5f * (ea * la + eb * lb);
       if (p.want_grad) {
         const float dqo12 = c_ial * ea * (la + 1.f), dqo21 = c_ial * eb * (lb + 1.f);
-        const float dqm12 = -c_ial * ea / m12.q, dqm21 = -c_ial * eb / m21.q;
+        const float dqm12 = __fdividef(-c_ial * ea, m12.q), dqm21 = __fdividef(-c_ial * eb, m21.q);
         d1 += dqo12 * o12.dg;
         d2 += dqo21 * o21.dg;
         acc[6] += dqo12 * o12.dsa; acc[7] += dqo12 * o12.dsb;
         acc[8] += dqo21 * o21.dsa; acc[9] += dqo21 * o21.dsb;
         acc[10] += dqm12 * m12.dsa; acc[11] += dqm12 * m12.dsb;
         acc[12] += dqm21 * m21.dsa; acc[13] += dqm21 * m21.dsb;
-        p.acc1[a * A + b] += dqm12 * m12.dg;
-        p.acc2[a * A + b] += dqm21 * m21.dg;
+        p.acc1[rowA + b] += dqm12 * m12.dg;
+        p.acc2[rowA + b] += dqm21 * m21.dg;
       }
     } else if (p.want_grad && p.acc1) {
-      d1 += p.acc1[a * A + b];
-      d2 += p.acc2[a * A + b];
+      d1 += p.acc1[rowA + b];
+      d2 += p.acc2[rowA + b];
     }
     if (p.want_grad) {
       p.F1m[off] = d1;
       p.F2m[off] = d2;
     }
+   }
   }
   __shared__ double* dst[14];
   if (threadIdx.x == 0) {
@@ -241,23 +226,29 @@ pair_kernel(PairArgs p) {
   block_reduce_add<14>(acc, dst);
 }
 
-// in place over the U blocks of F1 / F2: u -> sum_tau dS[tau][seg] / tau * exp(u / tau)
+// in place over the U blocks of F1 (blockIdx.y = 0) / F2 (1): u -> sum_tau dS[tau][seg] / tau * exp(u / tau)
+// (the same ex2.approx exponential as the forward epilogue that produced the sums)
 __global__ void __launch_bounds__(NT)
-coef_kernel(float* __restrict__ F, int A, int T, int ld, int c_split, const double* __restrict__ dS, int seg_lo, int seg_hi) {
-  const int64_t w = T - A, total = (int64_t)A * w;
+coef_kernel(float* __restrict__ F1, float* __restrict__ F2, int A, int T, int ld, int J1, int J2, const double* __restrict__ dS) {
+  const int dir = blockIdx.y;
+  float* __restrict__ F = dir == 0 ? F1 : F2;
+  const int c_split = A + (dir == 0 ? J1 : J2);
+  const int seg_lo = dir == 0 ? 0 : 2, seg_hi = seg_lo + 1;
   const float lo01 = (float)dS[seg_lo] * 10.f, lo1 = (float)dS[4 + seg_lo];
   const float hi01 = (float)dS[seg_hi] * 10.f, hi1 = (float)dS[4 + seg_hi];
-  for (int64_t t = (int64_t)blockIdx.x * NT + threadIdx.x; t < total; t += (int64_t)gridDim.x * NT) {
-    int64_t a = t / w, c = A + t % w;
-    float u = F[a * ld + c];
-    float e01 = expf(u / 0.1f), e1 = expf(u);
-    F[a * ld + c] = (c < c_split) ? lo01 * e01 + lo1 * e1 : hi01 * e01 + hi1 * e1;
+  for (int a = blockIdx.x; a < A; a += gridDim.x) {
+    float* row = F + (int64_t)a * ld;
+    for (int c = A + threadIdx.x; c < T; c += NT) {
+      const float u = row[c];
+      const float e01 = __expf(u * 10.f), e1 = __expf(u);
+      row[c] = (c < c_split) ? lo01 * e01 + lo1 * e1 : hi01 * e01 + hi1 * e1;
+    }
   }
 }
 
 // backward of F.normalize: dX = (dXh - Xh <Xh, dXh>) / max(||X||, eps)
 __global__ void __launch_bounds__(NT)
-normalize_bwd_kernel(const float* __restrict__ X, const float* __restrict__ norms, const float* __restrict__ dXh,
+normalize_bwd_kernel(const float* __restrict__ Xh, const float* __restrict__ norms, const float* __restrict__ dXh,
                      int64_t N, int D, float* __restrict__ dX) {
   int64_t row = (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
   if (row >= N) return;
@@ -265,11 +256,11 @@ normalize_bwd_kernel(const float* __restrict__ X, const float* __restrict__ norm
   const float nrm = norms[row];
   const float den = fmaxf(nrm, 1e-12f);
   float dot = 0.f;
-  for (int k = lane; k < D; k += 32) dot = fmaf(X[row * D + k] / den, dXh[row * D + k], dot);
+  for (int k = lane; k < D; k += 32) dot = fmaf(Xh[row * D + k], dXh[row * D + k], dot);
   dot = warp_sum(dot);
   const bool clamped = nrm < 1e-12f;   // below eps the denominator is a constant
   for (int k = lane; k < D; k += 32) {
-    float xh = X[row * D + k] / den;
+    float xh = Xh[row * D + k];
     dX[row * D + k] = (dXh[row * D + k] - (clamped ? 0.f : xh * dot)) / den;
   }
 }
@@ -302,12 +293,6 @@ __global__ void finalize_kernel(const double* __restrict__ icl_raw, const double
   losses_out[1] = icl_uni;
   losses_out[2] = icl_multi;
   losses_out[3] = ial_tot;
-}
-
-inline unsigned grid_for(int64_t total) {
-  int64_t b = (total + NT - 1) / NT;
-  int64_t cap = (int64_t)sm_count() * 8;
-  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
 }  // namespace
@@ -351,18 +336,21 @@ extern "C" int sga_loss_fwd_bwd(const float* const* embs_host, const int* dims_h
   build_ridx_kernel<<<(T + NT - 1) / NT, NT, 0, st>>>(e1i, e2i, e1j, e2j, A, J1, J2, ridx, r2idx);
   SGA_LAUNCH_CHECK();
 
-  // ---- forward Grams on the tensor cores; normalise + gather in the loader, exp-sums in the epilogue
+  // ---- forward Grams on the tensor cores: rows normalised once, gathers in the loader, exp-sums in the epilogue;
+  //      the 2 * n_emb Grams are ONE grouped launch (gemm_tc.cuh)
+  GemmParams probs[2 * 16];
+  int np = 0;
   for (int x = 0; x < n_emb; ++x) {
     const int d = dims_host[x];
-    const float* X = embs_host[x];
-    row_norm_kernel<<<(unsigned)((N + 7) / 8), NT, 0, st>>>(X, N, d, F(L.norms[x]), F(L.den[x]));
+    const float* Xh = F(L.Xh[x]);
+    row_norm_kernel<<<(unsigned)((N + 7) / 8), NT, 0, st>>>(embs_host[x], N, d, F(L.norms[x]), F(L.Xh[x]));
     SGA_LAUNCH_CHECK();
     double* Sx = S + (size_t)x * 8;
     for (int dir = 0; dir < 2; ++dir) {
-      GemmParams P;
+      GemmParams& P = probs[np++];
       memset(&P, 0, sizeof(P));
-      P.A = {X, d, dir == 0 ? e1i : e2i, F(L.den[x]), 0};
-      P.B = {X, d, dir == 0 ? ridx : r2idx, F(L.den[x]), 0};
+      P.A = {Xh, d, dir == 0 ? e1i : e2i, nullptr, 0};
+      P.B = {Xh, d, dir == 0 ? ridx : r2idx, nullptr, 0};
       P.M = A; P.N = T; P.K = d;
       P.C = F(dir == 0 ? L.F1[x] : L.F2[x]); P.ldc = ldF;
       P.mode = 1;
@@ -370,9 +358,11 @@ extern "C" int sga_loss_fwd_bwd(const float* const* embs_host, const int* dims_h
       P.es_split = A + (dir == 0 ? J1 : J2);
       const int lo = dir == 0 ? 0 : 2, hi = dir == 0 ? 1 : 3;   // {S11,S12} / {S22,S21}
       P.s01_lo = Sx + lo; P.s01_hi = Sx + hi; P.s1_lo = Sx + 4 + lo; P.s1_hi = Sx + 4 + hi;
-      int rc = launch_gemm_tc(P, st);
-      if (rc != SGA_OK) return rc;
     }
+  }
+  {
+    int rc = launch_gemm_tc_group(probs, np, st);
+    if (rc != SGA_OK) return rc;
   }
   // ---- element-wise loss terms (+ in-place gradient of the G blocks)
   const int xj = n_emb - 1;   // joint (or the single modality)
@@ -397,7 +387,7 @@ extern "C" int sga_loss_fwd_bwd(const float* const* embs_host, const int* dims_h
     p.zoom = zoom;
     p.modal = modal ? 1 : 0;
     p.want_grad = want_grad;
-    pair_kernel<<<grid_for((int64_t)A * A), NT, 0, st>>>(p);
+    pair_kernel<<<(unsigned)(A < 8 * sm_count() ? A : 8 * sm_count()), NT, 0, st>>>(p);
     SGA_LAUNCH_CHECK();
   }
   finalize_kernel<<<1, 32, 0, st>>>(icl_raw, ial_raw, M, n_emb, A, log_vars_ial, log_vars_icl, zoom, losses_out,
@@ -408,21 +398,25 @@ extern "C" int sga_loss_fwd_bwd(const float* const* embs_host, const int* dims_h
   // ---- backward: coefficient blocks in place, then 4 scatter-add GEMMs per embedding:
   //   dXh[e1i]  += dF1   Xh[R]      dXh[R]  += dF1^T Xh[e1i]
   //   dXh[e2i]  += dF2   Xh[R']     dXh[R'] += dF2^T Xh[e2i]
+  // split K so that the whole group (2 * n_emb problems per launch) fills the SMs for ~4 waves
   auto ksplit_for = [&](int Mr, int Nc, int Kc) {
     int tiles = ((Mr + 127) / 128) * ((Nc + 127) / 128);
     int chunks = (Kc + 31) / 32;
-    int want = (2 * sm_count() + tiles - 1) / tiles;
+    int per_problem = (4 * sm_count() + 2 * n_emb - 1) / (2 * n_emb);
+    int want = (per_problem + tiles - 1) / tiles;
     int cap = chunks / 4;
     if (want > cap) want = cap;
     return want < 1 ? 1 : want;
   };
+  // all 4 * n_emb GEMMs in TWO grouped launches (one per operand-layout combination)
+  GemmParams rowp[2 * 16], colp[2 * 16];
+  int nr = 0, nc = 0;
   for (int x = 0; x < n_emb; ++x) {
     const int d = dims_host[x];
-    const float* X = embs_host[x];
+    const float* Xh = F(L.Xh[x]);
     double* dSx = dS + (size_t)x * 8;
     if (T > A) {
-      coef_kernel<<<grid_for((int64_t)A * (T - A)), NT, 0, st>>>(F(L.F1[x]), A, T, ldF, A + J1, dSx, 0, 1);
-      coef_kernel<<<grid_for((int64_t)A * (T - A)), NT, 0, st>>>(F(L.F2[x]), A, T, ldF, A + J2, dSx, 2, 3);
+      coef_kernel<<<dim3((unsigned)(A < 4 * sm_count() ? A : 4 * sm_count()), 2), NT, 0, st>>>(F(L.F1[x]), F(L.F2[x]), A, T, ldF, J1, J2, dSx);
       SGA_LAUNCH_CHECK();
     }
     SGA_CUDA(cudaMemsetAsync(ws + L.dXh[x], 0, 4 * (size_t)N * d, st));
@@ -430,26 +424,32 @@ extern "C" int sga_loss_fwd_bwd(const float* const* embs_host, const int* dims_h
       const float* Fd = F(dir == 0 ? L.F1[x] : L.F2[x]);
       const int32_t* rows_i = dir == 0 ? e1i : e2i;
       const int32_t* rows_r = dir == 0 ? ridx : r2idx;
-      GemmParams P;
-      memset(&P, 0, sizeof(P));
       // dXh[rows_i[a]] += sum_t Fd[a,t] Xh[rows_r[t]]
+      GemmParams& P = rowp[nr++];
+      memset(&P, 0, sizeof(P));
       P.A = {Fd, ldF, nullptr, nullptr, 0};
-      P.B = {X, d, rows_r, F(L.den[x]), 1};
+      P.B = {Xh, d, rows_r, nullptr, 1};
       P.M = A; P.N = d; P.K = T;
       P.C = F(L.dXh[x]); P.ldc = d; P.mode = 2; P.c_idx = rows_i;
       P.ksplit = ksplit_for(A, d, T);
-      int rc = launch_gemm_tc(P, st);
-      if (rc != SGA_OK) return rc;
       // dXh[rows_r[t]] += sum_a Fd[a,t] Xh[rows_i[a]]
-      P.A = {Fd, ldF, nullptr, nullptr, 1};
-      P.B = {X, d, rows_i, F(L.den[x]), 1};
-      P.M = T; P.N = d; P.K = A;
-      P.c_idx = rows_r;
-      P.ksplit = ksplit_for(T, d, A);
-      rc = launch_gemm_tc(P, st);
-      if (rc != SGA_OK) return rc;
+      GemmParams& Q = colp[nc++];
+      Q = P;
+      Q.A = {Fd, ldF, nullptr, nullptr, 1};
+      Q.B = {Xh, d, rows_i, nullptr, 1};
+      Q.M = T; Q.N = d; Q.K = A;
+      Q.c_idx = rows_r;
+      Q.ksplit = ksplit_for(T, d, A);
     }
-    normalize_bwd_kernel<<<(unsigned)((N + 7) / 8), NT, 0, st>>>(embs_host[x], F(L.norms[x]), F(L.dXh[x]), N, d, g_embs_host[x]);
+  }
+  {
+    int rc = launch_gemm_tc_group(rowp, nr, st);
+    if (rc != SGA_OK) return rc;
+    rc = launch_gemm_tc_group(colp, nc, st);
+    if (rc != SGA_OK) return rc;
+  }
+  for (int x = 0; x < n_emb; ++x) {
+    normalize_bwd_kernel<<<(unsigned)((N + 7) / 8), NT, 0, st>>>(F(L.Xh[x]), F(L.norms[x]), F(L.dXh[x]), N, dims_host[x], g_embs_host[x]);
     SGA_LAUNCH_CHECK();
   }
   return SGA_OK;
