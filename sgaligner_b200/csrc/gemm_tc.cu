@@ -17,6 +17,7 @@
 // quarter each).
 #include "gemm_tc.cuh"
 #include "umma_tf32.cuh"
+#include <stdlib.h>
 
 namespace sga {
 
@@ -221,7 +222,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmGroup G) {
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
-      ptx::mbar_init(&full[s], kLoaders);
+      ptx::mbar_init(&full[s], kLoaders / 32);      // one elected arrive per loader warp
       ptx::mbar_init(&empty[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -269,23 +270,34 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmGroup G) {
         }
       };
       Piece fa, fb;
-      fetch(fa, fb, kc_beg);
+      const int dbg = P.dbg;
+      if (dbg & 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) fa.v[j] = fb.v[j] = make_float4(0.1f * tid, 0.2f, 0.3f, 0.4f);
+        fa.d = fb.d = 1.f;
+      }
+      if (!(dbg & 1)) fetch(fa, fb, kc_beg);
       advance_src(kc_beg + 1);
       for (int kc = kc_beg; kc < kc_end; ++kc, ++it) {
         const int s = it % kStages;
         const Piece ca = fa, cb = fb;
         if (kc + 1 < kc_end) {                // in flight during the conversion below
-          fetch(fa, fb, kc + 1);
+          if (!(dbg & 1)) fetch(fa, fb, kc + 1);
           advance_src(kc + 2);
         }
         if (it >= kStages) ptx::mbar_wait(&empty[s], (uint32_t)(((it / kStages) - 1) & 1));
         const uint32_t st = sm_base + s * tf32x3::kStageBytes;
-        if (A_MN) store_mn(st, st + tf32x3::kTileBytes, ca, a_div, tid);
-        else store_k(st, st + tf32x3::kTileBytes, ca, a_div, tid);
-        if (B_MN) store_mn(st + 2 * tf32x3::kTileBytes, st + 3 * tf32x3::kTileBytes, cb, b_div, tid);
-        else store_k(st + 2 * tf32x3::kTileBytes, st + 3 * tf32x3::kTileBytes, cb, b_div, tid);
+        if (!(dbg & 2)) {
+          if (A_MN) store_mn(st, st + tf32x3::kTileBytes, ca, a_div, tid);
+          else store_k(st, st + tf32x3::kTileBytes, ca, a_div, tid);
+          if (B_MN) store_mn(st + 2 * tf32x3::kTileBytes, st + 3 * tf32x3::kTileBytes, cb, b_div, tid);
+          else store_k(st + 2 * tf32x3::kTileBytes, st + 3 * tf32x3::kTileBytes, cb, b_div, tid);
+        } else if (ca.v[0].x == 1234.5f && cb.v[3].w == 5432.1f) {
+          sts128(st, reinterpret_cast<const uint32_t(&)[4]>(ca.v[1]));      // keep the loads alive
+        }
         ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive(&full[s]);
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_relaxed(&full[s]);
       }
     }
   } else if (warp == 8) {
@@ -311,7 +323,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmGroup G) {
         ptx::mbar_wait(&full[s], (uint32_t)((it / kStages) & 1));
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
-          issue_stage_any<A_MN, B_MN>(tmem_u + ab * 128, sm_base + s * tf32x3::kStageBytes, idesc, kc == kc_beg);
+          if (!(P.dbg & 8)) issue_stage_any<A_MN, B_MN>(tmem_u + ab * 128, sm_base + s * tf32x3::kStageBytes, idesc, kc == kc_beg);
           ptx::umma_commit(&empty[s]);
           if (kc == kc_end - 1) ptx::umma_commit(&acc_full[ab]);
         }
@@ -360,54 +372,52 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmGroup G) {
       float* crow = nullptr;
       if (row_ok) crow = P.C + (P.mode == 2 ? (int64_t)P.c_idx[row] : (int64_t)row) * P.ldc;
       const uint32_t base = tmem + ((uint32_t)(32 * q) << 16) + ab * 128;
+      const bool slice_ok = ksl * kc_per < nkc_all;
+      const int rows_here = slice_ok ? min(32, P.M - (m0 + 32 * q)) : 0;      // valid rows of this warp's 32-row band
+      float* xt = xpose + q * (32 * 33);
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         uint32_t v[32];
         ptx::tmem_ld32(base + cc * 32, v);
         ptx::tmem_ld_wait();
-        if (P.mode == 2) {
-          // scatter-add through a shared-memory transpose: lanes own consecutive COLUMNS of one output row, so each
-          // warp-level reduction is one contiguous <=128-byte request instead of 32 scattered ones
-          const int c0 = n0 + cc * 32;
-          float* xt = xpose + (warp & 3) * (32 * 33);
+        const int c0 = n0 + cc * 32;
+        if (c0 >= P.N || rows_here <= 0 || (P.dbg & 4)) continue;       // warp-uniform
+        if (P.mode == 1 && row_ok && c0 + 31 >= P.es_c0) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) xt[lane * 33 + e] = __uint_as_float(v[e]);
-          __syncwarp();
-          const unsigned long long cptr = reinterpret_cast<unsigned long long>(crow);   // 0 when this lane's row is out of range
-#pragma unroll 4
-          for (int rr = 0; rr < 32; ++rr) {
-            float* dst = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, cptr, rr));
-            if (dst && c0 + lane < P.N) atomicAdd(dst + c0 + lane, xt[rr * 33 + lane]);
-          }
-          __syncwarp();
-        } else if (row_ok) {
-          const int c0 = n0 + cc * 32;
-          {
-            if (c0 + 31 < P.N && (P.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0)) {
-#pragma unroll
-              for (int e = 0; e < 32; e += 4)
-                *reinterpret_cast<uint4*>(crow + c0 + e) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 32; ++e)
-                if (c0 + e < P.N) crow[c0 + e] = __uint_as_float(v[e]);
-            }
-            if (P.mode == 1 && c0 + 31 >= P.es_c0) {
-#pragma unroll
-              for (int e = 0; e < 32; ++e) {
-                const int c = c0 + e;
-                if (c >= P.es_c0 && c < P.N) {
-                  const float x = __uint_as_float(v[e]);
-                  // cosines: |x| <= 1, so the fast exponential (ex2.approx, ~2 ulp) is exact enough for sums of
-                  // 1e6 positive terms; 1/0.1f rounds to 10.f
-                  const float e01 = __expf(x * 10.f), e1 = __expf(x);
-                  if (c < P.es_split) { s_acc[0] += e01; s_acc[2] += e1; }
-                  else { s_acc[1] += e01; s_acc[3] += e1; }
-                }
-              }
+          for (int e = 0; e < 32; ++e) {
+            const int c = c0 + e;
+            if (c >= P.es_c0 && c < P.N) {
+              // cosines: |x| <= 1.  exp(x) by ex2.approx (~2 ulp); exp(x / 0.1) = exp(x)^10 by four multiplications
+              // (~20 ulp), half the SFU work of a second exponential: exact enough for sums of ~1e6 positive terms
+              const float e1 = __expf(__uint_as_float(v[e]));
+              const float e2 = e1 * e1, e4 = e2 * e2;
+              const float e01 = e4 * e4 * e2;
+              if (c < P.es_split) { s_acc[0] += e01; s_acc[2] += e1; }
+              else { s_acc[1] += e01; s_acc[3] += e1; }
             }
           }
         }
+        // Through a shared-memory transpose: lanes own consecutive COLUMNS of one output row, so every warp-level
+        // store / reduction is one contiguous 128-byte request (the TMEM load hands each lane a ROW, whose 16-byte
+        // pieces would otherwise reach L2 as 32 scattered partial-sector writes per instruction).
+#pragma unroll
+        for (int e = 0; e < 32; ++e) xt[lane * 33 + e] = __uint_as_float(v[e]);
+        __syncwarp();
+        const bool col_ok = c0 + lane < P.N;
+        if (P.mode == 2) {
+          const unsigned long long cptr = reinterpret_cast<unsigned long long>(crow);   // 0: this lane's row is out of range
+#pragma unroll 4
+          for (int rr = 0; rr < rows_here; ++rr) {
+            float* dst = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, cptr, rr));
+            if (col_ok) atomicAdd(dst + c0 + lane, xt[rr * 33 + lane]);
+          }
+        } else {
+          float* dst = P.C + (int64_t)(m0 + 32 * q) * P.ldc + c0 + lane;
+#pragma unroll 4
+          for (int rr = 0; rr < rows_here; ++rr, dst += P.ldc)
+            if (col_ok) *dst = xt[rr * 33 + lane];
+        }
+        __syncwarp();
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&acc_free[ab]);
@@ -454,6 +464,7 @@ int launch_gemm_tc_group(const GemmParams* problems, int n, cudaStream_t st) {
       }
       total += work_items(P);
       G.p[G.n] = P;
+      { const char* e = getenv("SGA_GEMM_DBG"); G.p[G.n].dbg = e ? atoi(e) : 0; }
       G.work_end[G.n] = total;
       ++G.n;
     }

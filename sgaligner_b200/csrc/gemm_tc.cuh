@@ -22,6 +22,7 @@ struct GemmParams {
   int es_c0, es_split;    // mode 1: columns >= es_c0 feed the sums; < es_split -> S_lo else S_hi
   double* s01_lo; double* s01_hi; double* s1_lo; double* s1_hi;   // sum exp(x/0.1), sum exp(x)
   int ksplit;             // mode 2 only: the K range is cut into ksplit slices, each adds its partial product
+  int dbg;                // profiling only (SGA_GEMM_DBG): 1 no global loads, 2 no convert/stores, 4 no C writes, 8 no MMA
 };
 
 // Several independent problems with the SAME operand majorness executed by ONE persistent launch: the

@@ -34,6 +34,13 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
+// Arrive without release semantics.  The default (.release.cta) arrive compiles to MEMBAR.ALL.CTA + SYNCS.ARRIVE, and
+// the MEMBAR also waits for the thread's outstanding GLOBAL loads -- i.e. for the operand prefetch a loader has just
+// issued for the next chunk, which serialises the pipeline.  Shared-memory stores of a warp are performed in order, so
+// for the "stores; fence.proxy.async; __syncwarp; one lane arrives" pattern the relaxed arrive is sufficient.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.relaxed.cta.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
