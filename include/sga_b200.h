@@ -194,6 +194,17 @@ int sga_match_anchor_pos(const float* sim, const int32_t* pair_off, const int64_
                          const int32_t* node_pair, const int32_t* e1i, const int32_t* e2i, int A,
                          int32_t* anchor_pos, void* stream);
 
+/* ---- a11: utils/alignment.py:27-89 on the device, one launch for all pairs: top1_idx/top1_dist [N] = the
+ * best match of every node once the node itself is removed (pair-local column; compute_node_corrs with
+ * k = 1 keeps the source nodes whose top1 is a reference node, i.e. top1_idx >= n_src[b]);
+ * pair_out [B,4] = {SGAR '2', SGAR '50', SGAR '100', alignment score} (SGAR = -1 for a pair without
+ * anchors, which the reference skips).  n_src [B]; e1i/e2i [A] GLOBAL node ids grouped by pair,
+ * anchor_off [B+1] their per-pair prefix (cumsum of e1i_count). */
+int sga_match_pair_metrics(const float* sim, const int32_t* pair_off, const int64_t* sim_off,
+                           const int32_t* n_src, const int32_t* e1i, const int32_t* e2i,
+                           const int32_t* anchor_off, int B, int32_t* top1_idx, float* top1_dist,
+                           float* pair_out, void* stream);
+
 /* ---- a12-a16: OverallLoss.forward (losses.py:114-152) and its gradient w.r.t. every embedding.
  * embs_host: host array of M+1 device pointers (M modal embeddings in module order, then the joint;
  * for M == 1 pass only the single embedding and n_emb = 1); dims_host [n_emb] feature widths.

@@ -352,6 +352,9 @@ def evaluate_batch(emb: Tensor, data: dict, ks=(1, 2, 3, 4, 5)):
     hits_tot = {k: 0 for k in ks}
     rr_all: List[float] = []
     total = 0
+    goc = np.asarray(data['graph_per_obj_count']).reshape(-1, 2)
+    sgar_all = {m: [] for m in ('2', '50', '100')}
+    align, corrs = [], []
     for b in range(int(data['batch_size'])):
         o0, o1 = int(offs[b]), int(offs[b + 1])
         na = int(e1c[b])
@@ -361,11 +364,18 @@ def evaluate_batch(emb: Tensor, data: dict, ks=(1, 2, 3, 4, 5)):
         sim, rank = match_pair(emb[o0:o1])
         ranks.append(rank.numpy())
         sims.append(sim.numpy())
+        ns, nr = int(goc[b, 0]), int(goc[b, 1])
+        align.append(alignment_score(ranks[-1], ns, nr) if nr else 0.0)
+        corrs.append(node_corrs(ranks[-1], ns, 1))
         if na:
             h, rr = hits_and_rr(ranks[-1], e1, e2, ks)
             for k in ks:
                 hits_tot[k] += h[k]
             rr_all.extend(rr)
             total += na
+            sv = sgar(sims[-1], ranks[-1], e1, e2)      # inference_align_reg.py:139-141
+            for m in sgar_all:
+                sgar_all[m].append(sv[m])
     return {'rank': ranks, 'sim': sims, 'hits': hits_tot, 'total': total,
-            'mrr': float(np.mean(rr_all)) if rr_all else 0.0}
+            'mrr': float(np.mean(rr_all)) if rr_all else 0.0, 'sgar': sgar_all, 'alignment_score': align,
+            'node_corrs': corrs}

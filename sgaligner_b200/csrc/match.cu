@@ -161,6 +161,75 @@ anchor_pos_kernel(const float* __restrict__ sim, const int32_t* __restrict__ pai
   if (lane == 0) pos[t] = cnt;
 }
 
+
+// SGAR, alignment score and the top-1 node correspondences of every pair (utils/alignment.py:27-89) in one launch,
+// one CTA per pair.
+//   phase 1  top1[i] = first entry of row i's ranking once i itself is removed (ties to the lowest column)
+//   phase 2  alignment score = #{src node i : top1[i] is a reference node} / n_ref           (alignment.py:80-89)
+//   phase 3  SGAR: anchors sorted by the distance of their top-1 prediction; all-correct over the first 2 /
+//            the first half / all of them (alignment.py:27-58).  Done without a sort: a wrong anchor's rank
+//            is the number of anchors that sort before it, and only the smallest such rank matters.
+// pair_out[b] = {sgar '2', sgar '50', sgar '100', alignment score}; the three SGAR values are -1 for a pair
+// without anchors (the reference skips such pairs, inference_align_reg.py:121).
+__global__ void __launch_bounds__(NT)
+pair_metrics_kernel(const float* __restrict__ sim, const int32_t* __restrict__ pair_off,
+                    const int64_t* __restrict__ sim_off, const int32_t* __restrict__ n_src,
+                    const int32_t* __restrict__ e1i, const int32_t* __restrict__ e2i,
+                    const int32_t* __restrict__ anchor_off, int32_t* __restrict__ top1_idx,
+                    float* __restrict__ top1_dist, float* __restrict__ pair_out) {
+  const int b = blockIdx.x;
+  const int o0 = pair_off[b], n = pair_off[b + 1] - o0;
+  const int ns = n_src[b], nr = n - ns;
+  const float* S = sim + sim_off[b];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ int s_cnt;
+  __shared__ int s_minwrong;
+  if (threadIdx.x == 0) {
+    s_cnt = 0;
+    s_minwrong = 0x7fffffff;
+  }
+  for (int r = warp; r < n; r += NT / 32) {
+    const float* srow = S + (int64_t)r * n;
+    unsigned long long best = ~0ull;
+    for (int j = lane; j < n; j += 32)
+      if (j != r) {
+        const unsigned long long k = sort_key(srow[j], j);
+        best = k < best ? k : best;
+      }
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other < best ? other : best;
+    }
+    if (lane == 0) {
+      top1_idx[o0 + r] = best == ~0ull ? -1 : (int32_t)(best & 0xFFFFFFFFull);
+      top1_dist[o0 + r] = best == ~0ull ? INFINITY : key_value(best);
+    }
+  }
+  __syncthreads();
+  int c = 0;
+  for (int r = threadIdx.x; r < ns; r += NT) c += top1_idx[o0 + r] >= ns ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0 && c) atomicAdd(&s_cnt, c);
+  const int a0 = anchor_off[b], na = anchor_off[b + 1] - a0;
+  for (int t = threadIdx.x; t < na; t += NT) {
+    const int g1 = e1i[a0 + t];
+    if (top1_idx[g1] == e2i[a0 + t] - o0) continue;
+    const unsigned long long kt = sort_key(top1_dist[g1], t);
+    int rank = 0;
+    for (int u = 0; u < na; ++u) rank += sort_key(top1_dist[e1i[a0 + u]], u) < kt ? 1 : 0;
+    atomicMin(&s_minwrong, rank);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float* out = pair_out + 4 * (int64_t)b;
+    const int mw = s_minwrong;
+    out[0] = na ? (mw >= (na < 2 ? na : 2) ? 1.f : 0.f) : -1.f;
+    out[1] = na ? (mw >= na / 2 ? 1.f : 0.f) : -1.f;
+    out[2] = na ? (mw >= na ? 1.f : 0.f) : -1.f;
+    out[3] = nr > 0 ? (float)s_cnt / (float)nr : 0.f;
+  }
+}
+
 }  // namespace
 }  // namespace sga
 
@@ -202,6 +271,17 @@ extern "C" int sga_match_anchor_pos(const float* sim, const int32_t* pair_off, c
                                     int32_t* anchor_pos, void* stream) {
   if (A <= 0) return SGA_OK;
   sga::anchor_pos_kernel<<<(A + 7) / 8, sga::NT, 0, (cudaStream_t)stream>>>(sim, pair_off, sim_off, node_pair, e1i, e2i, A, anchor_pos);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+extern "C" int sga_match_pair_metrics(const float* sim, const int32_t* pair_off, const int64_t* sim_off,
+                                      const int32_t* n_src, const int32_t* e1i, const int32_t* e2i,
+                                      const int32_t* anchor_off, int B, int32_t* top1_idx, float* top1_dist,
+                                      float* pair_out, void* stream) {
+  if (B <= 0) return SGA_OK;
+  sga::pair_metrics_kernel<<<B, sga::NT, 0, (cudaStream_t)stream>>>(sim, pair_off, sim_off, n_src, e1i, e2i, anchor_off, top1_idx,
+                                                                     top1_dist, pair_out);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }

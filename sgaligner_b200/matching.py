@@ -58,6 +58,50 @@ def evaluate_batch(embedding: torch.Tensor, data_dict: dict, ks: Sequence[int] =
     return {'hits': hits, 'total': int(pos.shape[0]), 'mrr': float(rr.mean()) if pos.size else 0.0, 'rr': rr, 'pos': pos}
 
 
+def evaluate_pairs(embedding: torch.Tensor, data_dict: dict, ks: Sequence[int] = (1, 2, 3, 4, 5),
+                   recall_modes: Sequence[str] = ('2', '50', '100'), tensor_cores: bool = True) -> dict:
+    """Everything the per-pair loop of ``inference_align_reg.py:107-145`` derives from the embedding -- Hits@k,
+    MRR, SGAR per recall mode, the alignment score and the top-1 node correspondences (``compute_node_corrs``
+    with ``k = 1``) -- for ALL pairs of the batch: similarity + anchor positions + pair metrics are three
+    launches and the results come back in one device-to-host copy (the reference moves ``rank_list`` to the host
+    seven times per pair).  Pairs without anchors are skipped for Hits/MRR/SGAR exactly as the reference does."""
+    dev = embedding.device
+    goc = np.asarray(data_dict['graph_per_obj_count']).reshape(-1, 2)
+    lay = ops.PairLayout(goc, dev)
+    if tensor_cores:
+        sim = ops.match_topk_tc(embedding.detach(), lay, 1, True)[2]
+    else:
+        sim = ops.match_sim(embedding.detach(), lay)
+    e1c = np.asarray(data_dict['e1i_count']).reshape(-1).astype(np.int64)
+    aoff_h = np.concatenate([[0], np.cumsum(e1c)]).astype(np.int32)
+    e1 = torch.as_tensor(np.asarray(data_dict['e1i']).astype(np.int32)).to(dev, non_blocking=True)
+    e2 = torch.as_tensor(np.asarray(data_dict['e2i']).astype(np.int32)).to(dev, non_blocking=True)
+    n_src = torch.as_tensor(goc[:, 0].astype(np.int32)).to(dev, non_blocking=True)
+    aoff = torch.as_tensor(aoff_h).to(dev, non_blocking=True)
+    pos = ops.match_anchor_pos(sim, lay, e1, e2)
+    top1, dist, pout = ops.match_pair_metrics(sim, lay, n_src, e1, e2, aoff)
+    # one transfer: [pos | top1 | pair_out bits]
+    packed = torch.cat([pos, top1, pout.reshape(-1).view(torch.int32)]).cpu().numpy()
+    A = int(pos.numel())
+    pos_h = packed[:A]
+    top1_h = packed[A:A + lay.N]
+    pout_h = packed[A + lay.N:].view(np.float32).reshape(lay.B, 4)
+    has_anchor = e1c > 0
+    hits = {int(k_): int((pos_h < k_).sum()) for k_ in ks}
+    rr = 1.0 / (pos_h.astype(np.float64) + 1.0)
+    mode_col = {'2': 0, '50': 1}
+    sgar = {m: [float(v) for v in pout_h[has_anchor, mode_col.get(m, 2)]] for m in recall_modes}
+    corrs = []
+    for b in range(lay.B):
+        o0, ns = int(lay.pair_off_host[b]), int(goc[b, 0])
+        t = top1_h[o0:o0 + ns]
+        src = np.nonzero(t >= ns)[0]
+        corrs.append([(int(i), int(t[i])) for i in src])
+    return {'hits': hits, 'total': A, 'mrr': float(rr.mean()) if A else 0.0, 'rr': rr, 'pos': pos_h, 'sgar': sgar,
+            'alignment_score': [float(v) for v in pout_h[:, 3]], 'node_corrs': corrs, 'anchors': [int(v) for v in e1c[has_anchor]],
+            'top1': top1_h}
+
+
 # ------------------------------------------------------------------------------ utils/alignment.py API
 def _np(x):
     return x.detach().cpu().numpy() if torch.is_tensor(x) else np.asarray(x)

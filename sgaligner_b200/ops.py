@@ -400,6 +400,21 @@ def match_anchor_pos(sim: torch.Tensor, lay: PairLayout, e1i: torch.Tensor, e2i:
     return pos
 
 
+def match_pair_metrics(sim: torch.Tensor, lay: PairLayout, n_src: torch.Tensor, e1i: torch.Tensor, e2i: torch.Tensor,
+                       anchor_off: torch.Tensor):
+    """SGAR / alignment score / top-1 correspondences of every pair (one launch).  Returns (top1_idx [N] int32
+    pair-local, top1_dist [N], pair_out [B,4] = sgar2, sgar50, sgar100, alignment score)."""
+    dev = sim.device
+    top1 = torch.empty(lay.N, device=dev, dtype=torch.int32)
+    dist = torch.empty(lay.N, device=dev, dtype=torch.float32)
+    out = torch.empty(lay.B, 4, device=dev, dtype=torch.float32)
+    check(get_lib().sga_match_pair_metrics(_ptr(sim), _ptr(lay.pair_off), _ptr(lay.sim_off), _ptr(n_src), _ptr(e1i), _ptr(e2i),
+                                           _ptr(anchor_off), lay.B, _ptr(top1), _ptr(dist), _ptr(out), _stream()),
+          'sga_match_pair_metrics')
+    _count(1)
+    return top1, dist, out
+
+
 # --------------------------------------------------------------------------------- loss
 _WS_CACHE = {}
 

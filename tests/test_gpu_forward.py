@@ -153,6 +153,52 @@ def test_matching_vs_golden(name, dev):
 
 
 @pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('tc', [True, False])
+def test_pair_metrics_vs_reference(name, tc, dev):
+    """Device-side SGAR / alignment score / node correspondences / Hits@k / MRR (one D2H copy for the whole batch)
+    against the values of the reference's ``utils/alignment.py`` on the golden embedding."""
+    import os
+    from sgaligner_b200 import matching
+    from tests.util import GOLD
+    ref = np.load(os.path.join(GOLD, 'metrics_ref.npz'))
+    c = load_case(name)
+    key = 'joint' if len(c['modules']) > 1 else c['modules'][0]
+    ev = matching.evaluate_pairs(c['out'][key].to(dev), c['data'], tensor_cores=tc)
+    assert [ev['hits'][k] for k in range(1, 6)] == c['hits'].tolist()
+    np.testing.assert_allclose(np.sort(ev['rr']), np.sort(c['rr']), rtol=0, atol=0)
+    si = 0
+    for b in range(c['data']['batch_size']):
+        assert abs(ev['alignment_score'][b] - float(ref[f'{name}/{b}/alignment_score'])) < 1e-6
+        assert ev['node_corrs'][b] == [tuple(int(v) for v in r) for r in ref[f'{name}/{b}/node_corrs']]
+        if int(c['data']['e1i_count'][b]):
+            assert [ev['sgar'][m][si] for m in ('2', '50', '100')] == ref[f'{name}/{b}/sgar'].tolist()
+            si += 1
+
+
+def test_pair_metrics_random_vs_oracle(dev):
+    """Untrained-looking embeddings (many wrong anchors, so every SGAR mode takes both values) at C2 shapes,
+    including a pair without anchors and a pair with one anchor."""
+    from oracle import sgaligner_oracle as O
+    from sgaligner_b200 import matching, synthetic
+    data = synthetic.make_batch([20, 33, 8, 64, 5], [25, 30, 9, 64, 7], [6, 9, 0, 32, 1], n_points=8, seed=11)
+    g = torch.Generator().manual_seed(3)
+    N = int(data['tot_obj_pts'].shape[0])
+    emb = torch.randn(N, 48, generator=g)
+    # make about half of the anchors easy: copy the source row onto its reference row (+ noise)
+    e1, e2 = np.asarray(data['e1i']), np.asarray(data['e2i'])
+    for t in range(0, len(e1), 2):
+        emb[int(e2[t])] = emb[int(e1[t])] + 0.05 * torch.randn(48, generator=g)
+    ev = matching.evaluate_pairs(emb.to(dev), data)
+    ref = O.evaluate_batch(emb, data)
+    assert ev['hits'] == ref['hits'] and abs(ev['mrr'] - ref['mrr']) < 1e-12
+    assert ev['sgar'] == ref['sgar']
+    assert ev['node_corrs'] == ref['node_corrs']
+    np.testing.assert_allclose(ev['alignment_score'], ref['alignment_score'], atol=1e-6)
+    vals = set(v for m in ev['sgar'].values() for v in m)
+    assert vals == {0.0, 1.0}
+
+
+@pytest.mark.parametrize('name', CASES)
 def test_loss_forward_vs_golden(name, dev):
     """OverallLoss on the GOLDEN embeddings (isolates the loss kernels)."""
     from sgaligner_b200.losses import CustomMultiLossLayer, OverallLoss

@@ -72,3 +72,24 @@ def test_bn_batch_stats_match_reference_side_effect():
         rv = 0.9 * c['params'][f'object_encoder.bn{i}.running_var'] + 0.1 * var
         assert rel_inf(rm, c['bn'][f'object_encoder.bn{i}.running_mean']) < 1e-5
         assert rel_inf(rv, c['bn'][f'object_encoder.bn{i}.running_var']) < 1e-5
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_oracle_pair_metrics_vs_reference(name):
+    """SGAR / alignment score / top-1 node correspondences of the restatement against the values the
+    reference's own ``utils/alignment.py`` functions produced (tests/golden/metrics_ref.npz, written by
+    oracle/make_golden_metrics.py)."""
+    import os
+    from tests.util import GOLD
+    ref = np.load(os.path.join(GOLD, 'metrics_ref.npz'))
+    c = load_case(name)
+    key = 'joint' if len(c['modules']) > 1 else c['modules'][0]
+    ev = O.evaluate_batch(c['out'][key], c['data'])
+    si = 0
+    for b in range(c['data']['batch_size']):
+        assert abs(ev['alignment_score'][b] - float(ref[f'{name}/{b}/alignment_score'])) < 1e-12
+        assert ev['node_corrs'][b] == [tuple(int(v) for v in r) for r in ref[f'{name}/{b}/node_corrs']]
+        if int(c['data']['e1i_count'][b]):
+            got = [ev['sgar'][m][si] for m in ('2', '50', '100')]
+            assert got == ref[f'{name}/{b}/sgar'].tolist()
+            si += 1
