@@ -194,6 +194,11 @@ int sga_match_anchor_pos(const float* sim, const int32_t* pair_off, const int64_
                          const int32_t* node_pair, const int32_t* e1i, const int32_t* e2i, int A,
                          int32_t* anchor_pos, void* stream);
 
+/* ---- 8(f)2 device-side collation: src/datasets/scan3r.py:99-100 (obj_points - pcl_center) in place on the
+ * raw points after the H2D copy.  pts [N,P,3] f32; center [B,3] f32; node_pair [N] int32 maps an object to
+ * its pair. */
+int sga_center_points(float* pts, int64_t N, int P, const float* center, const int32_t* node_pair, void* stream);
+
 /* ---- a11: utils/alignment.py:27-89 on the device, one launch for all pairs: top1_idx/top1_dist [N] = the
  * best match of every node once the node itself is removed (pair-local column; compute_node_corrs with
  * k = 1 keeps the source nodes whose top1 is a reference node, i.e. top1_idx >= n_src[b]);

@@ -400,6 +400,16 @@ def match_anchor_pos(sim: torch.Tensor, lay: PairLayout, e1i: torch.Tensor, e2i:
     return pos
 
 
+def center_points(pts: torch.Tensor, center: torch.Tensor, node_pair: torch.Tensor):
+    """In place ``pts[o] -= center[node_pair[o]]`` (the centring of ``scan3r.py:99-100`` on the device)."""
+    _need_cuda(pts, center, node_pair)
+    assert pts.dtype == torch.float32 and pts.is_contiguous() and center.dtype == torch.float32 and center.is_contiguous()
+    N, P = int(pts.shape[0]), int(pts.shape[1])
+    check(get_lib().sga_center_points(_ptr(pts), N, P, _ptr(center), _ptr(node_pair), _stream()), 'sga_center_points')
+    _count(1)
+    return pts
+
+
 def match_pair_metrics(sim: torch.Tensor, lay: PairLayout, n_src: torch.Tensor, e1i: torch.Tensor, e2i: torch.Tensor,
                        anchor_off: torch.Tensor):
     """SGAR / alignment score / top-1 correspondences of every pair (one launch).  Returns (top1_idx [N] int32
