@@ -301,6 +301,11 @@ def run_ours(args, out=sys.stdout):
     cap.capture_host_step(host, n_chunks=4)
     e2e_graph_ms, _, _ = timed(cap.run_host, args.steps, args.warmup)
     e2e_graph_ms /= args.steps
+    # the PCIe floor of this step on this box: the same bytes copied from pinned memory with nothing else running
+    pts_dev = torch.empty_like(data['tot_obj_pts'])
+    h2d_ms, _, _ = timed(lambda: pts_dev.copy_(host_pinned['tot_obj_pts'], non_blocking=True), args.steps, args.warmup)
+    h2d_ms /= args.steps
+    del pts_dev
     # both are public entry points for the same host-to-host step; report the faster one and say which
     e2e_ms = min(e2e_graph_ms, e2e_eager_ms)
     e2e_api = ('serving.CapturedInference.run_host(): one graph replay = H2D from pinned staging + step + D2H to pinned results, host sync included'
@@ -358,6 +363,7 @@ def run_ours(args, out=sys.stdout):
             'cpu_baseline': cpu,
             'e2e': {'value': world * PAIRS_PER_GPU / (e2e_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_ms, 'eager_ms_per_step': e2e_eager_ms,
                     'graph_ms_per_step': e2e_graph_ms, 'api': e2e_api,
+                    'h2d_points_only_ms': h2d_ms, 'h2d_points_only_gbs': host_pinned['tot_obj_pts'].numel() * 4 / (h2d_ms * 1e-3) / 1e9,
                     'h2d_bytes_per_step': h2d_bytes(host, KEYS), 'd2h_bytes_per_step': int(d2h),
                     'h2d': 'pinned host batch; only the tensors the configured modalities read are copied (points, rel_pose, edges, anchors)'},
             'gpu_launches': int(launches),
