@@ -17,6 +17,7 @@
 // quarter each).
 #include "gemm_tc.cuh"
 #include "umma_tf32.cuh"
+#include "epilogue.cuh"
 #include <stdlib.h>
 
 namespace sga {
@@ -397,27 +398,23 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmGroup G) {
             }
           }
         }
-        // Through a shared-memory transpose: lanes own consecutive COLUMNS of one output row, so every warp-level
-        // store / reduction is one contiguous 128-byte request (the TMEM load hands each lane a ROW, whose 16-byte
-        // pieces would otherwise reach L2 as 32 scattered partial-sector writes per instruction).
-#pragma unroll
-        for (int e = 0; e < 32; ++e) xt[lane * 33 + e] = __uint_as_float(v[e]);
-        __syncwarp();
-        const bool col_ok = c0 + lane < P.N;
         if (P.mode == 2) {
+          // scatter-add through a shared-memory transpose: lanes own consecutive COLUMNS of one output row, so each
+          // warp-level reduction is one contiguous 128-byte request instead of 32 scattered ones
+#pragma unroll
+          for (int e = 0; e < 32; ++e) xt[lane * 33 + e] = __uint_as_float(v[e]);
+          __syncwarp();
+          const bool col_ok = c0 + lane < P.N;
           const unsigned long long cptr = reinterpret_cast<unsigned long long>(crow);   // 0: this lane's row is out of range
 #pragma unroll 4
           for (int rr = 0; rr < rows_here; ++rr) {
             float* dst = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, cptr, rr));
             if (col_ok) atomicAdd(dst + c0 + lane, xt[rr * 33 + lane]);
           }
-        } else {
-          float* dst = P.C + (int64_t)(m0 + 32 * q) * P.ldc + c0 + lane;
-#pragma unroll 4
-          for (int rr = 0; rr < rows_here; ++rr, dst += P.ldc)
-            if (col_ok) *dst = xt[rr * 33 + lane];
+          __syncwarp();
+        } else if (row_ok) {
+          store_row32(crow + c0, v, P.N - c0);        // 128-bit stores straight from the registers (epilogue.cuh)
         }
-        __syncwarp();
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&acc_free[ab]);

@@ -16,6 +16,7 @@
 // backward GEMMs scatter-add straight into d(normalised embedding); F1/F2 are materialised in HBM
 // (A x T fp32 each) because the element-wise loss terms need the global normalisers first.
 #include "gemm_tc.cuh"
+#include "gram_ts.cuh"
 
 namespace sga {
 
@@ -29,12 +30,25 @@ struct Layout {
   size_t scal;                // doubles: S[n_emb][2][4], dS[n_emb][2][4], icl_raw[n_emb], ial_raw[n_emb]
   size_t ridx, r2idx;         // int32 [T]: rows [e2i;e1j;e2j] and [e1i;e2j;e1j]
   size_t norms[17], Xh[17], F1[17], F2[17], dXh[17];
+  size_t slot;                // int32 [N]: (row set << 28) | position, for the packed operand images
+  size_t img[17][4];          // operand images of the embeddings that take the gram_ts path (d <= 128), else 0
   size_t acc1, acc2;
   size_t total;
   int ldF;
 };
 
 inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// Embeddings up to 128 wide take the TMA-fed / A-in-tensor-memory Gram kernel (gram_ts.cu); SGA_LOSS_GRAM=legacy
+// forces the in-loader-split GEMM (gemm_tc.cu) for everything (A/B comparisons, profiling).
+inline bool gram_ts_ok(int d) {
+  static int legacy = -1;
+  if (legacy < 0) {
+    const char* e = getenv("SGA_LOSS_GRAM");
+    legacy = (e && strcmp(e, "legacy") == 0) ? 1 : 0;
+  }
+  return !legacy && d <= 128;
+}
 
 Layout make_layout(int n_emb, const int* dims, int64_t N, int A, int J1, int J2, int want_grad) {
   Layout L;
@@ -46,12 +60,22 @@ Layout make_layout(int n_emb, const int* dims, int64_t N, int A, int J1, int J2,
   o = al256(o + sizeof(double) * (size_t)n_emb * 18);
   L.ridx = o; o = al256(o + 4 * T);
   L.r2idx = o; o = al256(o + 4 * T);
+  L.slot = o; o = al256(o + 4 * (size_t)N);
   for (int x = 0; x < n_emb; ++x) {
     const size_t d = dims[x];
     L.norms[x] = o; o = al256(o + 4 * (size_t)N);
     L.Xh[x] = o; o = al256(o + 4 * (size_t)N * d);
     L.F1[x] = o; o = al256(o + 4 * (size_t)A * L.ldF);
     L.F2[x] = o; o = al256(o + 4 * (size_t)A * L.ldF);
+    if (gram_ts_ok((int)d)) {
+      const int rows[4] = {A, A, J1, J2};
+      for (int s4 = 0; s4 < 4; ++s4) {
+        o = (o + 1023) & ~(size_t)1023;      // bulk-copy sources: keep the images 1 KiB aligned
+        L.img[x][s4] = o;
+        o += gram_image_bytes(rows[s4], (int)d);
+      }
+      o = al256(o);
+    }
     if (want_grad) { L.dXh[x] = o; o = al256(o + 4 * (size_t)N * d); }
   }
   if (want_grad && n_emb > 1) {
@@ -303,6 +327,19 @@ extern "C" size_t sga_loss_workspace_bytes(int n_emb, const int* dims_host, int6
   return sga::make_layout(n_emb, dims_host, N, A, J1, J2, want_grad).total;
 }
 
+// Kernels one sga_loss_fwd_bwd call launches (for the caller's launch accounting; memsets are not kernels).
+extern "C" int sga_loss_launch_count(int n_emb, const int* dims_host, int J1, int J2, int want_grad) {
+  using namespace sga;
+  int n_ts = 0;
+  for (int x = 0; x < n_emb; ++x) n_ts += gram_ts_ok(dims_host[x]) ? 1 : 0;
+  const int n_wide = n_emb - n_ts;
+  int n = 2 + 2 * n_emb;                                   // ridx, finalize; per embedding: norm/pack, pair
+  if (n_ts) n += 1 + (2 * n_ts + kGramMaxGroup - 1) / kGramMaxGroup;     // slots + grouped gram_ts launches
+  if (n_wide) n += (2 * n_wide + kGemmMaxGroup - 1) / kGemmMaxGroup;
+  if (want_grad) n += n_emb * ((J1 + J2 > 0) ? 2 : 1) + 2 * ((2 * n_emb + kGemmMaxGroup - 1) / kGemmMaxGroup);
+  return n;
+}
+
 extern "C" int sga_loss_fwd_bwd(const float* const* embs_host, const int* dims_host, int n_emb, int64_t N,
                                 const int32_t* e1i, const int32_t* e2i, const int32_t* e1j, const int32_t* e2j,
                                 int A, int J1, int J2, const float* log_vars_ial, const float* log_vars_icl,
@@ -336,16 +373,44 @@ extern "C" int sga_loss_fwd_bwd(const float* const* embs_host, const int* dims_h
   build_ridx_kernel<<<(T + NT - 1) / NT, NT, 0, st>>>(e1i, e2i, e1j, e2j, A, J1, J2, ridx, r2idx);
   SGA_LAUNCH_CHECK();
 
-  // ---- forward Grams on the tensor cores: rows normalised once, gathers in the loader, exp-sums in the epilogue;
-  //      the 2 * n_emb Grams are ONE grouped launch (gemm_tc.cuh)
+  // ---- forward Grams on the tensor cores.  d <= 128: rows normalised, split and laid out as MMA tile images once
+  //      (pack_rows_kernel), Grams by the TMA-fed A-in-tensor-memory kernel (gram_ts.cu), all embeddings and both
+  //      directions in one grouped launch.  Wider embeddings: rows normalised once, gathers + split in the loader of
+  //      the generic GEMM (gemm_tc.cu), again one grouped launch.  Normaliser sums come out of the epilogues.
   GemmParams probs[2 * 16];
-  int np = 0;
+  GramProblem gprobs[2 * 16];
+  int np = 0, ngp = 0;
+  bool slots_built = false;
   for (int x = 0; x < n_emb; ++x) {
     const int d = dims_host[x];
     const float* Xh = F(L.Xh[x]);
+    double* Sx = S + (size_t)x * 8;
+    if (gram_ts_ok(d)) {
+      if (!slots_built) {
+        int rc = launch_build_slots(e1i, e2i, e1j, e2j, A, J1, J2, (int32_t*)(ws + L.slot), N, st);
+        if (rc != SGA_OK) return rc;
+        slots_built = true;
+      }
+      unsigned char* img[4] = {ws + L.img[x][0], ws + L.img[x][1], ws + L.img[x][2], ws + L.img[x][3]};
+      int rc = launch_pack_rows(embs_host[x], N, d, (const int32_t*)(ws + L.slot), img, F(L.norms[x]), F(L.Xh[x]), st);
+      if (rc != SGA_OK) return rc;
+      for (int dir = 0; dir < 2; ++dir) {
+        GramProblem& P = gprobs[ngp++];
+        memset(&P, 0, sizeof(P));
+        P.a_img = img[dir];                       // P1 = Xh[e1i] / P2 = Xh[e2i]
+        P.b_img[0] = img[1 - dir];                // [P2; Q1; Q2] / [P1; Q2; Q1]
+        P.b_img[1] = img[dir == 0 ? 2 : 3];
+        P.b_img[2] = img[dir == 0 ? 3 : 2];
+        P.seg_rows[0] = A; P.seg_rows[1] = dir == 0 ? J1 : J2; P.seg_rows[2] = dir == 0 ? J2 : J1;
+        P.M = A; P.nkc = (d + 31) / 32;
+        P.C = F(dir == 0 ? L.F1[x] : L.F2[x]); P.ldc = ldF;
+        const int lo = dir == 0 ? 0 : 2, hi = dir == 0 ? 1 : 3;   // {S11,S12} / {S22,S21}
+        P.s01[0] = Sx + lo; P.s01[1] = Sx + hi; P.s1[0] = Sx + 4 + lo; P.s1[1] = Sx + 4 + hi;
+      }
+      continue;
+    }
     row_norm_kernel<<<(unsigned)((N + 7) / 8), NT, 0, st>>>(embs_host[x], N, d, F(L.norms[x]), F(L.Xh[x]));
     SGA_LAUNCH_CHECK();
-    double* Sx = S + (size_t)x * 8;
     for (int dir = 0; dir < 2; ++dir) {
       GemmParams& P = probs[np++];
       memset(&P, 0, sizeof(P));
@@ -361,7 +426,9 @@ extern "C" int sga_loss_fwd_bwd(const float* const* embs_host, const int* dims_h
     }
   }
   {
-    int rc = launch_gemm_tc_group(probs, np, st);
+    int rc = launch_gram_ts(gprobs, ngp, st);
+    if (rc != SGA_OK) return rc;
+    rc = launch_gemm_tc_group(probs, np, st);
     if (rc != SGA_OK) return rc;
   }
   // ---- element-wise loss terms (+ in-place gradient of the G blocks)

@@ -463,10 +463,7 @@ def loss_forward_backward(embs: Sequence[torch.Tensor], idx: Sequence[torch.Tens
                                _ptr(None if lv_ial is None else _f32c(lv_ial)), _ptr(None if lv_icl is None else _f32c(lv_icl)),
                                float(zoom), _ptr(losses), 1 if want_grad else 0, g_ptrs, _ptr(g_ial), _ptr(g_icl),
                                _ptr(ws), ws.numel(), _stream()), 'sga_loss_fwd_bwd')
-    # index build + finalize; per embedding: norm, pair kernel; the 2*n_emb Grams as grouped launches of <= 16 problems;
-    # backward: per embedding coef (if there are non-anchors) + normalize, the 4*n_emb GEMMs as 2 grouped launch series
-    ng = (2 * n_emb + 15) // 16
-    _count(2 + 2 * n_emb + ng + ((n_emb * (2 if J1 + J2 > 0 else 1) + 2 * ng) if want_grad else 0))
+    _count(lib.sga_loss_launch_count(n_emb, dims, J1, J2, 1 if want_grad else 0))
     return losses, grads, g_ial, g_icl
 
 
