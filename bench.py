@@ -298,9 +298,17 @@ def run_ours(args, out=sys.stdout):
     e2e_eager_ms /= args.steps
     # the same host-to-host step as ONE graph: pinned staging buffers -> chunked H2D on a forked copy stream ->
     # encoder (point encoder chunk by chunk as copies land) -> matching -> D2H into pinned result buffers
-    cap.capture_host_step(host, n_chunks=4)
-    e2e_graph_ms, _, _ = timed(cap.run_host, args.steps, args.warmup)
-    e2e_graph_ms /= args.steps
+    # (the point copy is cut into object ranges so that the encoder trails the copy; finer ranges shorten the tail
+    #  after the last copy, coarser ones have less per-launch overhead: measure both, keep the better)
+    e2e_graph_ms, e2e_chunks = None, None
+    for n_chunks in (4, 8):
+        cap.capture_host_step(host, n_chunks=n_chunks)
+        ms, _, _ = timed(cap.run_host, args.steps, args.warmup)
+        ms /= args.steps
+        if e2e_graph_ms is None or ms < e2e_graph_ms:
+            e2e_graph_ms, e2e_chunks = ms, n_chunks
+    if e2e_chunks != 8:
+        cap.capture_host_step(host, n_chunks=e2e_chunks)
     # the PCIe floor of this step on this box: the same bytes copied from pinned memory with nothing else running
     pts_dev = torch.empty_like(data['tot_obj_pts'])
     h2d_ms, _, _ = timed(lambda: pts_dev.copy_(host_pinned['tot_obj_pts'], non_blocking=True), args.steps, args.warmup)
@@ -362,7 +370,7 @@ def run_ours(args, out=sys.stdout):
                                  'algorithmic_bytes_per_launch': BYTES_PER_OBJECT * N}},
             'cpu_baseline': cpu,
             'e2e': {'value': world * PAIRS_PER_GPU / (e2e_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_ms, 'eager_ms_per_step': e2e_eager_ms,
-                    'graph_ms_per_step': e2e_graph_ms, 'api': e2e_api,
+                    'graph_ms_per_step': e2e_graph_ms, 'graph_point_chunks': e2e_chunks, 'api': e2e_api,
                     'h2d_points_only_ms': h2d_ms, 'h2d_points_only_gbs': host_pinned['tot_obj_pts'].numel() * 4 / (h2d_ms * 1e-3) / 1e9,
                     'h2d_bytes_per_step': h2d_bytes(host, KEYS), 'd2h_bytes_per_step': int(d2h),
                     'h2d': 'pinned host batch; only the tensors the configured modalities read are copied (points, rel_pose, edges, anchors)'},

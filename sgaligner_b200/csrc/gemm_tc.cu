@@ -429,6 +429,15 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmGroup G) {
 }  // namespace
 
 namespace {
+// profiling switches (tools/gemm_probe.py): read once per process
+inline int gemm_dbg_flags() {
+  static int flags = -1;
+  if (flags < 0) {
+    const char* e = getenv("SGA_GEMM_DBG");
+    flags = e ? atoi(e) : 0;
+  }
+  return flags;
+}
 inline int work_items(const GemmParams& P) {
   return ((P.M + 127) / 128) * ((P.N + 127) / 128) * (P.ksplit > 1 ? P.ksplit : 1);
 }
@@ -461,7 +470,7 @@ int launch_gemm_tc_group(const GemmParams* problems, int n, cudaStream_t st) {
       }
       total += work_items(P);
       G.p[G.n] = P;
-      { const char* e = getenv("SGA_GEMM_DBG"); G.p[G.n].dbg = e ? atoi(e) : 0; }
+      G.p[G.n].dbg = gemm_dbg_flags();
       G.work_end[G.n] = total;
       ++G.n;
     }

@@ -9,8 +9,13 @@ Z = torch.randn(16384, K, device=dev)
 ia = torch.randint(0, 16384, (M,), device=dev, dtype=torch.int32)
 ib = torch.randint(0, 16384, (N,), device=dev, dtype=torch.int32)
 out = torch.empty(M, N, device=dev)
-for dbg in (0, 1, 2, 3, 4, 8, 12, 15):
-    os.environ['SGA_GEMM_DBG'] = str(dbg)
+dbg = int(os.environ.get('SGA_GEMM_DBG', '0'))      # read once by the library: one process per setting
+if len(sys.argv) <= 4 and 'SGA_GEMM_DBG' not in os.environ:
+    import subprocess
+    for d in (0, 1, 2, 3, 4, 8, 12, 15):
+        subprocess.run([sys.executable, __file__] + sys.argv[1:4], env=dict(os.environ, SGA_GEMM_DBG=str(d)), check=True)
+    sys.exit(0)
+for dbg in (dbg,):
     for _ in range(2):
         ops.gemm_tf32x3(Z, Z, M, N, K, a_idx=ia, b_idx=ib, out=out)
     a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
