@@ -301,14 +301,16 @@ def run_ours(args, out=sys.stdout):
     # (the point copy is cut into object ranges so that the encoder trails the copy; finer ranges shorten the tail
     #  after the last copy, coarser ones have less per-launch overhead: measure both, keep the better)
     e2e_graph_ms, e2e_chunks = None, None
-    for n_chunks in (4, 8):
-        cap.capture_host_step(host, n_chunks=n_chunks)
+    variants = [(4, False), (4, True), (6, True)]
+    for n_chunks, taper in variants:
+        cap.capture_host_step(host, n_chunks=n_chunks, taper=taper)
         ms, _, _ = timed(cap.run_host, args.steps, args.warmup)
         ms /= args.steps
         if e2e_graph_ms is None or ms < e2e_graph_ms:
-            e2e_graph_ms, e2e_chunks = ms, n_chunks
-    if e2e_chunks != 8:
-        cap.capture_host_step(host, n_chunks=e2e_chunks)
+            e2e_graph_ms, e2e_chunks = ms, (n_chunks, taper)
+    if e2e_chunks != variants[-1]:
+        cap.capture_host_step(host, n_chunks=e2e_chunks[0], taper=e2e_chunks[1])
+    e2e_chunks = '%d ranges%s' % (e2e_chunks[0], ', shrinking' if e2e_chunks[1] else '')
     # the PCIe floor of this step on this box: the same bytes copied from pinned memory with nothing else running
     pts_dev = torch.empty_like(data['tot_obj_pts'])
     h2d_ms, _, _ = timed(lambda: pts_dev.copy_(host_pinned['tot_obj_pts'], non_blocking=True), args.steps, args.warmup)

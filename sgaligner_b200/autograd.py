@@ -29,6 +29,7 @@ class PointNetFeat(torch.autograd.Function):
         if need:
             ctx.save_for_backward(pts, W1, b1, W2, b2, W3, b3, out, arg)
             ctx.mode = mode if W3.shape[0] % 128 == 0 else ops.POINTNET_SIMT
+            ctx.params = (W1, b1, W2, b2, W3, b3)
         if mom is not None:
             ctx.mark_non_differentiable(mom)
         return out, mom
@@ -36,8 +37,10 @@ class PointNetFeat(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout, _gmom=None):
         pts, W1, b1, W2, b2, W3, b3, out, arg = ctx.saved_tensors
-        gW1, gb1, gW2, gb2, gW3, gb3 = ops.pointnet_backward(pts, W1, b1, W2, b2, W3, b3, out, arg, gout.contiguous(), mode=ctx.mode)
-        return None, gW1.view_as(W1), gb1, gW2.view_as(W2), gb2, gW3.view_as(W3), gb3, None, None, None, None
+        into = [ops.grad_target(p) if need else None for p, need in zip(ctx.params, ctx.needs_input_grad[1:7])]
+        g = ops.pointnet_backward(pts, W1, b1, W2, b2, W3, b3, out, arg, gout.contiguous(), mode=ctx.mode, into=into)
+        g = [None if t is None else t.view_as(p) for t, p in zip(g, ctx.params)]     # None: accumulated into p.grad
+        return (None, *g, None, None, None, None)
 
 
 class GATLayer(torch.autograd.Function):
@@ -49,15 +52,19 @@ class GATLayer(torch.autograd.Function):
         out = ops.gat_aggregate(xs, a_s, a_d, graph, bias, apply_elu)
         ctx.graph, ctx.H, ctx.C, ctx.apply_elu = graph, H, C, apply_elu
         ctx.need_gx = x.requires_grad
+        ctx.params = (W, att_src, att_dst, bias)
         ctx.save_for_backward(x, W, att_src, att_dst, xs, a_s, a_d, out)
         return out
 
     @staticmethod
     def backward(ctx, gout):
         x, W, att_src, att_dst, xs, a_s, a_d, out = ctx.saved_tensors
-        g_xs, g_as, g_ad, g_bias = ops.gat_aggregate_backward(xs, a_s, a_d, ctx.graph, ctx.apply_elu, out, gout.contiguous())
-        gW, g_att_s, g_att_d, gx = ops.gat_linear_backward(x, W, att_src, att_dst, ctx.H, ctx.C, xs, g_xs, g_as, g_ad, ctx.need_gx)
-        return gx, gW, g_att_s.view_as(att_src), g_att_d.view_as(att_dst), g_bias, None, None, None, None
+        tW, ts, td, tb = [ops.grad_target(p) for p in ctx.params]
+        g_xs, g_as, g_ad, g_bias = ops.gat_aggregate_backward(xs, a_s, a_d, ctx.graph, ctx.apply_elu, out, gout.contiguous(), into_bias=tb)
+        gW, g_att_s, g_att_d, gx = ops.gat_linear_backward(x, W, att_src, att_dst, ctx.H, ctx.C, xs, g_xs, g_as, g_ad, ctx.need_gx,
+                                                           into=(tW, ts, td))
+        return (gx, gW, None if g_att_s is None else g_att_s.view_as(att_src), None if g_att_d is None else g_att_d.view_as(att_dst),
+                g_bias, None, None, None, None)
 
 
 class ProjectFuse(torch.autograd.Function):
@@ -82,6 +89,7 @@ class ProjectFuse(torch.autograd.Function):
                 col += out_dims[m]
         ctx.M, ctx.out_dims = M, out_dims
         ctx.need_gx = [x.requires_grad for x in xs]
+        ctx.params = (fusion_w, Ws, bs)
         ctx.save_for_backward(fusion_w, *xs, *Ws, *embs)
         return (*embs, joint) if M > 1 else (embs[0],)
 
@@ -93,16 +101,19 @@ class ProjectFuse(torch.autograd.Function):
         g_joint = gouts[M] if M > 1 else None
         if g_joint is not None:
             g_joint = g_joint.contiguous()
-        g_fw = torch.zeros(M, device=fusion_w.device, dtype=torch.float32)
+        p_fw, p_Ws, p_bs = ctx.params
+        t_fw = ops.grad_target(p_fw)
+        # the kernels ADD into g_fusion_w: one buffer (the parameter's own .grad when it is kept allocated) for all M
+        g_fw = t_fw if t_fw is not None else torch.zeros(M, device=fusion_w.device, dtype=torch.float32)
         grads, col = [], 0
         for m in range(M):
             g_emb = gouts[m]
-            gW, gb, gfw, gx = ops.project_fuse_backward(xs[m], Ws[m], embs[m], None if g_emb is None else g_emb.contiguous(),
-                                                        g_joint, col, fusion_w, M, m, ctx.need_gx[m])
-            g_fw += gfw
+            gW, gb, _, gx = ops.project_fuse_backward(xs[m], Ws[m], embs[m], None if g_emb is None else g_emb.contiguous(),
+                                                      g_joint, col, fusion_w, M, m, ctx.need_gx[m],
+                                                      into=(ops.grad_target(p_Ws[m]), ops.grad_target(p_bs[m]), g_fw.view(-1)))
             grads += [gx, gW, gb]
             col += ctx.out_dims[m]
-        return (g_fw.view_as(fusion_w), None, *grads)
+        return (None if t_fw is not None else g_fw.view_as(fusion_w), None, *grads)
 
 
 class OverallLossFn(torch.autograd.Function):

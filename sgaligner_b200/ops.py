@@ -134,17 +134,41 @@ def pointnet_forward_stats(pts, W1, b1, W2, b2, W3, b3, want_argmax: bool):
     return out, arg, buf[:n_mom]
 
 
-def pointnet_backward(pts, W1, b1, W2, b2, W3, b3, out, arg, gout, mode: int = POINTNET_SIMT):
+def grad_target(p: torch.Tensor):
+    """The tensor a backward kernel may accumulate a PARAMETER gradient into directly: ``p.grad`` when the
+    optimiser keeps gradients allocated (``trainer.FlatAdam`` points every ``.grad`` into one flat buffer and
+    zeroes it with one memset).  All parameter-gradient kernels accumulate (atomics / beta = 1), so writing
+    there removes a zero-fill and autograd's ``grad += new`` kernel per parameter (~40 launches per step)."""
+    g = getattr(p, 'grad', None)
+    if (g is not None and p.is_leaf and g.dtype == torch.float32 and g.is_cuda and g.is_contiguous()
+            and g.numel() == p.numel() and g.device == p.device):
+        return g
+    return None
+
+
+def _grad_buf(shape, dev, into):
+    """(buffer for the kernel, tensor to hand back to autograd or None when accumulated in place)"""
+    if into is not None:
+        return into, None
+    t = torch.zeros(shape, device=dev, dtype=torch.float32)
+    return t, t
+
+
+def pointnet_backward(pts, W1, b1, W2, b2, W3, b3, out, arg, gout, mode: int = POINTNET_SIMT, into=None):
+    """``into``: optional 6 tensors (or None entries) to accumulate gW1, gb1, gW2, gb2, gW3, gb3 into; the
+    corresponding returned entries are None."""
     pts, w = _pointnet_args(pts, W1, b1, W2, b2, W3, b3, mode)
     N, P, _ = pts.shape
     C3 = W3.shape[0]
     dev = pts.device
-    g = [torch.zeros(s, device=dev, dtype=torch.float32) for s in ((64, 3), (64,), (128, 64), (128,), (C3, 128), (C3,))]
+    into = into or [None] * 6
+    pairs = [_grad_buf(s, dev, t) for s, t in zip(((64, 3), (64,), (128, 64), (128,), (C3, 128), (C3,)), into)]
+    g = [b for b, _ in pairs]
     with _timed('pointnet_bwd'):
         check(get_lib().sga_pointnet_bwd_mode(_ptr(pts), N, P, *[_ptr(t) for t in w], C3, _ptr(out), _ptr(arg), _ptr(_f32c(gout)),
                                               *[_ptr(t) for t in g], mode, _stream()), 'sga_pointnet_bwd')
     _count(1)
-    return g
+    return [r for _, r in pairs]
 
 
 def pointnet_bn_moments(pts, W1, b1, W2, b2, W3, b3):
@@ -238,35 +262,37 @@ def as_f32(x: torch.Tensor) -> torch.Tensor:
     return _f32c(x)
 
 
-def gat_aggregate_backward(xs, a_s, a_d, graph: BatchGraph, apply_elu: bool, out, gout):
+def gat_aggregate_backward(xs, a_s, a_d, graph: BatchGraph, apply_elu: bool, out, gout, into_bias=None):
     H, N, C = xs.shape
     dev = xs.device
     g_xs = torch.zeros_like(xs)
     g_as = torch.zeros((N, H), device=dev, dtype=torch.float32)
     g_ad = torch.zeros((N, H), device=dev, dtype=torch.float32)
-    g_bias = torch.zeros(H * C, device=dev, dtype=torch.float32)
+    g_bias, g_bias_ret = _grad_buf(H * C, dev, into_bias)
     check(get_lib().sga_gat_aggregate_bwd(_ptr(xs), _ptr(a_s), _ptr(a_d), _ptr(graph.row_beg), _ptr(graph.row_cnt),
                                           _ptr(graph.col), _ptr(graph.node_off), graph.G, graph.max_nodes, N, H, C,
                                           1 if apply_elu else 0, _ptr(out), _ptr(_f32c(gout)),
                                           _ptr(g_xs), _ptr(g_as), _ptr(g_ad), _ptr(g_bias), _stream()),
           'sga_gat_aggregate_bwd')
     _count(1)
-    return g_xs, g_as, g_ad, g_bias
+    return g_xs, g_as, g_ad, g_bias_ret
 
 
-def gat_linear_backward(x, W, att_src, att_dst, H, C, xs, g_xs, g_as, g_ad, need_gx: bool):
+def gat_linear_backward(x, W, att_src, att_dst, H, C, xs, g_xs, g_as, g_ad, need_gx: bool, into=None):
+    """``into``: optional (gW, g_att_src, g_att_dst) accumulation targets (see :func:`grad_target`)."""
     x = as_f32(x)
     N, in_dim = x.shape
     dev = x.device
-    gW = torch.zeros((H * C, in_dim), device=dev, dtype=torch.float32)
-    g_att_s = torch.zeros(H * C, device=dev, dtype=torch.float32)
-    g_att_d = torch.zeros(H * C, device=dev, dtype=torch.float32)
+    into = into or (None, None, None)
+    gW, gW_ret = _grad_buf((H * C, in_dim), dev, into[0])
+    g_att_s, g_att_s_ret = _grad_buf(H * C, dev, into[1])
+    g_att_d, g_att_d_ret = _grad_buf(H * C, dev, into[2])
     gx = torch.empty((N, in_dim), device=dev, dtype=torch.float32) if need_gx else None
     check(get_lib().sga_gat_linear_bwd(_ptr(x), N, in_dim, _ptr(_f32c(W)), _ptr(_f32c(att_src).reshape(-1)),
                                        _ptr(_f32c(att_dst).reshape(-1)), H, C, _ptr(xs), _ptr(g_xs), _ptr(g_as), _ptr(g_ad),
                                        _ptr(gW), _ptr(g_att_s), _ptr(g_att_d), _ptr(gx), _stream()), 'sga_gat_linear_bwd')
     _count(1 + H * (2 if need_gx else 1))
-    return gW, g_att_s, g_att_d, gx
+    return gW_ret, g_att_s_ret, g_att_d_ret, gx
 
 
 # --------------------------------------------------------------------------------- projection + fusion
@@ -312,14 +338,17 @@ def project_fuse_multi(xs, Ws, bs, fusion_w, want_joint: bool):
     return embs, joint
 
 
-def project_fuse_backward(x, W, emb, g_emb, g_joint, joint_col: int, fusion_w, M: int, m: int, need_gx: bool):
+def project_fuse_backward(x, W, emb, g_emb, g_joint, joint_col: int, fusion_w, M: int, m: int, need_gx: bool, into=None):
+    """``into``: optional (gW, gb, g_fusion_w) accumulation targets (see :func:`grad_target`); the kernels add
+    into them, so one ``g_fusion_w`` buffer can be shared by the M calls of a step."""
     x = as_f32(x)
     N, in_dim = x.shape
     out_dim = W.shape[0]
     dev = x.device
-    gW = torch.zeros((out_dim, in_dim), device=dev, dtype=torch.float32)
-    gb = torch.zeros(out_dim, device=dev, dtype=torch.float32)
-    gfw = torch.zeros(M, device=dev, dtype=torch.float32)
+    into = into or (None, None, None)
+    gW, gW_ret = _grad_buf((out_dim, in_dim), dev, into[0])
+    gb, gb_ret = _grad_buf(out_dim, dev, into[1])
+    gfw, gfw_ret = _grad_buf(M, dev, into[2])
     gx = torch.empty((N, in_dim), device=dev, dtype=torch.float32) if need_gx else None
     ws = torch.empty(N * out_dim + 64, device=dev, dtype=torch.float32)
     fw = None if g_joint is None else _f32c(fusion_w).reshape(-1)
@@ -330,7 +359,7 @@ def project_fuse_backward(x, W, emb, g_emb, g_joint, joint_col: int, fusion_w, M
                                          _ptr(gW), _ptr(gb), _ptr(gfw), _ptr(gx), _ptr(ws), ws.numel() * 4, _stream()),
           'sga_project_fuse_bwd')
     _count(3 + (1 if g_joint is not None else 0) + (1 if need_gx else 0))
-    return gW, gb, gfw, gx
+    return gW_ret, gb_ret, gfw_ret, gx
 
 
 # --------------------------------------------------------------------------------- matching

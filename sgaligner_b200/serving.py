@@ -114,7 +114,7 @@ class CapturedInference:
         return self.out
 
     # ------------------------------------------------------------------ host-to-host step in one graph
-    def capture_host_step(self, host_batch: Dict, n_chunks: int = 8):
+    def capture_host_step(self, host_batch: Dict, n_chunks: int = 8, taper: bool = False):
         """Second graph for batches that start in HOST memory: pinned staging buffers (returned; a loader collates
         into them in place) -> H2D copies on a forked copy stream (small tensors first, then the points in
         ``n_chunks`` object ranges) -> graph branch as soon as the small tensors have landed, point encoder chunk by
@@ -128,8 +128,15 @@ class CapturedInference:
         self.host_e2 = torch.empty(self.n_anchor, dtype=torch.int32).pin_memory()
         self.fill_host(host_batch)
         N = int(self.static['tot_obj_pts'].shape[0])
-        per = -(-N // max(1, n_chunks))
-        ranges = [(s, min(N, s + per)) for s in range(0, N, per)]
+        if taper and n_chunks > 1:
+            # the step is PCIe bound: the encoder always waits for the copy, so what the step pays after the last
+            # copy is the encoder time of the LAST range -- make the ranges shrink (n : n-1 : ... : 1)
+            w = np.arange(n_chunks, 0, -1, dtype=np.float64)
+            cuts = np.concatenate([[0], np.round(np.cumsum(w) / w.sum() * N)]).astype(np.int64)
+            ranges = [(int(a), int(b)) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+        else:
+            per = -(-N // max(1, n_chunks))
+            ranges = [(s, min(N, s + per)) for s in range(0, N, per)]
         cs = torch.cuda.Stream(device=self.dev)
         self.host_out = {}
 

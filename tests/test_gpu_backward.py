@@ -146,3 +146,41 @@ def test_train_steps_reduce_loss(dev):
     losses = [float(train_step(model, fn, opt, data)['loss']) for _ in range(12)]
     assert all(np.isfinite(losses))
     assert losses[-1] < losses[0]
+
+
+def test_direct_grad_accumulation_matches_autograd(dev):
+    """When ``.grad`` tensors are kept allocated (FlatAdam, or ``zero_grad(set_to_none=False)``) the backward kernels
+    accumulate parameter gradients straight into them (``ops.grad_target``) instead of returning fresh tensors for
+    autograd to add: same values, and a second backward accumulates on top exactly like autograd would."""
+    from sgaligner_b200 import synthetic, to_cuda
+    from sgaligner_b200.losses import CustomMultiLossLayer, OverallLoss
+    from sgaligner_b200.sg_aligner import MultiModalEncoder
+    mods = ['point', 'gat', 'rel', 'attr']
+    data = to_cuda(synthetic.make_batch([9, 12, 7], [11, 8, 10], [5, 6, 4], n_points=128, edge_mode='complete', seed=5), dev)
+    torch.manual_seed(0)
+    model = MultiModalEncoder(modules=mods, rel_dim=41, attr_dim=164).to(dev).eval()
+    li, lc = CustomMultiLossLayer(4).to(dev), CustomMultiLossLayer(4).to(dev)
+    fn = OverallLoss(li, lc, dev, {'zoom': 0.1, 'wt_align_loss': 1.0, 'wt_contrastive_loss': 1.0, 'modules': mods})
+    params = [p for p in model.parameters() if p.requires_grad]
+
+    def backward():
+        fn(model(data), data)['loss'].backward()
+        torch.cuda.synchronize()
+
+    assert all(p.grad is None for p in params)
+    backward()                                          # fallback: autograd receives tensors
+    ref = [None if p.grad is None else p.grad.detach().clone() for p in params]
+    for p in params:
+        if p.grad is not None:
+            p.grad.zero_()                              # keep the tensors: the next backward goes direct
+    ptrs = [None if p.grad is None else p.grad.data_ptr() for p in params]
+    backward()
+    for p, r, q in zip(params, ref, ptrs):
+        if r is None:
+            continue
+        assert p.grad.data_ptr() == q                   # accumulated in place
+        assert grad_close(p.grad, r, rtol=1e-4, atol=1e-7 * float(r.abs().max()) + 1e-12)
+    backward()                                          # no zeroing: gradients accumulate
+    for p, r in zip(params, ref):
+        if r is not None:
+            assert grad_close(p.grad, 2 * r, rtol=1e-4, atol=2e-7 * float(r.abs().max()) + 1e-12)
