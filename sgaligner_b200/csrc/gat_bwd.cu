@@ -7,6 +7,7 @@
 //                   GEMMs (gW, gx) on the fp32 FMA path.
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "ptx.cuh"
 
 namespace sga {
@@ -269,6 +270,17 @@ extern "C" int sga_gat_linear_bwd(const float* x, int64_t N, int in_dim, const f
   SGA_LAUNCH_CHECK();
   for (int h = 0; h < H; ++h) {
     const float* gh = g_xs + (int64_t)h * N * C;
+    if (sga::gemm_tc_worth(C, in_dim)) {       // layer 1 (256 -> 2 x 128): tcgen05 GEMMs; layer 0 (in_dim = 3) stays on FMA
+      // gW[h*C + c][k] += sum_n gh[n][c] x[n][k]
+      int rc = sga::launch_gemm_tc_dense(gh, C, 1, x, in_dim, 1, C, in_dim, (int)N, gW + (int64_t)h * C * in_dim, in_dim, 1, st);
+      if (rc != SGA_OK) return rc;
+      // gx[n][k] (+)= sum_c gh[n][c] W[h*C + c][k]   (head 0 stores, the following launches add)
+      if (gx) {
+        rc = sga::launch_gemm_tc_dense(gh, C, 0, W + (int64_t)h * C * in_dim, in_dim, 1, (int)N, in_dim, C, gx, in_dim, h > 0, st);
+        if (rc != SGA_OK) return rc;
+      }
+      continue;
+    }
     // gW[h*C + c][k] += sum_n gh[n][c] x[n][k]
     SGA_CUDA(sga::launch_gemm(gh, 1, C, x, in_dim, 1, gW + (int64_t)h * C * in_dim, in_dim, C, in_dim, (int)N, 1, st,
                               sga::splitk_for(C, in_dim, (int)N)));

@@ -371,7 +371,7 @@ gemm_tf32x3_kernel(const __grid_constant__ GemmGroup G) {
       const int row = m0 + r;
       const bool row_ok = row < P.M && (ksl * kc_per < nkc_all);
       float* crow = nullptr;
-      if (row_ok) crow = P.C + (P.mode == 2 ? (int64_t)P.c_idx[row] : (int64_t)row) * P.ldc;
+      if (row_ok) crow = P.C + ((P.mode == 2 && P.c_idx) ? (int64_t)P.c_idx[row] : (int64_t)row) * P.ldc;
       const uint32_t base = tmem + ((uint32_t)(32 * q) << 16) + ab * 128;
       const bool slice_ok = ksl * kc_per < nkc_all;
       const int rows_here = slice_ok ? min(32, P.M - (m0 + 32 * q)) : 0;      // valid rows of this warp's 32-row band
@@ -489,6 +489,30 @@ int launch_gemm_tc_group(const GemmParams* problems, int n, cudaStream_t st) {
 }
 
 int launch_gemm_tc(const GemmParams& P, cudaStream_t st) { return launch_gemm_tc_group(&P, 1, st); }
+
+// Dense product without gathers: C[M,N] = (or +=) sum_k A(m,k) B(n,k).  accumulate: C already holds the value to
+// add to and the K range is cut into slices that add their partial products atomically (weight gradients: small
+// output, contraction over all nodes of the batch).
+int launch_gemm_tc_dense(const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb, int b_mn, int M, int N, int K,
+                         float* C, int64_t ldc, int accumulate, cudaStream_t st) {
+  GemmParams P;
+  memset(&P, 0, sizeof(P));
+  P.A = {A, lda, nullptr, nullptr, a_mn};
+  P.B = {B, ldb, nullptr, nullptr, b_mn};
+  P.M = M; P.N = N; P.K = K;
+  P.C = C; P.ldc = ldc;
+  P.mode = accumulate ? 2 : 0;
+  P.ksplit = 1;
+  if (accumulate) {
+    const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
+    const int chunks = (K + 31) / 32;
+    int want = (2 * sm_count() + tiles - 1) / tiles;
+    const int cap = chunks / 4;
+    if (want > cap) want = cap;
+    P.ksplit = want < 1 ? 1 : want;
+  }
+  return launch_gemm_tc_group(&P, 1, st);
+}
 
 }  // namespace sga
 

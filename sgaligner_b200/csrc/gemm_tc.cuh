@@ -38,5 +38,10 @@ struct GemmGroup {
 int launch_gemm_tc(const GemmParams& P, cudaStream_t st);
 // `n` problems (any n: launched in chunks of kGemmMaxGroup); all must share (A.mn_major, B.mn_major).
 int launch_gemm_tc_group(const GemmParams* problems, int n, cudaStream_t st);
+// dense product without gathers; accumulate = split-K with atomic adds into C
+int launch_gemm_tc_dense(const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb, int b_mn, int M, int N, int K,
+                         float* C, int64_t ldc, int accumulate, cudaStream_t st);
+// shapes worth a tensor-core launch (tiny feature widths stay on the FMA kernel)
+inline bool gemm_tc_worth(int feat_a, int feat_b) { return feat_a >= 32 && feat_b >= 32; }
 
 }  // namespace sga

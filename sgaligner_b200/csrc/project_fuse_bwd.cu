@@ -3,6 +3,7 @@
 // (src/aligner/sg_aligner.py:30-35 and :112-122).
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 
 namespace sga {
 namespace {
@@ -117,12 +118,23 @@ extern "C" int sga_project_fuse_bwd(const float* x, int64_t N, int in_dim, const
     sga::fusion_w_bwd_kernel<<<1, 32, 0, st>>>(fusion_w, M, m, t_acc, g_fusion_w);
     SGA_LAUNCH_CHECK();
   }
-  // gW[c][k] += sum_n g[n][c] x[n][k]
-  SGA_CUDA(sga::launch_gemm(g_total, 1, out_dim, x, in_dim, 1, gW, in_dim, out_dim, in_dim, (int)N, 1, st,
-                            sga::splitk_for(out_dim, in_dim, (int)N)));
+  // gW[c][k] += sum_n g[n][c] x[n][k]: contraction over the nodes, both operands read MN-major by the tcgen05 GEMM
+  const bool tc = sga::gemm_tc_worth(out_dim, in_dim);
+  if (tc) {
+    int rc = sga::launch_gemm_tc_dense(g_total, out_dim, 1, x, in_dim, 1, out_dim, in_dim, (int)N, gW, in_dim, 1, st);
+    if (rc != SGA_OK) return rc;
+  } else {
+    SGA_CUDA(sga::launch_gemm(g_total, 1, out_dim, x, in_dim, 1, gW, in_dim, out_dim, in_dim, (int)N, 1, st,
+                              sga::splitk_for(out_dim, in_dim, (int)N)));
+  }
   sga::colsum_kernel<<<(unsigned)((N + sga::CS_ROWS - 1) / sga::CS_ROWS), sga::NT, 0, st>>>(g_total, N, out_dim, gb);
   SGA_LAUNCH_CHECK();
   // gx[n][k] = sum_c g[n][c] W[c][k]
-  if (gx) SGA_CUDA(sga::launch_gemm(g_total, out_dim, 1, W, in_dim, 1, gx, in_dim, (int)N, in_dim, out_dim, 0, st));
+  if (gx && tc) {
+    int rc = sga::launch_gemm_tc_dense(g_total, out_dim, 0, W, in_dim, 1, (int)N, in_dim, out_dim, gx, in_dim, 0, st);
+    if (rc != SGA_OK) return rc;
+  } else if (gx) {
+    SGA_CUDA(sga::launch_gemm(g_total, out_dim, 1, W, in_dim, 1, gx, in_dim, (int)N, in_dim, out_dim, 0, st));
+  }
   return SGA_OK;
 }
