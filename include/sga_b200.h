@@ -221,6 +221,9 @@ size_t sga_loss_workspace_bytes(int n_emb, const int* dims_host, int64_t N, int 
 /* number of kernels one sga_loss_fwd_bwd call with these arguments launches (launch accounting of bench.py).
  * e1i/e2i/e1j/e2j must be pairwise disjoint and duplicate-free (they partition the nodes, scan3r.py:101-107). */
 int sga_loss_launch_count(int n_emb, const int* dims_host, int J1, int J2, int want_grad);
+/* legacy = 1: the index sets of the following sga_loss_fwd_bwd calls may overlap or repeat nodes (not the
+ * dataloader's partition): all Grams gather their rows in the GEMM loader.  Process-wide switch; default 0. */
+void sga_loss_set_gram_path(int legacy);
 int sga_loss_fwd_bwd(const float* const* embs_host, const int* dims_host, int n_emb, int64_t N,
                      const int32_t* e1i, const int32_t* e2i, const int32_t* e1j, const int32_t* e2j,
                      int A, int J1, int J2, const float* log_vars_ial, const float* log_vars_icl,

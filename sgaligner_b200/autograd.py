@@ -122,7 +122,8 @@ class OverallLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, idx, zoom, lv_ial, lv_icl, *embs):
         want_grad = any(ctx.needs_input_grad[2:])
-        losses, grads, g_ial, g_icl = ops.loss_forward_backward(embs, idx, lv_ial, lv_icl, zoom, want_grad)
+        losses, grads, g_ial, g_icl = ops.loss_forward_backward(embs, idx, lv_ial, lv_icl, zoom, want_grad,
+                                                                partition=getattr(idx, 'partition', True))
         ctx.n = len(embs)
         ctx.has_lv = lv_ial is not None
         if want_grad:

@@ -41,13 +41,14 @@ inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // Embeddings up to 128 wide take the TMA-fed / A-in-tensor-memory Gram kernel (gram_ts.cu); SGA_LOSS_GRAM=legacy
 // forces the in-loader-split GEMM (gemm_tc.cu) for everything (A/B comparisons, profiling).
+int g_gram_legacy_override = 0;      // sga_loss_set_gram_path(): 1 = the caller's index sets are not a partition
 inline bool gram_ts_ok(int d) {
   static int legacy = -1;
   if (legacy < 0) {
     const char* e = getenv("SGA_LOSS_GRAM");
     legacy = (e && strcmp(e, "legacy") == 0) ? 1 : 0;
   }
-  return !legacy && d <= 128;
+  return !legacy && !g_gram_legacy_override && d <= 128;
 }
 
 Layout make_layout(int n_emb, const int* dims, int64_t N, int A, int J1, int J2, int want_grad) {
@@ -326,6 +327,10 @@ extern "C" size_t sga_loss_workspace_bytes(int n_emb, const int* dims_host, int6
   if (n_emb < 1 || n_emb > 16) return 0;
   return sga::make_layout(n_emb, dims_host, N, A, J1, J2, want_grad).total;
 }
+
+// 0 (default): e1i/e2i/e1j/e2j partition the nodes (the dataloader contract), narrow embeddings take the packed-image
+// Gram kernel.  1: arbitrary (overlapping / repeated) index sets -- every Gram gathers rows in the GEMM loader instead.
+extern "C" void sga_loss_set_gram_path(int legacy) { sga::g_gram_legacy_override = legacy ? 1 : 0; }
 
 // Kernels one sga_loss_fwd_bwd call launches (for the caller's launch accounting; memsets are not kernels).
 extern "C" int sga_loss_launch_count(int n_emb, const int* dims_host, int J1, int J2, int want_grad) {

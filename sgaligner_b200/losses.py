@@ -13,14 +13,23 @@ from . import autograd as ag
 __all__ = ['torch', 'nn', 'F', 'calculate_prob_dist', 'CustomMultiLossLayer', 'ICLLoss', 'IALLoss', 'OverallLoss']
 
 
+class _IndexSets(list):
+    """[e1i, e2i, e1j, e2j] device tensors + ``partition`` (are the sets disjoint and duplicate-free?)."""
+    partition = True
+
+
 def _index_tensors(data_dict, device):
     """e1i/e2i/e1j/e2j arrive as host int32 numpy arrays (scan3r.py:168-171); cache the device copies
     in the dict so that several loss calls on one batch upload them once."""
     cached = data_dict.get('_sga_idx')
     if cached is not None and cached[0].device == device:
         return cached
-    idx = [torch.as_tensor(np.ascontiguousarray(np.asarray(data_dict[k]).astype(np.int32))).to(device, non_blocking=True)
-           for k in ('e1i', 'e2i', 'e1j', 'e2j')]
+    host = [np.ascontiguousarray(np.asarray(data_dict[k]).astype(np.int32)).reshape(-1) for k in ('e1i', 'e2i', 'e1j', 'e2j')]
+    idx = _IndexSets(torch.as_tensor(h).to(device, non_blocking=True) for h in host)
+    # the collated sets partition the nodes (scan3r.py:101-107); anything else (hand-made overlapping / repeated
+    # indices) is still computed correctly, by the Gram path that gathers rows instead of using packed images
+    allidx = np.concatenate(host)
+    idx.partition = bool(allidx.size == 0 or (allidx.min() >= 0 and np.bincount(allidx).max() <= 1))
     try:
         data_dict['_sga_idx'] = idx
     except TypeError:

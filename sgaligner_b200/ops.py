@@ -468,10 +468,14 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
 
 
 def loss_forward_backward(embs: Sequence[torch.Tensor], idx: Sequence[torch.Tensor], lv_ial, lv_icl, zoom: float,
-                          want_grad: bool):
+                          want_grad: bool, partition: bool = True):
     """embs: M modal embeddings then the joint (or a single embedding).  idx: e1i,e2i,e1j,e2j int32
-    device tensors.  Returns (losses[4], grads or None, g_lv_ial, g_lv_icl)."""
+    device tensors.  Returns (losses[4], grads or None, g_lv_ial, g_lv_icl).
+    ``partition``: the four index sets are disjoint and duplicate-free (true for every collated batch,
+    ``scan3r.py:101-107``; ``losses._index_tensors`` checks it on the host arrays) -- required by the packed-image
+    Gram kernel; False selects the gather-in-the-loader GEMM for all Grams."""
     lib = get_lib()
+    lib.sga_loss_set_gram_path(0 if partition else 1)
     embs = [_f32c(e) for e in embs]
     _need_cuda(*embs)
     n_emb = len(embs)

@@ -139,3 +139,29 @@ def test_ragged_pairs_matching_and_metrics(dev):
         ok[:, :-1] &= gaps
         assert (r[ok] == ref_rank[ok]).all(), b
         assert ok.mean() > 0.9 or r.shape[0] < 8
+
+
+def test_loss_with_overlapping_index_sets(dev):
+    """Index sets that are NOT the dataloader's partition (an anchor repeated, a node both anchor and non-anchor):
+    the public loss detects it on the host arrays and routes every Gram through the gathering GEMM."""
+    from sgaligner_b200 import synthetic
+    from sgaligner_b200.losses import CustomMultiLossLayer, OverallLoss, _index_tensors
+    data = synthetic.make_batch([12, 9], [10, 14], [6, 5], [4, 3], n_points=4, seed=9)
+    data['e1i'] = np.concatenate([data['e1i'], data['e1i'][:1]]).astype(np.int32)       # repeated anchor
+    data['e2i'] = np.concatenate([data['e2i'], data['e2i'][:1]]).astype(np.int32)
+    data['e1j'] = np.concatenate([data['e1j'], data['e1i'][1:2]]).astype(np.int32)      # anchor also listed as non-anchor
+    N = int(data['tot_obj_pts'].shape[0])
+    assert not _index_tensors(dict(data), dev).partition
+    embs = _embs(N, [100, 100, 200], 10)
+    mods = ['m0', 'm1']
+    li, lc = CustomMultiLossLayer(2).to(dev), CustomMultiLossLayer(2).to(dev)
+    fn = OverallLoss(li, lc, dev, {'zoom': 0.1, 'wt_align_loss': 1.0, 'wt_contrastive_loss': 1.0, 'modules': mods})
+    out = {'m0': embs[0].to(dev).requires_grad_(True), 'm1': embs[1].to(dev).requires_grad_(True), 'joint': embs[2].to(dev).requires_grad_(True)}
+    ld = fn(out, dict(data))
+    ld['loss'].backward()
+    ref_in = [e.clone().requires_grad_(True) for e in embs]
+    rl = O.overall_loss({'m0': ref_in[0], 'm1': ref_in[1], 'joint': ref_in[2]}, data, mods, torch.zeros(2), torch.zeros(2), 0.1)
+    rl['loss'].backward()
+    assert abs(float(ld['loss']) - float(rl['loss'])) <= 1e-3 * abs(float(rl['loss'])) + 1e-6
+    for k, r in zip(('m0', 'm1', 'joint'), ref_in):
+        assert grad_close(out[k].grad, r.grad, rtol=2e-3, atol=1e-7), k
