@@ -83,6 +83,13 @@ int sga_pointnet_bn_moments(const float* pts, int64_t N, int P,
                             const float* W1, const float* b1, const float* W2, const float* b2,
                             const float* W3, const float* b3, int C3, double* moments, void* stream);
 
+/* The running_mean / running_var / num_batches_tracked update the reference's discarded BatchNorm1d calls perform
+ * in train() (pointnet.py:141-142,154-155,158-159; momentum update with the unbiased batch variance) for the three
+ * layers in one launch.  moments as produced by sga_pointnet_bn_moments / sga_pointnet_fwd_stats; cnt = N*P. */
+int sga_bn_running_update(const double* moments, double cnt, float momentum, int C3, float* rm1, float* rv1,
+                          float* rm2, float* rv2, float* rm3, float* rv3, int64_t* nbt1, int64_t* nbt2,
+                          int64_t* nbt3, void* stream);
+
 /* Training-mode forward on the tensor cores: sga_pointnet_fwd(mode = SGA_POINTNET_TC) that ALSO accumulates
  * the statistics of sga_pointnet_bn_moments in the same pass (conv3 thread-locally in the max-pool
  * epilogue, conv2 by a warp transpose-reduce, conv1 analytically from the point moments), i.e. the whole

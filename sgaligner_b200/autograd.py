@@ -136,10 +136,11 @@ class OverallLossFn(torch.autograd.Function):
     def backward(ctx, g):
         # only losses[0] (= 'loss') carries gradient; the other three entries are reporting values
         s = g[0]
-        saved = ctx.saved_tensors
-        grads = [t * s for t in saved[:ctx.n]]
+        saved = list(ctx.saved_tensors)
+        scaled = torch._foreach_mul(saved, s)          # one multi-tensor launch for all embeddings (+ log_vars)
+        grads = scaled[:ctx.n]
         if ctx.has_lv:
-            g_ial, g_icl = saved[ctx.n] * s, saved[ctx.n + 1] * s
+            g_ial, g_icl = scaled[ctx.n], scaled[ctx.n + 1]
         else:
             g_ial = g_icl = None
         return (None, None, g_ial, g_icl, *grads)

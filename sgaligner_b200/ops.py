@@ -184,6 +184,18 @@ def pointnet_bn_moments(pts, W1, b1, W2, b2, W3, b3):
     return mom
 
 
+def bn_running_update(mom: torch.Tensor, cnt: float, bns):
+    """One launch for the train-mode running-statistics update of the three (output-discarded) BatchNorm layers."""
+    b1, b2, b3 = bns
+    assert b1.momentum == b2.momentum == b3.momentum and b1.momentum is not None
+    check(get_lib().sga_bn_running_update(_ptr(mom), float(cnt), float(b1.momentum), int(b3.running_mean.numel()),
+                                          _ptr(b1.running_mean), _ptr(b1.running_var), _ptr(b2.running_mean), _ptr(b2.running_var),
+                                          _ptr(b3.running_mean), _ptr(b3.running_var), _ptr(b1.num_batches_tracked),
+                                          _ptr(b2.num_batches_tracked), _ptr(b3.num_batches_tracked), _stream()),
+          'sga_bn_running_update')
+    _count(1)
+
+
 # --------------------------------------------------------------------------------- graphs
 class GraphLayout:
     """Per-graph node / edge offsets of a collated batch (host prefix sums of ``graph_per_obj_count`` /

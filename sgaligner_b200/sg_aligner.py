@@ -109,6 +109,11 @@ class PointNetfeat(nn.Module):
         """Train-mode side effect of the discarded BatchNorm calls (pointnet.py:141-142,154-155,
         158-159): running_mean/var <- momentum update with the batch statistics of the pre-ReLU
         conv outputs; outputs are unaffected.  ``mom``: f64 {sum1,sq1,sum2,sq2,sum3,sq3}."""
+        bns = (self.bn1, self.bn2, self.bn3)
+        if mom.is_cuda and all(b.running_mean.is_cuda and b.running_mean.dtype == torch.float32 and b.momentum is not None for b in bns) \
+                and len({b.momentum for b in bns}) == 1:
+            ops.bn_running_update(mom, cnt, bns)        # one launch instead of ~30 element-wise kernels
+            return
         o = 0
         for bn, c in ((self.bn1, 64), (self.bn2, 128), (self.bn3, self.out_size)):
             s, sq = mom[o:o + c], mom[o + c:o + 2 * c]
