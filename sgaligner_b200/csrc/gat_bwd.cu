@@ -22,7 +22,7 @@ gat_aggregate_bwd_kernel(const float* __restrict__ xs, const float* __restrict__
                          const int32_t* __restrict__ node_off, int64_t N, int H, int C, int apply_elu,
                          const float* __restrict__ out, const float* __restrict__ gout,
                          float* __restrict__ g_xs, float* __restrict__ g_a_src, float* __restrict__ g_a_dst,
-                         float* __restrict__ g_bias, int smem_nodes) {
+                         float* __restrict__ g_bias, int smem_nodes, int dense) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   const int g = blockIdx.x, h = blockIdx.y;
@@ -38,12 +38,21 @@ gat_aggregate_bwd_kernel(const float* __restrict__ xs, const float* __restrict__
   float* gtile = tile + (size_t)smem_nodes * C;
   float* gas = gtile + (size_t)smem_nodes * C;
   float* gbias = gas + smem_nodes;
+  // dense mode (graphs small enough for an n x n coefficient matrix in shared memory): instead of scattering
+  // alpha_ij * go_i into the source rows with four shared-memory atomics per lane and edge, the attention
+  // coefficients go into Aij and the upstream rows into gtile; a second phase gathers
+  // g_xs[j] = sum_i Aij[i][j] go_i per source row without atomics.
+  float* Aij = gbias + C;
   if (staged) {
     if (tid == 0) {
       ptx::mbar_init(&bar, 1);
       ptx::fence_mbar_init();
     }
-    for (int i = tid; i < n * C; i += NT) gtile[i] = 0.f;
+    if (dense) {
+      for (int i = tid; i < n * n; i += NT) Aij[i] = 0.f;
+    } else {
+      for (int i = tid; i < n * C; i += NT) gtile[i] = 0.f;
+    }
     for (int i = tid; i < n; i += NT) gas[i] = 0.f;
     __syncthreads();
     if (tid == 0) {
@@ -84,6 +93,7 @@ gat_aggregate_bwd_kernel(const float* __restrict__ xs, const float* __restrict__
           go[q][u] = gg[u];
           atomicAdd(&gbias[c + u], gg[u]);
         }
+        if (dense) *reinterpret_cast<float4*>(gtile + (int64_t)i * C + c) = make_float4(gg[0], gg[1], gg[2], gg[3]);
       }
     }
     // softmax statistics (as in the forward)
@@ -158,17 +168,20 @@ gat_aggregate_bwd_kernel(const float* __restrict__ xs, const float* __restrict__
           if (c < C) {
             float4 v = *reinterpret_cast<const float4*>(src + (int64_t)jt * C + c);
             dot += go[q][0] * v.x + go[q][1] * v.y + go[q][2] * v.z + go[q][3] * v.w;
-            float* gp = staged ? (gtile + (int64_t)jt * C + c) : (gdst + (int64_t)jt * C + c);
-            atomicAdd(gp + 0, at * go[q][0]);
-            atomicAdd(gp + 1, at * go[q][1]);
-            atomicAdd(gp + 2, at * go[q][2]);
-            atomicAdd(gp + 3, at * go[q][3]);
+            if (!dense) {
+              float* gp = staged ? (gtile + (int64_t)jt * C + c) : (gdst + (int64_t)jt * C + c);
+              atomicAdd(gp + 0, at * go[q][0]);
+              atomicAdd(gp + 1, at * go[q][1]);
+              atomicAdd(gp + 2, at * go[q][2]);
+              atomicAdd(gp + 3, at * go[q][3]);
+            }
           }
         }
         dot = warp_sum(dot);
         if (lane == t) my_dalpha = dot;
       }
       if (k < cnt) {
+        if (dense) atomicAdd(&Aij[i * n + (j - n0)], al);      // duplicates of an edge add up
         float de = al * (my_dalpha - D);
         float dz = de * (zraw > 0.f ? 1.f : 0.2f);
         gad += dz;
@@ -180,7 +193,31 @@ gat_aggregate_bwd_kernel(const float* __restrict__ xs, const float* __restrict__
     if (lane == 0) g_a_dst[(int64_t)(n0 + i) * H + h] = gad;
   }
   __syncthreads();
-  if (staged) {
+  if (dense) {
+    for (int j = warp; j < n; j += NT / 32) {
+      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      for (int i = 0; i < n; ++i) {
+        const float a = Aij[i * n + j];
+        if (a != 0.f) {                                          // warp-uniform: sparse graphs skip most rows
+          for (int q = 0; q < nq && q < 2; ++q) {
+            const int c = q * 128 + lane * 4;
+            if (c < C) {
+              const float4 gv = *reinterpret_cast<const float4*>(gtile + (int64_t)i * C + c);
+              acc[q][0] = fmaf(a, gv.x, acc[q][0]);
+              acc[q][1] = fmaf(a, gv.y, acc[q][1]);
+              acc[q][2] = fmaf(a, gv.z, acc[q][2]);
+              acc[q][3] = fmaf(a, gv.w, acc[q][3]);
+            }
+          }
+        }
+      }
+      for (int q = 0; q < nq && q < 2; ++q) {
+        const int c = q * 128 + lane * 4;
+        if (c < C) *reinterpret_cast<float4*>(gdst + (int64_t)j * C + c) = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+      }
+    }
+    for (int i = tid; i < n; i += NT) g_a_src[(int64_t)(n0 + i) * H + h] = gas[i];
+  } else if (staged) {
     for (int i = tid; i < n * C; i += NT) gdst[i] = gtile[i];
     for (int i = tid; i < n; i += NT) g_a_src[(int64_t)(n0 + i) * H + h] = gas[i];
   }
@@ -240,11 +277,16 @@ extern "C" int sga_gat_aggregate_bwd(const float* xs, const float* a_src, const 
   SGA_REQUIRE(C % 4 == 0 && C <= 256, "sga_gat_aggregate_bwd: C=%d must be a multiple of 4 and <= 256", C);
   const size_t cap = 200 * 1024;
   size_t need = ((size_t)2 * max_graph_nodes * C + max_graph_nodes + C) * sizeof(float);
-  int smem_nodes = 0;
+  int smem_nodes = 0, dense = 0;
   size_t smem = (size_t)C * sizeof(float);
   if (need <= cap) {
     smem_nodes = max_graph_nodes;
     smem = need;
+    const size_t need_dense = need + (size_t)max_graph_nodes * max_graph_nodes * sizeof(float);
+    if (need_dense <= cap) {
+      dense = 1;
+      smem = need_dense;
+    }
   }
   static size_t attr_smem = 48 * 1024;
   if (smem > attr_smem) {
@@ -254,7 +296,7 @@ extern "C" int sga_gat_aggregate_bwd(const float* xs, const float* a_src, const 
   dim3 grid(G, H);
   sga::gat_aggregate_bwd_kernel<<<grid, sga::NT, smem, (cudaStream_t)stream>>>(xs, a_src, a_dst, row_beg, row_cnt, col, node_off, N, H, C,
                                                                                apply_elu, out, grad_out, g_xs, g_a_src, g_a_dst, g_bias,
-                                                                               smem_nodes);
+                                                                               smem_nodes, dense);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }
