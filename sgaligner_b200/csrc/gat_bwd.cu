@@ -225,26 +225,42 @@ gat_aggregate_bwd_kernel(const float* __restrict__ xs, const float* __restrict__
 }
 
 // g_xs += g_as * att_src + g_ad * att_dst (in place);  g_att_* += sum_n g_a* xs
+constexpr int kFoldRows = 32;
 __global__ void __launch_bounds__(NT)
 gat_fold_kernel(const float* __restrict__ xs, float* __restrict__ g_xs, const float* __restrict__ g_as,
                 const float* __restrict__ g_ad, const float* __restrict__ att_src,
                 const float* __restrict__ att_dst, int64_t N, int H, int C, float* __restrict__ g_att_src,
                 float* __restrict__ g_att_dst) {
-  // grid (ceil(N/64), H); thread -> channel c = tid (+256), loops over 64 nodes
+  // grid (ceil(N/kFoldRows), H); thread -> channel c = tid % C, row group tid / C (all 256 threads busy at C = 128);
+  // four independent rows in flight per thread
   const int h = blockIdx.y;
-  const int64_t n0 = (int64_t)blockIdx.x * 64;
-  for (int c = threadIdx.x; c < C; c += NT) {
+  const int64_t n0 = (int64_t)blockIdx.x * kFoldRows;
+  const int groups = NT / C > 0 ? NT / C : 1;
+  const int rg = threadIdx.x / C;
+  if (rg >= groups) return;
+  for (int c = threadIdx.x % C; c < C; c += NT) {
     const float ws = att_src[h * C + c], wd = att_dst[h * C + c];
     float as = 0.f, adv = 0.f;
-    for (int r = 0; r < 64; ++r) {
-      int64_t n = n0 + r;
-      if (n >= N) break;
-      const float gs = g_as[n * H + h], gd = g_ad[n * H + h];
-      const int64_t o = ((int64_t)h * N + n) * C + c;
-      const float x = xs[o];
-      g_xs[o] += gs * ws + gd * wd;
-      as = fmaf(gs, x, as);
-      adv = fmaf(gd, x, adv);
+    for (int r0 = rg; r0 < kFoldRows; r0 += 4 * groups) {
+      float gs[4], gd[4], x[4], gx[4];
+      int64_t o[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t n = n0 + r0 + u * groups;
+        ok[u] = (r0 + u * groups < kFoldRows) && n < N;
+        o[u] = ((int64_t)h * N + (ok[u] ? n : 0)) * C + c;
+        gs[u] = ok[u] ? g_as[n * H + h] : 0.f;
+        gd[u] = ok[u] ? g_ad[n * H + h] : 0.f;
+        x[u] = ok[u] ? xs[o[u]] : 0.f;
+        gx[u] = ok[u] ? g_xs[o[u]] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (ok[u]) g_xs[o[u]] = gx[u] + (gs[u] * ws + gd[u] * wd);
+        as = fmaf(gs[u], x[u], as);
+        adv = fmaf(gd[u], x[u], adv);
+      }
     }
     atomicAdd(&g_att_src[h * C + c], as);
     atomicAdd(&g_att_dst[h * C + c], adv);
@@ -307,7 +323,7 @@ extern "C" int sga_gat_linear_bwd(const float* x, int64_t N, int in_dim, const f
                                   float* g_att_dst, float* gx, void* stream) {
   if (N <= 0) return SGA_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((unsigned)((N + 63) / 64), H);
+  dim3 grid((unsigned)((N + sga::kFoldRows - 1) / sga::kFoldRows), H);
   sga::gat_fold_kernel<<<grid, sga::NT, 0, st>>>(xs, g_xs, g_a_src, g_a_dst, att_src, att_dst, N, H, C, g_att_src, g_att_dst);
   SGA_LAUNCH_CHECK();
   for (int h = 0; h < H; ++h) {
