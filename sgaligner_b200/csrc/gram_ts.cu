@@ -27,12 +27,19 @@
 namespace sga {
 namespace {
 
-constexpr int kStages = 5;
 constexpr uint32_t kChunkBytes = 32768;            // one K chunk of one 128-row tile: hi 16 KiB | lo 16 KiB
-constexpr uint32_t BAR_OFF = kStages * kChunkBytes;
-constexpr int kXPitch = 36;                         // floats per row of an epilogue warp's [32 x 32] transpose tile (+16 B pad)
-constexpr uint32_t XPOSE_OFF = BAR_OFF + 256;
-constexpr uint32_t SMEM_BYTES = XPOSE_OFF + 8 * 32 * kXPitch * 4 + 1024;
+// Two variants.  Narrow (K <= 128): A lives in tensor memory, a ring stage is one B chunk.  Wide (K <= 512, the joint
+// embedding): A does not fit next to two accumulators, so a ring stage carries an A chunk AND a B chunk and the MMA
+// reads both from shared memory (SS mode: shared-memory bandwidth caps it near 60 % tensor-active).
+template <bool kWide>
+struct Cfg {
+  static constexpr int kStages = kWide ? 3 : 5;
+  static constexpr uint32_t kStageBytes = kWide ? 2 * kChunkBytes : kChunkBytes;
+  static constexpr int kXPitch = kWide ? 32 : 36;    // floats per row of an epilogue warp's [32 x 32] transpose tile
+  static constexpr uint32_t BAR_OFF = kStages * kStageBytes;
+  static constexpr uint32_t XPOSE_OFF = BAR_OFF + 256;
+  static constexpr uint32_t SMEM_BYTES = XPOSE_OFF + 8 * 32 * kXPitch * 4 + 1024;
+};
 constexpr int kEpiWarps = 8;                       // two per TMEM lane quarter: each takes two of the four 32-column slabs
 constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp 0 producer, warp 1 MMA issuer, warps 2..9 A staging + epilogue
 constexpr uint32_t ACC_COL = 0, AHI_COL = 256, ALO_COL = 384;
@@ -58,9 +65,9 @@ pack_rows_kernel(const float* __restrict__ X, int64_t N, int D, int nkc, const i
   const int set = sl >> 28, pos = sl & 0x0FFFFFFF;
   unsigned char* img = set == 0 ? img0 : (set == 1 ? img1 : (set == 2 ? img2 : img3));
   const int tile = pos >> 7, r = pos & 127;
-  // lane -> 16-byte piece `lane` of the row (4 k-values): chunk lane/8, piece lane%8
-  if (lane < 8 * nkc) {
-    const int k0 = 4 * lane;
+  // 16-byte piece p of the row (4 k-values): chunk p/8, piece p%8
+  for (int p = lane; p < 8 * nkc; p += 32) {
+    const int k0 = 4 * p;
     uint32_t h[4], l[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -68,7 +75,7 @@ pack_rows_kernel(const float* __restrict__ X, int64_t N, int D, int nkc, const i
       h[e] = tf32x3::rn_tf32(v);
       l[e] = tf32x3::rn_tf32(v - __uint_as_float(h[e]));
     }
-    unsigned char* dst = img + ((size_t)tile * nkc + (lane >> 3)) * kChunkBytes + ptx::sw128_offset(r, lane & 7);
+    unsigned char* dst = img + ((size_t)tile * nkc + (p >> 3)) * kChunkBytes + ptx::sw128_offset(r, p & 7);
     *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(dst + 16384) = make_uint4(l[0], l[1], l[2], l[3]);
   }
@@ -125,8 +132,14 @@ __device__ __forceinline__ NTile find_ntile(const GramProblem& P, int j) {
   return t;
 }
 
+template <bool kWide>
 __global__ void __launch_bounds__(kThreads, 1)
 gram_ts_kernel(const __grid_constant__ GramGroup G) {
+  using C_ = Cfg<kWide>;
+  constexpr int kStages = C_::kStages;
+  constexpr uint32_t kStageBytes = C_::kStageBytes;
+  constexpr int kXPitch = C_::kXPitch;
+  constexpr uint32_t BAR_OFF = C_::BAR_OFF, XPOSE_OFF = C_::XPOSE_OFF;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sm_base = ptx::smem_u32(sm);
@@ -168,11 +181,17 @@ gram_ts_kernel(const __grid_constant__ GramGroup G) {
         for (int j = I.nt_beg; j < I.nt_end; ++j) {
           const NTile T = find_ntile(P, j);
           const unsigned char* src = P.b_img[T.seg] + (size_t)T.lt * P.nkc * kChunkBytes;
+          const unsigned char* asrc = P.a_img + (size_t)(I.m0 >> 7) * P.nkc * kChunkBytes;
           for (int c = 0; c < P.nkc; ++c, ++it) {
             const int s = it % kStages;
             if (it >= kStages) ptx::mbar_wait(&empty[s], (uint32_t)(((it / kStages) - 1) & 1));
-            ptx::mbar_arrive_expect_tx(&full[s], kChunkBytes);
-            ptx::bulk_g2s(sm + (size_t)s * kChunkBytes, src + (size_t)c * kChunkBytes, kChunkBytes, &full[s]);
+            ptx::mbar_arrive_expect_tx(&full[s], kStageBytes);
+            unsigned char* dst = sm + (size_t)s * kStageBytes;
+            if (kWide) {
+              ptx::bulk_g2s(dst, asrc + (size_t)c * kChunkBytes, kChunkBytes, &full[s]);
+              dst += kChunkBytes;
+            }
+            ptx::bulk_g2s(dst, src + (size_t)c * kChunkBytes, kChunkBytes, &full[s]);
           }
         }
       }
@@ -185,8 +204,10 @@ gram_ts_kernel(const __grid_constant__ GramGroup G) {
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++ii) {
       const Item I = find_item(G, item);
       const GramProblem& P = G.p[I.g];
-      ptx::mbar_wait(a_ready, (uint32_t)(ii & 1));
-      ptx::tc_fence_after();
+      if (!kWide) {
+        ptx::mbar_wait(a_ready, (uint32_t)(ii & 1));
+        ptx::tc_fence_after();
+      }
       for (int j = I.nt_beg; j < I.nt_end; ++j, ++ti) {
         const int ab = ti & 1;
         if (ti >= 2) {
@@ -198,16 +219,27 @@ gram_ts_kernel(const __grid_constant__ GramGroup G) {
           ptx::mbar_wait(&full[s], (uint32_t)((it / kStages) & 1));
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
-            const uint32_t st = sm_base + (uint32_t)s * kChunkBytes;
-            const uint64_t dBhi = ptx::smem_desc_sw128(st), dBlo = ptx::smem_desc_sw128(st + 16384);
+            const uint32_t st = sm_base + (uint32_t)s * kStageBytes;
             const uint32_t d = tmem_u + ACC_COL + ab * 128;
-            const uint32_t ahi = tmem_u + AHI_COL + c * 32, alo = tmem_u + ALO_COL + c * 32;
+            if (kWide) {
+              const uint64_t dAhi = ptx::smem_desc_sw128(st), dAlo = ptx::smem_desc_sw128(st + 16384);
+              const uint64_t dBhi = ptx::smem_desc_sw128(st + kChunkBytes), dBlo = ptx::smem_desc_sw128(st + kChunkBytes + 16384);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) ptx::umma_tf32_ts(d, ahi + ks * 8, dBhi + (uint64_t)(ks * 2), idesc, (c | ks) != 0);
+              for (int ks = 0; ks < 4; ++ks) ptx::umma_tf32(d, dAhi + (uint64_t)(ks * 2), dBhi + (uint64_t)(ks * 2), idesc, (c | ks) != 0);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) ptx::umma_tf32_ts(d, alo + ks * 8, dBhi + (uint64_t)(ks * 2), idesc, 1);
+              for (int ks = 0; ks < 4; ++ks) ptx::umma_tf32(d, dAlo + (uint64_t)(ks * 2), dBhi + (uint64_t)(ks * 2), idesc, 1);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) ptx::umma_tf32_ts(d, ahi + ks * 8, dBlo + (uint64_t)(ks * 2), idesc, 1);
+              for (int ks = 0; ks < 4; ++ks) ptx::umma_tf32(d, dAhi + (uint64_t)(ks * 2), dBlo + (uint64_t)(ks * 2), idesc, 1);
+            } else {
+              const uint64_t dBhi = ptx::smem_desc_sw128(st), dBlo = ptx::smem_desc_sw128(st + 16384);
+              const uint32_t ahi = tmem_u + AHI_COL + c * 32, alo = tmem_u + ALO_COL + c * 32;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) ptx::umma_tf32_ts(d, ahi + ks * 8, dBhi + (uint64_t)(ks * 2), idesc, (c | ks) != 0);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) ptx::umma_tf32_ts(d, alo + ks * 8, dBhi + (uint64_t)(ks * 2), idesc, 1);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) ptx::umma_tf32_ts(d, ahi + ks * 8, dBlo + (uint64_t)(ks * 2), idesc, 1);
+            }
             ptx::umma_commit(&empty[s]);
             if (c == P.nkc - 1) ptx::umma_commit(&acc_full[ab]);
           }
@@ -246,7 +278,7 @@ gram_ts_kernel(const __grid_constant__ GramGroup G) {
       const bool row_ok = row < P.M;
       // ---- A rows -> tensor memory.  Every MMA of the previous item has completed (this warp waited for the
       //      accumulator of its last tile), so the columns are free.
-      {
+      if (!kWide) {
         const unsigned char* src = P.a_img + (size_t)(I.m0 >> 7) * P.nkc * kChunkBytes;
         for (int c = h; c < P.nkc; c += 2) {
 #pragma unroll
@@ -363,8 +395,8 @@ size_t gram_image_bytes(int rows, int D) {
 int launch_pack_rows(const float* X, int64_t N, int D, const int32_t* slot, unsigned char* const* img4, float* norms, float* Xh,
                      cudaStream_t st) {
   const int nkc = (D + 31) / 32;
-  if (nkc > 4) {
-    set_error("gram_ts: D=%d > 128", D);
+  if (nkc > 16) {
+    set_error("gram_ts: D=%d > 512", D);
     return SGA_EINVAL;
   }
   pack_rows_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(X, N, D, nkc, slot, img4[0], img4[1], img4[2], img4[3], norms, Xh);
@@ -383,27 +415,29 @@ int launch_build_slots(const int32_t* e1i, const int32_t* e2i, const int32_t* e1
   return SGA_OK;
 }
 
-int launch_gram_ts(const GramProblem* problems, int n, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    SGA_CUDA(cudaFuncSetAttribute(gram_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    attr_done = true;
-  }
+namespace {
+template <bool kWide>
+int launch_gram_variant(const GramProblem* problems, int n, cudaStream_t st) {
+  // problems of the other variant are skipped: narrow = K <= 128 (nkc <= 4), wide = the rest
+  auto mine = [](const GramProblem& P) { return (P.nkc > 4) == kWide && P.M > 0; };
   int i = 0;
   while (i < n) {
     GramGroup G;
     memset(&G, 0, sizeof(G));
-    int mt_total = 0;
-    const int first = i;
-    for (int k = first; k < n && k < first + kGramMaxGroup; ++k) mt_total += (problems[k].M + 127) / 128;
+    int mt_total = 0, cnt = 0;
+    for (int k = i; k < n && cnt < kGramMaxGroup; ++k)
+      if (mine(problems[k])) {
+        mt_total += (problems[k].M + 127) / 128;
+        ++cnt;
+      }
     int total = 0;
     for (; i < n && G.n < kGramMaxGroup; ++i) {
       const GramProblem& P = problems[i];
-      if (P.M <= 0) continue;
+      if (!mine(P)) continue;
       const int NT = (P.seg_rows[0] + 127) / 128 + (P.seg_rows[1] + 127) / 128 + (P.seg_rows[2] + 127) / 128;
       if (NT <= 0) continue;
       // split the column tiles of a row block so that the group has ~3 items per SM, but keep >= 4 tiles per
-      // item (the A operand is re-staged into tensor memory per item)
+      // item (narrow: the A operand is re-staged into tensor memory per item)
       int S = (3 * sm_count() + mt_total - 1) / (mt_total > 0 ? mt_total : 1);
       if (S > NT / 4) S = NT / 4;
       if (S < 1) S = 1;
@@ -415,10 +449,23 @@ int launch_gram_ts(const GramProblem* problems, int n, cudaStream_t st) {
     }
     if (G.n == 0) continue;
     const int grid = total < sm_count() ? total : sm_count();
-    gram_ts_kernel<<<grid, kThreads, SMEM_BYTES, st>>>(G);
+    gram_ts_kernel<kWide><<<grid, kThreads, Cfg<kWide>::SMEM_BYTES, st>>>(G);
     SGA_LAUNCH_CHECK();
   }
   return SGA_OK;
+}
+}  // namespace
+
+int launch_gram_ts(const GramProblem* problems, int n, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    SGA_CUDA(cudaFuncSetAttribute(gram_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<false>::SMEM_BYTES));
+    SGA_CUDA(cudaFuncSetAttribute(gram_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<true>::SMEM_BYTES));
+    attr_done = true;
+  }
+  int rc = launch_gram_variant<false>(problems, n, st);
+  if (rc != SGA_OK) return rc;
+  return launch_gram_variant<true>(problems, n, st);
 }
 
 }  // namespace sga

@@ -39,8 +39,9 @@ struct Layout {
 
 inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-// Embeddings up to 128 wide take the TMA-fed / A-in-tensor-memory Gram kernel (gram_ts.cu); SGA_LOSS_GRAM=legacy
-// forces the in-loader-split GEMM (gemm_tc.cu) for everything (A/B comparisons, profiling).
+// Embeddings up to 512 wide take the TMA-fed Gram kernel (gram_ts.cu: A in tensor memory up to 128 wide, both operands
+// streamed beyond that); SGA_LOSS_GRAM=legacy forces the in-loader-split GEMM (gemm_tc.cu) for everything (A/B
+// comparisons, profiling).
 int g_gram_legacy_override = 0;      // sga_loss_set_gram_path(): 1 = the caller's index sets are not a partition
 inline bool gram_ts_ok(int d) {
   static int legacy = -1;
@@ -48,7 +49,7 @@ inline bool gram_ts_ok(int d) {
     const char* e = getenv("SGA_LOSS_GRAM");
     legacy = (e && strcmp(e, "legacy") == 0) ? 1 : 0;
   }
-  return !legacy && !g_gram_legacy_override && d <= 128;
+  return !legacy && !g_gram_legacy_override && d <= 512;
 }
 
 Layout make_layout(int n_emb, const int* dims, int64_t N, int A, int J1, int J2, int want_grad) {
@@ -335,11 +336,14 @@ extern "C" void sga_loss_set_gram_path(int legacy) { sga::g_gram_legacy_override
 // Kernels one sga_loss_fwd_bwd call launches (for the caller's launch accounting; memsets are not kernels).
 extern "C" int sga_loss_launch_count(int n_emb, const int* dims_host, int J1, int J2, int want_grad) {
   using namespace sga;
-  int n_ts = 0;
-  for (int x = 0; x < n_emb; ++x) n_ts += gram_ts_ok(dims_host[x]) ? 1 : 0;
-  const int n_wide = n_emb - n_ts;
+  int n_narrow = 0, n_tswide = 0;
+  for (int x = 0; x < n_emb; ++x)
+    if (gram_ts_ok(dims_host[x])) (dims_host[x] <= 128 ? n_narrow : n_tswide) += 1;
+  const int n_wide = n_emb - n_narrow - n_tswide;          // beyond 512: generic GEMM
   int n = 2 + 2 * n_emb;                                   // ridx, finalize; per embedding: norm/pack, pair
-  if (n_ts) n += 1 + (2 * n_ts + kGramMaxGroup - 1) / kGramMaxGroup;     // slots + grouped gram_ts launches
+  if (n_narrow + n_tswide) n += 1;                         // slots
+  if (n_narrow) n += (2 * n_narrow + kGramMaxGroup - 1) / kGramMaxGroup;     // grouped gram_ts launches per variant
+  if (n_tswide) n += (2 * n_tswide + kGramMaxGroup - 1) / kGramMaxGroup;
   if (n_wide) n += (2 * n_wide + kGemmMaxGroup - 1) / kGemmMaxGroup;
   if (want_grad) n += n_emb * ((J1 + J2 > 0) ? 2 : 1) + 2 * ((2 * n_emb + kGemmMaxGroup - 1) / kGemmMaxGroup);
   return n;
