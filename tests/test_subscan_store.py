@@ -117,3 +117,37 @@ def test_to_device_centres_on_gpu(store, gold, split):
                      {'zoom': 0.1, 'wt_align_loss': 1.0, 'wt_contrastive_loss': 1.0, 'modules': mods})
     loss = fn(model(d), d)['loss']
     assert torch.isfinite(loss)
+
+
+def test_pack_from_reference_files_and_dataloader(gold, tmp_path):
+    """The converter reads the reference's own on-disk formats (``files/<mode>/data/<id>.pkl`` +
+    ``scans/<id>/data.npy``, written here exactly as preprocess.py / the 3RScan export lay them out) and a stock
+    ``torch.utils.data.DataLoader`` over the packed dataset yields the reference's batches."""
+    import pickle
+    from sgaligner_b200.subscan_store import Scan3RPacked, SubscanStore
+    files, scans = tmp_path / 'files', tmp_path / 'scans'
+    (files / 'orig' / 'data').mkdir(parents=True)
+    ids = [str(s) for s in gold['scan_ids']]
+    P = int(gold[f'scan/{ids[0]}/obj_points'].shape[1])
+    for sid in ids:
+        d = {k: gold[f'scan/{sid}/{k}'] for k in ('objects_id', 'objects_cat', 'edges', 'rel_trans', 'bow_vec_object_attr_feats',
+                                                   'bow_vec_object_edge_feats')}
+        d['obj_points'] = {P: gold[f'scan/{sid}/obj_points']}
+        d['object_id2idx'] = {int(v): i for i, v in enumerate(d['objects_id'])}
+        with open(files / 'orig' / 'data' / f'{sid}.pkl', 'wb') as h:
+            pickle.dump(d, h)
+        # a point cloud whose mean is the stored centre (the converter only takes the mean, scan3r.py:66-75)
+        c = gold[f'scan/{sid}/center'].astype(np.float32)
+        ply = np.zeros(1, dtype=[('x', 'f4'), ('y', 'f4'), ('z', 'f4'), ('objectId', 'i4')])
+        ply['x'], ply['y'], ply['z'] = c[0], c[1], c[2]
+        (scans / sid).mkdir(parents=True)
+        np.save(scans / sid / 'data.npy', ply)
+    path = SubscanStore.pack_from_reference_files(str(files), str(scans), 'orig', ids, str(tmp_path / 'packed.sga'), n_points=P)
+    ds = Scan3RPacked(SubscanStore(path), json.loads(str(gold['anchor_data'])), split='val', pinned=False)
+    loader = torch.utils.data.DataLoader(ds, batch_size=len(ds), shuffle=False, collate_fn=ds.collate_fn, num_workers=0)
+    out = next(iter(loader))
+    _check(out, gold, 'val', out['tot_obj_pts'])
+    # two batches of two pairs: per-batch index offsets restart
+    parts = list(torch.utils.data.DataLoader(ds, batch_size=2, shuffle=False, collate_fn=ds.collate_fn))
+    assert [p['batch_size'] for p in parts] == [2, 2]
+    assert int(parts[1]['e1i'].min()) < int(parts[1]['tot_obj_count'][0])
