@@ -441,6 +441,20 @@ int launch_gram_variant(const GramProblem* problems, int n, cudaStream_t st) {
       int S = (3 * sm_count() + mt_total - 1) / (mt_total > 0 ? mt_total : 1);
       if (S > NT / 4) S = NT / 4;
       if (S < 1) S = 1;
+      {
+        // the items of a group are equal-sized, so the launch runs in ceil(items / SMs) rounds: among a few larger
+        // splits take the one that wastes the least of its last round
+        const int sms = sm_count();
+        const int smax = NT / 4 < S + 8 ? NT / 4 : S + 8;
+        double best = 0.0;
+        int bestS = S;
+        for (int c = S; c <= smax; ++c) {
+          const int items = mt_total * c;
+          const double eff = (double)items / (double)(((items + sms - 1) / sms) * sms);
+          if (eff > best + 0.02) { best = eff; bestS = c; }
+        }
+        S = bestS;
+      }
       total += ((P.M + 127) / 128) * S;
       G.p[G.n] = P;
       G.item_end[G.n] = total;
