@@ -252,6 +252,129 @@ pair_kernel(PairArgs p) {
   block_reduce_add<14>(acc, dst);
 }
 
+// All embeddings in ONE pass over the A x A anchor block (M <= kPairMaxModal modalities + the joint): the joint's
+// similarities are read once and its tau = 1 probabilities computed once instead of once per modality, and the
+// gradient the M IAL terms send into the joint stays in registers (no [A,A] accumulator arrays in HBM).
+constexpr int kPairMaxModal = 4;
+struct PairAllArgs {
+  float* F1[kPairMaxModal + 1]; float* F2[kPairMaxModal + 1];   // modal embeddings, then the joint (or the single embedding)
+  int M;                     // modal embeddings (0: a single embedding, ICL only)
+  int A, T;
+  const double* S; double* dS;            // [M+1][2][4]
+  double* icl_raw; double* ial_raw;       // [M+1]
+  const float* lv_icl; const float* lv_ial;
+  float zoom;
+  int want_grad;
+};
+
+__global__ void __launch_bounds__(NT)
+pair_all_kernel(PairAllArgs p) {
+  constexpr int MM = kPairMaxModal;
+  constexpr int NV = 10 * MM + 9;         // per modality {icl, ial, dS01[4], dS1[4]}; joint {icl, dS01[4], dSj1[4]}
+  const int A = p.A, T = p.T, M = p.M;
+  __shared__ float s_is[MM + 1][8];       // reciprocals of the normalisers (+1e-9, losses.py:12-13)
+  __shared__ float s_c[MM][2];            // {c_icl, c_ial} per modality
+  __shared__ float red[NT / 32][NV];
+  const float invA2 = 1.f / ((float)A * (float)A);
+  if (threadIdx.x < (M + 1) * 8) s_is[threadIdx.x >> 3][threadIdx.x & 7] = 1.f / ((float)p.S[threadIdx.x] + kEps);
+  if (threadIdx.x < M) {
+    s_c[threadIdx.x][0] = expf(-p.lv_icl[threadIdx.x]) * invA2;
+    s_c[threadIdx.x][1] = p.zoom * expf(-p.lv_ial[threadIdx.x]) * 0.1f * 0.5f;
+  }
+  __syncthreads();
+  float acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+  const float* isj = s_is[M];
+  for (int a = blockIdx.x; a < A; a += gridDim.x) {
+    const int64_t rowF = (int64_t)a * T;
+    for (int b = threadIdx.x; b < A; b += NT) {
+      const int64_t off = rowF + b;
+      const float j1 = p.F1[M][off], j2 = p.F2[M][off];
+      QD m12, m21;
+      float lm12 = 0.f, lm21 = 0.f, accJ1 = 0.f, accJ2 = 0.f;
+      if (M > 0) {
+        m12 = cpd(j1, 1.f, isj[4], isj[5]);
+        m21 = cpd(j2, 1.f, isj[6], isj[7]);
+        lm12 = __logf(m12.q);
+        lm21 = __logf(m21.q);
+      }
+#pragma unroll
+      for (int x = 0; x < MM; ++x) {
+        if (x < M) {
+          const float* is = s_is[x];
+          const float c_icl = s_c[x][0], c_ial = s_c[x][1];
+          const float g1 = p.F1[x][off], g2 = p.F2[x][off];
+          // ---- ICL, tau = 0.1 (losses.py:43-58)
+          QD q12 = cpd(g1, 10.f, is[0], is[1]);
+          QD q21 = cpd(g2, 10.f, is[2], is[3]);
+          const float w = 0.5f * q12.q + 0.5f * q21.q;
+          acc[10 * x] += -__logf(w);
+          // ---- IAL, tau = 1.0 (losses.py:68-97): target = modal q, input = log(joint q)
+          QD o12 = cpd(g1, 1.f, is[4], is[5]);
+          QD o21 = cpd(g2, 1.f, is[6], is[7]);
+          const float ea = __expf(o12.q), eb = __expf(o21.q);
+          const float la = o12.q - lm12, lb = o21.q - lm21;
+          acc[10 * x + 1] += 0.5f * (ea * la + eb * lb);
+          if (p.want_grad) {
+            const float dq = __fdividef(-0.5f * c_icl, w);
+            float d1 = dq * q12.dg, d2 = dq * q21.dg;
+            acc[10 * x + 2] += dq * q12.dsa; acc[10 * x + 3] += dq * q12.dsb;
+            acc[10 * x + 4] += dq * q21.dsa; acc[10 * x + 5] += dq * q21.dsb;
+            const float dqo12 = c_ial * ea * (la + 1.f), dqo21 = c_ial * eb * (lb + 1.f);
+            const float dqm12 = __fdividef(-c_ial * ea, m12.q), dqm21 = __fdividef(-c_ial * eb, m21.q);
+            d1 += dqo12 * o12.dg;
+            d2 += dqo21 * o21.dg;
+            acc[10 * x + 6] += dqo12 * o12.dsa; acc[10 * x + 7] += dqo12 * o12.dsb;
+            acc[10 * x + 8] += dqo21 * o21.dsa; acc[10 * x + 9] += dqo21 * o21.dsb;
+            acc[10 * MM + 5] += dqm12 * m12.dsa; acc[10 * MM + 6] += dqm12 * m12.dsb;
+            acc[10 * MM + 7] += dqm21 * m21.dsa; acc[10 * MM + 8] += dqm21 * m21.dsb;
+            accJ1 += dqm12 * m12.dg;
+            accJ2 += dqm21 * m21.dg;
+            p.F1[x][off] = d1;
+            p.F2[x][off] = d2;
+          }
+        }
+      }
+      // ---- the joint (or the single embedding): ICL only; coefficient 1 (losses.py:139-141)
+      QD q12 = cpd(j1, 10.f, isj[0], isj[1]);
+      QD q21 = cpd(j2, 10.f, isj[2], isj[3]);
+      const float w = 0.5f * q12.q + 0.5f * q21.q;
+      acc[10 * MM] += -__logf(w);
+      if (p.want_grad) {
+        const float dq = __fdividef(-0.5f * invA2, w);
+        acc[10 * MM + 1] += dq * q12.dsa; acc[10 * MM + 2] += dq * q12.dsb;
+        acc[10 * MM + 3] += dq * q21.dsa; acc[10 * MM + 4] += dq * q21.dsb;
+        p.F1[M][off] = dq * q12.dg + accJ1;
+        p.F2[M][off] = dq * q21.dg + accJ2;
+      }
+    }
+  }
+  // block reduction, one double atomic per (block, value)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float v = warp_sum(acc[i]);
+    if (lane == 0) red[warp][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    const int i = threadIdx.x;
+    double v = 0.0;
+    for (int w = 0; w < NT / 32; ++w) v += (double)red[w][i];
+    double* dst = nullptr;
+    if (i < 10 * MM) {
+      const int x = i / 10, k = i % 10;
+      if (x < M) dst = k == 0 ? p.icl_raw + x : (k == 1 ? p.ial_raw + x : (p.want_grad ? p.dS + (size_t)x * 8 + (k - 2) : nullptr));
+    } else {
+      const int k = i - 10 * MM;
+      if (k == 0) dst = p.icl_raw + M;
+      else if (p.want_grad) dst = p.dS + (size_t)M * 8 + (k - 1);     // k 1..4 -> dS01[0..3], 5..8 -> dS1[0..3]
+    }
+    if (dst && v != 0.0) atomicAdd(dst, v);
+  }
+}
+
 // in place over the U blocks of F1 (blockIdx.y = 0) / F2 (1): u -> sum_tau dS[tau][seg] / tau * exp(u / tau)
 // (the same ex2.approx exponential as the forward epilogue that produced the sums)
 __global__ void __launch_bounds__(NT)
@@ -340,7 +463,7 @@ extern "C" int sga_loss_launch_count(int n_emb, const int* dims_host, int J1, in
   for (int x = 0; x < n_emb; ++x)
     if (gram_ts_ok(dims_host[x])) (dims_host[x] <= 128 ? n_narrow : n_tswide) += 1;
   const int n_wide = n_emb - n_narrow - n_tswide;          // beyond 512: generic GEMM
-  int n = 2 + 2 * n_emb;                                   // ridx, finalize; per embedding: norm/pack, pair
+  int n = 2 + n_emb + ((n_emb - 1) <= kPairMaxModal ? 1 : n_emb);   // ridx, finalize; per embedding: norm/pack; pair kernel(s)
   if (n_narrow + n_tswide) n += 1;                         // slots
   if (n_narrow) n += (2 * n_narrow + kGramMaxGroup - 1) / kGramMaxGroup;     // grouped gram_ts launches per variant
   if (n_tswide) n += (2 * n_tswide + kGramMaxGroup - 1) / kGramMaxGroup;
@@ -442,11 +565,23 @@ extern "C" int sga_loss_fwd_bwd(const float* const* embs_host, const int* dims_h
   }
   // ---- element-wise loss terms (+ in-place gradient of the G blocks)
   const int xj = n_emb - 1;   // joint (or the single modality)
-  if (want_grad && n_emb > 1) {
+  const bool fused_pairs = (n_emb - 1) <= kPairMaxModal;
+  if (fused_pairs) {
+    PairAllArgs p;
+    memset(&p, 0, sizeof(p));
+    for (int x = 0; x < n_emb; ++x) { p.F1[x] = F(L.F1[x]); p.F2[x] = F(L.F2[x]); }
+    p.M = n_emb - 1; p.A = A; p.T = ldF;
+    p.S = S; p.dS = dS; p.icl_raw = icl_raw; p.ial_raw = ial_raw;
+    p.lv_icl = log_vars_icl; p.lv_ial = log_vars_ial;
+    p.zoom = zoom; p.want_grad = want_grad;
+    pair_all_kernel<<<(unsigned)(A < 8 * sm_count() ? A : 8 * sm_count()), NT, 0, st>>>(p);
+    SGA_LAUNCH_CHECK();
+  }
+  if (!fused_pairs && want_grad && n_emb > 1) {
     SGA_CUDA(cudaMemsetAsync(ws + L.acc1, 0, 4 * (size_t)A * A, st));
     SGA_CUDA(cudaMemsetAsync(ws + L.acc2, 0, 4 * (size_t)A * A, st));
   }
-  for (int x = 0; x < n_emb; ++x) {
+  for (int x = 0; x < n_emb && !fused_pairs; ++x) {
     PairArgs p;
     memset(&p, 0, sizeof(p));
     const bool modal = (n_emb > 1 && x < xj);
