@@ -89,13 +89,17 @@ def _pointnet_args(pts, W1, b1, W2, b2, W3, b3, mode):
     return pts, (W1c, _f32c(b1), W2c, _f32c(b2), W3c, _f32c(b3))
 
 
-def pointnet_forward(pts, W1, b1, W2, b2, W3, b3, want_argmax: bool, mode: int = POINTNET_TC, chunks=None):
+def pointnet_forward(pts, W1, b1, W2, b2, W3, b3, want_argmax: bool, mode: int = POINTNET_TC, chunks=None, out=None):
     """chunks: optional [(obj_start, obj_end, cuda_event)] -- the object ranges of ``pts`` become valid
-    when their event fires (streamed H2D copy, ``data.to_cuda_streamed``); one launch per range."""
+    when their event fires (streamed H2D copy, ``data.to_cuda_streamed``); one launch per range.
+    ``out``: optional preallocated [N, C3] f32 result buffer (a static buffer a captured graph reads)."""
     pts, w = _pointnet_args(pts, W1, b1, W2, b2, W3, b3, mode)
     N, P, _ = pts.shape
     C3 = W3.shape[0]
-    out = torch.empty((N, C3), device=pts.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((N, C3), device=pts.device, dtype=torch.float32)
+    else:
+        assert out.shape == (N, C3) and out.dtype == torch.float32 and out.is_contiguous() and out.device == pts.device
     arg = torch.empty((N, C3), device=pts.device, dtype=torch.int32) if want_argmax else None
     lib = get_lib()
     if chunks:

@@ -194,6 +194,136 @@ class CapturedInference:
             self.model.train()
         return self.host_in
 
+    # ------------------------------------------------------------------ host-to-host step, copies outside the graph
+    def capture_host_hybrid(self, host_batch: Dict, n_chunks: int = 4):
+        """Third form of the host-to-host step.  H2D memcpy NODES inside a CUDA graph showed box-dependent gaps (the
+        same captured step took 0.71-1.17 ms on different hosts while stream-ordered copies were stable), so here
+        the copies are issued eagerly on the copy stream (they pipeline back to back on the DMA engine), the point
+        encoder is launched range by range as they land, and only the compute around it is replayed from two small
+        graphs: the graph branch (CSR + GAT, needs the small tensors only) and the tail (projection / fusion,
+        matching head, anchor positions, D2H of the results).  Host cost: ~10 copy calls, ``n_chunks`` launches, two
+        graph launches -- hidden under the copy itself."""
+        from . import autograd as ag
+        from .data import needed_keys
+        if not ('point' in self.modules and len(self.modules) > 1):
+            raise NotImplementedError('hybrid host step: needs the point modality plus at least one more')
+        self.check_layout(host_batch)
+        m = self.model
+        keys = [k for k in needed_keys(self.modules) if k in self.static and torch.is_tensor(self.static[k])]
+        if not hasattr(self, 'host_in'):
+            self.host_in = {k: torch.empty(self.static[k].shape, dtype=self.static[k].dtype).pin_memory() for k in keys}
+            self.host_e1 = torch.empty(self.n_anchor, dtype=torch.int32).pin_memory()
+            self.host_e2 = torch.empty(self.n_anchor, dtype=torch.int32).pin_memory()
+        self.fill_host(host_batch)
+        N = int(self.static['tot_obj_pts'].shape[0])
+        per = -(-N // max(1, n_chunks))
+        self.hy_ranges = [(s_, min(N, s_ + per)) for s_ in range(0, N, per)]
+        self.hy_keys = keys
+        self.hy_cs = torch.cuda.Stream(device=self.dev)
+        self.hy_side = torch.cuda.Stream(device=self.dev)
+        self.hy_px = torch.empty((N, m.object_encoder.out_size), device=self.dev, dtype=torch.float32)
+        self.hy_events = [torch.cuda.Event() for _ in self.hy_ranges]
+        self.hy_ev_small = torch.cuda.Event()
+        self.hy_ev_gat = torch.cuda.Event()
+        was_training = m.training
+        m.eval()
+        d = self.static
+        mods = self.modules
+
+        def graph_branch():
+            with torch.no_grad():
+                graph = ops.BatchGraph(d['edges'], self.oc, self.ec, layout=self.graph_layout)
+                return m.structure_encoder(d['tot_rel_pose'], graph)
+
+        def tail(gat_out):
+            with torch.no_grad():
+                args = []
+                for module in mods:
+                    if module == 'gat':
+                        args += [gat_out, m.structure_embedding.weight, m.structure_embedding.bias]
+                    elif module == 'point':
+                        args += [self.hy_px, m.object_embedding.weight, m.object_embedding.bias]
+                    elif module == 'rel':
+                        args += [d['tot_bow_vec_object_edge_feats'], m.meta_embedding_rel.weight, m.meta_embedding_rel.bias]
+                    elif module == 'attr':
+                        args += [d['tot_bow_vec_object_attr_feats'], m.meta_embedding_attr.weight, m.meta_embedding_attr.bias]
+                    else:
+                        raise NotImplementedError
+                outs = ag.ProjectFuse.apply(m.fusion.weight, len(mods), *args)
+                t_idx, t_dist, sim = ops.match_topk_tc(outs[len(mods)], self.pair_layout, self.k, True)
+                pos = ops.match_anchor_pos(sim, self.pair_layout, self.e1, self.e2) if self.n_anchor else None
+                if not hasattr(self, 'hy_out'):
+                    self.hy_out = {'topk_idx': torch.empty(t_idx.shape, dtype=torch.int32).pin_memory()}
+                    if pos is not None:
+                        self.hy_out['anchor_pos'] = torch.empty(pos.shape, dtype=torch.int32).pin_memory()
+                self.hy_out['topk_idx'].copy_(t_idx, non_blocking=True)
+                if pos is not None:
+                    self.hy_out['anchor_pos'].copy_(pos, non_blocking=True)
+                return outs, t_idx, pos, sim
+
+        has_gat = 'gat' in mods
+        cur = torch.cuda.current_stream(self.dev)
+        warm = torch.cuda.Stream(device=self.dev)
+        warm.wait_stream(cur)
+        with torch.cuda.stream(warm):
+            g0 = graph_branch() if has_gat else None
+            tail(g0)
+        cur.wait_stream(warm)
+        torch.cuda.synchronize(self.dev)
+        self.hy_gat = None
+        if has_gat:
+            self.hy_graph_a = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.hy_graph_a):
+                self.hy_gat = graph_branch()
+        self.hy_graph_b = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.hy_graph_b):
+            self.hy_tail_out = tail(self.hy_gat)
+        if was_training:
+            m.train()
+        return self.host_in
+
+    def run_host_hybrid(self) -> Dict:
+        """Eager stream-ordered H2D copies + range-by-range point encoder + two graph replays; blocks until the pinned
+        results are valid."""
+        m = self.model
+        cur = torch.cuda.current_stream(self.dev)
+        cs = self.hy_cs
+        cs.wait_stream(cur)
+        with torch.cuda.stream(cs):
+            for k in self.hy_keys:
+                if k != 'tot_obj_pts':
+                    self.static[k].copy_(self.host_in[k], non_blocking=True)
+            if self.n_anchor:
+                self.e1.copy_(self.host_e1, non_blocking=True)
+                self.e2.copy_(self.host_e2, non_blocking=True)
+            self.hy_ev_small.record(cs)
+            chunks = []
+            for (a, b), ev in zip(self.hy_ranges, self.hy_events):
+                self.static['tot_obj_pts'][a:b].copy_(self.host_in['tot_obj_pts'][a:b], non_blocking=True)
+                ev.record(cs)
+                chunks.append((a, b, ev))
+        if self.hy_gat is not None:
+            self.hy_side.wait_stream(cur)
+            self.hy_side.wait_event(self.hy_ev_small)
+            with torch.cuda.stream(self.hy_side):
+                self.hy_graph_a.replay()
+                self.hy_ev_gat.record(self.hy_side)
+        enc = m.object_encoder
+        ops.pointnet_set_max_ctas(self.pointnet_ctas)
+        try:
+            with torch.no_grad():
+                ops.pointnet_forward(self.static['tot_obj_pts'], enc.conv1.weight, enc.conv1.bias, enc.conv2.weight, enc.conv2.bias,
+                                     enc.conv3.weight, enc.conv3.bias, want_argmax=False, mode=enc.kernel_mode, chunks=chunks,
+                                     out=self.hy_px)
+        finally:
+            ops.pointnet_set_max_ctas(0)
+        cur.wait_event(self.hy_ev_small)
+        if self.hy_gat is not None:
+            cur.wait_event(self.hy_ev_gat)
+        self.hy_graph_b.replay()
+        cur.synchronize()
+        return self.hy_out
+
     def fill_host(self, host_batch: Dict):
         """Slow path: copy a host batch into the pinned staging buffers (a production loader collates into
         ``host_in`` directly)."""

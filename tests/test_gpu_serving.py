@@ -74,3 +74,12 @@ def test_captured_host_to_host_step(dev):
             torch.cuda.synchronize()
             assert torch.equal(got['topk_idx'], res['topk_idx'].cpu())
             assert torch.equal(got['anchor_pos'], pos.cpu())
+        # the hybrid form (stream-ordered copies + range-by-range point encoder + two small graphs)
+        cap.capture_host_hybrid(host_a, n_chunks=3)
+        for host in (host_b, host_a, host_b):
+            cap.fill_host(host)
+            got = cap.run_host_hybrid()
+            out, res, pos = _eager(model, to_cuda(dict(host), dev), 6)
+            torch.cuda.synchronize()
+            assert torch.equal(got['topk_idx'], res['topk_idx'].cpu())
+            assert torch.equal(got['anchor_pos'], pos.cpu())
