@@ -83,6 +83,14 @@ int sga_pointnet_bn_moments(const float* pts, int64_t N, int P,
                             const float* W1, const float* b1, const float* W2, const float* b2,
                             const float* W3, const float* b3, int C3, double* moments, void* stream);
 
+/* Same statistics as sga_pointnet_bn_moments (added into moments[2*(64+128+C3)], f64), computed from Gram matrices
+ * of the ReLU outputs on the tensor cores (csrc/pointnet_gram.cu) instead of summing every conv output: about a
+ * third of a forward pass.  scratch >= sga_pointnet_gram_scratch_bytes(), 16-byte aligned; W2 16-byte aligned. */
+size_t sga_pointnet_gram_scratch_bytes(void);
+int sga_pointnet_bn_moments_gram(const float* pts, int64_t N, int P, const float* W1, const float* b1,
+                                 const float* W2, const float* b2, const float* W3, const float* b3, int C3,
+                                 double* moments, void* scratch, size_t scratch_bytes, void* stream);
+
 /* The running_mean / running_var / num_batches_tracked update the reference's discarded BatchNorm1d calls perform
  * in train() (pointnet.py:141-142,154-155,158-159; momentum update with the unbiased batch variance) for the three
  * layers in one launch.  moments as produced by sga_pointnet_bn_moments / sga_pointnet_fwd_stats; cnt = N*P. */

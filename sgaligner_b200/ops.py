@@ -188,6 +188,34 @@ def pointnet_bn_moments(pts, W1, b1, W2, b2, W3, b3):
     return mom
 
 
+def pointnet_bn_moments_gram(pts, W1, b1, W2, b2, W3, b3):
+    """BatchNorm batch statistics from tensor-core Gram matrices (csrc/pointnet_gram.cu); same layout as
+    :func:`pointnet_bn_moments`."""
+    pts, w = _pointnet_args(pts, W1, b1, W2, b2, W3, b3, POINTNET_TC)
+    N, P, _ = pts.shape
+    C3 = W3.shape[0]
+    lib = get_lib()
+    mom = torch.zeros(2 * (64 + 128 + C3), device=pts.device, dtype=torch.float64)
+    nb = int(lib.sga_pointnet_gram_scratch_bytes())
+    scratch = _workspace_named('gram', nb, pts.device)
+    check(lib.sga_pointnet_bn_moments_gram(_ptr(pts), N, P, *[_ptr(t) for t in w], C3, _ptr(mom), _ptr(scratch), scratch.numel(),
+                                           _stream()), 'sga_pointnet_bn_moments_gram')
+    _count(3)
+    return mom
+
+
+_NAMED_WS = {}
+
+
+def _workspace_named(name: str, nbytes: int, device) -> torch.Tensor:
+    key = (name, device.index if device.index is not None else torch.cuda.current_device())
+    ws = _NAMED_WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes) + 256, device=device, dtype=torch.uint8)
+        _NAMED_WS[key] = ws
+    return ws
+
+
 def bn_running_update(mom: torch.Tensor, cnt: float, bns):
     """One launch for the train-mode running-statistics update of the three (output-discarded) BatchNorm layers."""
     b1, b2, b3 = bns

@@ -12,6 +12,8 @@ from __future__ import annotations
 import math
 from contextlib import nullcontext as _nullcontext
 
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -79,6 +81,9 @@ class PointNetfeat(nn.Module):
             self.bn3 = nn.BatchNorm1d(out_size)
         self.track_bn_stats = True
         self.kernel_mode = ops.POINTNET_TC if out_size % 128 == 0 else ops.POINTNET_SIMT
+        # how train() obtains the BatchNorm batch statistics on the tensor-core path: 'fused' = summed in the forward
+        # kernel's epilogues (one launch), 'gram' = from Gram matrices by a separate kernel (ops.pointnet_bn_moments_gram)
+        self.bn_stats_mode = os.environ.get('SGA_BN_STATS', 'fused')
         if init_weights:
             # networks/base.py:5-56 as called at pointnet.py:116-118: xavier_normal(gain 1), zero bias,
             # BatchNorm weight 1 / bias 0
@@ -90,8 +95,19 @@ class PointNetfeat(nn.Module):
         """``pts_npc``: [N, P, 3] (the collated layout; the reference permutes to [N,3,P] first).
         ``chunks``: readiness events of a streamed host-to-device copy (``data.to_cuda_streamed``)."""
         want_stats = self.use_batch_norm and self.training and self.track_bn_stats
-        fused = want_stats and self.kernel_mode == ops.POINTNET_TC
-        if want_stats and not fused:        # fp32 FMA kernel (pt_out_dim not a multiple of 128): separate statistics pass
+        gram = want_stats and self.kernel_mode == ops.POINTNET_TC and self.bn_stats_mode == 'gram' and self.conv3.weight.shape[1] == 128
+        fused = want_stats and self.kernel_mode == ops.POINTNET_TC and not gram
+        if gram:
+            # statistics from tensor-core Gram matrices of the ReLU outputs (a third of a forward) + the plain forward,
+            # instead of summing every conv output in the forward's epilogues
+            if chunks:
+                for (_, _, ev) in chunks:
+                    torch.cuda.current_stream().wait_event(ev)
+            with torch.no_grad():
+                mom = ops.pointnet_bn_moments_gram(pts_npc, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
+                                                   self.conv3.weight, self.conv3.bias)
+            self._update_bn_running_stats(mom, float(pts_npc.shape[0] * pts_npc.shape[1]))
+        if want_stats and not fused and not gram:   # fp32 FMA kernel (pt_out_dim not a multiple of 128): separate statistics pass
             if chunks:
                 for (_, _, ev) in chunks:
                     torch.cuda.current_stream().wait_event(ev)

@@ -208,3 +208,27 @@ def test_gemm_tf32x3_layouts(layout, shape, dev):
         torch.cuda.synchronize()
         want = torch.zeros(50, N, dtype=torch.float64).index_add_(0, ci, ref)
         assert rel_inf(acc, want) < 1e-5
+
+
+@pytest.mark.parametrize('N,P', [(37, 512), (300, 200), (5, 1000)])
+def test_pointnet_bn_moments_from_gram_matrices(N, P, dev):
+    """ops.pointnet_bn_moments_gram (tensor-core Gram matrices + fp64 finalize) against the fp32 FMA statistics pass
+    (ops.pointnet_bn_moments): per-channel mean and (biased) variance of the three pre-ReLU conv outputs."""
+    from sgaligner_b200 import ops
+    g = torch.Generator().manual_seed(N)
+    pts = (torch.randn(N, P, 3, generator=g) + torch.rand(N, 1, 3, generator=g) * 4 - 2).to(dev)
+    C3 = 256
+    W1, b1 = torch.randn(64, 3, generator=g) * 0.5, torch.randn(64, generator=g) * 0.1
+    W2, b2 = torch.randn(128, 64, generator=g) * 0.15, torch.randn(128, generator=g) * 0.1
+    W3, b3 = torch.randn(C3, 128, generator=g) * 0.1, torch.randn(C3, generator=g) * 0.1
+    args = [t.to(dev) for t in (W1, b1, W2, b2, W3, b3)]
+    ref = ops.pointnet_bn_moments(pts, *args).cpu()
+    got = ops.pointnet_bn_moments_gram(pts, *args).cpu()
+    n = float(N * P)
+    o = 0
+    for c in (64, 128, C3):
+        mr, mg = ref[o:o + c] / n, got[o:o + c] / n
+        vr, vg = ref[o + c:o + 2 * c] / n - mr * mr, got[o + c:o + 2 * c] / n - mg * mg
+        o += 2 * c
+        assert float((mg - mr).abs().max()) <= 2e-4 * float(mr.abs().max() + vr.sqrt().max()), (c, float((mg - mr).abs().max()))
+        assert float(((vg - vr).abs() / vr.clamp_min(1e-12)).max()) <= 2e-3, (c, float(((vg - vr).abs() / vr.clamp_min(1e-12)).max()))
