@@ -26,28 +26,28 @@ constexpr int kThreads = kComputeThreads + 32;
 constexpr uint32_t kBlk = 16384;
 constexpr int kTile = 128;
 
-// shared-memory map
+// shared-memory map (A1 / H2 / the point table are double-buffered: conv1 of tile t+1 runs under the MMAs of tile t)
 constexpr uint32_t W2HI = 0;                 // [128 k2 rows][64 k1] K-major SW128: B of conv2
 constexpr uint32_t W2LO = W2HI + kBlk;
-constexpr uint32_t A1 = W2LO + kBlk;         // [128 pts][64 ch] bf16: A of conv2 (K-major), both operands of G1 (MN-major)
-constexpr uint32_t E1 = A1 + kBlk;           //   second MN atom of G1's A operand: channel 0 = 1 (first moments), rest 0
-constexpr uint32_t H2 = E1 + kBlk;           // 2 blocks [128 pts][64 ch] bf16: both operands of G2 (MN-major)
-constexpr uint32_t E2 = H2 + 2 * kBlk;       //   third MN atom of G2's B operand: ones column
-constexpr uint32_t SMALL = E2 + kBlk;        // 114688
+constexpr uint32_t A1 = W2LO + kBlk;         // 2 x { [128 pts][64 ch] bf16: A of conv2 (K-major), both operands of G1 (MN-major);
+constexpr uint32_t A1_STRIDE = 2 * kBlk;     //       E1: second MN atom of G1's A operand, channel 0 = 1 (first moments) }
+constexpr uint32_t H2 = A1 + 2 * A1_STRIDE;  // 2 x { 2 blocks [128 pts][64 ch] bf16: both operands of G2 (MN-major);
+constexpr uint32_t H2_STRIDE = 3 * kBlk;     //       E2: third MN atom of G2's B operand, the ones column }
+constexpr uint32_t SMALL = H2 + 2 * H2_STRIDE;   // 196608
 constexpr uint32_t W1B1 = SMALL;             // float4[64] = {w0,w1,w2,b}
 constexpr uint32_t B2 = W1B1 + 1024;         // float[128]
-constexpr uint32_t XS = B2 + 512;            // float4[128] = {x,y,z,valid} of the current tile
-constexpr uint32_t BARS = XS + 2048;
+constexpr uint32_t XS = B2 + 512;            // 2 x float4[128] = {x,y,z,valid}
+constexpr uint32_t BARS = XS + 4096;
 constexpr uint32_t TMEMPTR = BARS + 64;
 constexpr uint32_t SMEM_BYTES = TMEMPTR + 16 + 1024;
 
 constexpr uint32_t D1_COL = 0;     // [128 x 64]  rows 0..63 = G1, row 64 = sum h1
-constexpr uint32_t D2_COL = 64;    // [128 pts x 128 ch] conv2 accumulator
-constexpr uint32_t D3_COL = 192;   // [128 x 192] cols 0..127 = G2, col 128 = sum h2
+constexpr uint32_t D2_COL = 64;    // 2 x [128 pts x 128 ch] conv2 accumulators
+constexpr uint32_t D3_COL = 320;   // [128 x 192] cols 0..127 = G2, col 128 = sum h2
 constexpr int kTmemCols = 512;
 constexpr int kPartial = 128 * 64 + 128 * 192;      // floats one CTA writes
 
-enum { BAR_A1_FULL = 0, BAR_D2_FULL = 1, BAR_H2_FULL = 2, BAR_G2_DONE = 3 };
+enum { BAR_A1_FULL = 0, BAR_D2_FULL = 2, BAR_H2_FULL = 4, BAR_G2_DONE = 6 };     // two of each (buffer t & 1)
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {   // a -> low half (lower channel)
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -104,17 +104,22 @@ pointnet_gram_kernel(const float* __restrict__ pts, int64_t N, int P, const floa
     const int r = i >> 3, j = i & 7;
     const uint4 v = make_uint4(j == 0 ? 0x00003F80u : 0u, 0u, 0u, 0u);
     const uint32_t off = ptx::sw128_offset(r, j);
-    st_chunk(sm_base + E1 + off, v);
-    st_chunk(sm_base + E2 + off, v);
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      st_chunk(sm_base + A1 + b * A1_STRIDE + kBlk + off, v);
+      st_chunk(sm_base + H2 + b * H2_STRIDE + 2 * kBlk + off, v);
+    }
   }
   for (int i = tid; i < 64; i += kThreads)
     reinterpret_cast<float4*>(sm + W1B1)[i] = make_float4(W1[i * 3], W1[i * 3 + 1], W1[i * 3 + 2], b1[i]);
   for (int i = tid; i < 128; i += kThreads) reinterpret_cast<float*>(sm + B2)[i] = b2[i];
   if (tid == 0) {
-    ptx::mbar_init(&bars[BAR_A1_FULL], kComputeThreads);
-    ptx::mbar_init(&bars[BAR_D2_FULL], 1);
-    ptx::mbar_init(&bars[BAR_H2_FULL], kComputeThreads);
-    ptx::mbar_init(&bars[BAR_G2_DONE], 1);
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&bars[BAR_A1_FULL + b], kComputeThreads);
+      ptx::mbar_init(&bars[BAR_D2_FULL + b], 1);
+      ptx::mbar_init(&bars[BAR_H2_FULL + b], kComputeThreads);
+      ptx::mbar_init(&bars[BAR_G2_DONE + b], 1);
+    }
     ptx::fence_mbar_init();
   }
   if (warp == 8) ptx::tmem_alloc<kTmemCols>(tmem_slot);
@@ -130,42 +135,47 @@ pointnet_gram_kernel(const float* __restrict__ pts, int64_t N, int P, const floa
 
   if (warp == 8) {
     // =============================== MMA issuer ===============================
+    // issue order: G1 + conv2 of tile t+1 go out BEFORE the wait for H2 of tile t, so they run under its epilogue
     const uint32_t idesc2 = ptx::make_idesc(1, 128, 128);
     const uint32_t idesc_g1 = ptx::make_idesc(1, 128, 64) | (1u << 15) | (1u << 16);    // both operands MN-major
     const uint32_t idesc_g2 = ptx::make_idesc(1, 128, 192) | (1u << 15) | (1u << 16);
-    const uint64_t dA1 = ptx::smem_desc_sw128(sm_base + A1);
     const uint64_t dW2hi = ptx::smem_desc_sw128(sm_base + W2HI), dW2lo = ptx::smem_desc_sw128(sm_base + W2LO);
-    const uint64_t mA1 = desc_mn_sw128(sm_base + A1, kBlk);      // atoms: A1, E1 (A of G1) / A1 alone (B of G1, N = 64)
-    const uint64_t mH2 = desc_mn_sw128(sm_base + H2, kBlk);      // atoms: H2 block 0, block 1 (A of G2), + E2 (B of G2, N = 192)
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-    for (int64_t t = 0; t < G; ++t) {
-      const uint32_t ph = (uint32_t)(t & 1);
-      ptx::mbar_wait(&bars[BAR_A1_FULL], ph);
+    auto issue_front = [&](int64_t t) {        // G1 += A1^T [A1 | 1];  D2[b] = A1 W2^T (W2 hi, lo)
+      const int b = (int)(t & 1);
+      ptx::mbar_wait(&bars[BAR_A1_FULL + b], (uint32_t)((t >> 1) & 1));
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
-        // G1[ch x ch] += A1^T A1 over the 128 points of the tile (K = 128: 8 steps of 16 rows = 2048 B)
+        const uint32_t a1 = sm_base + A1 + b * A1_STRIDE;
+        const uint64_t dA1 = ptx::smem_desc_sw128(a1);
+        const uint64_t mA1 = desc_mn_sw128(a1, kBlk);          // atoms: A1, E1 (A of G1) / A1 alone (B of G1, N = 64)
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)
           ptx::umma_bf16(tmem_u + D1_COL, mA1 + (uint64_t)(ks * 128), mA1 + (uint64_t)(ks * 128), idesc_g1, (t | ks) != 0);
-        // conv2: D2[pts x ch] = A1 W2^T, W2 in two passes (hi, lo)
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
           const uint64_t bb = pass ? dW2lo : dW2hi;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            ptx::umma_bf16(tmem_u + D2_COL, dA1 + (uint64_t)(ks * 2), bb + (uint64_t)(ks * 2), idesc2, (pass | ks) != 0);
+            ptx::umma_bf16(tmem_u + D2_COL + b * 128, dA1 + (uint64_t)(ks * 2), bb + (uint64_t)(ks * 2), idesc2, (pass | ks) != 0);
         }
-        ptx::umma_commit(&bars[BAR_D2_FULL]);
+        ptx::umma_commit(&bars[BAR_D2_FULL + b]);
       }
       __syncwarp();
-      ptx::mbar_wait(&bars[BAR_H2_FULL], ph);
+    };
+    if (G > 0) issue_front(0);
+    for (int64_t t = 0; t < G; ++t) {
+      const int b = (int)(t & 1);
+      if (t + 1 < G) issue_front(t + 1);
+      ptx::mbar_wait(&bars[BAR_H2_FULL + b], (uint32_t)((t >> 1) & 1));
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         // G2[ch x (ch | 1)] += H2^T [H2 | 1]
+        const uint64_t mH2 = desc_mn_sw128(sm_base + H2 + b * H2_STRIDE, kBlk);   // atoms: H2 block 0, block 1 (A), + E2 (B, N = 192)
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)
           ptx::umma_bf16(tmem_u + D3_COL, mH2 + (uint64_t)(ks * 128), mH2 + (uint64_t)(ks * 128), idesc_g2, (t | ks) != 0);
-        ptx::umma_commit(&bars[BAR_G2_DONE]);
+        ptx::umma_commit(&bars[BAR_G2_DONE + b]);
       }
       __syncwarp();
     }
@@ -176,8 +186,10 @@ pointnet_gram_kernel(const float* __restrict__ pts, int64_t N, int P, const floa
     const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
     const int pg = tid & 31, cg = tid >> 5;              // conv1 mapping: 8 channels (cg) x 4 rows (pg + 32 i)
     double pm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};          // threads < 128: sum x,y,z, xx,xy,xz,yy,yz,zz
-    for (int64_t t = 0; t < G; ++t) {
-      const uint32_t ph = (uint32_t)(t & 1);
+    // point table + conv1 of tile t into buffer t & 1 (A1[b] is free: this thread has waited for D2_FULL of tile t-2)
+    auto front = [&](int64_t t) -> bool {
+      const int b = (int)(t & 1);
+      float4* xb = xs + 128 * b;
       const int64_t n = blockIdx.x + (t / ntile) * (int64_t)gridDim.x;
       const int p0 = (int)(t % ntile) * kTile;
       if (tid < 128) {
@@ -191,13 +203,13 @@ pointnet_gram_kernel(const float* __restrict__ pts, int64_t N, int P, const floa
           pm[3] += (double)x * x; pm[4] += (double)x * y; pm[5] += (double)x * z;
           pm[6] += (double)y * y; pm[7] += (double)y * z; pm[8] += (double)z * z;
         }
-        xs[tid] = make_float4(x, y, z, ok ? 1.f : 0.f);
+        xb[tid] = make_float4(x, y, z, ok ? 1.f : 0.f);
       }
       compute_barrier();
-      // ---- conv1 -> A1 (single bf16; rows beyond P are zero so that they drop out of every sum)
+      // conv1 -> A1 (single bf16; rows beyond P are zero so that they drop out of every sum)
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 xr = xs[pg + 32 * i];
+        const float4 xr = xb[pg + 32 * i];
         float f[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -205,22 +217,29 @@ pointnet_gram_kernel(const float* __restrict__ pts, int64_t N, int P, const floa
           const float v = fmaf(w.x, xr.x, fmaf(w.y, xr.y, fmaf(w.z, xr.z, w.w)));
           f[e] = (v > 0.f && xr.w != 0.f) ? v : 0.f;
         }
-        st_chunk(sm_base + A1 + ptx::sw128_offset(pg + 32 * i, cg),
+        st_chunk(sm_base + A1 + b * A1_STRIDE + ptx::sw128_offset(pg + 32 * i, cg),
                  make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7])));
       }
-      const bool row_ok = xs[row].w != 0.f;              // read before the arrive (xs is rewritten for the next tile)
+      const bool ok_row = xb[row].w != 0.f;
       ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&bars[BAR_A1_FULL]);
+      ptx::mbar_arrive(&bars[BAR_A1_FULL + b]);
+      return ok_row;
+    };
+    bool row_ok = G > 0 ? front(0) : false;
+    for (int64_t t = 0; t < G; ++t) {
+      const int b = (int)(t & 1);
+      const uint32_t ph = (uint32_t)((t >> 1) & 1);
+      const bool row_ok_next = (t + 1 < G) ? front(t + 1) : false;     // runs under the MMAs of tile t
 
-      // ---- E2: h2 = relu(D2 + b2) -> H2 (single bf16), this thread's 64 channels [64 wh, +64)
-      ptx::mbar_wait(&bars[BAR_D2_FULL], ph);
+      // ---- E2: h2 = relu(D2[b] + b2) -> H2[b] (single bf16), this thread's 64 channels [64 wh, +64)
+      ptx::mbar_wait(&bars[BAR_D2_FULL + b], ph);
       ptx::tc_fence_after();
       uint32_t v[4][16];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) ptx::tmem_ld16(tmem + lane_addr + D2_COL + 64 * wh + 16 * c, v[c]);
+      for (int c = 0; c < 4; ++c) ptx::tmem_ld16(tmem + lane_addr + D2_COL + b * 128 + 64 * wh + 16 * c, v[c]);
       ptx::tmem_ld_wait();
-      if (t > 0) {                                       // G2 of the previous tile has finished reading H2
-        ptx::mbar_wait(&bars[BAR_G2_DONE], (uint32_t)((t - 1) & 1));
+      if (t >= 2) {                                      // G2 of tile t-2 has finished reading H2[b]
+        ptx::mbar_wait(&bars[BAR_G2_DONE + b], ph ^ 1u);
       }
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -230,7 +249,7 @@ pointnet_gram_kernel(const float* __restrict__ pts, int64_t N, int P, const floa
           const float z = __uint_as_float(v[c][e]) + b2s[64 * wh + 16 * c + e];
           f[e] = (z > 0.f && row_ok) ? z : 0.f;
         }
-        const uint32_t base = sm_base + H2 + (uint32_t)wh * kBlk;
+        const uint32_t base = sm_base + H2 + b * H2_STRIDE + (uint32_t)wh * kBlk;
         st_chunk(base + ptx::sw128_offset(row, 2 * c),
                  make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7])));
         st_chunk(base + ptx::sw128_offset(row, 2 * c + 1),
@@ -238,11 +257,13 @@ pointnet_gram_kernel(const float* __restrict__ pts, int64_t N, int P, const floa
       }
       ptx::tc_fence_before();
       ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&bars[BAR_H2_FULL]);
+      ptx::mbar_arrive(&bars[BAR_H2_FULL + b]);
+      row_ok = row_ok_next;
     }
     // ---- drain: the accumulators of this CTA -> its slot of `partial`
     if (G > 0) {
-      ptx::mbar_wait(&bars[BAR_G2_DONE], (uint32_t)((G - 1) & 1));
+      // the commit of the last tile covers every MMA issued before it (G1 included)
+      ptx::mbar_wait(&bars[BAR_G2_DONE + (int)((G - 1) & 1)], (uint32_t)(((G - 1) >> 1) & 1));
       ptx::tc_fence_after();
       float* out = partial + (size_t)blockIdx.x * kPartial;
       if (wh == 0) {

@@ -83,7 +83,7 @@ class PointNetfeat(nn.Module):
         self.kernel_mode = ops.POINTNET_TC if out_size % 128 == 0 else ops.POINTNET_SIMT
         # how train() obtains the BatchNorm batch statistics on the tensor-core path: 'fused' = summed in the forward
         # kernel's epilogues (one launch), 'gram' = from Gram matrices by a separate kernel (ops.pointnet_bn_moments_gram)
-        self.bn_stats_mode = os.environ.get('SGA_BN_STATS', 'fused')
+        self.bn_stats_mode = os.environ.get('SGA_BN_STATS', 'gram')
         if init_weights:
             # networks/base.py:5-56 as called at pointnet.py:116-118: xavier_normal(gain 1), zero bias,
             # BatchNorm weight 1 / bias 0
