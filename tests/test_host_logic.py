@@ -118,3 +118,30 @@ def test_flat_adam_views_on_cpu():
     assert float(opt.flat_grad[:15].sum()) == 30.0 and float(opt.flat_grad[64:71].sum()) == 7.0
     opt.zero_grad()
     assert float(opt.flat_grad.abs().sum()) == 0.0
+
+
+def test_loss_host_side_accounting_and_partition_check():
+    """Host-only entry points of the loss (no GPU): launch accounting, workspace sizing, and the partition check that
+    decides between the packed-image Gram kernel and the gathering GEMM."""
+    import ctypes
+    from sgaligner_b200 import _lib
+    from sgaligner_b200.losses import _index_tensors
+    lib = _lib.get_lib()
+    dims = (ctypes.c_int * 3)(100, 100, 200)
+    fwd = lib.sga_loss_launch_count(3, dims, 10, 10, 0)
+    both = lib.sga_loss_launch_count(3, dims, 10, 10, 1)
+    # forward: ridx + finalize + 3 pack + 1 pair + slots + narrow Gram group + wide Gram group
+    assert fwd == 9 and both > fwd
+    one = (ctypes.c_int * 1)(100)
+    assert lib.sga_loss_launch_count(1, one, 0, 0, 0) < fwd
+    w_small = lib.sga_loss_workspace_bytes(3, dims, 4096, 1024, 1024, 1024, 0)
+    w_grad = lib.sga_loss_workspace_bytes(3, dims, 4096, 1024, 1024, 1024, 1)
+    assert 0 < w_small < w_grad
+    # two [A, T] fp32 similarity blocks per embedding dominate
+    assert w_small >= 3 * 2 * 1024 * 3072 * 4
+    d = {'e1i': np.array([0, 1]), 'e2i': np.array([4, 5]), 'e1j': np.array([2, 3]), 'e2j': np.array([6, 7])}
+    assert _index_tensors(dict(d), torch.device('cpu')).partition
+    d['e1j'] = np.array([2, 1])          # node 1 is both an anchor and a non-anchor
+    assert not _index_tensors(dict(d), torch.device('cpu')).partition
+    d['e1j'] = np.array([2, 2])          # repeated node
+    assert not _index_tensors(dict(d), torch.device('cpu')).partition
