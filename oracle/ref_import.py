@@ -59,11 +59,20 @@ class _GATConvStub(nn.Module):
 
 
 class _GCNConvStub(nn.Module):
-    def __init__(self, *a, **kw):
-        super().__init__()
+    """PyG 2.2.0 ``GCNConv`` parameter layout (``lin.weight`` [out, in] glorot, no bias inside ``lin``; ``bias`` zeros);
+    arithmetic delegated to :func:`oracle.eva_oracle.gcn_conv` (restated, parity unpinned like ``GATConv``)."""
 
-    def forward(self, *a, **kw):
-        raise NotImplementedError('GCNConv (EVA baseline) is out of scope')
+    def __init__(self, in_channels, out_channels, cached=False, **kw):
+        super().__init__()
+        self.lin = nn.Linear(in_channels, out_channels, bias=False)
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+        a = math.sqrt(6.0 / (in_channels + out_channels))
+        with torch.no_grad():
+            self.lin.weight.uniform_(-a, a)
+
+    def forward(self, x, edge_index):
+        from oracle.eva_oracle import gcn_conv
+        return gcn_conv(x, edge_index, self.lin.weight, self.bias)
 
 
 def _install_stubs():
