@@ -3,6 +3,8 @@
 import os
 import re
 
+import pytest
+
 from tests.util import ROOT
 
 
@@ -54,3 +56,15 @@ def test_no_cpu_fallback_in_product_path():
             if f.endswith('.py'):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert 'import oracle' not in txt and 'from oracle' not in txt, f
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/sga_b200.h must compile as C99 (no C++ or torch types in the signatures)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('gcc not available')
+    hdr = os.path.join(ROOT, 'include', 'sga_b200.h')
+    r = subprocess.run([gcc, '-x', 'c', '-std=c99', '-Wall', '-Werror', '-fsyntax-only', hdr], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
