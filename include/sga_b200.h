@@ -46,7 +46,8 @@ int sga_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* ---- a3: PointNetfeat.forward (src/aligner/networks/pointnet.py:120-175; conv1..3 + ReLU + max)
  * pts [N,P,3] f32 (data_dict['tot_obj_pts'] as collated, NOT permuted); W1 [64,3] b1 [64];
  * W2 [128,64] b2 [128]; W3 [C3,128] b3 [C3]; out [N,C3]; argmax [N,C3] int32 (point index that
- * attains the max, lowest index on ties) or NULL.  mode: SGA_POINTNET_*. */
+ * attains the max, lowest index on ties) or NULL.  mode: SGA_POINTNET_*.  With SGA_POINTNET_TC and argmax != NULL
+ * (P <= 32767) a second launch re-evaluates near-ties of the max-pool in fp32, so argmax is the fp32 argmax. */
 int sga_pointnet_fwd(const float* pts, int64_t N, int P,
                      const float* W1, const float* b1, const float* W2, const float* b2,
                      const float* W3, const float* b3, int C3,
@@ -261,6 +262,20 @@ int sga_gemm_tf32x3(const float* A, int64_t lda, int a_mn_major, const int32_t* 
 int sga_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                   float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                   float grad_scale, void* stream);
+
+/* the same over a flat buffer made of `nseg` parameter segments (seg_off [nseg+1] int64, device): a segment whose
+ * gradient is exactly zero -- a parameter that produced no gradient in this step, torch's `.grad is None` -- is
+ * skipped entirely, as torch.optim.Adam skips it (no weight-decay drift, moments untouched).  seg_active [nseg]
+ * int32 device scratch. */
+int sga_adam_step_segments(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                           const int64_t* seg_off, int nseg, int32_t* seg_active, float lr, float beta1,
+                           float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+
+/* diagnostics only: the tensor-core forward, when it tracks the argmax, re-evaluates near-ties of the max-pool in
+ * fp32 (pointnet_tie_fix_kernel, so that the gradient is routed through the point the fp32 reference selects,
+ * pointnet.py:162-163).  counts_host[2] (HOST pointer, may be NULL) receives {near-ties re-evaluated, of those
+ * reordered} since the last reset; reset != 0 zeroes the counters.  Synchronises the device. */
+int sga_debug_tie_stats(unsigned long long* counts_host, int reset);
 
 /* diagnostics only: device buffer of >= 2048 int64 that CTA 0 of the tensor-core PointNet kernel fills
  * with clock64() stamps of its pipeline events (profiles/trace_pointnet.py); NULL switches it off. */

@@ -59,12 +59,15 @@ class GATLayer(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         x, W, att_src, att_dst, xs, a_s, a_d, out = ctx.saved_tensors
-        tW, ts, td, tb = [ops.grad_target(p) for p in ctx.params]
+        need = ctx.needs_input_grad[1:5]
+        tW, ts, td, tb = [ops.grad_target(p, n) for p, n in zip(ctx.params, need)]
         g_xs, g_as, g_ad, g_bias = ops.gat_aggregate_backward(xs, a_s, a_d, ctx.graph, ctx.apply_elu, out, gout.contiguous(), into_bias=tb)
         gW, g_att_s, g_att_d, gx = ops.gat_linear_backward(x, W, att_src, att_dst, ctx.H, ctx.C, xs, g_xs, g_as, g_ad, ctx.need_gx,
                                                            into=(tW, ts, td))
-        return (gx, gW, None if g_att_s is None else g_att_s.view_as(att_src), None if g_att_d is None else g_att_d.view_as(att_dst),
-                g_bias, None, None, None, None)
+        return (gx, gW if need[0] else None,
+                None if (g_att_s is None or not need[1]) else g_att_s.view_as(att_src),
+                None if (g_att_d is None or not need[2]) else g_att_d.view_as(att_dst),
+                g_bias if need[3] else None, None, None, None, None)
 
 
 class ProjectFuse(torch.autograd.Function):
@@ -102,7 +105,8 @@ class ProjectFuse(torch.autograd.Function):
         if g_joint is not None:
             g_joint = g_joint.contiguous()
         p_fw, p_Ws, p_bs = ctx.params
-        t_fw = ops.grad_target(p_fw)
+        nig = ctx.needs_input_grad
+        t_fw = ops.grad_target(p_fw, nig[0])
         # the kernels ADD into g_fusion_w: one buffer (the parameter's own .grad when it is kept allocated) for all M
         g_fw = t_fw if t_fw is not None else torch.zeros(M, device=fusion_w.device, dtype=torch.float32)
         grads, col = [], 0
@@ -110,10 +114,11 @@ class ProjectFuse(torch.autograd.Function):
             g_emb = gouts[m]
             gW, gb, _, gx = ops.project_fuse_backward(xs[m], Ws[m], embs[m], None if g_emb is None else g_emb.contiguous(),
                                                       g_joint, col, fusion_w, M, m, ctx.need_gx[m],
-                                                      into=(ops.grad_target(p_Ws[m]), ops.grad_target(p_bs[m]), g_fw.view(-1)))
-            grads += [gx, gW, gb]
+                                                      into=(ops.grad_target(p_Ws[m], nig[3 + 3 * m]),
+                                                            ops.grad_target(p_bs[m], nig[4 + 3 * m]), g_fw.view(-1)))
+            grads += [gx, gW if nig[3 + 3 * m] else None, gb if nig[4 + 3 * m] else None]
             col += ctx.out_dims[m]
-        return (None if t_fw is not None else g_fw.view_as(fusion_w), None, *grads)
+        return (None if (t_fw is not None or not nig[0]) else g_fw.view_as(fusion_w), None, *grads)
 
 
 class OverallLossFn(torch.autograd.Function):
@@ -144,3 +149,27 @@ class OverallLossFn(torch.autograd.Function):
         else:
             g_ial = g_icl = None
         return (None, None, g_ial, g_icl, *grads)
+
+
+class StandaloneIAL(torch.autograd.Function):
+    """``IALLoss.forward(src_emb, ref_emb)`` (losses.py:68-97) on its own.  The fused kernel evaluates
+    ``zoom * IAL + ICL terms`` (log_vars = 0); the value is its ``ial`` output at zoom = 1 and, the loss being affine
+    in zoom, the gradient is (fused gradient at zoom 1) - (fused gradient at zoom 0).  Off the hot path (the trainer
+    goes through ``OverallLoss``): two fused passes are fine."""
+
+    @staticmethod
+    def forward(ctx, idx, src_emb, ref_emb):
+        dev = src_emb.device
+        zero = torch.zeros(1, device=dev)
+        want_grad = any(ctx.needs_input_grad[1:])
+        part = getattr(idx, 'partition', True)
+        l1, g1, _, _ = ops.loss_forward_backward([src_emb, ref_emb], idx, zero, zero, 1.0, want_grad, partition=part)
+        if want_grad:
+            _, g0, _, _ = ops.loss_forward_backward([src_emb, ref_emb], idx, zero, zero, 0.0, True, partition=part)
+            ctx.save_for_backward(g1[0] - g0[0], g1[1] - g0[1])
+        return l1[3].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        gs, gr = ctx.saved_tensors
+        return None, gs * g, gr * g

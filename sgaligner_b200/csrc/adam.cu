@@ -20,8 +20,68 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     p[i] = pi - (lr / bc1) * (mi / denom);
   }
 }
+
+// ---- torch.optim.Adam skips a parameter whose .grad is None (never produced in the step: a module that is not
+// selected, BatchNorm affine parameters whose outputs the reference discards).  Over a flat buffer every gradient is
+// allocated, so "not produced" is recognised as a segment that is exactly zero: such a segment is left untouched
+// (no weight-decay drift, no moment update), as torch leaves a grad-None parameter.
+__global__ void __launch_bounds__(256)
+seg_nonzero_kernel(const float* __restrict__ g, const int64_t* __restrict__ seg_off, int32_t* __restrict__ active) {
+  const int s = blockIdx.x;
+  const int64_t a = seg_off[s], b = seg_off[s + 1];
+  int any = 0;
+  for (int64_t i = a + threadIdx.x; i < b && !any; i += 256) any |= (g[i] != 0.f);
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) active[s] = any;
+}
+
+__global__ void __launch_bounds__(256)
+adam_seg_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                int64_t n, const int64_t* __restrict__ seg_off, const int32_t* __restrict__ active, int nseg,
+                float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+  extern __shared__ int64_t soff[];
+  for (int i = threadIdx.x; i <= nseg; i += 256) soff[i] = seg_off[i];
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    int lo = 0, hi = nseg;                 // segment with soff[lo] <= i < soff[lo + 1]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (soff[mid] <= i) lo = mid; else hi = mid;
+    }
+    if (!active[lo]) continue;
+    float gi = g[i] * gscale;
+    float pi = p[i];
+    gi = fmaf(wd, pi, gi);
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
 }  // namespace
 }  // namespace sga
+
+extern "C" int sga_adam_step_segments(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                      const int64_t* seg_off, int nseg, int32_t* seg_active, float lr, float beta1,
+                                      float beta2, float eps, float weight_decay, int step, float grad_scale,
+                                      void* stream) {
+  if (n <= 0) return SGA_OK;
+  SGA_REQUIRE(step >= 1 && nseg >= 1 && nseg <= 4096 && seg_off && seg_active, "sga_adam_step_segments: step=%d nseg=%d", step, nseg);
+  double bc1 = 1.0 - pow((double)beta1, (double)step);
+  double bc2 = 1.0 - pow((double)beta2, (double)step);
+  sga::seg_nonzero_kernel<<<nseg, 256, 0, (cudaStream_t)stream>>>(grad, seg_off, seg_active);
+  SGA_LAUNCH_CHECK();
+  int64_t blocks = (n + 255) / 256;
+  int64_t cap = (int64_t)sga::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  sga::adam_seg_kernel<<<(unsigned)blocks, 256, (nseg + 1) * sizeof(int64_t), (cudaStream_t)stream>>>(
+      param, grad, exp_avg, exp_avg_sq, n, seg_off, seg_active, nseg, lr, beta1, beta2, eps, weight_decay, (float)bc1,
+      (float)sqrt(bc2), grad_scale);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
 
 extern "C" int sga_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                              float lr, float beta1, float beta2, float eps, float weight_decay, int step,

@@ -9,6 +9,7 @@ int pointnet_fwd_tc(const float*, int64_t, int, const float*, const float*, cons
 size_t pointnet_tc_raw_doubles(int C3);
 void pointnet_tc_set_max_ctas(int n);
 int debug_set_trace(long long* ptr);
+int debug_tie_stats(unsigned long long* host_out2, int reset);
 }  // namespace sga
 
 extern "C" int sga_pointnet_fwd(const float* pts, int64_t N, int P, const float* W1, const float* b1,
@@ -60,6 +61,7 @@ extern "C" int sga_pointnet_bn_moments(const float* pts, int64_t N, int P, const
 /* diagnostics only: device buffer of >= 2048 int64 that CTA 0 of the tensor-core PointNet kernel
  * fills with clock64() stamps of its pipeline events (NULL switches tracing off) */
 extern "C" int sga_debug_set_trace(long long* trace) { return sga::debug_set_trace(trace); }
+extern "C" int sga_debug_tie_stats(unsigned long long* counts_host, int reset) { return sga::debug_tie_stats(counts_host, reset); }
 
 // Train-mode side effect of the discarded BatchNorm1d calls (pointnet.py:141-142,154-155,158-159; torch BatchNorm:
 // running <- (1 - momentum) running + momentum batch_stat, unbiased variance, num_batches_tracked += 1) for the three

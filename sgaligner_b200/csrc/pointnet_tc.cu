@@ -91,6 +91,11 @@ constexpr int RAW_S2 = 16;      // 128: sum_p d2[p,c]   (d = conv output WITHOUT
 constexpr int RAW_Q2 = 144;     // 128: sum_p d2[p,c]^2
 constexpr int RAW_S3 = 272;     // C3, then C3 squares
 
+// max-pool near-tie window (see pointnet_tie_fix_kernel): |max - runner-up| <= kTieRel*|max| + kTieAbs
+constexpr float kTieRel = 2e-4f;
+constexpr float kTieAbs = 2e-5f;
+constexpr int kTieMaxP = 32767;          // the runner-up index shares the 32-bit argmax word
+
 __device__ __forceinline__ uint32_t pack2(float a, float b) {   // a -> low half (lower address / lower k)
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -383,8 +388,8 @@ pointnet_fwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
       if (++s1_t == ntile) s1_t = 0;
     };
 
-    float rmax = -INFINITY;
-    int ridx = 0;
+    float rmax = -INFINITY, r2 = -INFINITY;
+    int ridx = 0, r2idx = 0;
     // ---- E3: running max over the 128 points (columns) of tile gp; output at the end of an object
     auto stage_e3 = [&](int64_t gp) {
       const int t = e3_t;
@@ -401,12 +406,19 @@ pointnet_fwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
           ptx::tmem_ld32(base + cc * 32, v);
           ptx::tmem_ld_wait();
           if (kArgmax) {
+            // (max, first argmax) and the runner-up = the largest value STRICTLY below the max (exact duplicates of
+            // the max -- resampled points -- are not rivals: they resolve to the lowest index as in the reference)
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
               float f = __uint_as_float(v[e]);
               if (f > rmax) {
+                r2 = rmax;
+                r2idx = ridx;
                 rmax = f;
                 ridx = t * kTile + cc * 32 + e;
+              } else if (f < rmax && f > r2) {
+                r2 = f;
+                r2idx = t * kTile + cc * 32 + e;
               }
             }
           } else {
@@ -453,10 +465,25 @@ pointnet_fwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
           const int ch = cb0 + wh * 128 + row;
           const float o = rmax + b3[ch];
           out[n * C3 + ch] = o > 0.f ? o : 0.f;
-          if (kArgmax) argmax[n * C3 + ch] = min(ridx, P - 1);
+          if (kArgmax) {
+            // Near-tie of the max-pool: the bf16x3 error (~1e-5) could have ordered the two candidates differently
+            // from fp32.  The runner-up rides in the upper half of the argmax word; pointnet_tie_fix_kernel
+            // re-evaluates both candidates in fp32 (reference summation order) and rewrites the entry.
+            // The same re-evaluation (with the max as its own rival) pins the sign of a pooled pre-activation that
+            // sits on the ReLU kink, which is the mask the backward applies.
+            int code = min(ridx, P - 1);
+            const float tol = kTieRel * fabsf(rmax) + kTieAbs;
+            if (P <= kTieMaxP && o > -tol) {
+              if (rmax - r2 <= tol) code |= (min(r2idx, P - 1) + 1) << 16;
+              else if (o <= tol) code |= (code + 1) << 16;
+            }
+            argmax[n * C3 + ch] = code;
+          }
         }
         rmax = -INFINITY;
         ridx = 0;
+        r2 = -INFINITY;
+        r2idx = 0;
         e3_n += gridDim.x;
       }
     };
@@ -587,6 +614,90 @@ pointnet_fwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
   if (warp == 8) ptx::tmem_dealloc<kTmemCols>(tmem);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp32 re-check of max-pool near-ties (tensor-core forward, argmax-tracking variant).  An entry of `argmax` whose
+// upper half is non-zero carries two candidate points; both pre-activations are recomputed on the FMA pipe in the
+// summation order of the fp32 kernel (pointnet_simt.cu: bias first, k ascending) and the entry becomes the fp32
+// argmax (lowest index on an exact tie, as torch.max does), the pooled feature the fp32 value.  One warp per 32
+// entries; W2 is staged in shared memory only by CTAs that found a flagged entry.
+__device__ unsigned long long g_tie_stats[2];     // {flagged, reordered} since the last reset (diagnostics)
+
+constexpr int kFixThreads = 256;
+__global__ void __launch_bounds__(kFixThreads)
+pointnet_tie_fix_kernel(const float* __restrict__ pts, int64_t total, int P, const float* __restrict__ W1,
+                        const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ b2,
+                        const float* __restrict__ W3, const float* __restrict__ b3, int C3, float* __restrict__ out,
+                        int32_t* __restrict__ argmax) {
+  __shared__ float W2t[64 * 128];            // [k][c]
+  __shared__ float h2s[kFixThreads / 32][2][128];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t i = (int64_t)blockIdx.x * kFixThreads + tid;
+  const int code = i < total ? argmax[i] : 0;
+  const bool flagged = (code >> 16) != 0;
+  if (!__syncthreads_or(flagged)) return;
+  for (int j = tid; j < 64 * 128; j += kFixThreads) W2t[j] = W2[(j & 127) * 64 + (j >> 7)];
+  __syncthreads();
+  unsigned m = __ballot_sync(0xffffffffu, flagged);
+  unsigned long long nflag = 0, nswap = 0;
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    const int cd = __shfl_sync(0xffffffffu, code, src);
+    const int64_t idx = (int64_t)blockIdx.x * kFixThreads + warp * 32 + src;
+    const int64_t n = idx / C3;
+    const int ch = (int)(idx - n * C3);
+    const int pa = cd & 0xFFFF, pb = (cd >> 16) - 1;
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const float* pp = pts + (n * P + (w ? pb : pa)) * 3;
+      const float x = pp[0], y = pp[1], z = pp[2];
+      float h1[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = lane + 32 * j;
+        float v = b1[c];
+        v = fmaf(W1[c * 3 + 0], x, v);
+        v = fmaf(W1[c * 3 + 1], y, v);
+        v = fmaf(W1[c * 3 + 2], z, v);
+        h1[j] = v > 0.f ? v : 0.f;
+      }
+      float acc[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = b2[lane + 32 * j];
+#pragma unroll 8
+      for (int k = 0; k < 64; ++k) {
+        const float a = __shfl_sync(0xffffffffu, k < 32 ? h1[0] : h1[1], k & 31);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(a, W2t[k * 128 + lane + 32 * j], acc[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h2s[warp][w][lane + 32 * j] = acc[j] > 0.f ? acc[j] : 0.f;
+    }
+    __syncwarp();
+    float zv = 0.f;
+    if (lane < 2) {
+      zv = b3[ch];
+      const float* wr = W3 + (int64_t)ch * 128;
+      for (int k = 0; k < 128; ++k) zv = fmaf(h2s[warp][lane][k], wr[k], zv);
+    }
+    const float za = __shfl_sync(0xffffffffu, zv, 0), zb = __shfl_sync(0xffffffffu, zv, 1);
+    if (lane == 0) {
+      const bool take_b = zb > za || (zb == za && pb < pa);
+      const float zm = take_b ? zb : za;
+      argmax[idx] = take_b ? pb : pa;
+      out[idx] = zm > 0.f ? zm : 0.f;
+      ++nflag;
+      if (take_b) ++nswap;
+    }
+    __syncwarp();
+  }
+  if (lane == 0 && nflag) {
+    atomicAdd(&g_tie_stats[0], nflag);
+    if (nswap) atomicAdd(&g_tie_stats[1], nswap);
+  }
+}
+
 // raw accumulators -> {sum1[64], sq1[64], sum2[128], sq2[128], sum3[C3], sq3[C3]} of the pre-ReLU conv
 // outputs z = d + b:  sum z = S + n b,  sum z^2 = Q + 2 b S + n b^2;  conv1 is affine in the point.
 __global__ void pointnet_moments_finalize_kernel(const double* __restrict__ raw, const float* __restrict__ W1,
@@ -618,6 +729,16 @@ __global__ void pointnet_moments_finalize_kernel(const double* __restrict__ raw,
 
 int debug_set_trace(long long* ptr) {
   SGA_CUDA(cudaMemcpyToSymbol(g_trace, &ptr, sizeof(ptr)));
+  return SGA_OK;
+}
+
+// diagnostics: {near-ties re-evaluated, of those reordered} since the last reset
+int debug_tie_stats(unsigned long long* host_out2, int reset) {
+  if (host_out2) SGA_CUDA(cudaMemcpyFromSymbol(host_out2, g_tie_stats, 2 * sizeof(unsigned long long)));
+  if (reset) {
+    const unsigned long long z[2] = {0, 0};
+    SGA_CUDA(cudaMemcpyToSymbol(g_tie_stats, z, sizeof(z)));
+  }
   return SGA_OK;
 }
 
@@ -659,6 +780,12 @@ int pointnet_fwd_tc(const float* pts, int64_t N, int P, const float* W1, const f
   }
 #undef SGA_PN_LAUNCH
   SGA_LAUNCH_CHECK();
+  if (argmax && P <= kTieMaxP) {
+    const int64_t total = N * (int64_t)C3;
+    pointnet_tie_fix_kernel<<<(unsigned)((total + kFixThreads - 1) / kFixThreads), kFixThreads, 0, st>>>(
+        pts, total, P, W1, b1, W2, b2, W3, b3, C3, out, argmax);
+    SGA_LAUNCH_CHECK();
+  }
   if (raw) {
     const int n = 64 + 128 + C3;
     pointnet_moments_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(raw, W1, b1, b2, b3, C3, (double)N * (double)P, moments);

@@ -16,19 +16,29 @@ __all__ = ['torch', 'nn', 'F', 'calculate_prob_dist', 'CustomMultiLossLayer', 'I
 class _IndexSets(list):
     """[e1i, e2i, e1j, e2j] device tensors + ``partition`` (are the sets disjoint and duplicate-free?)."""
     partition = True
+    max_index = -1
 
 
-def _index_tensors(data_dict, device):
+def _index_tensors(data_dict, device, n_rows=None):
     """e1i/e2i/e1j/e2j arrive as host int32 numpy arrays (scan3r.py:168-171); cache the device copies
-    in the dict so that several loss calls on one batch upload them once."""
+    in the dict so that several loss calls on one batch upload them once.  ``n_rows``: rows of the embedding the
+    indices address -- an index outside [0, n_rows) raises ``IndexError`` like the reference's ``emb[e1i]`` gather
+    (``losses.py:46-49``) instead of reaching the kernels (negative indices are rejected too, not wrapped)."""
     cached = data_dict.get('_sga_idx')
     if cached is not None and cached[0].device == device:
+        if n_rows is not None and cached.max_index >= n_rows:
+            raise IndexError(f'index {cached.max_index} is out of bounds for dimension 0 with size {n_rows}')
         return cached
     host = [np.ascontiguousarray(np.asarray(data_dict[k]).astype(np.int32)).reshape(-1) for k in ('e1i', 'e2i', 'e1j', 'e2j')]
     idx = _IndexSets(torch.as_tensor(h).to(device, non_blocking=True) for h in host)
     # the collated sets partition the nodes (scan3r.py:101-107); anything else (hand-made overlapping / repeated
     # indices) is still computed correctly, by the Gram path that gathers rows instead of using packed images
     allidx = np.concatenate(host)
+    idx.max_index = int(allidx.max()) if allidx.size else -1
+    if allidx.size and int(allidx.min()) < 0:
+        raise IndexError(f'negative node index {int(allidx.min())} in e1i/e2i/e1j/e2j')
+    if n_rows is not None and idx.max_index >= n_rows:
+        raise IndexError(f'index {idx.max_index} is out of bounds for dimension 0 with size {n_rows}')
     idx.partition = bool(allidx.size == 0 or (allidx.min() >= 0 and np.bincount(allidx).max() <= 1))
     try:
         data_dict['_sga_idx'] = idx
@@ -75,14 +85,15 @@ class ICLLoss(nn.Module):
         self.device = device
 
     def forward(self, emb, data_dict):
-        idx = _index_tensors(data_dict, emb.device)
+        idx = _index_tensors(data_dict, emb.device, emb.shape[0])
         return ag.OverallLossFn.apply(idx, 0.1, None, None, emb)[0]
 
 
 class IALLoss(nn.Module):
-    """``losses.py:60-97``.  Stand-alone IAL of one (modal, joint) pair is obtained from the fused
-    kernel by differencing: with log_vars = 0 and zoom = 1 the kernel's ``ial`` output for M = 1
-    modality equals this loss."""
+    """``losses.py:60-97``.  Stand-alone IAL of one (modal, joint) pair from the fused kernel: with log_vars = 0
+    and zoom = 1 the kernel's ``ial`` output for M = 1 modality equals this loss, and because the fused loss is
+    affine in ``zoom`` its gradient is the difference of the fused gradients at zoom = 1 and zoom = 0
+    (``autograd.StandaloneIAL``).  Differentiable w.r.t. both embeddings like the reference's."""
 
     def __init__(self, device, temperature=0.05, alpha=0.5):
         super().__init__()
@@ -92,9 +103,8 @@ class IALLoss(nn.Module):
         self.zoom = 0.1
 
     def forward(self, src_emb, ref_emb, data_dict):
-        idx = _index_tensors(data_dict, src_emb.device)
-        zero = torch.zeros(1, device=src_emb.device)
-        return ag.OverallLossFn.apply(idx, 1.0, zero, zero, src_emb.detach(), ref_emb.detach())[3]
+        idx = _index_tensors(data_dict, src_emb.device, src_emb.shape[0])
+        return ag.StandaloneIAL.apply(idx, src_emb, ref_emb)
 
 
 class OverallLoss(nn.Module):
@@ -115,7 +125,7 @@ class OverallLoss(nn.Module):
     def forward(self, output_dict, data_dict):
         mods = self.modules
         dev = output_dict[mods[0]].device
-        idx = _index_tensors(data_dict, dev)
+        idx = _index_tensors(data_dict, dev, output_dict[mods[0]].shape[0])
         if len(mods) > 1:
             embs = [output_dict[m] for m in mods] + [output_dict['joint']]
             lv_ial = self.align_multi_loss_layer.log_vars

@@ -110,13 +110,21 @@ def pointnet_forward(pts, W1, b1, W2, b2, W3, b3, want_argmax: bool, mode: int =
                                        ctypes.c_void_p(out.data_ptr() + s * C3 * 4),
                                        ctypes.c_void_p(0 if arg is None else arg.data_ptr() + s * C3 * 4), mode, _stream()),
                   'sga_pointnet_fwd')
-            _count(1)
+            _count(2 if (want_argmax and mode == POINTNET_TC) else 1)
         return out, arg
     with _timed('pointnet_fwd'):
         check(lib.sga_pointnet_fwd(_ptr(pts), N, P, *[_ptr(t) for t in w], C3, _ptr(out), _ptr(arg), mode, _stream()),
               'sga_pointnet_fwd')
-    _count(1)
+    _count(2 if (want_argmax and mode == POINTNET_TC) else 1)     # + the fp32 near-tie re-check of the max-pool
     return out, arg
+
+
+def pointnet_tie_stats(reset: bool = False):
+    """Diagnostics: (near-ties of the max-pool re-evaluated in fp32, of those reordered) by the tensor-core forward
+    since the last reset.  Synchronises."""
+    buf = (ctypes.c_ulonglong * 2)()
+    check(get_lib().sga_debug_tie_stats(ctypes.cast(buf, ctypes.c_void_p), 1 if reset else 0), 'sga_debug_tie_stats')
+    return int(buf[0]), int(buf[1])
 
 
 def pointnet_forward_stats(pts, W1, b1, W2, b2, W3, b3, want_argmax: bool):
@@ -134,15 +142,37 @@ def pointnet_forward_stats(pts, W1, b1, W2, b2, W3, b3, want_argmax: bool):
     with _timed('pointnet_fwd_stats'):
         check(lib.sga_pointnet_fwd_stats(_ptr(pts), N, P, *[_ptr(t) for t in w], C3, _ptr(out), _ptr(arg), _ptr(buf),
                                          ctypes.c_void_p(buf.data_ptr() + n_mom * 8), sbytes, _stream()), 'sga_pointnet_fwd_stats')
-    _count(2)
+    _count(3 if want_argmax else 2)
     return out, arg, buf[:n_mom]
 
 
-def grad_target(p: torch.Tensor):
-    """The tensor a backward kernel may accumulate a PARAMETER gradient into directly: ``p.grad`` when the
-    optimiser keeps gradients allocated (``trainer.FlatAdam`` points every ``.grad`` into one flat buffer and
-    zeroes it with one memset).  All parameter-gradient kernels accumulate (atomics / beta = 1), so writing
-    there removes a zero-fill and autograd's ``grad += new`` kernel per parameter (~40 launches per step)."""
+_DIRECT_GRAD = {}      # id(parameter) -> weakref: parameters whose owner opted in to direct gradient accumulation
+
+
+def enable_direct_grad(params, on: bool = True):
+    """Opt the given parameters in to (or out of) DIRECT gradient accumulation: the backward kernels then add a
+    parameter's gradient straight into its kept-allocated ``.grad`` tensor and hand ``None`` to autograd
+    (``trainer.FlatAdam`` does this for its flat gradient buffer: no zero-fill and no ``grad += new`` kernel per
+    parameter, ~40 launches per step).  It is strictly opt-in, because in that state ``torch.autograd.grad``,
+    ``backward(inputs=...)``, gradient hooks and DDP-style reducers do not see these gradients; without it every
+    backward returns ordinary gradient tensors to autograd."""
+    import weakref
+    for p in params:
+        if on:
+            _DIRECT_GRAD[id(p)] = weakref.ref(p)
+        else:
+            _DIRECT_GRAD.pop(id(p), None)
+
+
+def grad_target(p: torch.Tensor, needed: bool = True):
+    """The tensor a backward kernel may accumulate a PARAMETER gradient into directly, or None: ``p.grad`` of a
+    parameter that was opted in with :func:`enable_direct_grad` (and needs a gradient at all).  All
+    parameter-gradient kernels accumulate (atomics / beta = 1)."""
+    if not needed:
+        return None
+    r = _DIRECT_GRAD.get(id(p))
+    if r is None or r() is not p:
+        return None
     g = getattr(p, 'grad', None)
     if (g is not None and p.is_leaf and g.dtype == torch.float32 and g.is_cuda and g.is_contiguous()
             and g.numel() == p.numel() and g.device == p.device):
@@ -562,6 +592,15 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_de
     check(get_lib().sga_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), lr, beta1, beta2,
                                   eps, weight_decay, int(step), float(grad_scale), _stream()), 'sga_adam_step')
     _count(1)
+
+
+def adam_step_segments(param, grad, exp_avg, exp_avg_sq, seg_off, seg_active, lr, beta1, beta2, eps, weight_decay, step,
+                       grad_scale=1.0):
+    """Adam over a flat buffer that leaves segments with an all-zero gradient untouched (torch skips grad-None params)."""
+    check(get_lib().sga_adam_step_segments(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), _ptr(seg_off),
+                                           int(seg_off.numel() - 1), _ptr(seg_active), lr, beta1, beta2, eps, weight_decay,
+                                           int(step), float(grad_scale), _stream()), 'sga_adam_step_segments')
+    _count(2)
 
 
 def selftest_umma(A: torch.Tensor, B: torch.Tensor, kind: int) -> torch.Tensor:

@@ -164,11 +164,19 @@ class SubscanStore:
 
 
 class _Staging:
-    """Reusable pinned host buffers of one batch (grown on demand)."""
+    """Reusable pinned host buffers of ONE batch (grown on demand).  ``busy`` is the CUDA event recorded after the
+    last asynchronous H2D copy that reads these buffers (:func:`to_device` sets it); :meth:`wait` blocks the host
+    until that copy has drained, so the buffers are never rewritten under a queued copy."""
 
     def __init__(self, pinned: bool):
         self.pinned = pinned
         self.buf: Dict[str, torch.Tensor] = {}
+        self.busy = None
+
+    def wait(self):
+        if self.busy is not None:
+            self.busy.synchronize()
+            self.busy = None
 
     def get(self, key: str, shape, dtype) -> torch.Tensor:
         n = int(np.prod(shape))
@@ -190,11 +198,16 @@ class Scan3RPacked(torch.utils.data.Dataset):
     what the reference returns; :meth:`collate_pairs` is the fast path (one pass into pinned memory, raw
     points + ``pcl_center``; pair with :func:`to_device`)."""
 
-    def __init__(self, store: SubscanStore, anchor_data: Sequence[dict], split: str = 'train', pinned: Optional[bool] = None):
+    def __init__(self, store: SubscanStore, anchor_data: Sequence[dict], split: str = 'train', pinned: Optional[bool] = None,
+                 n_staging: int = 2):
         self.store = store
         self.anchor_data = list(anchor_data)
         self.split = split
-        self._stage = _Staging(torch.cuda.is_available() if pinned is None else pinned)
+        # ring of staging sets: batch k+1 is assembled while the H2D copy of batch k is still queued; a set is
+        # only rewritten after the event of its last copy has fired (checked in collate_pairs, not left to the caller)
+        pin_ = torch.cuda.is_available() if pinned is None else pinned
+        self._stages = [_Staging(pin_) for _ in range(max(2, int(n_staging)))]
+        self._stage_next = 0
 
     def __len__(self):
         return len(self.anchor_data)
@@ -283,8 +296,10 @@ class Scan3RPacked(torch.utils.data.Dataset):
         """One batch assembled straight from the mapping into (pinned) staging buffers.  Same dict as
         ``collate_fn([self[i] for i in indices])`` EXCEPT that ``tot_obj_pts`` holds the RAW (un-centred)
         points and ``'_sga_center'`` (f32 ``[B,3]``) + ``'_sga_raw_points'`` ask :func:`to_device` to do
-        the centring on the GPU.  The buffers are reused by the next call (double-buffer with two
-        ``Scan3RPacked`` objects, or consume the batch before the next call)."""
+        the centring on the GPU.  The staging buffers come from a ring of ``n_staging`` sets; a set is reused only
+        after the H2D copies :func:`to_device` queued from it have completed (event-guarded), so
+        ``to_device(ds.collate_pairs(idx))`` is safe with the host running ahead of the GPU.  A caller that reads
+        the host tensors directly must be done with batch k before batch k + n_staging is collated."""
         metas = [self._sample_meta(i) for i in indices]
         B = len(metas)
         st = self.store
@@ -292,7 +307,9 @@ class Scan3RPacked(torch.utils.data.Dataset):
         n_obj = [m['src']['n'] + m['ref']['n'] for m in metas]
         n_edge = [m['src']['e'] + m['ref']['e'] for m in metas]
         N, E = int(sum(n_obj)), int(sum(n_edge))
-        S = self._stage
+        S = self._stages[self._stage_next]
+        self._stage_next = (self._stage_next + 1) % len(self._stages)
+        S.wait()                                   # the H2D copies of the batch that last used this set
         pts = S.get('pts', (N, P, 3), torch.float32)
         attr = S.get('attr', (N, st.attr_dim), torch.float64)
         rel = S.get('rel', (N, st.rel_dim), torch.float64)
@@ -332,6 +349,7 @@ class Scan3RPacked(torch.utils.data.Dataset):
         out['batch_size'] = B
         out['_sga_center'] = torch.from_numpy(np.stack([m['center'] for m in metas]).astype(np.float32))
         out['_sga_raw_points'] = True
+        out['_sga_stage'] = S
         return out
 
 
@@ -344,6 +362,12 @@ def to_device(batch: dict, device, n_chunks: int = 4, keys=None) -> dict:
     raw = batch.get('_sga_raw_points', False)
     host = {k: v for k, v in batch.items() if not k.startswith('_sga_')}
     d = to_cuda_streamed(host, device, n_chunks=n_chunks, keys=keys)
+    stage = batch.get('_sga_stage')
+    if stage is not None and stage.pinned:
+        # every copy that reads the pinned staging set is queued on the copy stream by now: guard the set
+        ev = torch.cuda.Event()
+        ev.record(d['_sga_ready']['stream'])
+        stage.busy = ev
     if raw:
         dev = d['tot_obj_pts'].device
         ready = d.pop('_sga_ready')

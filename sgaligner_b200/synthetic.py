@@ -135,8 +135,13 @@ def shard_batch(data: dict, rank: int, world: int) -> dict:
     """Contiguous split of the pairs of a collated batch across ``world`` ranks (never splits a
     pair).  Index arrays are re-based to the shard's first object."""
     B = int(data['batch_size'])
-    per = (B + world - 1) // world
-    b0, b1 = min(B, rank * per), min(B, (rank + 1) * per)
+    if B < world:
+        raise ValueError(f'cannot shard {B} pairs over {world} ranks: every rank needs at least one pair '
+                         '(an empty shard would fail in the loss while the others wait in the all-reduce)')
+    # balanced split (np.array_split boundaries): the first B % world ranks get one pair more
+    base, extra = divmod(B, world)
+    b0 = rank * base + min(rank, extra)
+    b1 = b0 + base + (1 if rank < extra else 0)
     return slice_pairs(data, b0, b1)
 
 

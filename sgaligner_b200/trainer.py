@@ -53,10 +53,27 @@ class FlatAdam:
                 view.copy_(p.data)
                 p.data = view
                 p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
-        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        # torch.optim.Optimizer surface the reference's trainer touches: ``param_groups[0]['lr']`` is read by
+        # ``base_trainer.get_lr``, scaled by the world size in ``register_optimizer`` and written by lr schedulers
+        self.param_groups = [{'params': self.params, 'lr': lr, 'betas': tuple(betas), 'eps': eps, 'weight_decay': weight_decay,
+                              'amsgrad': False, 'maximize': False}]
+        self.defaults = {k: v for k, v in self.param_groups[0].items() if k != 'params'}
         self.step_count = 0
+        # parameter segments of the flat buffer (padding belongs to the preceding parameter; its gradient stays 0)
+        self._seg_off = torch.tensor(self.offsets + [total], dtype=torch.int64, device=dev)
+        self._seg_active = torch.zeros(len(self.params), dtype=torch.int32, device=dev)
+        # the backward kernels may add parameter gradients straight into the flat buffer (explicit opt-in)
+        ops.enable_direct_grad(self.params)
 
-    def zero_grad(self):
+    # single-group conveniences (kept for callers that set them directly)
+    lr = property(lambda self: self.param_groups[0]['lr'], lambda self, v: self.param_groups[0].__setitem__('lr', v))
+    betas = property(lambda self: self.param_groups[0]['betas'])
+    eps = property(lambda self: self.param_groups[0]['eps'])
+    weight_decay = property(lambda self: self.param_groups[0]['weight_decay'])
+
+    def zero_grad(self, set_to_none: bool = False):
+        """One memset of the flat gradient buffer (``set_to_none`` is accepted for signature compatibility and
+        ignored: the gradients are views of one allocation)."""
         self.flat_grad.zero_()
         for p, o in zip(self.params, self.offsets):   # re-attach in case something replaced .grad
             if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * o:
@@ -69,18 +86,49 @@ class FlatAdam:
             return dist.get_world_size(group)
         return 1
 
-    def step(self, grad_scale: float = 1.0):
+    def step(self, grad_scale: float = 1.0, closure=None):
+        """One Adam update of the whole flat buffer.  A parameter whose gradient is exactly zero in this step (torch:
+        ``.grad is None`` -- modules that are not selected, the BatchNorm affine parameters whose outputs the
+        reference discards) is skipped like torch.optim.Adam skips it: no weight-decay drift, moments untouched.
+        Deviation: one global step counter (torch keeps one per parameter; they only differ for a parameter that
+        receives gradients in some steps and none in others)."""
+        g = self.param_groups[0]
         self.step_count += 1
-        ops.adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
-                      self.eps, self.weight_decay, self.step_count, grad_scale)
+        ops.adam_step_segments(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self._seg_off, self._seg_active,
+                               float(g['lr']), g['betas'][0], g['betas'][1], g['eps'], g['weight_decay'], self.step_count, grad_scale)
 
     def state_dict(self):
-        return {'step': self.step_count, 'exp_avg': self.exp_avg.clone(), 'exp_avg_sq': self.exp_avg_sq.clone()}
+        """``torch.optim.Adam.state_dict()`` layout (``state[i] = {step, exp_avg, exp_avg_sq}`` per parameter index,
+        ``param_groups`` with index lists), so the reference's ``save_snapshot`` / ``load_snapshot`` round-trip and a
+        checkpoint written by ``torch.optim.Adam`` over the same parameter list loads here."""
+        state = {}
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+            n = p.numel()
+            state[i] = {'step': torch.tensor(float(self.step_count)),
+                        'exp_avg': self.exp_avg[o:o + n].view_as(p).clone(),
+                        'exp_avg_sq': self.exp_avg_sq[o:o + n].view_as(p).clone()}
+        groups = [{**{k: v for k, v in self.param_groups[0].items() if k != 'params'}, 'params': list(range(len(self.params)))}]
+        return {'state': state, 'param_groups': groups}
 
     def load_state_dict(self, sd):
-        self.step_count = int(sd['step'])
-        self.exp_avg.copy_(sd['exp_avg'])
-        self.exp_avg_sq.copy_(sd['exp_avg_sq'])
+        if 'state' not in sd:                      # round-1 flat format
+            self.step_count = int(sd['step'])
+            self.exp_avg.copy_(sd['exp_avg'])
+            self.exp_avg_sq.copy_(sd['exp_avg_sq'])
+            return
+        steps = []
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+            st = sd['state'].get(i, sd['state'].get(str(i)))
+            if st is None:                          # torch keeps no state for a parameter that never had a gradient
+                continue
+            n = p.numel()
+            self.exp_avg[o:o + n].copy_(st['exp_avg'].reshape(-1))
+            self.exp_avg_sq[o:o + n].copy_(st['exp_avg_sq'].reshape(-1))
+            steps.append(int(float(st['step'])))
+        self.step_count = max(steps) if steps else 0
+        for k, v in sd['param_groups'][0].items():
+            if k != 'params' and k in self.param_groups[0]:
+                self.param_groups[0][k] = tuple(v) if k == 'betas' else v
 
 
 def train_step(model, loss_fn, optimizer: FlatAdam, data_dict: dict, group=None) -> dict:

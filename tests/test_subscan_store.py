@@ -119,6 +119,32 @@ def test_to_device_centres_on_gpu(store, gold, split):
     assert torch.isfinite(loss)
 
 
+@pytest.mark.gpu
+def test_staging_ring_is_safe_with_the_host_running_ahead(store, gold):
+    """``to_device(ds.collate_pairs(idx))`` in a loop with NO synchronisation and a busy GPU: the pinned staging sets
+    are event-guarded, so no batch is overwritten while its H2D copy is still queued (silent corruption)."""
+    from sgaligner_b200.subscan_store import Scan3RPacked, to_device
+    dev = torch.device('cuda:0')
+    ds = Scan3RPacked(store, json.loads(str(gold['anchor_data'])), split='val', n_staging=2)
+    n = len(ds)
+    want = {}
+    for i in range(n):
+        b = Scan3RPacked(store, json.loads(str(gold['anchor_data'])), split='val', pinned=False).collate_pairs([i])
+        pair = np.repeat(np.arange(b['batch_size']), b['tot_obj_count'])
+        want[i] = (b['tot_obj_pts'].numpy() - b['_sga_center'].numpy()[pair][:, None, :], b['tot_rel_pose'].numpy().copy())
+    big = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+    got = []
+    order = [i % n for i in range(24)]
+    for i in order:
+        for _ in range(4):
+            big.zero_()                               # keep the compute stream (which the copy stream waits for) busy
+        got.append(to_device(ds.collate_pairs([i]), dev, n_chunks=2))
+    torch.cuda.synchronize()
+    for i, d in zip(order, got):
+        assert np.array_equal(d['tot_obj_pts'].cpu().numpy(), want[i][0]), i
+        assert np.array_equal(d['tot_rel_pose'].cpu().numpy(), want[i][1]), i
+
+
 def test_pack_from_reference_files_and_dataloader(gold, tmp_path):
     """The converter reads the reference's own on-disk formats (``files/<mode>/data/<id>.pkl`` +
     ``scans/<id>/data.npy``, written here exactly as preprocess.py / the 3RScan export lay them out) and a stock
