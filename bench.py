@@ -48,6 +48,13 @@ def workload_name():
             f'modules {"+".join(MODULES)}, joint 200-d, top-6 matching')
 
 
+def shared_config():
+    """The `config` object of BOTH arms (identical, so the driver's same_config check compares like with like);
+    arm-specific remarks live under other keys of the line."""
+    return {'workload': workload_name(), 'pairs_per_gpu': PAIRS_PER_GPU, 'objects_per_gpu': 2 * N_OBJ * PAIRS_PER_GPU,
+            'points_per_object': N_PTS, 'modules': '+'.join(MODULES), 'topk': 6, 'baseline_config': 'BASELINE.json configs[1]'}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -128,8 +135,9 @@ def run_reference(args, out=sys.stdout):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(), 'sample_pairs_per_step': n,
-                   'note': 'reference CPU path (PyTorch fp32 restatement of src/aligner + matching head), host cores only'},
+        'config': shared_config(),
+        'arm': {'sample_pairs_per_step': n,
+                'note': 'reference CPU path (PyTorch fp32 restatement of src/aligner + matching head), host cores only'},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': f'{n} pairs/step of the C2 workload, {torch.get_num_threads()} threads'},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -202,6 +210,15 @@ def run_ours(args, out=sys.stdout):
         raise RuntimeError('bench.py (impl=ours) needs a CUDA device: the hot path has no CPU fallback')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    # NUMA: run on (and therefore pin host memory on) the CPUs of this GPU's node; ranks sharing a node split its CPUs
+    from sgaligner_b200 import numa
+    try:
+        nodes = [numa.gpu_numa_node(g) for g in range(max(1, world))]
+        mine = nodes[local] if local < len(nodes) else None
+        same = [g for g, nd in enumerate(nodes) if nd == mine]
+        numa_info = numa.bind_to_gpu_node(local, same.index(local) if local in same else 0, len(same))
+    except Exception as e:   # noqa: BLE001
+        numa_info = {'bound': False, 'why': str(e)}
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
@@ -342,6 +359,132 @@ def run_ours(args, out=sys.stdout):
     assert torch.equal(g['topk_idx'], tk) and torch.equal(g['anchor_pos'], pos), 'graph replay differs from the eager step'
     del cap
 
+    # ---- (2b) steady-state host-to-host loop: step k+1's H2D copy under step k's compute (serving.PipelinedServing).
+    #      Enough input slots that one rotation moves more bytes than L2 holds (no L2 flush inside the loop: the slots
+    #      ARE the "inputs larger than L2"); at most 3 steps in flight; every step does its own H2D and D2H.
+    from sgaligner_b200.serving import PipelinedServing
+    slot_bytes = h2d_bytes(host, KEYS)
+    n_slots = int(max(3, min(8, -(-(160 << 20) // max(1, slot_bytes)))))
+    pipe = PipelinedServing(model, data, k=6, n_slots=n_slots)
+    for s_ in range(n_slots):
+        pipe.fill(s_, host)
+
+    def pipelined(steps):
+        in_flight = 3
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for k_ in range(steps):
+            s_ = k_ % n_slots
+            if k_ >= in_flight:
+                pipe.wait((k_ - in_flight) % n_slots)     # the host reads the results of step k - 3
+            pipe.submit(s_)
+        for k_ in range(max(0, steps - in_flight), steps):
+            pipe.wait(k_ % n_slots)
+        t1.record()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1)
+
+    pipelined(max(n_slots, args.warmup))
+    barrier()
+    t = torch.tensor([pipelined(max(args.steps, 2 * n_slots))], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    barrier()
+    pipe_steps = max(args.steps, 2 * n_slots)
+    e2e_pipe_ms = float(t.item()) / pipe_steps
+    got = pipe.wait(0)
+    assert torch.equal(got['topk_idx'], tk_e) and torch.equal(got['anchor_pos'], pos_e), 'pipelined step differs from the eager e2e step'
+    del pipe
+    torch.cuda.empty_cache()
+
+    # ---- (2c) the other BASELINE.json configurations, driver-visible: C2 with all four modalities, C3 (configs[2]:
+    #      128 3RScan-shaped pairs; under --gpus N it is STRONG-scaled, B_local = 128 / N pairs per rank, one flat
+    #      gradient all-reduce per training step = configs[3]) and the per-GPU share of C5 (configs[4]).
+    ALL4 = ['point', 'gat', 'rel', 'attr']
+    cfg_steps = max(3, min(args.steps, 10))
+
+    def run_config(make_host, mods, kw, total_pairs_fn):
+        h = make_host()
+        d = to_cuda(dict(h), dev)
+        Bl = int(h['batch_size'])
+        torch.manual_seed(0)
+        mdl = MultiModalEncoder(modules=mods, rel_dim=41, attr_dim=164, **kw).to(dev)
+        Mm = len(mods)
+        l_i, l_c = CustomMultiLossLayer(Mm).to(dev), CustomMultiLossLayer(Mm).to(dev)
+        lf = OverallLoss(l_i, l_c, dev, {'zoom': 0.1, 'wt_align_loss': 1.0, 'wt_contrastive_loss': 1.0, 'modules': mods})
+        mdl.eval()
+        cp = CapturedInference(mdl, d, k=6)
+        sv_ms, _, _ = timed(cp.replay, cfg_steps, 3)
+        sv_ms /= cfg_steps
+        del cp
+        mdl.train()
+        op = FlatAdam(list(mdl.parameters()) + list(l_i.parameters()) + list(l_c.parameters()), lr=1e-3, weight_decay=1e-6)
+        tr, _, _ = timed(lambda: train_step(mdl, lf, op, d), cfg_steps, 3)
+        tr /= cfg_steps
+        tot = total_pairs_fn(Bl)
+        res = {'pairs_per_gpu': Bl, 'objects_per_gpu': int(d['tot_obj_pts'].shape[0]), 'anchors_per_gpu': int(len(h['e1i'])),
+               'serve_ms_per_step': sv_ms, 'serve_pairs_per_s': tot / (sv_ms * 1e-3),
+               'train_ms_per_step': tr, 'train_pairs_per_s': tot / (tr * 1e-3)}
+        del mdl, op, d
+        torch.cuda.empty_cache()
+        return res
+
+    configs = {}
+    configs['C2_4mod'] = dict(run_config(lambda: synthetic.config_c2(batch=PAIRS_PER_GPU, seed=100 + rank, n_obj=N_OBJ, n_points=N_PTS),
+                                         ALL4, {}, lambda b: world * b), scaling='weak',
+                              workload='C2 shapes with all four modalities (joint 400-d)')
+    c3_full = synthetic.config_c3(batch=128, seed=1)
+    configs['C3'] = dict(run_config(lambda: synthetic.shard_batch(c3_full, rank, world), ALL4, {}, lambda b: 128),
+                         scaling='strong' if world > 1 else 'n/a',
+                         workload='BASELINE configs[2]/[3]: 128 3RScan-shaped pairs (complete digraphs, P+S+R+A, 512 pts), '
+                                  'sharded B_local = 128/N pairs per rank, local-batch loss, one flat-gradient all-reduce')
+    del c3_full
+    configs['C5_share'] = dict(run_config(lambda: synthetic.config_c5(batch=8, seed=2 + rank), ALL4, {'pt_out_dim': 512, 'emb_dim': 128},
+                                          lambda b: world * b), scaling='weak',
+                               workload='BASELINE configs[4] per-GPU share: 8 pairs x (256+256) objects x 1024 pts, pt_out 512, emb 128 (joint 512-d)')
+
+    # ---- (2d) second baseline: the reference's own op sequence in PyTorch eager on THIS GPU
+    #      (cuDNN Conv1d + discarded BatchNorm calls, per-graph GAT loop, per-pair matching loop with the rank lists
+    #      moved to the host) -- the kernel-to-beat on the same box; rank 0 only, same batch, CUDA events.
+    eager = None
+    if rank == 0:
+        from oracle import sgaligner_oracle as O
+        p_dev = {k_: v_.detach().clone() for k_, v_ in model.state_dict().items()}
+        hd = {k_: (v_ if not torch.is_tensor(v_) else v_) for k_, v_ in data.items()}
+
+        def eager_step():
+            with torch.no_grad():
+                o_ = O.encoder_forward(p_dev, hd, MODULES, reference_ops=True)
+                return O.evaluate_batch(o_['joint'], hd)
+
+        def eager_pointnet():
+            with torch.no_grad():
+                return O.pointnet_feat_reference_ops(hd['tot_obj_pts'], p_dev)
+
+        def ev_time(fn, n_, w_):
+            for _ in range(w_):
+                fn()
+            torch.cuda.synchronize()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            for _ in range(n_):
+                fn()
+            b_.record()
+            torch.cuda.synchronize()
+            return a_.elapsed_time(b_) / n_
+        n_e = max(3, min(args.steps, 5))
+        pn_ms = ev_time(eager_pointnet, n_e, 2)
+        st_ms = ev_time(eager_step, n_e, 1)
+        ev_e = eager_step()
+        eager = {'what': 'reference op sequence (oracle with reference_ops: Conv1d via cuDNN + discarded BatchNorm, per-graph GAT loop, '
+                         'per-pair normalise/Gram/argsort + host-side rank metrics) in PyTorch eager on cuda:0, same batch and weights',
+                 'ms_per_step': st_ms, 'pairs_per_s': PAIRS_PER_GPU / (st_ms * 1e-3), 'pointnet_ms': pn_ms,
+                 'hits_at_1': ev_e['hits'][1] / max(1, ev_e['total']),
+                 'cudnn_allow_tf32': bool(torch.backends.cudnn.allow_tf32), 'matmul_allow_tf32': bool(torch.backends.cuda.matmul.allow_tf32)}
+        del p_dev
+        torch.cuda.empty_cache()
+
     # ---- (3) training step (forward + loss + backward + gradient all-reduce + Adam)
     model.train()
     opt = FlatAdam(list(model.parameters()) + list(li.parameters()) + list(lc.parameters()), lr=1e-3, weight_decay=1e-6)
@@ -364,9 +507,11 @@ def run_ours(args, out=sys.stdout):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32 (PointNet convs: bf16x3 split-operand tcgen05, fp32 accumulate)', 'data': 'synthetic',
-            'config': {'workload': workload_name(), 'pairs_per_gpu': PAIRS_PER_GPU, 'objects': N,
-                       'l2': 'flushed between timed steps (512 MiB memset, untimed)', 'timing': 'per-step CUDA events, max over ranks',
-                       'launch': 'one CUDA-graph replay per step (serving.CapturedInference: graph branch on a forked stream, 16 SMs left to it); eager_ms_per_step = same kernels issued from Python on one stream'},
+            'config': shared_config(),
+            'arm': {'l2': 'flushed between timed steps (512 MiB memset, untimed); the pipelined e2e loop rotates through input slots larger than L2 instead',
+                    'timing': 'per-step CUDA events, max over ranks',
+                    'launch': 'one CUDA-graph replay per step (serving.CapturedInference: graph branch on a forked stream, 16 SMs left to it); eager_ms_per_step = same kernels issued from Python on one stream',
+                    'numa': numa_info},
             'eager_ms_per_step': eager_ms_step,
             'roofline': {'kernel': 'pointnet_fwd_tc_kernel', 'bound': 'tensor', 'achieved': achieved, 'peak': tf_peak, 'unit': 'TFLOP/s',
                          'frac': (achieved / tf_peak) if achieved else None, 'traffic': PROFILED_TRAFFIC_BYTES, 'peak_source': peak_src,
@@ -380,7 +525,14 @@ def run_ours(args, out=sys.stdout):
                          'hbm': {'achieved_gbs': BYTES_PER_OBJECT * N / (k_ms * 1e-3) / 1e9 if k_ms else None, 'peak_gbs': hbm_peak,
                                  'algorithmic_bytes_per_launch': BYTES_PER_OBJECT * N}},
             'cpu_baseline': cpu,
-            'e2e': {'value': world * PAIRS_PER_GPU / (e2e_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_ms, 'eager_ms_per_step': e2e_eager_ms,
+            'e2e': {'value': world * PAIRS_PER_GPU / (min(e2e_ms, e2e_pipe_ms) * 1e-3), 'unit': UNIT,
+                    'ms_per_step': min(e2e_ms, e2e_pipe_ms),
+                    'pipelined_ms_per_step': e2e_pipe_ms, 'pipelined_slots': n_slots, 'pipelined_steps_timed': pipe_steps,
+                    'pipelined_api': 'serving.PipelinedServing: per step H2D from pinned staging (copy stream) -> graph replay -> D2H to pinned '
+                                     'results; up to 3 steps in flight, the host reads step k-3 before submitting step k; steady-state '
+                                     'throughput = 1 / max(copy, compute)',
+                    'single_step_latency_ms': e2e_ms, 'single_step_pairs_per_s': world * PAIRS_PER_GPU / (e2e_ms * 1e-3),
+                    'eager_ms_per_step': e2e_eager_ms,
                     'graph_ms_per_step': e2e_graph_ms, 'graph_point_chunks': e2e_chunks, 'hybrid_ms_per_step': e2e_hybrid_ms, 'api': e2e_api,
                     'h2d_points_only_ms': h2d_ms, 'h2d_points_only_gbs': host_pinned['tot_obj_pts'].numel() * 4 / (h2d_ms * 1e-3) / 1e9,
                     'h2d_bytes_per_step': h2d_bytes(host, KEYS), 'd2h_bytes_per_step': int(d2h),
@@ -388,6 +540,8 @@ def run_ours(args, out=sys.stdout):
             'gpu_launches': int(launches),
             'clocks': clocks,
             'hits_at_1': hits1,
+            'configs': configs,
+            'gpu_eager_baseline': eager,
             'train': {'pairs_per_s': world * PAIRS_PER_GPU / (tr_ms * 1e-3), 'ms_per_step': tr_ms, 'gpu_launches': int(tr_launches),
                       'pairs_per_s_without_bn_running_stats': world * PAIRS_PER_GPU / (tr2_ms * 1e-3),
                       'what': 'forward + OverallLoss + backward + flat-gradient all-reduce + fused Adam, same workload'},

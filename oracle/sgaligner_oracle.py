@@ -107,6 +107,20 @@ def pointnet_feat(pts: Tensor, p: Dict[str, Tensor], prefix: str = 'object_encod
     return h.max(dim=1).values                              # [N, out]
 
 
+def pointnet_feat_reference_ops(pts: Tensor, p: Dict[str, Tensor], training: bool = False, prefix: str = 'object_encoder') -> Tensor:
+    """The same function with the reference's OWN op sequence (``pointnet.py:140-163``): permute to [N,3,P], ``Conv1d``
+    (kernel size 1), the BatchNorm call whose output is discarded, ReLU, max over the last axis.  Used by the
+    eager-CUDA baseline leg of ``bench.py`` (cuDNN / ATen on the same B200) -- numerically equal to
+    :func:`pointnet_feat` up to summation order (and to cuDNN's TF32 convolutions when torch's default allows them)."""
+    x = pts.permute(0, 2, 1)
+    for i in (1, 2, 3):
+        x = F.conv1d(x, p[f'{prefix}.conv{i}.weight'], p[f'{prefix}.conv{i}.bias'])
+        _ = F.batch_norm(x, p[f'{prefix}.bn{i}.running_mean'], p[f'{prefix}.bn{i}.running_var'], p[f'{prefix}.bn{i}.weight'],
+                         p[f'{prefix}.bn{i}.bias'], training, 0.1, 1e-5)          # invoked, result dropped
+        x = F.relu(x)
+    return torch.max(x, 2, keepdim=True)[0].view(x.shape[0], -1)
+
+
 def pointnet_bn_batch_stats(pts: Tensor, p: Dict[str, Tensor], prefix: str = 'object_encoder'):
     """Per-channel batch mean / unbiased variance of the three *pre-ReLU* conv outputs: what a
     train-mode forward folds into ``bn{1,2,3}.running_*`` (momentum 0.1) as a side effect."""
@@ -133,16 +147,16 @@ def gat_conv(x: Tensor, edge_index: Tensor, w: Tensor, att_src: Tensor, att_dst:
     a_d = (xs * att_dst.view(1, H, C)).sum(-1)
     ei = edge_index.long()
     keep = ei[0] != ei[1]
-    loops = torch.arange(n, dtype=torch.long)
+    loops = torch.arange(n, dtype=torch.long, device=x.device)
     j = torch.cat([ei[0][keep], loops])
     i = torch.cat([ei[1][keep], loops])
     e = F.leaky_relu(a_s[j] + a_d[i], negative_slope)       # [E',H]
-    m = torch.full((n, H), -float('inf'), dtype=e.dtype)
+    m = torch.full((n, H), -float('inf'), dtype=e.dtype, device=x.device)
     m = m.scatter_reduce(0, i.view(-1, 1).expand(-1, H), e, reduce='amax', include_self=True)
     pexp = torch.exp(e - m[i])
-    den = torch.zeros((n, H), dtype=e.dtype).index_add_(0, i, pexp) + 1e-16
+    den = torch.zeros((n, H), dtype=e.dtype, device=x.device).index_add_(0, i, pexp) + 1e-16
     alpha = pexp / den[i]
-    out = torch.zeros((n, H, C), dtype=x.dtype).index_add_(0, i, alpha.unsqueeze(-1) * xs[j])
+    out = torch.zeros((n, H, C), dtype=x.dtype, device=x.device).index_add_(0, i, alpha.unsqueeze(-1) * xs[j])
     return out.reshape(n, H * C) + bias
 
 
@@ -167,9 +181,10 @@ def fusion(embs: List[Tensor], weight: Tensor) -> Tensor:
 
 
 def encoder_forward(p: Dict[str, Tensor], data: dict, modules: Sequence[str],
-                    heads=(2, 2)) -> Dict[str, Tensor]:
+                    heads=(2, 2), reference_ops: bool = False) -> Dict[str, Tensor]:
     """``sg_aligner.py:71-137``.  ``data`` follows the Scan3R collate contract
-    (``src/datasets/scan3r.py:179-209``)."""
+    (``src/datasets/scan3r.py:179-209``).  Device-agnostic (the eager-CUDA baseline leg of ``bench.py`` passes CUDA
+    tensors); ``reference_ops`` selects the Conv1d + discarded-BatchNorm op sequence for the point encoder."""
     dt = p['object_embedding.weight'].dtype
     pts = data['tot_obj_pts'].to(dt)
     attr = data['tot_bow_vec_object_attr_feats'].to(dt)
@@ -191,7 +206,8 @@ def encoder_forward(p: Dict[str, Tensor], data: dict, modules: Sequence[str],
                     e += ne
             emb = torch.cat(outs) @ p['structure_embedding.weight'].t() + p['structure_embedding.bias']
         elif mod == 'point':
-            emb = pointnet_feat(pts, p) @ p['object_embedding.weight'].t() + p['object_embedding.bias']
+            feat = pointnet_feat_reference_ops(pts, p) if reference_ops else pointnet_feat(pts, p)
+            emb = feat @ p['object_embedding.weight'].t() + p['object_embedding.bias']
         elif mod == 'rel':
             emb = rel @ p['meta_embedding_rel.weight'].t() + p['meta_embedding_rel.bias']
         elif mod == 'attr':
@@ -362,8 +378,8 @@ def evaluate_batch(emb: Tensor, data: dict, ks=(1, 2, 3, 4, 5)):
         e2 = np.asarray(data['e2i'][a0:a0 + na]).astype(np.int64) - o0
         a0 += na
         sim, rank = match_pair(emb[o0:o1])
-        ranks.append(rank.numpy())
-        sims.append(sim.numpy())
+        ranks.append(rank.cpu().numpy())             # the reference moves rank_list to the host per metric call
+        sims.append(sim.cpu().numpy())
         ns, nr = int(goc[b, 0]), int(goc[b, 1])
         align.append(alignment_score(ranks[-1], ns, nr) if nr else 0.0)
         corrs.append(node_corrs(ranks[-1], ns, 1))

@@ -344,3 +344,141 @@ class CapturedInference:
     def __call__(self, batch: Dict, **kw) -> Dict:
         self.load(batch, **kw)
         return self.replay()
+
+
+class PipelinedServing:
+    """Steady-state host-to-host serving: step k+1's H2D copy runs under step k's compute.
+
+    ``CapturedInference.run_host`` is ONE synchronous step (copy -> compute -> copy back -> host sync): its time is
+    the SUM of the PCIe time and the compute time.  A serving loop does not need that: with ``n_slots`` >= 2
+    independent slots (static device buffers + captured graph + pinned staging / result buffers each) the copy
+    engine fills slot k+1 while the SMs work on slot k, and throughput becomes 1 / max(copy, compute).
+
+        pipe = PipelinedServing(model, example_device_batch, n_slots=3)
+        pipe.staging(s)          # pinned host tensors of slot s: the loader collates INTO them
+        pipe.submit(s)           # enqueue H2D -> graph -> D2H for slot s; returns at once
+        pipe.wait(s)             # block until slot s's pinned results are valid, return them
+
+    Every slot's batch must have the captured layout (see ``LayoutCache`` for ragged streams).  Reference loop this
+    replaces: ``inference_align_reg.py:98-145`` (synchronous per-batch ``to_cuda`` + model call + per-pair matching).
+    """
+
+    def __init__(self, model, example: Dict, k: int = 6, n_slots: int = 2):
+        from .data import needed_keys
+        assert n_slots >= 2
+        self.dev = example['tot_obj_pts'].device
+        self.slots = [CapturedInference(model, example, k=k) for _ in range(n_slots)]
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        c0 = self.slots[0]
+        keys = [k_ for k_ in needed_keys(c0.modules) if k_ in c0.static and torch.is_tensor(c0.static[k_])]
+        self.keys = keys
+        for c in self.slots:
+            c.p_in = {k_: torch.empty(c.static[k_].shape, dtype=c.static[k_].dtype).pin_memory() for k_ in keys}
+            c.p_e1 = torch.empty(c.n_anchor, dtype=torch.int32).pin_memory()
+            c.p_e2 = torch.empty(c.n_anchor, dtype=torch.int32).pin_memory()
+            c.p_out = {'topk_idx': torch.empty(c.out['topk_idx'].shape, dtype=torch.int32).pin_memory()}
+            if c.out['anchor_pos'] is not None:
+                c.p_out['anchor_pos'] = torch.empty(c.out['anchor_pos'].shape, dtype=torch.int32).pin_memory()
+            c.ev_in = torch.cuda.Event()
+            c.ev_done = torch.cuda.Event()
+            c.in_flight = False
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in c0.p_in.values()) + 8 * c0.n_anchor
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in c0.p_out.values())
+
+    def staging(self, slot: int) -> Dict:
+        c = self.slots[slot]
+        return {**c.p_in, 'e1i': c.p_e1, 'e2i': c.p_e2}
+
+    def fill(self, slot: int, host_batch: Dict):
+        """Slow path for callers whose batch is not already in the staging buffers (a loader collates into them)."""
+        c = self.slots[slot]
+        c.check_layout(host_batch)
+        for k_, dst in c.p_in.items():
+            dst.copy_(host_batch[k_])
+        if c.n_anchor:
+            c.p_e1.copy_(torch.as_tensor(np.asarray(host_batch['e1i']).astype(np.int32)))
+            c.p_e2.copy_(torch.as_tensor(np.asarray(host_batch['e2i']).astype(np.int32)))
+
+    def submit(self, slot: int):
+        c = self.slots[slot]
+        cur = torch.cuda.current_stream(self.dev)
+        cs = self.copy_stream
+        if c.in_flight:
+            cs.wait_event(c.ev_done)        # the slot's previous compute has read its static buffers
+        with torch.cuda.stream(cs):
+            for k_ in self.keys:
+                c.static[k_].copy_(c.p_in[k_], non_blocking=True)
+            if c.n_anchor:
+                c.e1.copy_(c.p_e1, non_blocking=True)
+                c.e2.copy_(c.p_e2, non_blocking=True)
+            c.ev_in.record(cs)
+        cur.wait_event(c.ev_in)
+        c.graph.replay()
+        c.p_out['topk_idx'].copy_(c.out['topk_idx'], non_blocking=True)
+        if 'anchor_pos' in c.p_out:
+            c.p_out['anchor_pos'].copy_(c.out['anchor_pos'], non_blocking=True)
+        c.ev_done.record(cur)
+        c.in_flight = True
+
+    def wait(self, slot: int) -> Dict:
+        c = self.slots[slot]
+        if c.in_flight:
+            c.ev_done.synchronize()
+        return c.p_out
+
+
+class LayoutCache:
+    """Ragged serving: real 3RScan batches differ in object / edge / anchor counts, and a captured graph is frozen to
+    one layout.  This cache keeps one :class:`CapturedInference` per layout it has seen (LRU, ``capacity`` entries)
+    and falls back to eager launches for a layout the first time it appears (the capture costs a few steps; a layout
+    is captured once it has been seen ``capture_after`` times).  Results are identical either way (same kernels)."""
+
+    def __init__(self, model, k: int = 6, capacity: int = 16, capture_after: int = 2):
+        from collections import OrderedDict
+        self.model, self.k = model, k
+        self.capacity, self.capture_after = capacity, capture_after
+        self.graphs = OrderedDict()
+        self.seen = {}
+        self.hits = self.misses = 0
+
+    @staticmethod
+    def layout_key(batch: Dict):
+        return (np.asarray(batch['graph_per_obj_count']).astype(np.int64).tobytes(),
+                np.asarray(batch['graph_per_edge_count']).astype(np.int64).tobytes(), int(np.asarray(batch['e1i']).size),
+                tuple(batch['tot_obj_pts'].shape))
+
+    def __call__(self, batch: Dict) -> Dict:
+        """``batch``: device-resident collated batch.  Returns the dict ``CapturedInference.replay`` returns."""
+        key = self.layout_key(batch)
+        cap = self.graphs.get(key)
+        if cap is not None:
+            self.graphs.move_to_end(key)
+            self.hits += 1
+            return cap(batch)
+        self.misses += 1
+        n = self.seen.get(key, 0) + 1
+        self.seen[key] = n
+        if n >= self.capture_after:
+            cap = CapturedInference(self.model, batch, k=self.k)
+            self.graphs[key] = cap
+            if len(self.graphs) > self.capacity:
+                self.graphs.popitem(last=False)
+            return cap(batch)
+        return self._eager(batch)
+
+    def _eager(self, batch: Dict) -> Dict:
+        mods = list(self.model.modules)
+        lay = ops.PairLayout(np.asarray(batch['graph_per_obj_count']), batch['tot_obj_pts'].device)
+        with torch.no_grad():
+            out = self.model(batch)
+            emb = out['joint'] if len(mods) > 1 else out[mods[0]]
+            res = matching.match_batch(emb, batch, k=self.k, full_rank=False, want_sim=True, layout=lay)
+            na = int(np.asarray(batch['e1i']).size)
+            dev = emb.device
+            pos = None
+            if na:
+                e1 = torch.as_tensor(np.asarray(batch['e1i']).astype(np.int32)).to(dev, non_blocking=True)
+                e2 = torch.as_tensor(np.asarray(batch['e2i']).astype(np.int32)).to(dev, non_blocking=True)
+                pos = ops.match_anchor_pos(res['sim'], lay, e1, e2)
+        return {'embeddings': out, 'topk_idx': res['topk_idx'], 'topk_dist': res['topk_dist'], 'sim': res['sim'],
+                'anchor_pos': pos, 'layout': lay}

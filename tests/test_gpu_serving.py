@@ -83,3 +83,56 @@ def test_captured_host_to_host_step(dev):
             torch.cuda.synchronize()
             assert torch.equal(got['topk_idx'], res['topk_idx'].cpu())
             assert torch.equal(got['anchor_pos'], pos.cpu())
+
+
+def test_pipelined_serving_overlaps_slots_and_matches_eager(dev):
+    """Steady-state loop: three slots in flight with DIFFERENT batches, nothing synchronised between submissions;
+    every slot's pinned results equal the eager step on its batch, also after the slots have been reused."""
+    from sgaligner_b200 import synthetic, to_cuda
+    from sgaligner_b200.serving import PipelinedServing
+    from sgaligner_b200.sg_aligner import MultiModalEncoder
+    torch.manual_seed(0)
+    modules = ['point', 'gat']
+    model = MultiModalEncoder(modules=modules, rel_dim=41, attr_dim=164).to(dev).eval()
+    ns, nr, na = [9, 12, 7, 30], [11, 8, 10, 25], [5, 6, 4, 12]
+    hosts = [synthetic.make_batch(ns, nr, na, n_points=256, edge_mode='complete', seed=30 + i) for i in range(5)]
+    want = []
+    for h in hosts:
+        _, res, pos = _eager(model, to_cuda(dict(h), dev), 6)
+        want.append((res['topk_idx'].cpu(), pos.cpu()))
+    pipe = PipelinedServing(model, to_cuda(dict(hosts[0]), dev), k=6, n_slots=3)
+    assert pipe.h2d_bytes > 0 and pipe.d2h_bytes > 0
+    order = [0, 1, 2, 3, 4, 2, 0, 4, 1, 3, 3, 0]
+    pending = {}
+    for step, b in enumerate(order):
+        s = step % 3
+        if s in pending:
+            got = pipe.wait(s)
+            tk, pos = want[pending.pop(s)]
+            assert torch.equal(got['topk_idx'], tk) and torch.equal(got['anchor_pos'], pos)
+        pipe.fill(s, hosts[b])
+        pipe.submit(s)
+        pending[s] = b
+    for s, b in pending.items():
+        got = pipe.wait(s)
+        assert torch.equal(got['topk_idx'], want[b][0]) and torch.equal(got['anchor_pos'], want[b][1])
+
+
+def test_layout_cache_serves_ragged_batches(dev):
+    """Ragged stream: batches of three different layouts interleaved; a layout is served eagerly at first, from its
+    own captured graph from the second time on -- identical results throughout."""
+    from sgaligner_b200 import synthetic, to_cuda
+    from sgaligner_b200.serving import LayoutCache
+    from sgaligner_b200.sg_aligner import MultiModalEncoder
+    torch.manual_seed(0)
+    model = MultiModalEncoder(modules=['point', 'gat', 'rel', 'attr'], rel_dim=41, attr_dim=164).to(dev).eval()
+    layouts = [([9, 12], [11, 8], [5, 6]), ([20, 7, 14], [18, 9, 11], [9, 3, 7]), ([33], [29], [15])]
+    cache = LayoutCache(model, k=6, capacity=2, capture_after=2)
+    for step in range(12):
+        ns, nr, na = layouts[step % 3]
+        d = to_cuda(dict(synthetic.make_batch(ns, nr, na, n_points=128, edge_mode='complete', seed=50 + step)), dev)
+        got = cache(d)
+        torch.cuda.synchronize()
+        _, res, pos = _eager(model, d, 6)
+        assert torch.equal(got['topk_idx'], res['topk_idx']) and torch.equal(got['anchor_pos'], pos), step
+    assert cache.hits > 0 and len(cache.graphs) <= 2
