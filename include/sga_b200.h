@@ -266,10 +266,59 @@ int sga_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
 /* the same over a flat buffer made of `nseg` parameter segments (seg_off [nseg+1] int64, device): a segment whose
  * gradient is exactly zero -- a parameter that produced no gradient in this step, torch's `.grad is None` -- is
  * skipped entirely, as torch.optim.Adam skips it (no weight-decay drift, moments untouched).  seg_active [nseg]
- * int32 device scratch. */
+ * int32 device scratch.  Every seg_off entry is a multiple of 4 floats and grad is 16-byte aligned. */
 int sga_adam_step_segments(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                            const int64_t* seg_off, int nseg, int32_t* seg_active, float lr, float beta1,
                            float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+
+/* ==== 8(f)1: NaivePCT object encoder (src/aligner/networks/pct.py:275-317; the 'pct' module of
+ * MultiModalEncoder, sg_aligner.py:59-60).  Activations are fp32 [N,P,C] (one row of C channels per point); every
+ * BatchNorm is applied as a folded per-channel affine pair (a, b) -- BN(z) = a z + b -- by the prologue of the NEXT
+ * kernel, so train mode (batch statistics) and eval mode (running statistics) run the same kernels; the kernels that
+ * produce a BatchNorm input also accumulate its batch statistics {sum [C], sum of squares [C]} (f64, zeroed by the
+ * caller, NULL = not wanted).  All contractions: tcgen05, bf16x3 split operands, fp32 accumulate.  P <= 512. ---- */
+
+/* first / second moments of all N*P points: mom9 = {sum x,y,z, sum xx,xy,xz,yy,yz,zz} (f64, zeroed by the caller) */
+int sga_pct_point_moments(const float* pts, int64_t NP, double* mom9, void* stream);
+/* batch statistics of z = W p (a bias-free 3 -> C conv, Embedding.conv1 pct.py:106) from the point moments */
+int sga_pct_affine_stats(const double* mom9, const float* W, int C, double* stats, void* stream);
+/* nn.BatchNorm1d bookkeeping (pct.py:109-110,203,287,293-294): stats {sum, sumsq} [2C] over cnt values per channel of
+ * the STORED tensor z; lin_bias (may be NULL): a bias the producing layer has but did not add to z.  training != 0:
+ * batch statistics, and running_mean / running_var / num_batches_tracked get torch's momentum update (unbiased
+ * variance); else running statistics (stats may be NULL).  a_out/b_out [C]: BN(z + lin_bias) = a z + b. */
+int sga_bn_fold(const double* stats, double cnt, const float* lin_bias, const float* gamma, const float* beta,
+                float* running_mean, float* running_var, int64_t* num_batches_tracked, int training,
+                float momentum, float eps, int C, float* a_out, float* b_out, void* stream);
+/* Embedding (pct.py:120-125): z2 [N,P,128] = conv2(relu(bn1(conv1(pts)))); W1 [128,3], (a1,b1) = folded bn1,
+ * W2 [128,128]; stats [256] of z2 or NULL. */
+int sga_pct_embed(const float* pts, int64_t N, int P, const float* W1, const float* a1, const float* b1,
+                  const float* W2, float* z2, double* stats, void* stream);
+/* 128-input-channel pointwise convolution with a fused prologue  X = g1(src1) + g2(src2),  g(s) = s (a == NULL) or
+ * relu(a s + b); src2 may be NULL.  Y = X W^T + bias, W [Cout,128], Cout = 128, or 160 = k_conv (32 rows) | v_conv (128
+ * rows) of one SA layer (pct.py:197-200,213-215): columns [0,c0) go to out0 [N,P,c0], the rest to out1 [N,P,Cout-c0].
+ * out_x (may be NULL) receives X [N,P,128] (the SA residual x_l, pct.py:228-230).  stats [2 Cout] of Y or NULL. */
+int sga_pct_pointwise(const float* src1, const float* a1, const float* b1, const float* src2, const float* a2,
+                      const float* b2, int64_t N, int P, const float* W, const float* bias, int Cout, int c0,
+                      float* out_x, float* out0, float* out1, double* stats, void* stream);
+/* SA attention (pct.py:217-224), q and k share one weight: k [N,P,32], v [N,P,128].
+ * sga_pct_attn_stats: c2 [N, Ppad] (Ppad = P rounded up to 128) = log2-domain softmax normaliser of every row i of
+ * energy = k k^T / sqrt(32) (row max * log2e/sqrt(32) + log2 of the row's sum of exponentials; +inf for padding).
+ * sga_pct_attn: xs [N,P,128], xs[j,:] = sum_i softmax(energy)[i,j] v[i,:]  (= torch.bmm(x_v, attention)). */
+int sga_pct_attn_stats(const float* k, int64_t N, int P, float* c2, void* stream);
+int sga_pct_attn(const float* k, const float* v, const float* c2, int64_t N, int P, float* xs, void* stream);
+/* cat(x1..x4) -> Conv1d(512,1024,bias=False) (pct.py:285-289,306-308) with x4 = x3 + relu(a4 t4 + b4) formed on the fly.
+ * WL [1024,512].  Per object and channel only max_p z and min_p z are kept (zmax/zmin [N,2,1024]: the two 64-point
+ * column halves of the tiles separately) plus the statistics [2048] of z: BN + LeakyReLU + max commute with them. */
+int sga_pct_cat_linear(const float* x1, const float* x2, const float* x3, const float* t4, const float* a4,
+                       const float* b4, int64_t N, int P, const float* WL, float* zmax, float* zmin,
+                       double* stats, void* stream);
+/* pooled [N,1024] = LeakyReLU_0.2(a * (a >= 0 ? max : min) + b) = max_p LeakyReLU(BN(z)) (pct.py:310) */
+int sga_pct_pool_act(const float* zmax, const float* zmin, const float* a, const float* b, int64_t N, int P,
+                     float* out, void* stream);
+/* head (pct.py:311-316): column statistics of x [N,C] over the objects; out = relu(a x + b) * (mask ? mask*scale : 1) */
+int sga_col_stats(const float* x, int64_t N, int C, double* stats, void* stream);
+int sga_bn_act_rows(const float* x, const float* a, const float* b, const float* mask, float scale, int64_t N, int C,
+                    float* out, void* stream);
 
 /* diagnostics only: the tensor-core forward, when it tracks the argmax, re-evaluates near-ties of the max-pool in
  * fp32 (pointnet_tie_fix_kernel, so that the gradient is routed through the point the fp32 reference selects,

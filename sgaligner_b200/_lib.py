@@ -66,6 +66,18 @@ def _declare(lib):
     sig('sga_gemm_tf32x3', c_i, c_p, c_l, c_i, c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_l, c_p, c_i, c_p)
     sig('sga_adam_step', c_i, c_p, c_p, c_p, c_p, c_l, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_p)
     sig('sga_adam_step_segments', c_i, c_p, c_p, c_p, c_p, c_l, c_p, c_i, c_p, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_p)
+    c_d = ctypes.c_double
+    sig('sga_pct_point_moments', c_i, c_p, c_l, c_p, c_p)
+    sig('sga_pct_affine_stats', c_i, c_p, c_p, c_i, c_p, c_p)
+    sig('sga_bn_fold', c_i, c_p, c_d, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_f, c_f, c_i, c_p, c_p, c_p)
+    sig('sga_pct_embed', c_i, c_p, c_l, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p)
+    sig('sga_pct_pointwise', c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p)
+    sig('sga_pct_attn_stats', c_i, c_p, c_l, c_i, c_p, c_p)
+    sig('sga_pct_attn', c_i, c_p, c_p, c_p, c_l, c_i, c_p, c_p)
+    sig('sga_pct_cat_linear', c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p, c_p)
+    sig('sga_pct_pool_act', c_i, c_p, c_p, c_p, c_p, c_l, c_i, c_p, c_p)
+    sig('sga_col_stats', c_i, c_p, c_l, c_i, c_p, c_p)
+    sig('sga_bn_act_rows', c_i, c_p, c_p, c_p, c_p, c_f, c_l, c_i, c_p, c_p)
     sig('sga_selftest_umma', c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_p)
     sig('sga_debug_set_trace', c_i, c_p)
     sig('sga_debug_tie_stats', c_i, c_p, c_i)
@@ -75,7 +87,9 @@ EXPORTS = ['sga_last_error', 'sga_version', 'sga_device_info', 'sga_pointnet_fwd
            'sga_pointnet_bn_moments', 'sga_pointnet_set_max_ctas', 'sga_pointnet_stats_scratch_bytes', 'sga_pointnet_fwd_stats', 'sga_csr_build', 'sga_gat_linear', 'sga_gat_aggregate',
            'sga_gat_aggregate_bwd', 'sga_gat_linear_bwd', 'sga_cast_f64_f32', 'sga_project_fuse_fwd', 'sga_project_fuse_fwd_multi', 'sga_project_fuse_bwd',
            'sga_match_sim', 'sga_match_topk_tc', 'sga_match_rank', 'sga_match_anchor_pos', 'sga_match_pair_metrics', 'sga_center_points', 'sga_loss_workspace_bytes', 'sga_loss_launch_count', 'sga_loss_set_gram_path', 'sga_bn_running_update', 'sga_pointnet_gram_scratch_bytes', 'sga_pointnet_bn_moments_gram',
-           'sga_loss_fwd_bwd', 'sga_gemm_tf32x3', 'sga_adam_step', 'sga_adam_step_segments', 'sga_selftest_umma', 'sga_debug_set_trace', 'sga_debug_tie_stats']
+           'sga_loss_fwd_bwd', 'sga_gemm_tf32x3', 'sga_adam_step', 'sga_adam_step_segments', 'sga_selftest_umma', 'sga_debug_set_trace', 'sga_debug_tie_stats',
+           'sga_pct_point_moments', 'sga_pct_affine_stats', 'sga_bn_fold', 'sga_pct_embed', 'sga_pct_pointwise', 'sga_pct_attn_stats',
+           'sga_pct_attn', 'sga_pct_cat_linear', 'sga_pct_pool_act', 'sga_col_stats', 'sga_bn_act_rows']
 
 
 def lib_path() -> str:

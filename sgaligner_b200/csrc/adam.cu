@@ -25,12 +25,17 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 // selected, BatchNorm affine parameters whose outputs the reference discards).  Over a flat buffer every gradient is
 // allocated, so "not produced" is recognised as a segment that is exactly zero: such a segment is left untouched
 // (no weight-decay drift, no moment update), as torch leaves a grad-None parameter.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 seg_nonzero_kernel(const float* __restrict__ g, const int64_t* __restrict__ seg_off, int32_t* __restrict__ active) {
   const int s = blockIdx.x;
-  const int64_t a = seg_off[s], b = seg_off[s + 1];
+  const int64_t a = seg_off[s], b = seg_off[s + 1];     // segments start 256-byte aligned and are padded to 64 floats
+  const float4* g4 = reinterpret_cast<const float4*>(g + a);
+  const int64_t n4 = (b - a) >> 2;
   int any = 0;
-  for (int64_t i = a + threadIdx.x; i < b && !any; i += 256) any |= (g[i] != 0.f);
+  for (int64_t i = threadIdx.x; i < n4; i += 1024) {
+    const float4 v = g4[i];
+    any |= (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f) | (v.w != 0.f);
+  }
   any = __syncthreads_or(any);
   if (threadIdx.x == 0) active[s] = any;
 }
@@ -69,9 +74,10 @@ extern "C" int sga_adam_step_segments(float* param, const float* grad, float* ex
                                       void* stream) {
   if (n <= 0) return SGA_OK;
   SGA_REQUIRE(step >= 1 && nseg >= 1 && nseg <= 4096 && seg_off && seg_active, "sga_adam_step_segments: step=%d nseg=%d", step, nseg);
+  SGA_REQUIRE(((uintptr_t)grad & 15) == 0, "sga_adam_step_segments: grad must be 16-byte aligned (segments start at multiples of 4 floats)");
   double bc1 = 1.0 - pow((double)beta1, (double)step);
   double bc2 = 1.0 - pow((double)beta2, (double)step);
-  sga::seg_nonzero_kernel<<<nseg, 256, 0, (cudaStream_t)stream>>>(grad, seg_off, seg_active);
+  sga::seg_nonzero_kernel<<<nseg, 1024, 0, (cudaStream_t)stream>>>(grad, seg_off, seg_active);
   SGA_LAUNCH_CHECK();
   int64_t blocks = (n + 255) / 256;
   int64_t cap = (int64_t)sga::sm_count() * 8;

@@ -1,0 +1,410 @@
+// NaivePCT self-attention on the tensor cores (reference: SA.forward, src/aligner/networks/pct.py:211-232).
+//   x_q = x_k^T (ONE shared weight, :199)   energy = x_k^T x_k / sqrt(32)   attention = softmax(energy, dim=-1)
+//   x_s[:, j] = sum_i x_v[:, i] attention[i, j]            (torch.bmm(x_v, attention), :224)
+// The softmax normalises over j while the product contracts i, so the normaliser of row i must be known before any
+// output column can be finished: two kernels, and the [P x P] map never leaves the SM.
+//
+//   pct_attn_stats_kernel  per object: S = K K^T (tcgen05, K = 32 channels as bf16 hi|lo side by side in one 128-byte
+//       swizzled row, so the hi/lo partial products are descriptor offsets into the same image), a whole 128-row
+//       block of S (<= 512 columns) in tensor memory, thread-local row max and sum of exponentials ->
+//       c_i = max_i * a + log2(sum_i)   (a = log2(e) / sqrt(32); +inf for padding rows)
+//   pct_attn_kernel        per (object, 128-column block j): for every 128-row block i:
+//       S^T[j, i] (tensor memory) -> E = exp2(S a - c_i) = attention[i, j] -> bf16 hi / lo BACK INTO TENSOR MEMORY as the
+//       A operand of  O[j, :] += E V[i, :]   (tcgen05.mma A-from-TMEM; V tile read MN-major from shared memory);
+//       S double-buffered, the V tile of block i+1 is loaded while block i is in the tensor pipe.
+// Everything is bf16x3 (three passes over split operands, fp32 accumulate): attention weights and outputs agree with
+// the fp32 reference to ~1e-5.  P <= 512 (the [128 x P] score block must fit the 512 columns of tensor memory).
+#include "pct_common.cuh"
+
+namespace sga {
+namespace pct {
+namespace {
+
+constexpr int kMaxT = 4;                               // P <= 512
+constexpr float kAlpha = 1.4426950408889634f * 0.17677669529663687f;   // log2(e) / sqrt(32)
+
+// ---- K image: per tile of 128 points one 16 KiB block of 128-byte rows [k.hi (32 bf16) | k.lo (32 bf16)]
+__device__ __forceinline__ void load_k_image(const float* __restrict__ k, int64_t rowbase0, int P, int T, uint32_t kimg_addr, int tid) {
+  for (int t = 0; t < T; ++t) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int idx = tid + 256 * u;
+      const int row = idx >> 2, j = idx & 3;
+      const bool ok = t * kTile + row < P;
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (ok) {
+        const float4* src = reinterpret_cast<const float4*>(k + (rowbase0 + (int64_t)t * kTile + row) * 32 + j * 8);
+        const float4 x = __ldg(src), y = __ldg(src + 1);
+        f[0] = x.x; f[1] = x.y; f[2] = x.z; f[3] = x.w; f[4] = y.x; f[5] = y.y; f[6] = y.z; f[7] = y.w;
+      }
+      uint4 hi, lo;
+      split8(f, hi, lo);
+      const uint32_t base = kimg_addr + (uint32_t)t * kBlk;
+      st_chunk(base + ptx::sw128_offset(row, j), hi);
+      st_chunk(base + ptx::sw128_offset(row, 4 + j), lo);
+    }
+  }
+}
+
+// D[128 x 128] = K_a K_b^T with split operands: (A offset, B offset) pairs into the hi|lo images, K = 32.  The
+// scores sit in an exponent, so all FOUR partial products are taken here (lo*lo included: 2 of 8 cheap K = 16 steps).
+__device__ __forceinline__ void issue_s_block(uint32_t d_tmem, uint64_t dKa, uint64_t dKb, uint32_t idesc) {
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const uint64_t ao = (pass >= 2) ? 4 : 0;        // lo half of the row starts 64 bytes in
+    const uint64_t bo = (pass & 1) ? 4 : 0;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) ptx::umma_bf16(d_tmem, dKa + ao + (uint64_t)(ks * 2), dKb + bo + (uint64_t)(ks * 2), idesc, (pass | ks) != 0);
+  }
+}
+
+// =====================================================================================================================
+namespace st {
+constexpr uint32_t KIMG = 0;
+constexpr uint32_t XCH = KIMG + kMaxT * kBlk;          // float[2][2][128]
+constexpr uint32_t BARS = XCH + 2 * 2 * 128 * 4;
+constexpr uint32_t TMEMPTR = BARS + 64;
+constexpr uint32_t SMEM_BYTES = TMEMPTR + 16 + 1024;
+enum { BAR_K_FULL = 0, BAR_S_FULL = 1, BAR_S_FREE = 2 };
+}  // namespace st
+
+__global__ void __launch_bounds__(kThreads, 1)
+pct_attn_stats_kernel(const float* __restrict__ k, int64_t N, int P, float* __restrict__ c2) {
+  using namespace st;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sm_base = ptx::smem_u32(sm);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + BARS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + TMEMPTR);
+  float* xch = reinterpret_cast<float*>(sm + XCH);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = (P + kTile - 1) / kTile;
+  if (tid == 0) {
+    ptx::mbar_init(&bars[BAR_K_FULL], kComputeThreads);
+    ptx::mbar_init(&bars[BAR_S_FULL], 1);
+    ptx::mbar_init(&bars[BAR_S_FREE], kComputeThreads);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 8) ptx::tmem_alloc<512>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 8) {
+    const uint32_t idesc = ptx::make_idesc(1, 128, 128);
+    const uint64_t dK = ptx::smem_desc_sw128(sm_base + KIMG);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    uint32_t obj_it = 0, blk = 0;
+    for (int64_t n = blockIdx.x; n < N; n += gridDim.x, ++obj_it) {
+      ptx::mbar_wait(&bars[BAR_K_FULL], obj_it & 1);
+      for (int it = 0; it < T; ++it, ++blk) {
+        if (blk > 0) ptx::mbar_wait(&bars[BAR_S_FREE], (blk - 1) & 1);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          for (int jt = 0; jt < T; ++jt)
+            issue_s_block(tmem_u + (uint32_t)jt * 128, dK + (uint64_t)it * (kBlk >> 4), dK + (uint64_t)jt * (kBlk >> 4), idesc);
+          ptx::umma_commit(&bars[BAR_S_FULL]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int q = warp & 3, hc = warp >> 2;
+    const int row = 32 * q + lane;
+    const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+    const int Ppad = T * kTile;
+    const int ncols = T * 64;                       // this warp's column half
+    uint32_t blk = 0;
+    for (int64_t n = blockIdx.x; n < N; n += gridDim.x) {
+      load_k_image(k, n * (int64_t)P, P, T, sm_base + KIMG, tid);
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&bars[BAR_K_FULL]);
+      for (int it = 0; it < T; ++it, ++blk) {
+        ptx::mbar_wait(&bars[BAR_S_FULL], blk & 1);
+        ptx::tc_fence_after();
+        // ---- pass 1: row maximum over the valid columns
+        float m = -INFINITY;
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld32(tmem + lane_addr + (uint32_t)(hc * ncols + c0), v);
+          ptx::tmem_ld_wait();
+          const int jbase = hc * ncols + c0;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) m = fmaxf(m, (jbase + e < P) ? __uint_as_float(v[e]) : -INFINITY);
+        }
+        xch[hc * 128 + row] = m;
+        compute_barrier();
+        m = fmaxf(xch[row], xch[128 + row]);
+        // ---- pass 2: sum of exp2((s - m) a)
+        float l = 0.f;
+        const float ma = m * kAlpha;
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld32(tmem + lane_addr + (uint32_t)(hc * ncols + c0), v);
+          ptx::tmem_ld_wait();
+          const int jbase = hc * ncols + c0;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) l += (jbase + e < P) ? ex2(fmaf(__uint_as_float(v[e]), kAlpha, -ma)) : 0.f;
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&bars[BAR_S_FREE]);
+        xch[256 + hc * 128 + row] = l;
+        compute_barrier();
+        if (hc == 0) {
+          l = xch[256 + row] + xch[256 + 128 + row];
+          const int i = it * kTile + row;
+          c2[n * Ppad + i] = (i < P) ? ma + lg2(l) : INFINITY;
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) ptx::tmem_dealloc<512>(tmem);
+}
+
+// =====================================================================================================================
+namespace at {
+constexpr uint32_t KIMG = 0;
+constexpr uint32_t VHI = KIMG + kMaxT * kBlk;          // 2 buffers x 2 channel blocks
+constexpr uint32_t VLO = VHI + 4 * kBlk;
+constexpr uint32_t STAGE = VLO + 4 * kBlk;             // 196608
+constexpr uint32_t C2S = STAGE + 8 * kStageFloats * 4;
+constexpr uint32_t BARS = C2S + kMaxT * kTile * 4;
+constexpr uint32_t TMEMPTR = BARS + 128;
+constexpr uint32_t SMEM_BYTES = TMEMPTR + 16 + 1024;
+constexpr uint32_t S_COL = 0, O_COL = 256, EHI_COL = 384, ELO_COL = 448;
+enum { BAR_K_FULL = 0, BAR_V_FULL = 1 /*,2*/, BAR_S_FULL = 3 /*,4*/, BAR_S_FREE = 5 /*,6*/, BAR_E_FULL = 7, BAR_PV_DONE = 8, BAR_O_FREE = 9, kNumBars = 10 };
+}  // namespace at
+
+__global__ void __launch_bounds__(kThreads, 1)
+pct_attn_kernel(const float* __restrict__ k, const float* __restrict__ v, const float* __restrict__ c2, int64_t N, int P,
+                float* __restrict__ xs) {
+  using namespace at;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sm_base = ptx::smem_u32(sm);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + BARS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + TMEMPTR);
+  float* c2s = reinterpret_cast<float*>(sm + C2S);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = (P + kTile - 1) / kTile;
+  const int Ppad = T * kTile;
+  if (tid == 0) {
+    ptx::mbar_init(&bars[BAR_K_FULL], kComputeThreads);
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&bars[BAR_V_FULL + b], kComputeThreads);
+      ptx::mbar_init(&bars[BAR_S_FULL + b], 1);
+      ptx::mbar_init(&bars[BAR_S_FREE + b], kComputeThreads);
+    }
+    ptx::mbar_init(&bars[BAR_E_FULL], kComputeThreads);
+    ptx::mbar_init(&bars[BAR_PV_DONE], 1);
+    ptx::mbar_init(&bars[BAR_O_FREE], kComputeThreads);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 8) ptx::tmem_alloc<512>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int64_t W = N * T;                           // work items (object, column block), column block fastest
+
+  if (warp == 8) {
+    // =============================== MMA issuer ===============================
+    const uint32_t idesc_s = ptx::make_idesc(1, 128, 128);
+    const uint32_t idesc_pv = ptx::make_idesc(1, 128, 128) | (1u << 16);      // B (= V tile) read MN-major
+    const uint64_t dK = ptx::smem_desc_sw128(sm_base + KIMG);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    uint32_t u = 0, wi = 0;                          // running i-block counter, work-item counter
+    for (int64_t w = blockIdx.x; w < W; w += gridDim.x, ++wi) {
+      const int jt = (int)(w % T);
+      ptx::mbar_wait(&bars[BAR_K_FULL], wi & 1);
+      auto issue_s = [&](uint32_t uu, int it) {      // S^T[j block, i block it] into buffer uu & 1
+        const uint32_t b = uu & 1;
+        if (uu >= 2) ptx::mbar_wait(&bars[BAR_S_FREE + b], ((uu - 2) >> 1) & 1);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          issue_s_block(tmem_u + S_COL + b * 128, dK + (uint64_t)jt * (kBlk >> 4), dK + (uint64_t)it * (kBlk >> 4), idesc_s);
+          ptx::umma_commit(&bars[BAR_S_FULL + b]);
+        }
+        __syncwarp();
+      };
+      issue_s(u, 0);
+      for (int it = 0; it < T; ++it, ++u) {
+        if (it + 1 < T) issue_s(u + 1, it + 1);
+        const uint32_t b = u & 1;
+        ptx::mbar_wait(&bars[BAR_E_FULL], u & 1);
+        ptx::mbar_wait(&bars[BAR_V_FULL + b], (u >> 1) & 1);
+        if (it == 0 && wi > 0) ptx::mbar_wait(&bars[BAR_O_FREE], (wi - 1) & 1);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint64_t mVhi = desc_mn_sw128(sm_base + VHI + b * 2 * kBlk, kBlk);
+          const uint64_t mVlo = desc_mn_sw128(sm_base + VLO + b * 2 * kBlk, kBlk);
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a_tm = tmem_u + ((pass == 2) ? ELO_COL : EHI_COL);
+            const uint64_t bd = (pass == 1) ? mVlo : mVhi;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              ptx::umma_bf16_ts(tmem_u + O_COL, a_tm + (uint32_t)(ks * 8), bd + (uint64_t)(ks * 128), idesc_pv, (it | pass | ks) != 0);
+          }
+          ptx::umma_commit(&bars[BAR_PV_DONE]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =============================== compute warps ===============================
+    const int q = warp & 3, hc = warp >> 2;
+    const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+    const int cc = tid & 15, r0 = tid >> 4;
+    float* stage = reinterpret_cast<float*>(sm + STAGE) + warp * kStageFloats;
+    uint32_t u = 0;
+    // PV_DONE completions this thread has already observed.  An mbarrier can only be waited on for its LATEST
+    // completed phase (the parity test cannot tell phase x from phase x + 2), so every wait goes through here.
+    uint32_t pv_seen = 0;
+    auto wait_pv = [&](uint32_t x) {
+      if (x + 1 > pv_seen) {
+        ptx::mbar_wait(&bars[BAR_PV_DONE], x & 1);
+        pv_seen = x + 1;
+      }
+    };
+    auto load_v = [&](int64_t n, int it, uint32_t uu) {     // V rows of i block `it` -> buffer uu & 1 (hi / lo, 2 channel blocks)
+      const uint32_t b = uu & 1;
+      if (uu >= 2) wait_pv(uu - 2);
+      const int64_t rowbase = n * (int64_t)P + (int64_t)it * kTile;
+      const int valid = min(kTile, P - it * kTile);
+      const uint32_t blk_off = (uint32_t)(b * 2 + (cc >> 3)) * kBlk;
+#pragma unroll 1
+      for (int bt = 0; bt < 4; ++bt) {
+        float4 x[2][2];
+#pragma unroll
+        for (int qq = 0; qq < 2; ++qq) {
+          const int row = r0 + 16 * (bt * 2 + qq);
+          const float4* src = reinterpret_cast<const float4*>(v + (rowbase + row) * 128 + cc * 8);
+          const bool ok = row < valid;
+          x[qq][0] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+          x[qq][1] = ok ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int qq = 0; qq < 2; ++qq) {
+          const int row = r0 + 16 * (bt * 2 + qq);
+          const float f[8] = {x[qq][0].x, x[qq][0].y, x[qq][0].z, x[qq][0].w, x[qq][1].x, x[qq][1].y, x[qq][1].z, x[qq][1].w};
+          uint4 hi, lo;
+          split8(f, hi, lo);
+          const uint32_t off = blk_off + ptx::sw128_offset(row, cc & 7);
+          st_chunk(sm_base + VHI + off, hi);
+          st_chunk(sm_base + VLO + off, lo);
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&bars[BAR_V_FULL + b]);
+    };
+
+    for (int64_t w = blockIdx.x; w < W; w += gridDim.x) {
+      const int64_t n = w / T;
+      const int jt = (int)(w - n * T);
+      // the previous item's score MMAs have all completed (every S_FULL was waited for): the K image is free
+      load_k_image(k, n * (int64_t)P, P, T, sm_base + KIMG, tid);
+      for (int i = tid; i < Ppad; i += kComputeThreads) c2s[i] = c2[n * Ppad + i];
+      ptx::fence_proxy_async_smem();
+      compute_barrier();                              // c2s visible to every compute thread
+      ptx::mbar_arrive(&bars[BAR_K_FULL]);
+      load_v(n, 0, u);
+      for (int it = 0; it < T; ++it, ++u) {
+        if (it + 1 < T) load_v(n, it + 1, u + 1);
+        const uint32_t b = u & 1;
+        // ---- E = exp2(S a - c_i) for this thread's row j and 64 columns i
+        ptx::mbar_wait(&bars[BAR_S_FULL + b], (u >> 1) & 1);
+        ptx::tc_fence_after();
+        uint32_t eh[32], el[32];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t sv[32];
+          ptx::tmem_ld32(tmem + lane_addr + S_COL + b * 128 + (uint32_t)(hc * 64 + h * 32), sv);
+          ptx::tmem_ld_wait();
+          const float* cp = c2s + it * kTile + hc * 64 + h * 32;
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float e0 = ex2(fmaf(__uint_as_float(sv[e]), kAlpha, -cp[e]));
+            const float e1 = ex2(fmaf(__uint_as_float(sv[e + 1]), kAlpha, -cp[e + 1]));
+            const uint32_t hw = pack2(e0, e1);
+            eh[h * 16 + e / 2] = hw;
+            el[h * 16 + e / 2] = pack2(e0 - bf_lo(hw), e1 - bf_hi(hw));
+          }
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&bars[BAR_S_FREE + b]);
+        if (u >= 1) wait_pv(u - 1);      // the previous block's MMAs have consumed E
+        ptx::tc_fence_after();
+        ptx::tmem_st32(tmem + lane_addr + EHI_COL + (uint32_t)(hc * 32), eh);
+        ptx::tmem_st32(tmem + lane_addr + ELO_COL + (uint32_t)(hc * 32), el);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&bars[BAR_E_FULL]);
+      }
+      // ---- O[j, :] -> x_s rows
+      wait_pv(u - 1);
+      ptx::tc_fence_after();
+      const int64_t rowbase = n * (int64_t)P + (int64_t)jt * kTile;
+      const int nvalid = max(0, min(32, P - jt * kTile - 32 * q));
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t ov[16];
+        ptx::tmem_ld16(tmem + lane_addr + O_COL + (uint32_t)(hc * 64 + ch * 16), ov);
+        ptx::tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(ov[e]);
+        float s = 0.f, qv = 0.f;
+        stage_store16(stage, f, xs + (rowbase + 32 * q) * 128 + hc * 64 + ch * 16, 128, nvalid, lane, s, qv, false);
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bars[BAR_O_FREE]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) ptx::tmem_dealloc<512>(tmem);
+}
+
+}  // namespace
+}  // namespace pct
+}  // namespace sga
+
+extern "C" int sga_pct_attn_stats(const float* k, int64_t N, int P, float* c2, void* stream) {
+  if (N <= 0) return SGA_OK;
+  SGA_REQUIRE(k && c2 && P >= 1 && P <= sga::pct::kMaxT * sga::pct::kTile, "sga_pct_attn_stats: P=%d (1..512)", P);
+  SGA_REQUIRE(((uintptr_t)k & 15) == 0, "sga_pct_attn_stats: k must be 16-byte aligned");
+  using namespace sga::pct;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SGA_CUDA(cudaFuncSetAttribute(pct_attn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st::SMEM_BYTES));
+    attr_done = true;
+  }
+  int grid = sga::sm_count();
+  if ((int64_t)grid > N) grid = (int)N;
+  pct_attn_stats_kernel<<<grid, kThreads, st::SMEM_BYTES, (cudaStream_t)stream>>>(k, N, P, c2);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+extern "C" int sga_pct_attn(const float* k, const float* v, const float* c2, int64_t N, int P, float* xs, void* stream) {
+  if (N <= 0) return SGA_OK;
+  SGA_REQUIRE(k && v && c2 && xs && P >= 1 && P <= sga::pct::kMaxT * sga::pct::kTile, "sga_pct_attn: P=%d (1..512)", P);
+  SGA_REQUIRE((((uintptr_t)k | (uintptr_t)v) & 15) == 0, "sga_pct_attn: k / v must be 16-byte aligned");
+  using namespace sga::pct;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SGA_CUDA(cudaFuncSetAttribute(pct_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int T = (P + kTile - 1) / kTile;
+  int64_t W = N * T;
+  int grid = sga::sm_count();
+  if ((int64_t)grid > W) grid = (int)W;
+  pct_attn_kernel<<<grid, kThreads, at::SMEM_BYTES, (cudaStream_t)stream>>>(k, v, c2, N, P, xs);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}

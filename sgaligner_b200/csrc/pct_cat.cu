@@ -1,0 +1,296 @@
+// NaivePCT: concat(x1..x4) -> Conv1d(512, 1024, bias=False) -> BatchNorm -> LeakyReLU(0.2) -> max over the points
+// (reference: src/aligner/networks/pct.py:285-289 `self.linear`, :308-313) -- half of the encoder's FLOPs.
+// The [N, 1024, P] activation is never formed: BatchNorm is a per-channel affine map and LeakyReLU is monotone, so
+//     max_p lrelu(a z_p + b) = lrelu(a * (a >= 0 ? max_p z_p : min_p z_p) + b),
+// and the kernel keeps only max_p z, min_p z per (object, channel) plus the per-channel sum / sum of squares of z (the
+// batch statistics of that BatchNorm in train mode) -- 8 KB out per object instead of 2 MB.
+//
+// Channels on TMEM lanes (the max / min / sums over points are thread-local): D[ch, pts] = W[ch, 512] X^T.  One CTA
+// owns a block of 128 output channels for the whole launch: W.hi lives in TENSOR MEMORY (256 columns of packed bf16
+// pairs; the A operand of two of the three bf16x3 passes costs no shared-memory bandwidth), W.lo in shared memory
+// (128 KiB).  X^T streams through a 3-slot ring of [128 points x 64 channels] hi/lo half-chunks that the 8 compute
+// warps produce from the fp32 activations (x4 = x3 + relu(after_norm(t4)) is formed on the fly, pct.py:230), 12
+// tcgen05.mma per half-chunk, two accumulators so that the pooling epilogue of tile g-1 runs under the MMAs of tile g.
+#include "pct_common.cuh"
+
+namespace sga {
+namespace pct {
+namespace {
+
+namespace ct {
+constexpr uint32_t WLO = 0;                               // 8 blocks (kc * 2 + blk) x 16 KiB
+constexpr uint32_t RING = WLO + 8 * kBlk;                 // 3 slots x {hi 16 KiB, lo 16 KiB}
+constexpr uint32_t SLOT = 2 * kBlk;
+constexpr uint32_t AB4 = RING + 3 * SLOT;                 // a4[128], b4[128]
+constexpr uint32_t BARS = AB4 + 1024;
+constexpr uint32_t TMEMPTR = BARS + 128;
+constexpr uint32_t SMEM_BYTES = TMEMPTR + 16 + 1024;
+constexpr uint32_t D_COL = 0, WHI_COL = 256;
+enum { BAR_FULL = 0 /*..2*/, BAR_FREE = 3 /*..5*/, BAR_D_FULL = 6 /*,7*/, BAR_D_FREE = 8 /*,9*/, kNumBars = 10 };
+}  // namespace ct
+
+__global__ void __launch_bounds__(kThreads, 1)
+pct_cat_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const float* __restrict__ x3,
+               const float* __restrict__ t4, const float* __restrict__ a4, const float* __restrict__ b4, int64_t N, int P,
+               const float* __restrict__ WL, float* __restrict__ zmax, float* __restrict__ zmin, double* __restrict__ stats) {
+  using namespace ct;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sm_base = ptx::smem_u32(sm);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + BARS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + TMEMPTR);
+  float* ab4 = reinterpret_cast<float*>(sm + AB4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cb0 = blockIdx.y * 128;                     // first output channel of this CTA
+
+  // ---- setup: W.lo image, a4/b4, barriers, TMEM, W.hi -> TMEM
+  for (int i = tid; i < 128 * 64; i += kThreads) {        // [128 rows][64 chunks of 8 k]
+    const int r = i >> 6, j = i & 63;
+    const float4* src = reinterpret_cast<const float4*>(WL + (int64_t)(cb0 + r) * 512 + j * 8);
+    const float4 x = src[0], y = src[1];
+    const float f[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+    uint4 hi, lo;
+    split8(f, hi, lo);
+    st_chunk(sm_base + WLO + (uint32_t)(j >> 3) * kBlk + ptx::sw128_offset(r, j & 7), lo);
+  }
+  for (int i = tid; i < 128; i += kThreads) {
+    ab4[i] = a4[i];
+    ab4[128 + i] = b4[i];
+  }
+  if (tid == 0) {
+    for (int s = 0; s < 3; ++s) {
+      ptx::mbar_init(&bars[BAR_FULL + s], kComputeThreads);
+      ptx::mbar_init(&bars[BAR_FREE + s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&bars[BAR_D_FULL + b], 1);
+      ptx::mbar_init(&bars[BAR_D_FREE + b], kComputeThreads);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 8) ptx::tmem_alloc<512>(tmem_slot);
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp < 4) {       // W.hi: output channel on the TMEM lane, 512 k packed two per 32-bit column (lower k in the low half)
+    const int r = 32 * warp + lane;
+    const float4* src = reinterpret_cast<const float4*>(WL + (int64_t)(cb0 + r) * 512);
+#pragma unroll 1
+    for (int grp = 0; grp < 16; ++grp) {
+      uint32_t w[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 a = src[grp * 8 + j];
+        w[2 * j] = pack2(a.x, a.y);
+        w[2 * j + 1] = pack2(a.z, a.w);
+      }
+      ptx::tmem_st16(tmem + ((uint32_t)(32 * warp) << 16) + WHI_COL + grp * 16, w);
+    }
+    ptx::tmem_st_wait();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+
+  const int T = (P + kTile - 1) / kTile;
+  const int64_t nobj = (N > (int64_t)blockIdx.x) ? (N - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t G = nobj * T;                             // point tiles this CTA walks, as one stream
+
+  if (warp == 8) {
+    // =============================== MMA issuer ===============================
+    const uint32_t idesc = ptx::make_idesc(1, 128, 128);
+    const uint64_t dWlo = ptx::smem_desc_sw128(sm_base + WLO);
+    const uint64_t dRing = ptx::smem_desc_sw128(sm_base + RING);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    uint32_t hg = 0;
+    for (int64_t g = 0; g < G; ++g) {
+      const uint32_t b = (uint32_t)(g & 1);
+      if (g >= 2) ptx::mbar_wait(&bars[BAR_D_FREE + b], (uint32_t)(((g - 2) >> 1) & 1));
+      for (int h = 0; h < 8; ++h, ++hg) {
+        const uint32_t slot = hg % 3;
+        ptx::mbar_wait(&bars[BAR_FULL + slot], (hg / 3) & 1);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t d = tmem_u + D_COL + b * 128;
+          const uint64_t xh = dRing + (uint64_t)slot * (SLOT >> 4), xl = xh + (uint64_t)(kBlk >> 4);
+          const uint32_t wh = tmem_u + WHI_COL + (uint32_t)h * 32;
+          const uint64_t wl = dWlo + (uint64_t)h * (kBlk >> 4);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) ptx::umma_bf16_ts(d, wh + ks * 8, xh + (uint64_t)(ks * 2), idesc, (h | ks) != 0);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) ptx::umma_bf16_ts(d, wh + ks * 8, xl + (uint64_t)(ks * 2), idesc, 1);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) ptx::umma_bf16(d, wl + (uint64_t)(ks * 2), xh + (uint64_t)(ks * 2), idesc, 1);
+          ptx::umma_commit(&bars[BAR_FREE + slot]);
+          if (h == 7) ptx::umma_commit(&bars[BAR_D_FULL + b]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =============================== compute warps ===============================
+    const int cc = tid & 7, r0 = tid >> 3;                 // loader: 8-channel chunk cc of rows r0 + 32 q
+    const int q = warp & 3, hc = warp >> 2;                // epilogue: lane quarter (channel), column half (points)
+    const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+    const int ch = cb0 + 32 * q + lane;
+    float vmax = -INFINITY, vmin = INFINITY;
+    double dsum = 0, dsq = 0;
+    uint32_t hg = 0;
+    int e_t = 0;                                           // epilogue cursor: tile within object
+    int64_t e_n = blockIdx.x;
+
+    auto epilogue = [&](int64_t gp) {
+      const uint32_t b = (uint32_t)(gp & 1);
+      ptx::mbar_wait(&bars[BAR_D_FULL + b], (uint32_t)((gp >> 1) & 1));
+      ptx::tc_fence_after();
+      const int valid = min(kTile, P - e_t * kTile) - hc * 64;     // valid columns of this half
+      float s = 0.f, sq = 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem + lane_addr + D_COL + b * 128 + (uint32_t)(hc * 64 + h * 32), v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float f = __uint_as_float(v[e]);
+          const bool ok = h * 32 + e < valid;
+          vmax = fmaxf(vmax, ok ? f : -INFINITY);
+          vmin = fminf(vmin, ok ? f : INFINITY);
+          const float g0 = ok ? f : 0.f;
+          s += g0;
+          sq = fmaf(g0, g0, sq);
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bars[BAR_D_FREE + b]);
+      dsum += (double)s;
+      dsq += (double)sq;
+      if (++e_t == T) {                                    // object complete: this half's max / min
+        zmax[(e_n * 2 + hc) * 1024 + ch] = vmax;
+        zmin[(e_n * 2 + hc) * 1024 + ch] = vmin;
+        vmax = -INFINITY;
+        vmin = INFINITY;
+        e_t = 0;
+        e_n += gridDim.x;
+      }
+    };
+
+    int64_t n = blockIdx.x;
+    int t = 0;
+    for (int64_t g = 0; g < G; ++g) {
+      const int64_t rowbase = n * (int64_t)P + (int64_t)t * kTile;
+      const int valid = min(kTile, P - t * kTile);
+#pragma unroll 1
+      for (int h = 0; h < 8; ++h, ++hg) {
+        const int kc = h >> 1;
+        const uint32_t slot = hg % 3;
+        const float* src = (kc == 0) ? x1 : (kc == 1) ? x2 : x3;
+        const int chb = (h & 1) * 64 + cc * 8;             // channel of this thread's chunk inside the 128-channel source
+        float4 u[4][2], w[4][2];
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          const int row = r0 + 32 * qq;
+          const bool ok = row < valid;
+          const float4* s1 = reinterpret_cast<const float4*>(src + (rowbase + row) * 128 + chb);
+          u[qq][0] = ok ? __ldg(s1) : make_float4(0.f, 0.f, 0.f, 0.f);
+          u[qq][1] = ok ? __ldg(s1 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kc == 3) {
+            const float4* s2 = reinterpret_cast<const float4*>(t4 + (rowbase + row) * 128 + chb);
+            w[qq][0] = ok ? __ldg(s2) : make_float4(0.f, 0.f, 0.f, 0.f);
+            w[qq][1] = ok ? __ldg(s2 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        if (hg >= 3) ptx::mbar_wait(&bars[BAR_FREE + slot], (hg / 3 - 1) & 1);   // the slot's previous half-chunk is consumed
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          const int row = r0 + 32 * qq;
+          float f[8] = {u[qq][0].x, u[qq][0].y, u[qq][0].z, u[qq][0].w, u[qq][1].x, u[qq][1].y, u[qq][1].z, u[qq][1].w};
+          if (kc == 3) {
+            const float tv[8] = {w[qq][0].x, w[qq][0].y, w[qq][0].z, w[qq][0].w, w[qq][1].x, w[qq][1].y, w[qq][1].z, w[qq][1].w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float r = fmaf(ab4[chb + e], tv[e], ab4[128 + chb + e]);
+              f[e] += r > 0.f ? r : 0.f;
+            }
+            if (row >= valid) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = 0.f;
+            }
+          }
+          uint4 hi, lo;
+          split8(f, hi, lo);
+          const uint32_t off = RING + slot * SLOT + ptx::sw128_offset(row, cc);
+          st_chunk(sm_base + off, hi);
+          st_chunk(sm_base + off + kBlk, lo);
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&bars[BAR_FULL + slot]);
+      }
+      if (g > 0) epilogue(g - 1);
+      if (++t == T) {
+        t = 0;
+        n += gridDim.x;
+      }
+    }
+    if (G > 0) epilogue(G - 1);
+    atomicAdd(&stats[ch], dsum);
+    atomicAdd(&stats[1024 + ch], dsq);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) ptx::tmem_dealloc<512>(tmem);
+}
+
+// pooled[n, c] = lrelu_0.2(a_c * (a_c >= 0 ? max : min) + b_c), the two column halves combined (pct.py:288-289, :310)
+__global__ void pct_pool_act_kernel(const float* __restrict__ zmax, const float* __restrict__ zmin, const float* __restrict__ a,
+                                    const float* __restrict__ b, int64_t N, int P, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * 1024) return;
+  const int64_t n = i >> 10;
+  const int c = (int)(i & 1023);
+  float mx = zmax[(n * 2) * 1024 + c], mn = zmin[(n * 2) * 1024 + c];
+  if (P > 64) {                                           // the second column half holds points only then
+    mx = fmaxf(mx, zmax[(n * 2 + 1) * 1024 + c]);
+    mn = fminf(mn, zmin[(n * 2 + 1) * 1024 + c]);
+  }
+  const float ac = a[c];
+  const float y = fmaf(ac, ac >= 0.f ? mx : mn, b[c]);
+  out[i] = y > 0.f ? y : 0.2f * y;
+}
+
+}  // namespace
+}  // namespace pct
+}  // namespace sga
+
+extern "C" int sga_pct_cat_linear(const float* x1, const float* x2, const float* x3, const float* t4, const float* a4,
+                                  const float* b4, int64_t N, int P, const float* WL, float* zmax, float* zmin,
+                                  double* stats, void* stream) {
+  if (N <= 0) return SGA_OK;
+  SGA_REQUIRE(x1 && x2 && x3 && t4 && a4 && b4 && WL && zmax && zmin && stats && P >= 1, "sga_pct_cat_linear: bad arguments");
+  SGA_REQUIRE((((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)x3 | (uintptr_t)t4 | (uintptr_t)WL) & 15) == 0,
+              "sga_pct_cat_linear: activations / weights must be 16-byte aligned");
+  using namespace sga::pct;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SGA_CUDA(cudaFuncSetAttribute(pct_cat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct::SMEM_BYTES));
+    attr_done = true;
+  }
+  int gx = sga::sm_count() / 8;
+  if (gx < 1) gx = 1;
+  if ((int64_t)gx > N) gx = (int)N;
+  pct_cat_kernel<<<dim3(gx, 8), kThreads, ct::SMEM_BYTES, (cudaStream_t)stream>>>(x1, x2, x3, t4, a4, b4, N, P, WL, zmax, zmin, stats);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+extern "C" int sga_pct_pool_act(const float* zmax, const float* zmin, const float* a, const float* b, int64_t N, int P,
+                                float* out, void* stream) {
+  if (N <= 0) return SGA_OK;
+  SGA_REQUIRE(zmax && zmin && a && b && out, "sga_pct_pool_act: null pointer");
+  const int64_t total = N * 1024;
+  sga::pct::pct_pool_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(zmax, zmin, a, b, N, P, out);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}

@@ -1,0 +1,339 @@
+// NaivePCT: the 128-input-channel pointwise convolutions on the tensor cores (reference:
+// src/aligner/networks/pct.py -- Embedding.conv2 :107, SA.k_conv/v_conv :197-200, SA.trans_conv :202), one launch
+// per BatchNorm segment.  Y[pts, Cout] = X[pts, 128] W^T (+ bias), where X is produced on the fly by a PROLOGUE:
+//     X = g1(src1) + g2(src2),   g(s) = s  or  relu(a_c s + b_c)          (BatchNorm folded into a_c, b_c)
+// which covers  x0 = relu(bn2(z2)),  x_l = x_{l-1} + relu(after_norm(t_l))  (the SA residual, pct.py:228-230) and the
+// plain x_s -> trans_conv input; the EMBED variant computes X = relu(bn1(conv1(point))) from the raw points
+// (pct.py:122).  X itself can be written out (x_l is needed again by the next layer and by the concat).
+// EPILOGUE: + bias, fp32 rows to one or two row-major tensors (k | v share one launch: Cout = 32 + 128), per-channel
+// sum / sum of squares of what was stored (the batch statistics of the NEXT BatchNorm) as fp64 atomics.
+//
+// bf16x3 split operands (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM): ~1e-5, where one bf16 / tf32 pass is not
+// inside the 1e-4 gate.  Per tile of 128 points: 8 compute warps load + prologue + split -> A tile (128B-swizzled
+// K-major smem image), one elected thread issues 24 tcgen05.mma (M = 128 points, N = Cout, K = 16), the same 8 warps
+// drain the accumulator through a coalescing stage.  These convolutions are HBM bound (0.13-0.27 MB in+out per tile
+// against 0.5 us of MMAs), so the tile pipeline is kept simple: what matters is bytes, and those are minimal.
+#include "pct_common.cuh"
+
+namespace sga {
+namespace pct {
+namespace {
+
+constexpr int kMaxCout = 160;
+constexpr uint32_t WBLK = kMaxCout * 128;                    // one 64-channel K block of the weights (<= 160 rows)
+constexpr uint32_t WHI = 0;
+constexpr uint32_t WLO = WHI + 2 * WBLK;
+constexpr uint32_t AHI = WLO + 2 * WBLK;                     // 81920
+constexpr uint32_t ALO = AHI + 2 * kBlk;
+constexpr uint32_t STAGE = ALO + 2 * kBlk;                   // 147456
+constexpr uint32_t BIAS = STAGE + 8 * kStageFloats * 4;      // + 17408
+constexpr uint32_t BARS = BIAS + kMaxCout * 4;
+constexpr uint32_t TMEMPTR = BARS + 64;
+constexpr uint32_t SMEM_USED = TMEMPTR + 16;
+constexpr uint32_t SMEM_BYTES = SMEM_USED + 1024;
+constexpr int kTmemCols = 256;
+
+enum { BAR_A_FULL = 0, BAR_D_FULL = 1 };
+
+struct PwArgs {
+  const float* src1; const float* a1; const float* b1; int mode1;    // 0 absent, 1 identity, 2 relu(a s + b)
+  const float* src2; const float* a2; const float* b2; int mode2;
+  const float* pts; const float* w1;                                  // EMBED: points [N,P,3], conv1 weight [128,3] (a1, b1 = folded bn1)
+  int64_t N; int P;
+  const float* W; const float* bias; int Cout; int c0;
+  float* out_x; float* out0; float* out1; double* stats;
+};
+
+template <bool kEmbed>
+__global__ void __launch_bounds__(kThreads, 1) pct_pw_kernel(const PwArgs A) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sm_base = ptx::smem_u32(sm);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + BARS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + TMEMPTR);
+  float* bias_s = reinterpret_cast<float*>(sm + BIAS);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Cout = A.Cout;
+
+  // ---- one-time setup: weights -> bf16 hi/lo K-major images, bias, barriers, TMEM
+  for (int i = tid; i < Cout * 16; i += kThreads) {
+    const int r = i >> 4, j = i & 15;
+    const float4* src = reinterpret_cast<const float4*>(A.W + (int64_t)r * 128 + j * 8);
+    const float4 x = src[0], y = src[1];
+    const float f[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+    uint4 hi, lo;
+    split8(f, hi, lo);
+    const uint32_t off = (uint32_t)(j >> 3) * WBLK + ptx::sw128_offset(r, j & 7);
+    st_chunk(sm_base + WHI + off, hi);
+    st_chunk(sm_base + WLO + off, lo);
+  }
+  for (int i = tid; i < Cout; i += kThreads) bias_s[i] = A.bias ? A.bias[i] : 0.f;
+  if (tid == 0) {
+    ptx::mbar_init(&bars[BAR_A_FULL], kComputeThreads);
+    ptx::mbar_init(&bars[BAR_D_FULL], 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 8) ptx::tmem_alloc<kTmemCols>(tmem_slot);
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int T = (A.P + kTile - 1) / kTile;
+  const int64_t G = A.N * T;
+
+  if (warp == 8) {
+    // =============================== MMA issuer ===============================
+    const uint32_t idesc = ptx::make_idesc(1, 128, Cout);
+    const uint64_t dAhi = ptx::smem_desc_sw128(sm_base + AHI), dAlo = ptx::smem_desc_sw128(sm_base + ALO);
+    const uint64_t dWhi = ptx::smem_desc_sw128(sm_base + WHI), dWlo = ptx::smem_desc_sw128(sm_base + WLO);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    uint32_t it = 0;
+    for (int64_t g = blockIdx.x; g < G; g += gridDim.x, ++it) {
+      ptx::mbar_wait(&bars[BAR_A_FULL], it & 1);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint64_t ab = (pass == 1) ? dAlo : dAhi;
+          const uint64_t bb = (pass == 2) ? dWlo : dWhi;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t ao = (uint64_t)((ks >> 2) * (kBlk >> 4) + (ks & 3) * 2);
+            const uint64_t bo = (uint64_t)((ks >> 2) * (WBLK >> 4) + (ks & 3) * 2);
+            ptx::umma_bf16(tmem_u, ab + ao, bb + bo, idesc, (pass | ks) != 0);
+          }
+        }
+        ptx::umma_commit(&bars[BAR_D_FULL]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // =============================== compute warps ===============================
+    const int cc = tid & 15, r0 = tid >> 4;          // loader: 8-channel chunk cc of rows r0 + 16 q
+    const int ch0 = cc * 8;
+    // per-channel prologue parameters of this thread's 8 channels, resident in registers for the whole kernel
+    // (EMBED: the folded conv1 rows; otherwise the two BatchNorm affine pairs)
+    float pa1[8], pb1[8], pa2[8], pb2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (kEmbed) {      // bn1(conv1(p)) = (a w) . p + b: the BatchNorm scale folded into the three conv1 weights of the channel
+        const float a = A.a1[ch0 + e];
+        pa1[e] = a * A.w1[(ch0 + e) * 3];
+        pb1[e] = a * A.w1[(ch0 + e) * 3 + 1];
+        pa2[e] = a * A.w1[(ch0 + e) * 3 + 2];
+        pb2[e] = A.b1[ch0 + e];
+      } else {
+        pa1[e] = (A.mode1 == 2) ? A.a1[ch0 + e] : 1.f;
+        pb1[e] = (A.mode1 == 2) ? A.b1[ch0 + e] : 0.f;
+        pa2[e] = (A.mode2 == 2) ? A.a2[ch0 + e] : 1.f;
+        pb2[e] = (A.mode2 == 2) ? A.b2[ch0 + e] : 0.f;
+      }
+    }
+    const uint32_t a_off_blk = (uint32_t)(cc >> 3) * kBlk;
+    const int q = warp & 3, hc = warp >> 2;           // epilogue: TMEM lane quarter, column half
+    const int ncol_half = Cout >> 1, nch = ncol_half >> 4;
+    float* stage = reinterpret_cast<float*>(sm + STAGE) + warp * kStageFloats;
+    double ds[5] = {0, 0, 0, 0, 0}, dq[5] = {0, 0, 0, 0, 0};
+    const bool want_stats = A.stats != nullptr;
+
+    uint32_t it = 0;
+    for (int64_t g = blockIdx.x; g < G; g += gridDim.x, ++it) {
+      const int64_t n = g / T;
+      const int t = (int)(g - n * T);
+      const int64_t rowbase = n * A.P + (int64_t)t * kTile;
+      const int valid = min(kTile, A.P - t * kTile);
+      // ---- load + prologue + split -> A tile (the previous tile's MMAs have completed: D_FULL was waited for)
+#pragma unroll 1
+      for (int bt = 0; bt < 4; ++bt) {            // 4 batches of 2 rows: the loads of a batch are in flight together
+        float4 u[2][2], w[2][2];
+        float3 p3[2];
+#pragma unroll
+        for (int qq = 0; qq < 2; ++qq) {
+          const int row = r0 + 16 * (bt * 2 + qq);
+          const bool ok = row < valid;
+          if (kEmbed) {
+            const float* pp = A.pts + (rowbase + row) * 3;
+            p3[qq] = ok ? make_float3(__ldg(pp), __ldg(pp + 1), __ldg(pp + 2)) : make_float3(0.f, 0.f, 0.f);
+          } else {
+            const float4* s1 = reinterpret_cast<const float4*>(A.src1 + (rowbase + row) * 128 + ch0);
+            u[qq][0] = ok ? __ldg(s1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            u[qq][1] = ok ? __ldg(s1 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (A.mode2) {
+              const float4* s2 = reinterpret_cast<const float4*>(A.src2 + (rowbase + row) * 128 + ch0);
+              w[qq][0] = ok ? __ldg(s2) : make_float4(0.f, 0.f, 0.f, 0.f);
+              w[qq][1] = ok ? __ldg(s2 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+        }
+#pragma unroll
+        for (int qq = 0; qq < 2; ++qq) {
+          const int row = r0 + 16 * (bt * 2 + qq);
+          const bool ok = row < valid;
+          float f[8];
+          if (kEmbed) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float v = fmaf(pa1[e], p3[qq].x, fmaf(pb1[e], p3[qq].y, fmaf(pa2[e], p3[qq].z, pb2[e])));
+              f[e] = v > 0.f ? v : 0.f;
+            }
+          } else {
+            const float s1[8] = {u[qq][0].x, u[qq][0].y, u[qq][0].z, u[qq][0].w, u[qq][1].x, u[qq][1].y, u[qq][1].z, u[qq][1].w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float v = s1[e];
+              if (A.mode1 == 2) {
+                v = fmaf(pa1[e], v, pb1[e]);
+                v = v > 0.f ? v : 0.f;
+              }
+              f[e] = v;
+            }
+            if (A.mode2) {
+              const float s2[8] = {w[qq][0].x, w[qq][0].y, w[qq][0].z, w[qq][0].w, w[qq][1].x, w[qq][1].y, w[qq][1].z, w[qq][1].w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float v = s2[e];
+                if (A.mode2 == 2) {
+                  v = fmaf(pa2[e], v, pb2[e]);
+                  v = v > 0.f ? v : 0.f;
+                }
+                f[e] += v;
+              }
+            }
+          }
+          if (!ok) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = 0.f;
+          }
+          if (!kEmbed && A.out_x && ok) {
+            float4* ox = reinterpret_cast<float4*>(A.out_x + (rowbase + row) * 128 + ch0);
+            ox[0] = make_float4(f[0], f[1], f[2], f[3]);
+            ox[1] = make_float4(f[4], f[5], f[6], f[7]);
+          }
+          uint4 hi, lo;
+          split8(f, hi, lo);
+          const uint32_t off = a_off_blk + ptx::sw128_offset(row, cc & 7);
+          st_chunk(sm_base + AHI + off, hi);
+          st_chunk(sm_base + ALO + off, lo);
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&bars[BAR_A_FULL]);
+
+      // ---- epilogue: accumulator -> (+ bias) -> coalesced rows, BatchNorm sums
+      ptx::mbar_wait(&bars[BAR_D_FULL], it & 1);
+      ptx::tc_fence_after();
+      const int nvalid = max(0, min(32, valid - 32 * q));
+#pragma unroll
+      for (int ch = 0; ch < 5; ++ch) {
+        if (ch >= nch) break;
+        const int col0 = hc * ncol_half + ch * 16;
+        uint32_t v[16];
+        ptx::tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, v);
+        ptx::tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]) + bias_s[col0 + e];
+        float* dst;
+        int64_t ld;
+        if (col0 < A.c0) {
+          ld = A.c0;
+          dst = A.out0 + (rowbase + 32 * q) * ld + col0;
+        } else {
+          ld = Cout - A.c0;
+          dst = A.out1 + (rowbase + 32 * q) * ld + (col0 - A.c0);
+        }
+        float s = 0.f, qv = 0.f;
+        stage_store16(stage, f, dst, ld, nvalid, lane, s, qv, want_stats);
+        if (want_stats) {
+          ds[ch] += (double)s;
+          dq[ch] += (double)qv;
+        }
+      }
+      ptx::tc_fence_before();     // the next A_FULL arrival orders the next tile's MMAs after these TMEM reads
+    }
+    if (want_stats) {
+#pragma unroll
+      for (int ch = 0; ch < 5; ++ch) {
+        if (ch >= nch) break;
+        const double s = ds[ch] + __shfl_xor_sync(0xffffffffu, ds[ch], 16);
+        const double qv = dq[ch] + __shfl_xor_sync(0xffffffffu, dq[ch], 16);
+        if (lane < 16) {
+          const int col = hc * ncol_half + ch * 16 + lane;
+          atomicAdd(&A.stats[col], s);
+          atomicAdd(&A.stats[Cout + col], qv);
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) ptx::tmem_dealloc<kTmemCols>(tmem);
+}
+
+}  // namespace
+
+int pw_launch(const PwArgs& a, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    SGA_CUDA(cudaFuncSetAttribute(pct_pw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    SGA_CUDA(cudaFuncSetAttribute(pct_pw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    attr_done = true;
+  }
+  const int T = (a.P + kTile - 1) / kTile;
+  int64_t G = a.N * T;
+  int grid = sm_count();
+  if ((int64_t)grid > G) grid = (int)G;
+  if (a.pts) pct_pw_kernel<true><<<grid, kThreads, SMEM_BYTES, st>>>(a);
+  else pct_pw_kernel<false><<<grid, kThreads, SMEM_BYTES, st>>>(a);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+}  // namespace pct
+}  // namespace sga
+
+using sga::pct::PwArgs;
+
+static int check_pw_common(const char* who, int64_t N, int P, const float* W, int Cout) {
+  SGA_REQUIRE(N >= 1 && P >= 1, "%s: N=%lld P=%d", who, (long long)N, P);
+  SGA_REQUIRE(W && ((uintptr_t)W & 15) == 0, "%s: W must be a 16-byte aligned device pointer", who);
+  SGA_REQUIRE(Cout == 128 || Cout == 160, "%s: Cout=%d (128, or 160 = 32 + 128 for the fused k | v convolution)", who, Cout);
+  return SGA_OK;
+}
+
+extern "C" int sga_pct_pointwise(const float* src1, const float* a1, const float* b1, const float* src2, const float* a2,
+                                 const float* b2, int64_t N, int P, const float* W, const float* bias, int Cout, int c0,
+                                 float* out_x, float* out0, float* out1, double* stats, void* stream) {
+  if (N <= 0) return SGA_OK;
+  int rc = check_pw_common("sga_pct_pointwise", N, P, W, Cout);
+  if (rc) return rc;
+  SGA_REQUIRE(src1 && out0, "sga_pct_pointwise: null pointer");
+  SGA_REQUIRE((a1 == nullptr) == (b1 == nullptr) && (a2 == nullptr) == (b2 == nullptr), "sga_pct_pointwise: a/b must come in pairs");
+  SGA_REQUIRE(src2 || (!a2 && !b2), "sga_pct_pointwise: a2/b2 without src2");
+  SGA_REQUIRE(c0 == Cout || (c0 == 32 && Cout == 160 && out1), "sga_pct_pointwise: c0=%d Cout=%d", c0, Cout);
+  SGA_REQUIRE((((uintptr_t)src1 | (uintptr_t)src2 | (uintptr_t)out_x) & 15) == 0, "sga_pct_pointwise: activations must be 16-byte aligned");
+  PwArgs a{};
+  a.src1 = src1; a.a1 = a1; a.b1 = b1; a.mode1 = a1 ? 2 : 1;
+  a.src2 = src2; a.a2 = a2; a.b2 = b2; a.mode2 = src2 ? (a2 ? 2 : 1) : 0;
+  a.pts = nullptr; a.w1 = nullptr;
+  a.N = N; a.P = P; a.W = W; a.bias = bias; a.Cout = Cout; a.c0 = c0;
+  a.out_x = out_x; a.out0 = out0; a.out1 = out1; a.stats = stats;
+  return sga::pct::pw_launch(a, (cudaStream_t)stream);
+}
+
+extern "C" int sga_pct_embed(const float* pts, int64_t N, int P, const float* W1, const float* a1, const float* b1,
+                             const float* W2, float* z2, double* stats, void* stream) {
+  if (N <= 0) return SGA_OK;
+  int rc = check_pw_common("sga_pct_embed", N, P, W2, 128);
+  if (rc) return rc;
+  SGA_REQUIRE(pts && W1 && a1 && b1 && z2, "sga_pct_embed: null pointer");
+  PwArgs a{};
+  a.mode1 = 0; a.mode2 = 0;
+  a.a1 = a1; a.b1 = b1;
+  a.pts = pts; a.w1 = W1;
+  a.N = N; a.P = P; a.W = W2; a.bias = nullptr; a.Cout = 128; a.c0 = 128;
+  a.out_x = nullptr; a.out0 = z2; a.out1 = nullptr; a.stats = stats;
+  return sga::pct::pw_launch(a, (cudaStream_t)stream);
+}

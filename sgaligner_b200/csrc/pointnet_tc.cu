@@ -388,8 +388,12 @@ pointnet_fwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
       if (++s1_t == ntile) s1_t = 0;
     };
 
-    float rmax = -INFINITY, r2 = -INFINITY;
-    int ridx = 0, r2idx = 0;
+    float rmax = -INFINITY;
+    // argmax variant: FOUR independent (max, argmax, runner-up, its index) trackers over the columns e mod 4 -- one
+    // tracker is a serial dependency chain of ~10 operations per element (4.5 k cycles per tile, longer than the MMAs
+    // it should hide under); four chains interleave.  Merged once per object.
+    float smx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, sr2[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int six[4] = {0, 0, 0, 0}, sr2i[4] = {0, 0, 0, 0};
     // ---- E3: running max over the 128 points (columns) of tile gp; output at the end of an object
     auto stage_e3 = [&](int64_t gp) {
       const int t = e3_t;
@@ -408,18 +412,18 @@ pointnet_fwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
           if (kArgmax) {
             // (max, first argmax) and the runner-up = the largest value STRICTLY below the max (exact duplicates of
             // the max -- resampled points -- are not rivals: they resolve to the lowest index as in the reference)
+            const int col0 = t * kTile + cc * 32;
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
-              float f = __uint_as_float(v[e]);
-              if (f > rmax) {
-                r2 = rmax;
-                r2idx = ridx;
-                rmax = f;
-                ridx = t * kTile + cc * 32 + e;
-              } else if (f < rmax && f > r2) {
-                r2 = f;
-                r2idx = t * kTile + cc * 32 + e;
-              }
+              const float f = __uint_as_float(v[e]);
+              const int s = e & 3;
+              const bool gt = f > smx[s];
+              const bool mid = (f < smx[s]) && (f > sr2[s]);
+              const bool u2 = gt || mid;
+              sr2i[s] = u2 ? (gt ? six[s] : col0 + e) : sr2i[s];
+              sr2[s] = u2 ? (gt ? smx[s] : f) : sr2[s];
+              six[s] = gt ? col0 + e : six[s];
+              smx[s] = gt ? f : smx[s];
             }
           } else {
             float m0 = rmax, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
@@ -463,6 +467,25 @@ pointnet_fwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
         if (wh < nmt) {
           const int64_t n = e3_n;
           const int ch = cb0 + wh * 128 + row;
+          int ridx = 0, r2idx = 0;
+          float r2 = -INFINITY;
+          if (kArgmax) {
+            // merge the four trackers: (max, lowest index attaining it) and the largest value strictly below it
+            rmax = smx[0]; ridx = six[0]; r2 = sr2[0]; r2idx = sr2i[0];
+#pragma unroll
+            for (int s = 1; s < 4; ++s) {
+              const float m = smx[s], q = sr2[s];
+              if (m > rmax) {
+                if (rmax > q) { r2 = rmax; r2idx = ridx; } else { r2 = q; r2idx = sr2i[s]; }   // old max vs the stream's runner-up
+                rmax = m; ridx = six[s];
+              } else if (m == rmax) {
+                if (six[s] < ridx) ridx = six[s];
+                if (q > r2) { r2 = q; r2idx = sr2i[s]; }
+              } else {
+                if (m > r2) { r2 = m; r2idx = six[s]; }
+              }
+            }
+          }
           const float o = rmax + b3[ch];
           out[n * C3 + ch] = o > 0.f ? o : 0.f;
           if (kArgmax) {
@@ -481,9 +504,8 @@ pointnet_fwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
           }
         }
         rmax = -INFINITY;
-        ridx = 0;
-        r2 = -INFINITY;
-        r2idx = 0;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) { smx[s] = -INFINITY; sr2[s] = -INFINITY; six[s] = 0; sr2i[s] = 0; }
         e3_n += gridDim.x;
       }
     };
@@ -619,78 +641,86 @@ pointnet_fwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
 // fp32 re-check of max-pool near-ties (tensor-core forward, argmax-tracking variant).  An entry of `argmax` whose
 // upper half is non-zero carries two candidate points; both pre-activations are recomputed on the FMA pipe in the
 // summation order of the fp32 kernel (pointnet_simt.cu: bias first, k ascending) and the entry becomes the fp32
-// argmax (lowest index on an exact tie, as torch.max does), the pooled feature the fp32 value.  One warp per 32
+// argmax (lowest index on an exact tie, as torch.max does); the pooled feature is only touched when the fp32 value
+// falls on the other side of the ReLU kink (the mask of the backward must be the fp32 mask).  One warp per 32
 // entries; W2 is staged in shared memory only by CTAs that found a flagged entry.
 __device__ unsigned long long g_tie_stats[2];     // {flagged, reordered} since the last reset (diagnostics)
 
 constexpr int kFixThreads = 256;
+constexpr int kW2Ld = 129;     // padded row of the transposed conv2 weights: conflict-free both ways
 __global__ void __launch_bounds__(kFixThreads)
 pointnet_tie_fix_kernel(const float* __restrict__ pts, int64_t total, int P, const float* __restrict__ W1,
                         const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ b2,
                         const float* __restrict__ W3, const float* __restrict__ b3, int C3, float* __restrict__ out,
                         int32_t* __restrict__ argmax) {
-  __shared__ float W2t[64 * 128];            // [k][c]
+  __shared__ float W2t[64 * kW2Ld];          // [k][c]
   __shared__ float h2s[kFixThreads / 32][2][128];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t i = (int64_t)blockIdx.x * kFixThreads + tid;
-  const int code = i < total ? argmax[i] : 0;
-  const bool flagged = (code >> 16) != 0;
-  if (!__syncthreads_or(flagged)) return;
-  for (int j = tid; j < 64 * 128; j += kFixThreads) W2t[j] = W2[(j & 127) * 64 + (j >> 7)];
+  // persistent grid: every CTA stages W2^T once (coalesced reads of the row-major weights), then its warps walk the
+  // argmax array in groups of 32 entries and stop at the flagged ones
+  for (int j = tid; j < 64 * 128; j += kFixThreads) W2t[(j & 63) * kW2Ld + (j >> 6)] = W2[j];
   __syncthreads();
-  unsigned m = __ballot_sync(0xffffffffu, flagged);
   unsigned long long nflag = 0, nswap = 0;
-  while (m) {
-    const int src = __ffs(m) - 1;
-    m &= m - 1;
-    const int cd = __shfl_sync(0xffffffffu, code, src);
-    const int64_t idx = (int64_t)blockIdx.x * kFixThreads + warp * 32 + src;
-    const int64_t n = idx / C3;
-    const int ch = (int)(idx - n * C3);
-    const int pa = cd & 0xFFFF, pb = (cd >> 16) - 1;
+  const int64_t ngroup = (total + 31) >> 5;
+  for (int64_t grp = (int64_t)blockIdx.x * (kFixThreads / 32) + warp; grp < ngroup; grp += (int64_t)gridDim.x * (kFixThreads / 32)) {
+    const int64_t i = grp * 32 + lane;
+    const int code = i < total ? argmax[i] : 0;
+    unsigned m = __ballot_sync(0xffffffffu, (code >> 16) != 0);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const int cd = __shfl_sync(0xffffffffu, code, src);
+      const int64_t idx = grp * 32 + src;
+      const int64_t n = idx / C3;
+      const int ch = (int)(idx - n * C3);
+      const int pa = cd & 0xFFFF, pb = (cd >> 16) - 1;
 #pragma unroll
-    for (int w = 0; w < 2; ++w) {
-      const float* pp = pts + (n * P + (w ? pb : pa)) * 3;
-      const float x = pp[0], y = pp[1], z = pp[2];
-      float h1[2];
+      for (int w = 0; w < 2; ++w) {
+        const float* pp = pts + (n * P + (w ? pb : pa)) * 3;
+        const float x = pp[0], y = pp[1], z = pp[2];
+        float h1[2];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int c = lane + 32 * j;
-        float v = b1[c];
-        v = fmaf(W1[c * 3 + 0], x, v);
-        v = fmaf(W1[c * 3 + 1], y, v);
-        v = fmaf(W1[c * 3 + 2], z, v);
-        h1[j] = v > 0.f ? v : 0.f;
-      }
-      float acc[4];
+        for (int j = 0; j < 2; ++j) {
+          const int c = lane + 32 * j;
+          float v = b1[c];
+          v = fmaf(W1[c * 3 + 0], x, v);
+          v = fmaf(W1[c * 3 + 1], y, v);
+          v = fmaf(W1[c * 3 + 2], z, v);
+          h1[j] = v > 0.f ? v : 0.f;
+        }
+        float acc[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = b2[lane + 32 * j];
+        for (int j = 0; j < 4; ++j) acc[j] = b2[lane + 32 * j];
 #pragma unroll 8
-      for (int k = 0; k < 64; ++k) {
-        const float a = __shfl_sync(0xffffffffu, k < 32 ? h1[0] : h1[1], k & 31);
+        for (int k = 0; k < 64; ++k) {
+          const float a = __shfl_sync(0xffffffffu, k < 32 ? h1[0] : h1[1], k & 31);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] = fmaf(a, W2t[k * 128 + lane + 32 * j], acc[j]);
+          for (int j = 0; j < 4; ++j) acc[j] = fmaf(a, W2t[k * kW2Ld + lane + 32 * j], acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h2s[warp][w][lane + 32 * j] = acc[j] > 0.f ? acc[j] : 0.f;
       }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) h2s[warp][w][lane + 32 * j] = acc[j] > 0.f ? acc[j] : 0.f;
+      __syncwarp();
+      float zv = 0.f;
+      if (lane < 2) {
+        zv = b3[ch];
+        const float* wr = W3 + (int64_t)ch * 128;
+        for (int k = 0; k < 128; ++k) zv = fmaf(h2s[warp][lane][k], wr[k], zv);
+      }
+      const float za = __shfl_sync(0xffffffffu, zv, 0), zb = __shfl_sync(0xffffffffu, zv, 1);
+      if (lane == 0) {
+        const bool take_b = zb > za || (zb == za && pb < pa);
+        const float zm = take_b ? zb : za;
+        argmax[idx] = take_b ? pb : pa;
+        // the pooled feature keeps its tensor-core value (identical to what the serving variant of the kernel
+        // writes) unless the fp32 value lies on the other side of the ReLU kink: then the fp32 mask wins
+        const float relu = zm > 0.f ? zm : 0.f;
+        if ((relu > 0.f) != (out[idx] > 0.f)) out[idx] = relu;
+        ++nflag;
+        if (take_b) ++nswap;
+      }
+      __syncwarp();
     }
-    __syncwarp();
-    float zv = 0.f;
-    if (lane < 2) {
-      zv = b3[ch];
-      const float* wr = W3 + (int64_t)ch * 128;
-      for (int k = 0; k < 128; ++k) zv = fmaf(h2s[warp][lane][k], wr[k], zv);
-    }
-    const float za = __shfl_sync(0xffffffffu, zv, 0), zb = __shfl_sync(0xffffffffu, zv, 1);
-    if (lane == 0) {
-      const bool take_b = zb > za || (zb == za && pb < pa);
-      const float zm = take_b ? zb : za;
-      argmax[idx] = take_b ? pb : pa;
-      out[idx] = zm > 0.f ? zm : 0.f;
-      ++nflag;
-      if (take_b) ++nswap;
-    }
-    __syncwarp();
   }
   if (lane == 0 && nflag) {
     atomicAdd(&g_tie_stats[0], nflag);
@@ -782,7 +812,9 @@ int pointnet_fwd_tc(const float* pts, int64_t N, int P, const float* W1, const f
   SGA_LAUNCH_CHECK();
   if (argmax && P <= kTieMaxP) {
     const int64_t total = N * (int64_t)C3;
-    pointnet_tie_fix_kernel<<<(unsigned)((total + kFixThreads - 1) / kFixThreads), kFixThreads, 0, st>>>(
+    int64_t nb = (total + kFixThreads - 1) / kFixThreads;
+    if (nb > 4 * (int64_t)sm_count()) nb = 4 * (int64_t)sm_count();
+    pointnet_tie_fix_kernel<<<(unsigned)nb, kFixThreads, 0, st>>>(
         pts, total, P, W1, b1, W2, b2, W3, b3, C3, out, argmax);
     SGA_LAUNCH_CHECK();
   }

@@ -258,6 +258,124 @@ def bn_running_update(mom: torch.Tensor, cnt: float, bns):
     _count(1)
 
 
+# --------------------------------------------------------------------------------- NaivePCT (pct.py:275-317)
+def _f64z(n, dev):
+    return torch.zeros(n, device=dev, dtype=torch.float64)
+
+
+def pct_point_moments(pts: torch.Tensor) -> torch.Tensor:
+    pts = _f32c(pts)
+    mom = _f64z(9, pts.device)
+    check(get_lib().sga_pct_point_moments(_ptr(pts), pts.shape[0] * pts.shape[1], _ptr(mom), _stream()), 'sga_pct_point_moments')
+    _count(1)
+    return mom
+
+
+def pct_affine_stats(mom: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
+    C = W.shape[0]
+    stats = torch.empty(2 * C, device=mom.device, dtype=torch.float64)
+    check(get_lib().sga_pct_affine_stats(_ptr(mom), _ptr(_f32c(W.reshape(C, 3))), C, _ptr(stats), _stream()), 'sga_pct_affine_stats')
+    _count(1)
+    return stats
+
+
+def bn_fold(bn: torch.nn.BatchNorm1d, stats: Optional[torch.Tensor], cnt: float, training: bool, lin_bias=None):
+    """(a, b) with BN(z + lin_bias) = a z + b for the stored tensor z; in training the module's running statistics get
+    torch's momentum update as a side effect (one launch)."""
+    C = bn.num_features
+    dev = bn.weight.device
+    a = torch.empty(C, device=dev, dtype=torch.float32)
+    b = torch.empty(C, device=dev, dtype=torch.float32)
+    mom = 0.1 if bn.momentum is None else float(bn.momentum)
+    check(get_lib().sga_bn_fold(_ptr(stats), float(cnt), _ptr(lin_bias), _ptr(bn.weight), _ptr(bn.bias), _ptr(bn.running_mean),
+                                _ptr(bn.running_var), _ptr(bn.num_batches_tracked), 1 if training else 0, mom, float(bn.eps), C,
+                                _ptr(a), _ptr(b), _stream()), 'sga_bn_fold')
+    _count(1)
+    return a, b
+
+
+def pct_embed(pts, W1, a1, b1, W2, want_stats: bool):
+    pts = _f32c(pts)
+    N, P, _ = pts.shape
+    z2 = torch.empty((N, P, 128), device=pts.device, dtype=torch.float32)
+    stats = _f64z(256, pts.device) if want_stats else None
+    check(get_lib().sga_pct_embed(_ptr(pts), N, P, _ptr(_f32c(W1.reshape(128, 3))), _ptr(a1), _ptr(b1), _ptr(_f32c(W2.reshape(128, 128))),
+                                  _ptr(z2), _ptr(stats), _stream()), 'sga_pct_embed')
+    _count(1)
+    return z2, stats
+
+
+def pct_pointwise(src1, ab1, src2, ab2, W, bias, c0: int, want_x: bool, want_stats: bool):
+    """Y = (g1(src1) + g2(src2)) W^T + bias; ab = (a, b) -> g(s) = relu(a s + b), None -> identity.  Returns
+    (out0 [N,P,c0], out1 [N,P,Cout-c0] or None, X or None, stats or None)."""
+    N, P, _ = src1.shape
+    Cout = W.shape[0]
+    dev = src1.device
+    out0 = torch.empty((N, P, c0), device=dev, dtype=torch.float32)
+    out1 = torch.empty((N, P, Cout - c0), device=dev, dtype=torch.float32) if c0 < Cout else None
+    out_x = torch.empty((N, P, 128), device=dev, dtype=torch.float32) if want_x else None
+    stats = _f64z(2 * Cout, dev) if want_stats else None
+    a1, b1 = ab1 if ab1 is not None else (None, None)
+    a2, b2 = ab2 if ab2 is not None else (None, None)
+    with _timed('pct_pointwise'):
+        check(get_lib().sga_pct_pointwise(_ptr(src1), _ptr(a1), _ptr(b1), _ptr(src2), _ptr(a2), _ptr(b2), N, P, _ptr(W), _ptr(bias),
+                                          Cout, c0, _ptr(out_x), _ptr(out0), _ptr(out1), _ptr(stats), _stream()), 'sga_pct_pointwise')
+    _count(1)
+    return out0, out1, out_x, stats
+
+
+def pct_attention(k, v):
+    """x_s = torch.bmm(x_v, softmax(x_k^T x_k / sqrt(32), -1)) for every object (pct.py:217-224), [N,P,128]."""
+    N, P, _ = k.shape
+    Ppad = (P + 127) // 128 * 128
+    c2 = torch.empty((N, Ppad), device=k.device, dtype=torch.float32)
+    xs = torch.empty((N, P, 128), device=k.device, dtype=torch.float32)
+    lib = get_lib()
+    with _timed('pct_attn_stats'):
+        check(lib.sga_pct_attn_stats(_ptr(k), N, P, _ptr(c2), _stream()), 'sga_pct_attn_stats')
+    with _timed('pct_attn'):
+        check(lib.sga_pct_attn(_ptr(k), _ptr(v), _ptr(c2), N, P, _ptr(xs), _stream()), 'sga_pct_attn')
+    _count(2)
+    return xs
+
+
+def pct_cat_linear(x1, x2, x3, t4, ab4, WL):
+    N, P, _ = x1.shape
+    dev = x1.device
+    zmax = torch.empty((N, 2, 1024), device=dev, dtype=torch.float32)
+    zmin = torch.empty((N, 2, 1024), device=dev, dtype=torch.float32)
+    stats = _f64z(2048, dev)
+    with _timed('pct_cat_linear'):
+        check(get_lib().sga_pct_cat_linear(_ptr(x1), _ptr(x2), _ptr(x3), _ptr(t4), _ptr(ab4[0]), _ptr(ab4[1]), N, P, _ptr(WL), _ptr(zmax),
+                                           _ptr(zmin), _ptr(stats), _stream()), 'sga_pct_cat_linear')
+    _count(1)
+    return zmax, zmin, stats
+
+
+def pct_pool_act(zmax, zmin, a, b, P: int):
+    N = zmax.shape[0]
+    out = torch.empty((N, 1024), device=zmax.device, dtype=torch.float32)
+    check(get_lib().sga_pct_pool_act(_ptr(zmax), _ptr(zmin), _ptr(a), _ptr(b), N, int(P), _ptr(out), _stream()), 'sga_pct_pool_act')
+    _count(1)
+    return out
+
+
+def col_stats(x):
+    N, C = x.shape
+    stats = _f64z(2 * C, x.device)
+    check(get_lib().sga_col_stats(_ptr(x), N, C, _ptr(stats), _stream()), 'sga_col_stats')
+    _count(1)
+    return stats
+
+
+def bn_act_rows(x, a, b, mask=None, scale: float = 1.0):
+    N, C = x.shape
+    out = torch.empty_like(x)
+    check(get_lib().sga_bn_act_rows(_ptr(x), _ptr(a), _ptr(b), _ptr(mask), float(scale), N, C, _ptr(out), _stream()), 'sga_bn_act_rows')
+    _count(1)
+    return out
+
+
 # --------------------------------------------------------------------------------- graphs
 class GraphLayout:
     """Per-graph node / edge offsets of a collated batch (host prefix sums of ``graph_per_obj_count`` /

@@ -212,7 +212,8 @@ class MultiModalEncoder(nn.Module):
             self.object_encoder = PointNetfeat(global_feat=True, batch_norm=True, point_size=3, input_transform=False,
                                                feature_transform=False, out_size=self.pt_out_dim)
         elif 'pct' in self.modules:
-            raise NotImplementedError("the 'pct' object encoder is outside the B200 hot path (SURVEY.md 8(f))")
+            from .pct import NaivePCT
+            self.object_encoder = NaivePCT()
         else:
             raise NotImplementedError
         self.object_embedding = nn.Linear(self.pt_out_dim, self.emb_dim)
@@ -240,6 +241,11 @@ class MultiModalEncoder(nn.Module):
             side.wait_stream(cur)
         if 'point' in self.modules and ready is None:
             point_x = self.object_encoder(pts, None)
+        elif 'pct' in self.modules:
+            if ready is not None:
+                for (_, _, ev) in ready['pts']:
+                    cur.wait_event(ev)
+            point_x = self.object_encoder(pts)
         gat_out = None
         if 'gat' in self.modules:
             with torch.cuda.stream(side) if side is not None else _nullcontext():
@@ -257,6 +263,8 @@ class MultiModalEncoder(nn.Module):
             elif module == 'point':
                 x = point_x if point_x is not None else self.object_encoder(pts, None if ready is None else ready['pts'])
                 args += [x, self.object_embedding.weight, self.object_embedding.bias]
+            elif module == 'pct':
+                args += [point_x, self.object_embedding.weight, self.object_embedding.bias]
             elif module == 'rel':
                 args += [data_dict['tot_bow_vec_object_edge_feats'], self.meta_embedding_rel.weight, self.meta_embedding_rel.bias]
             elif module == 'attr':
