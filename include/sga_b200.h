@@ -301,8 +301,9 @@ int sga_pct_pointwise(const float* src1, const float* a1, const float* b1, const
                       const float* b2, int64_t N, int P, const float* W, const float* bias, int Cout, int c0,
                       float* out_x, float* out0, float* out1, double* stats, void* stream);
 /* SA attention (pct.py:217-224), q and k share one weight: k [N,P,32], v [N,P,128].
- * sga_pct_attn_stats: c2 [N, Ppad] (Ppad = P rounded up to 128) = log2-domain softmax normaliser of every row i of
- * energy = k k^T / sqrt(32) (row max * log2e/sqrt(32) + log2 of the row's sum of exponentials; +inf for padding).
+ * sga_pct_attn_stats: c2 [N, 2, Ppad] (Ppad = P rounded up to 128) = log2-domain softmax normaliser of every row i of
+ * energy = k k^T / sqrt(32), in two parts that are never added in fp32: [n,0,i] = row max * log2e/sqrt(32) (+inf for
+ * padding rows), [n,1,i] = log2 of the row's sum of exponentials.
  * sga_pct_attn: xs [N,P,128], xs[j,:] = sum_i softmax(energy)[i,j] v[i,:]  (= torch.bmm(x_v, attention)). */
 int sga_pct_attn_stats(const float* k, int64_t N, int P, float* c2, void* stream);
 int sga_pct_attn(const float* k, const float* v, const float* c2, int64_t N, int P, float* xs, void* stream);

@@ -4,16 +4,16 @@
 // The softmax normalises over j while the product contracts i, so the normaliser of row i must be known before any
 // output column can be finished: two kernels, and the [P x P] map never leaves the SM.
 //
-//   pct_attn_stats_kernel  per object: S = K K^T (tcgen05, K = 32 channels as bf16 hi|lo side by side in one 128-byte
+//   pct_attn_stats_kernel  per object: S = K K^T (tcgen05, K = 32 channels as fp16 hi|lo side by side in one 128-byte
 //       swizzled row, so the hi/lo partial products are descriptor offsets into the same image), a whole 128-row
 //       block of S (<= 512 columns) in tensor memory, thread-local row max and sum of exponentials ->
-//       c_i = max_i * a + log2(sum_i)   (a = log2(e) / sqrt(32); +inf for padding rows)
+//       (max_i * a, log2(sum_i))   (a = log2(e) / sqrt(32); max = +inf for padding rows)
 //   pct_attn_kernel        per (object, 128-column block j): for every 128-row block i:
-//       S^T[j, i] (tensor memory) -> E = exp2(S a - c_i) = attention[i, j] -> bf16 hi / lo BACK INTO TENSOR MEMORY as the
+//       S^T[j, i] (tensor memory) -> E = exp2((S a - max_i a) - log2 sum_i) = attention[i, j] -> fp16 hi / lo BACK INTO TENSOR MEMORY as the
 //       A operand of  O[j, :] += E V[i, :]   (tcgen05.mma A-from-TMEM; V tile read MN-major from shared memory);
 //       S double-buffered, the V tile of block i+1 is loaded while block i is in the tensor pipe.
-// Everything is bf16x3 (three passes over split operands, fp32 accumulate): attention weights and outputs agree with
-// the fp32 reference to ~1e-5.  P <= 512 (the [128 x P] score block must fit the 512 columns of tensor memory).
+// Split fp16 operands (pct_common.cuh), fp32 accumulate: three passes for x_v * attention, all four partial products for
+// the scores.  P <= 512 (the [128 x P] score block must fit the 512 columns of tensor memory).
 #include "pct_common.cuh"
 
 namespace sga {
@@ -23,7 +23,7 @@ namespace {
 constexpr int kMaxT = 4;                               // P <= 512
 constexpr float kAlpha = 1.4426950408889634f * 0.17677669529663687f;   // log2(e) / sqrt(32)
 
-// ---- K image: per tile of 128 points one 16 KiB block of 128-byte rows [k.hi (32 bf16) | k.lo (32 bf16)]
+// ---- K image: per tile of 128 points one 16 KiB block of 128-byte rows [k.hi (32 fp16) | k.lo (32 fp16)]
 __device__ __forceinline__ void load_k_image(const float* __restrict__ k, int64_t rowbase0, int P, int T, uint32_t kimg_addr, int tid) {
   for (int t = 0; t < T; ++t) {
 #pragma unroll
@@ -92,7 +92,7 @@ pct_attn_stats_kernel(const float* __restrict__ k, int64_t N, int P, float* __re
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 8) {
-    const uint32_t idesc = ptx::make_idesc(1, 128, 128);
+    const uint32_t idesc = ptx::make_idesc(kFmt, 128, 128);
     const uint64_t dK = ptx::smem_desc_sw128(sm_base + KIMG);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
     uint32_t obj_it = 0, blk = 0;
@@ -154,7 +154,10 @@ pct_attn_stats_kernel(const float* __restrict__ k, int64_t N, int P, float* __re
         if (hc == 0) {
           l = xch[256 + row] + xch[256 + 128 + row];
           const int i = it * kTile + row;
-          c2[n * Ppad + i] = (i < P) ? ma + lg2(l) : INFINITY;
+          // kept apart: their sum would be rounded at the magnitude of ma (energies of 10^4 -> ulp 4e-3 -> every
+          // weight of the row off by the same 0.3 %); (s a - ma) is one fused rounding of a small difference
+          c2[(n * 2) * Ppad + i] = (i < P) ? ma : INFINITY;
+          c2[(n * 2 + 1) * Ppad + i] = (i < P) ? lg2(l) : 0.f;
         }
       }
     }
@@ -171,7 +174,7 @@ constexpr uint32_t VHI = KIMG + kMaxT * kBlk;          // 2 buffers x 2 channel 
 constexpr uint32_t VLO = VHI + 4 * kBlk;
 constexpr uint32_t STAGE = VLO + 4 * kBlk;             // 196608
 constexpr uint32_t C2S = STAGE + 8 * kStageFloats * 4;
-constexpr uint32_t BARS = C2S + kMaxT * kTile * 4;
+constexpr uint32_t BARS = C2S + 2 * kMaxT * kTile * 4;
 constexpr uint32_t TMEMPTR = BARS + 128;
 constexpr uint32_t SMEM_BYTES = TMEMPTR + 16 + 1024;
 constexpr uint32_t S_COL = 0, O_COL = 256, EHI_COL = 384, ELO_COL = 448;
@@ -212,8 +215,8 @@ pct_attn_kernel(const float* __restrict__ k, const float* __restrict__ v, const 
 
   if (warp == 8) {
     // =============================== MMA issuer ===============================
-    const uint32_t idesc_s = ptx::make_idesc(1, 128, 128);
-    const uint32_t idesc_pv = ptx::make_idesc(1, 128, 128) | (1u << 16);      // B (= V tile) read MN-major
+    const uint32_t idesc_s = ptx::make_idesc(kFmt, 128, 128);
+    const uint32_t idesc_pv = ptx::make_idesc(kFmt, 128, 128) | (1u << 16);      // B (= V tile) read MN-major
     const uint64_t dK = ptx::smem_desc_sw128(sm_base + KIMG);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
     uint32_t u = 0, wi = 0;                          // running i-block counter, work-item counter
@@ -307,7 +310,7 @@ pct_attn_kernel(const float* __restrict__ k, const float* __restrict__ v, const 
       const int jt = (int)(w - n * T);
       // the previous item's score MMAs have all completed (every S_FULL was waited for): the K image is free
       load_k_image(k, n * (int64_t)P, P, T, sm_base + KIMG, tid);
-      for (int i = tid; i < Ppad; i += kComputeThreads) c2s[i] = c2[n * Ppad + i];
+      for (int i = tid; i < 2 * Ppad; i += kComputeThreads) c2s[(i < Ppad) ? i : i - Ppad + kMaxT * kTile] = c2[n * 2 * Ppad + i];
       ptx::fence_proxy_async_smem();
       compute_barrier();                              // c2s visible to every compute thread
       ptx::mbar_arrive(&bars[BAR_K_FULL]);
@@ -325,10 +328,11 @@ pct_attn_kernel(const float* __restrict__ k, const float* __restrict__ v, const 
           ptx::tmem_ld32(tmem + lane_addr + S_COL + b * 128 + (uint32_t)(hc * 64 + h * 32), sv);
           ptx::tmem_ld_wait();
           const float* cp = c2s + it * kTile + hc * 64 + h * 32;
+          const float* cl = cp + kMaxT * kTile;
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
-            const float e0 = ex2(fmaf(__uint_as_float(sv[e]), kAlpha, -cp[e]));
-            const float e1 = ex2(fmaf(__uint_as_float(sv[e + 1]), kAlpha, -cp[e + 1]));
+            const float e0 = ex2(fmaf(__uint_as_float(sv[e]), kAlpha, -cp[e]) - cl[e]);
+            const float e1 = ex2(fmaf(__uint_as_float(sv[e + 1]), kAlpha, -cp[e + 1]) - cl[e + 1]);
             const uint32_t hw = pack2(e0, e1);
             eh[h * 16 + e / 2] = hw;
             el[h * 16 + e / 2] = pack2(e0 - bf_lo(hw), e1 - bf_hi(hw));

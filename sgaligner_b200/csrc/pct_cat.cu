@@ -100,7 +100,7 @@ pct_cat_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const
 
   if (warp == 8) {
     // =============================== MMA issuer ===============================
-    const uint32_t idesc = ptx::make_idesc(1, 128, 128);
+    const uint32_t idesc = ptx::make_idesc(kFmt, 128, 128);
     const uint64_t dWlo = ptx::smem_desc_sw128(sm_base + WLO);
     const uint64_t dRing = ptx::smem_desc_sw128(sm_base + RING);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);

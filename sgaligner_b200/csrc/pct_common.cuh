@@ -8,6 +8,7 @@
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
+#include <cuda_fp16.h>
 
 namespace sga {
 namespace pct {
@@ -17,14 +18,24 @@ constexpr int kThreads = kComputeThreads + 32;       // + the MMA-issuing warp
 constexpr int kTile = 128;                           // points per tile
 constexpr uint32_t kBlk = 16384;                     // [128 rows x 128 B]
 
+// Split-operand format of every NaivePCT contraction: FP16 pairs.  x = hi + lo with hi = fp16(x), lo = fp16(x - hi)
+// carries 22 significant bits (|x| >= 2^-3; below that the lo part is subnormal: absolute error <= 2^-25), against 16
+// for a bf16 pair -- and the self-attention needs them: the energies k_i . k_j / sqrt(32) sit in an exponent, so an
+// operand error of 2^-17 (bf16 pair) on energies of 10^3..10^4 is an O(1) error of attention weights (measured on the
+// golden input: 3.3e-4 on the encoder output with bf16 pairs, tools/pct_numerics_emul.py; 1.4e-6 emulated with fp16
+// pairs at the same three tensor passes).  Price: the fp16 range -- an activation beyond 65504 becomes inf and the
+// output NaN (loud), where the fp32 reference carries on; BatchNorm after every convolution keeps real activations
+// orders of magnitude below that.
+constexpr int kFmt = 0;                               // tcgen05 instruction descriptor a_format / b_format: 0 = F16, 1 = BF16
+
 __device__ __forceinline__ uint32_t pack2(float a, float b) {   // a -> low half (lower k)
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  __half2 v = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __low2float(*reinterpret_cast<const __half2*>(&w)); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __high2float(*reinterpret_cast<const __half2*>(&w)); }
 
-// 8 fp32 -> bf16 hi / lo parts as two 16-byte chunks (x = hi + lo to ~2^-17 relative)
+// 8 fp32 -> fp16 hi / lo parts as two 16-byte chunks (x = hi + lo to ~2^-22 relative)
 __device__ __forceinline__ void split8(const float (&f)[8], uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll

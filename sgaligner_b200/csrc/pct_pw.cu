@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kThreads, 1) pct_pw_kernel(const PwArgs A) {
 
   if (warp == 8) {
     // =============================== MMA issuer ===============================
-    const uint32_t idesc = ptx::make_idesc(1, 128, Cout);
+    const uint32_t idesc = ptx::make_idesc(kFmt, 128, Cout);
     const uint64_t dAhi = ptx::smem_desc_sw128(sm_base + AHI), dAlo = ptx::smem_desc_sw128(sm_base + ALO);
     const uint64_t dWhi = ptx::smem_desc_sw128(sm_base + WHI), dWlo = ptx::smem_desc_sw128(sm_base + WLO);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);

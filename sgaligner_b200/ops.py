@@ -328,7 +328,7 @@ def pct_attention(k, v):
     """x_s = torch.bmm(x_v, softmax(x_k^T x_k / sqrt(32), -1)) for every object (pct.py:217-224), [N,P,128]."""
     N, P, _ = k.shape
     Ppad = (P + 127) // 128 * 128
-    c2 = torch.empty((N, Ppad), device=k.device, dtype=torch.float32)
+    c2 = torch.empty((N, 2, Ppad), device=k.device, dtype=torch.float32)      # per row: max * log2(e)/sqrt(32), log2(sum of exponentials)
     xs = torch.empty((N, P, 128), device=k.device, dtype=torch.float32)
     lib = get_lib()
     with _timed('pct_attn_stats'):

@@ -95,6 +95,25 @@ def test_attention_vs_fp64(N, P, dev):
     assert rel_inf(xs, ref) < 3e-5
 
 
+@pytest.mark.parametrize('N,P,scale', [(4, 128, 12.0), (6, 512, 40.0)])
+def test_attention_large_energies(N, P, scale, dev):
+    """Energies of 10^3..10^5 (what an untrained / badly scaled network produces, and what the golden input reaches in
+    sa3/sa4): the softmax normaliser must not be rounded at the magnitude of the row maximum.  Judged against fp64
+    next to torch's own fp32 evaluation of the reference formula on the same inputs."""
+    from sgaligner_b200 import ops
+    k = _rand((N, P, 32), dev, 1, scale)
+    v = _rand((N, P, 128), dev, 2, 5.0)
+    xs = ops.pct_attention(k, v)
+    kd, vd = k.double(), v.double()
+    ref = torch.softmax(kd @ kd.transpose(1, 2) / math.sqrt(32), dim=-1).transpose(1, 2) @ vd
+    f32 = torch.softmax(torch.bmm(k, k.transpose(1, 2)) / math.sqrt(32), dim=-1).transpose(1, 2) @ v
+    torch.cuda.synchronize()
+    e_ours, e_f32 = rel_inf(xs, ref), rel_inf(f32, ref)
+    print('attention at |energy| ~ %.0f: ours %.2e, torch fp32 %.2e vs fp64' % (float((kd * kd).sum(-1).max() / math.sqrt(32)), e_ours, e_f32))
+    assert torch.isfinite(xs).all()
+    assert e_ours < max(3e-5, 4 * e_f32)
+
+
 @pytest.mark.parametrize('N,P', [(3, 40), (4, 96), (5, 300), (40, 512)])
 def test_cat_linear_pooling(N, P, dev):
     from sgaligner_b200 import ops
