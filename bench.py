@@ -444,6 +444,78 @@ def run_ours(args, out=sys.stdout):
                                           lambda b: world * b), scaling='weak',
                                workload='BASELINE configs[4] per-GPU share: 8 pairs x (256+256) objects x 1024 pts, pt_out 512, emb 128 (joint 512-d)')
 
+    # ---- (2c') the module list of the reference's SHIPPED config (scan3r_ground_truth.yaml:5): NaivePCT object encoder
+    #       + gat + rel + attr on the C2 shapes.  Serving only (the PCT backward is not built);
+    #      per-kernel times of the PCT launches, and on rank 0 the reference's NaivePCT op sequence in PyTorch eager
+    #      on this GPU (cuBLAS / cuDNN fp32) as the kernel-to-beat.
+    def run_pct_config():
+        import collections
+        PCT = ['pct', 'gat', 'rel', 'attr']
+        h = synthetic.config_c2(batch=PAIRS_PER_GPU, seed=100 + rank, n_obj=N_OBJ, n_points=N_PTS)
+        d = to_cuda(dict(h), dev)
+        e1_, e2_ = torch.as_tensor(h['e1i']).to(dev), torch.as_tensor(h['e2i']).to(dev)
+        torch.manual_seed(0)
+        mdl = MultiModalEncoder(modules=PCT, rel_dim=41, attr_dim=164).to(dev).eval()
+
+        def step():
+            with torch.no_grad():
+                o_ = mdl(d)
+                r_ = matching.match_batch(o_['joint'], d, k=6, full_rank=False)
+                return ops.match_anchor_pos(r_['sim'], r_['layout'], e1_, e2_)
+        sv_ms, _, _ = timed(step, cfg_steps, 3)
+        sv_ms /= cfg_steps
+        ops.KERNEL_EVENTS = []
+        step()
+        torch.cuda.synchronize()
+        agg = collections.OrderedDict()
+        for nme, a_, b_ in ops.KERNEL_EVENTS:
+            if nme.startswith('pct_'):
+                agg[nme] = agg.get(nme, 0.0) + a_.elapsed_time(b_)
+        ops.KERNEL_EVENTS = None
+        n_obj = int(d['tot_obj_pts'].shape[0])
+        Pp = N_PTS
+        flop_obj = (2 * Pp * (3 * 128 + 128 * 128) + 4 * (2 * Pp * (128 * 32 + 2 * 128 * 128) + 2 * Pp * Pp * 160) + 2 * Pp * 512 * 1024
+                    + 2 * (1024 * 512 + 512 * 256))
+        k_tot = sum(agg.values())
+        res = {'pairs_per_gpu': PAIRS_PER_GPU, 'objects_per_gpu': n_obj, 'modules': '+'.join(PCT),
+               'serve_ms_per_step': sv_ms, 'serve_pairs_per_s': world * PAIRS_PER_GPU / (sv_ms * 1e-3),
+               'train_ms_per_step': None, 'train': 'not built: the NaivePCT backward raises NotImplementedError',
+               'pct_kernel_ms': {k_: round(v_, 4) for k_, v_ in agg.items()}, 'pct_kernels_total_ms': k_tot,
+               'pct_flop_per_object': flop_obj,
+               'pct_algorithmic_tflops': flop_obj * n_obj / (k_tot * 1e-3) / 1e12 if k_tot else None,
+               'pct_tensor_frac_of_bf16_burst_peak': (3 * flop_obj * n_obj / (k_tot * 1e-3) / 1e12 / measured_peaks()['burst']) if k_tot else None,
+               'pct_numerics': 'fp16 split operands, 3 tensor passes per algorithmic FLOP (4 for the attention scores), fp32 accumulate',
+               'scaling': 'weak', 'workload': 'C2 shapes, modules of configs/scan3r/scan3r_ground_truth.yaml:5 (NaivePCT point encoder, joint 400-d)'}
+        if rank == 0:
+            from oracle import pct_oracle as PO
+            pp = {k_: v_.detach() for k_, v_ in mdl.object_encoder.state_dict().items()}
+            xin = d['tot_obj_pts'].permute(0, 2, 1)
+
+            def eager_pct():
+                with torch.no_grad():
+                    return torch.cat([PO.naive_pct(xin[i:i + 512], pp, False) for i in range(0, n_obj, 512)])
+            for _ in range(2):
+                y_ref = eager_pct()
+            torch.cuda.synchronize()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            for _ in range(3):
+                y_ref = eager_pct()
+            b_.record()
+            torch.cuda.synchronize()
+            with torch.no_grad():
+                y_our = mdl.object_encoder(d['tot_obj_pts'])
+            res['pct_gpu_eager_baseline'] = {
+                'what': 'reference NaivePCT op sequence (oracle/pct_oracle.py: einsum / bmm / softmax / batch_norm) in PyTorch eager fp32 on cuda:0, '
+                        'same points and weights, 512 objects per call',
+                'ms': a_.elapsed_time(b_) / 3, 'matmul_allow_tf32': bool(torch.backends.cuda.matmul.allow_tf32),
+                'max_rel_diff_ours_vs_eager': float((y_our - y_ref).abs().max() / y_ref.abs().max())}
+        del mdl, d
+        torch.cuda.empty_cache()
+        return res
+
+    configs['C2_pct'] = run_pct_config()
+
     # ---- (2d) second baseline: the reference's own op sequence in PyTorch eager on THIS GPU
     #      (cuDNN Conv1d + discarded BatchNorm calls, per-graph GAT loop, per-pair matching loop with the rank lists
     #      moved to the host) -- the kernel-to-beat on the same box; rank 0 only, same batch, CUDA events.

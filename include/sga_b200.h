@@ -321,6 +321,40 @@ int sga_col_stats(const float* x, int64_t N, int C, double* stats, void* stream)
 int sga_bn_act_rows(const float* x, const float* a, const float* b, const float* mask, float scale, int64_t N, int C,
                     float* out, void* stream);
 
+/* ==== 8(f)4: EVA baseline path (src/aligner/eva.py:9-96; MultiGCN, src/aligner/networks/gat.py:6-25, over
+ * torch_geometric 2.2.0 GCNConv; NCALoss / OverallNCALoss, src/aligner/losses.py:154-205).  The dense products of this
+ * path (GCN layer 2, the NCA score matrix, its two gradient products) go through sga_gemm_tf32x3. */
+/* GCNConv aggregation (gcn_norm + propagate): out_i = sum_{j in row i} h_j / sqrt(deg_i deg_j) (+ bias) (ReLU if
+ * relu != 0); row_beg/row_cnt/col: block-diagonal CSR of sga_csr_build (self loops removed, one appended per node =
+ * add_remaining_self_loops); deg [N] = in-degree incl. the self loop = row_cnt of the FORWARD (by-destination) CSR.
+ * The backward of the aggregation is the same call over the CSR of the reversed edges with the same deg. */
+int sga_gcn_aggregate(const float* h, int64_t N, int C, const int32_t* row_beg, const int32_t* row_cnt,
+                      const int32_t* col, const int32_t* deg, const float* bias, int relu, float* out, void* stream);
+/* Y [N,C] = X [N,K] W^T, W [C,K], K <= 8 (GCN layer 1: 3 -> 200, gat.py:15); gW [C,K] += G^T X. */
+int sga_linear_smallk(const float* X, int64_t N, int K, const float* W, int C, float* Y, void* stream);
+int sga_wgrad_smallk(const float* G, const float* X, int64_t N, int K, int C, float* gW, void* stream);
+/* out = g * (y > 0)  (ReLU backward, gat.py:23);  s [C] += column sums of x [N,C] (bias gradients). */
+int sga_relu_mask(const float* g, const float* y, int64_t n, float* out, void* stream);
+int sga_colsum_rows(const float* x, int64_t N, int C, float* s, void* stream);
+/* F.normalize (losses.py:193): norms [N] = max(||x_i||, eps);  backward in place on g [N,D]:
+ * g_i <- (g_i - xh_i (xh_i . g_i)) / norms_i. */
+int sga_row_l2norm(const float* x, int64_t N, int D, float eps, float* norms, void* stream);
+int sga_normalize_bwd_rows(const float* x, const float* norms, int64_t N, int D, float eps, float* g, void* stream);
+/* MultiModalFusion (sg_aligner.py:23-35) for M <= 8 modalities of different widths dims[m] (EVA fuses raw 400-d / 200-d
+ * / 100-d embeddings, eva.py:72-76): joint [N, ld] = cat_m softmax(fusion_w)_m * x_m / max(||x_m||, 1e-12).
+ * x_host / gx_host: HOST arrays of M device pointers.  Backward: gx_m written, g_fusion_w [M] accumulated (+=);
+ * scratch_M: M floats of device scratch. */
+int sga_fuse_rows_fwd(const float* const* x_host, const int* dims_host, int M, const float* fusion_w, int64_t N,
+                      float* joint, int ld, void* stream);
+int sga_fuse_rows_bwd(const float* const* x_host, const int* dims_host, int M, const float* fusion_w, int64_t N,
+                      const float* g_joint, int ld, float* const* gx_host, float* g_fusion_w, float* scratch_M, void* stream);
+/* NCALoss (losses.py:161-176) over the score matrix S [A,A] = src_emb ref_emb^T: rs/cs [A] = row / column sums of
+ * exp(alpha (S - ep)) off the diagonal, diag [A], loss [1] = mean log(1+cs)/alpha + mean log(1+rs)/alpha
+ * - beta mean log(1 + relu(diag)).  sga_nca_coef turns S into dLoss/dS in place. */
+int sga_nca_forward(const float* S, int A, float alpha, float beta, float ep, float* rs, float* cs, float* diag,
+                    float* loss, void* stream);
+int sga_nca_coef(float* S, int A, float alpha, float beta, float ep, const float* rs, const float* cs, void* stream);
+
 /* diagnostics only: the tensor-core forward, when it tracks the argmax, re-evaluates near-ties of the max-pool in
  * fp32 (pointnet_tie_fix_kernel, so that the gradient is routed through the point the fp32 reference selects,
  * pointnet.py:162-163).  counts_host[2] (HOST pointer, may be NULL) receives {near-ties re-evaluated, of those

@@ -78,6 +78,17 @@ def _declare(lib):
     sig('sga_pct_pool_act', c_i, c_p, c_p, c_p, c_p, c_l, c_i, c_p, c_p)
     sig('sga_col_stats', c_i, c_p, c_l, c_i, c_p, c_p)
     sig('sga_bn_act_rows', c_i, c_p, c_p, c_p, c_p, c_f, c_l, c_i, c_p, c_p)
+    sig('sga_gcn_aggregate', c_i, c_p, c_l, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p)
+    sig('sga_linear_smallk', c_i, c_p, c_l, c_i, c_p, c_i, c_p, c_p)
+    sig('sga_wgrad_smallk', c_i, c_p, c_p, c_l, c_i, c_i, c_p, c_p)
+    sig('sga_relu_mask', c_i, c_p, c_p, c_l, c_p, c_p)
+    sig('sga_colsum_rows', c_i, c_p, c_l, c_i, c_p, c_p)
+    sig('sga_row_l2norm', c_i, c_p, c_l, c_i, c_f, c_p, c_p)
+    sig('sga_normalize_bwd_rows', c_i, c_p, c_p, c_l, c_i, c_f, c_p, c_p)
+    sig('sga_fuse_rows_fwd', c_i, POINTER(c_p), POINTER(c_i), c_i, c_p, c_l, c_p, c_i, c_p)
+    sig('sga_fuse_rows_bwd', c_i, POINTER(c_p), POINTER(c_i), c_i, c_p, c_l, c_p, c_i, POINTER(c_p), c_p, c_p, c_p)
+    sig('sga_nca_forward', c_i, c_p, c_i, c_f, c_f, c_f, c_p, c_p, c_p, c_p, c_p)
+    sig('sga_nca_coef', c_i, c_p, c_i, c_f, c_f, c_f, c_p, c_p, c_p)
     sig('sga_selftest_umma', c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_p)
     sig('sga_debug_set_trace', c_i, c_p)
     sig('sga_debug_tie_stats', c_i, c_p, c_i)
@@ -89,7 +100,9 @@ EXPORTS = ['sga_last_error', 'sga_version', 'sga_device_info', 'sga_pointnet_fwd
            'sga_match_sim', 'sga_match_topk_tc', 'sga_match_rank', 'sga_match_anchor_pos', 'sga_match_pair_metrics', 'sga_center_points', 'sga_loss_workspace_bytes', 'sga_loss_launch_count', 'sga_loss_set_gram_path', 'sga_bn_running_update', 'sga_pointnet_gram_scratch_bytes', 'sga_pointnet_bn_moments_gram',
            'sga_loss_fwd_bwd', 'sga_gemm_tf32x3', 'sga_adam_step', 'sga_adam_step_segments', 'sga_selftest_umma', 'sga_debug_set_trace', 'sga_debug_tie_stats',
            'sga_pct_point_moments', 'sga_pct_affine_stats', 'sga_bn_fold', 'sga_pct_embed', 'sga_pct_pointwise', 'sga_pct_attn_stats',
-           'sga_pct_attn', 'sga_pct_cat_linear', 'sga_pct_pool_act', 'sga_col_stats', 'sga_bn_act_rows']
+           'sga_pct_attn', 'sga_pct_cat_linear', 'sga_pct_pool_act', 'sga_col_stats', 'sga_bn_act_rows',
+           'sga_gcn_aggregate', 'sga_linear_smallk', 'sga_wgrad_smallk', 'sga_relu_mask', 'sga_colsum_rows', 'sga_row_l2norm',
+           'sga_normalize_bwd_rows', 'sga_fuse_rows_fwd', 'sga_fuse_rows_bwd', 'sga_nca_forward', 'sga_nca_coef']
 
 
 def lib_path() -> str:

@@ -173,3 +173,81 @@ class StandaloneIAL(torch.autograd.Function):
     def backward(ctx, g):
         gs, gr = ctx.saved_tensors
         return None, gs * g, gr * g
+
+
+# ------------------------------------------------------------------------------------------- EVA baseline
+class GCNLayer(torch.autograd.Function):
+    """One PyG-2.2.0 ``GCNConv`` (gat.py:15,21) over the block-diagonal batch graph: linear map without bias, symmetric
+    normalisation, sum aggregation, bias afterwards (+ the ReLU between layers, gat.py:22-23)."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, graph, graph_t, relu):
+        xw = ops.linear_nobias(x, W)
+        out = ops.gcn_aggregate(xw, graph, graph.row_cnt, bias, relu)
+        ctx.graph, ctx.graph_t, ctx.relu = graph, graph_t, relu
+        ctx.need_gx = x.requires_grad
+        ctx.save_for_backward(x, W, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, W, out = ctx.saved_tensors
+        g = gout.contiguous()
+        if ctx.relu:
+            g = ops.relu_mask(g, out)
+        g_bias = ops.colsum_rows(g) if ctx.needs_input_grad[2] else None
+        g_xw = ops.gcn_aggregate(g, ctx.graph_t, ctx.graph.row_cnt)        # transpose of the normalised adjacency
+        gW, gx = ops.linear_nobias_backward(x, W, g_xw, ctx.need_gx)
+        return gx, (gW if ctx.needs_input_grad[1] else None), g_bias, None, None, None
+
+
+class FuseRows(torch.autograd.Function):
+    """MultiModalFusion (sg_aligner.py:23-35) over embeddings of different widths: forward(fusion_w, *embs) -> joint."""
+
+    @staticmethod
+    def forward(ctx, fusion_w, *embs):
+        joint = ops.fuse_rows(embs, fusion_w)
+        ctx.save_for_backward(fusion_w, *embs)
+        return joint
+
+    @staticmethod
+    def backward(ctx, g_joint):
+        fusion_w, *embs = ctx.saved_tensors
+        gxs, g_fw = ops.fuse_rows_backward(embs, fusion_w, g_joint.contiguous())
+        return (g_fw.view_as(fusion_w) if ctx.needs_input_grad[0] else None,
+                *[g if need else None for g, need in zip(gxs, ctx.needs_input_grad[1:])])
+
+
+def _nca_forward(ctx, normalize, emb, e1, e2, alpha, beta, ep):
+    want = ctx.needs_input_grad[0]
+    loss, g = ops.nca_loss_forward_backward(emb, e1, e2, alpha, beta, ep, want, normalize=normalize)
+    if want:
+        ctx.save_for_backward(g)
+    return loss.clone()
+
+
+class NCAFn(torch.autograd.Function):
+    """NCALoss of one embedding (losses.py:161-176 as called at :189-200: F.normalize + the e1i / e2i gathers included);
+    the gradient is produced with the value."""
+
+    @staticmethod
+    def forward(ctx, emb, e1, e2, alpha, beta, ep):
+        return _nca_forward(ctx, True, emb, e1, e2, alpha, beta, ep)
+
+    @staticmethod
+    def backward(ctx, gl):
+        (g,) = ctx.saved_tensors
+        return g * gl, None, None, None, None, None
+
+
+class NCAPairFn(torch.autograd.Function):
+    """NCALoss.forward(src_emb, ref_emb) on rows that are already normalised and gathered (losses.py:161-176)."""
+
+    @staticmethod
+    def forward(ctx, emb, e1, e2, alpha, beta, ep):
+        return _nca_forward(ctx, False, emb, e1, e2, alpha, beta, ep)
+
+    @staticmethod
+    def backward(ctx, gl):
+        (g,) = ctx.saved_tensors
+        return g * gl, None, None, None, None, None

@@ -10,7 +10,7 @@ from torch import nn
 
 from . import autograd as ag
 
-__all__ = ['torch', 'nn', 'F', 'calculate_prob_dist', 'CustomMultiLossLayer', 'ICLLoss', 'IALLoss', 'OverallLoss']
+__all__ = ['torch', 'nn', 'F', 'calculate_prob_dist', 'CustomMultiLossLayer', 'ICLLoss', 'IALLoss', 'OverallLoss', 'NCALoss', 'OverallNCALoss']
 
 
 class _IndexSets(list):
@@ -135,3 +135,45 @@ class OverallLoss(nn.Module):
                     'ial_loss': losses[3].detach()}
         losses = ag.OverallLossFn.apply(idx, float(self.zoom), None, None, output_dict[mods[0]])
         return {'loss': losses[0], 'icl_loss_unimodal': losses[1].detach(), 'icl_loss_multimodal': 0.0, 'ial_loss': 0.0}
+
+
+class NCALoss(nn.Module):
+    """``losses.py:154-176``.  ``forward(src_emb, ref_emb)`` takes the two already normalised and gathered row sets, as
+    the reference does; ``OverallNCALoss`` goes through the fused form (normalise + gather inside the GEMM loaders)."""
+
+    def __init__(self, alpha, beta, ep):
+        super().__init__()
+        self.alpha = alpha
+        self.beta = beta
+        self.ep = ep
+
+    def forward(self, src_emb, ref_emb):
+        if not src_emb.is_cuda:
+            raise RuntimeError('sgaligner_b200.NCALoss needs CUDA tensors (no CPU fallback)')
+        n = src_emb.shape[0]
+        both = torch.cat([src_emb, ref_emb])
+        ar = torch.arange(2 * n, device=src_emb.device, dtype=torch.int32)
+        return ag.NCAPairFn.apply(both, ar[:n].contiguous(), ar[n:].contiguous(), float(self.alpha), float(self.beta), float(self.ep))
+
+
+class OverallNCALoss(nn.Module):
+    """``losses.py:178-205``: one NCA term per entry of the output dict (the joint embedding included), summed."""
+
+    def __init__(self, modules, device):
+        super().__init__()
+        self.device = device
+        self.criterion_dict = {module: NCALoss(alpha=1, beta=1, ep=0.0) for module in modules}
+        self.criterion_dict['joint'] = NCALoss(alpha=1, beta=1, ep=0.0)
+
+    def forward(self, output_dict, data_dict):
+        loss_dict = {}
+        first = next(iter(output_dict.values()))
+        idx = _index_tensors(data_dict, first.device, first.shape[0])
+        for module in output_dict.keys():
+            c = self.criterion_dict[module]
+            loss_dict[module] = ag.NCAFn.apply(output_dict[module], idx[0], idx[1], float(c.alpha), float(c.beta), float(c.ep))
+        loss_sum = 0
+        for module in loss_dict.keys():
+            loss_sum = loss_sum + loss_dict[module]
+        loss_dict['loss'] = loss_sum
+        return loss_dict

@@ -705,6 +705,142 @@ def gemm_tf32x3(A, B, M, N, K, a_mn=False, b_mn=False, a_idx=None, b_idx=None, a
     return out
 
 
+# --------------------------------------------------------------------------------- EVA baseline (eva.py, gat.py:6-25, losses.py:154-205)
+def gcn_aggregate(h, graph: 'BatchGraph', deg, bias=None, relu: bool = False):
+    """out_i = sum_{j in CSR row i of ``graph``} h_j / sqrt(deg_i deg_j) (+ bias) (ReLU); ``deg`` = row_cnt of the forward graph."""
+    h = _f32c(h)
+    N, C = h.shape
+    out = torch.empty_like(h)
+    check(get_lib().sga_gcn_aggregate(_ptr(h), N, C, _ptr(graph.row_beg), _ptr(graph.row_cnt), _ptr(graph.col), _ptr(deg),
+                                      _ptr(None if bias is None else _f32c(bias)), 1 if relu else 0, _ptr(out), _stream()), 'sga_gcn_aggregate')
+    _count(1)
+    return out
+
+
+def linear_nobias(x, W):
+    """x [N,K] W^T, W [C,K]: the small-K kernel for K <= 8 (GCN layer 1), the tf32x3 tensor-core GEMM otherwise."""
+    x, W = _f32c(x), _f32c(W)
+    N, K = x.shape
+    C = W.shape[0]
+    if K <= 8:
+        y = torch.empty((N, C), device=x.device, dtype=torch.float32)
+        check(get_lib().sga_linear_smallk(_ptr(x), N, K, _ptr(W), C, _ptr(y), _stream()), 'sga_linear_smallk')
+        _count(1)
+        return y
+    return gemm_tf32x3(x, W, N, C, K)
+
+
+def linear_nobias_backward(x, W, g, need_gx: bool):
+    """(gW [C,K], gx [N,K] or None) of y = x W^T."""
+    x, W, g = _f32c(x), _f32c(W), _f32c(g)
+    N, K = x.shape
+    C = W.shape[0]
+    if K <= 8:
+        gW = torch.zeros((C, K), device=x.device, dtype=torch.float32)
+        check(get_lib().sga_wgrad_smallk(_ptr(g), _ptr(x), N, K, C, _ptr(gW), _stream()), 'sga_wgrad_smallk')
+        _count(1)
+        gx = gemm_tf32x3(g, W, N, K, C, b_mn=True) if need_gx else None
+        return gW, gx
+    gW = gemm_tf32x3(g, x, C, K, N, a_mn=True, b_mn=True)          # gW[c,k] = sum_i g[i,c] x[i,k]
+    gx = gemm_tf32x3(g, W, N, K, C, b_mn=True) if need_gx else None   # gx[i,k] = sum_c g[i,c] W[c,k]
+    return gW, gx
+
+
+def relu_mask(g, y):
+    g, y = _f32c(g), _f32c(y)
+    out = torch.empty_like(g)
+    check(get_lib().sga_relu_mask(_ptr(g), _ptr(y), g.numel(), _ptr(out), _stream()), 'sga_relu_mask')
+    _count(1)
+    return out
+
+
+def colsum_rows(x):
+    x = _f32c(x)
+    N, C = x.shape
+    s = torch.zeros(C, device=x.device, dtype=torch.float32)
+    check(get_lib().sga_colsum_rows(_ptr(x), N, C, _ptr(s), _stream()), 'sga_colsum_rows')
+    _count(1)
+    return s
+
+
+def row_l2norm(x, eps: float = 1e-12):
+    x = _f32c(x)
+    N, D = x.shape
+    n = torch.empty(N, device=x.device, dtype=torch.float32)
+    check(get_lib().sga_row_l2norm(_ptr(x), N, D, float(eps), _ptr(n), _stream()), 'sga_row_l2norm')
+    _count(1)
+    return n
+
+
+def normalize_backward_rows_(x, norms, g, eps: float = 1e-12):
+    """in place on g [N,D]: the backward of F.normalize(x, eps)."""
+    N, D = x.shape
+    check(get_lib().sga_normalize_bwd_rows(_ptr(_f32c(x)), _ptr(norms), N, D, float(eps), _ptr(g), _stream()), 'sga_normalize_bwd_rows')
+    _count(1)
+    return g
+
+
+def fuse_rows(xs, fusion_w):
+    """MultiModalFusion over modalities of different widths -> joint [N, sum d_m]."""
+    xs = [_f32c(x) for x in xs]
+    _need_cuda(*xs)
+    M, N = len(xs), xs[0].shape[0]
+    dims = [int(x.shape[1]) for x in xs]
+    joint = torch.empty((N, sum(dims)), device=xs[0].device, dtype=torch.float32)
+    arr_p, arr_i = ctypes.c_void_p * M, ctypes.c_int * M
+    check(get_lib().sga_fuse_rows_fwd(arr_p(*[x.data_ptr() for x in xs]), arr_i(*dims), M, _ptr(_f32c(fusion_w).reshape(-1)), N,
+                                      _ptr(joint), joint.shape[1], _stream()), 'sga_fuse_rows_fwd')
+    _count(1)
+    return joint
+
+
+def fuse_rows_backward(xs, fusion_w, g_joint):
+    xs = [_f32c(x) for x in xs]
+    M, N = len(xs), xs[0].shape[0]
+    dims = [int(x.shape[1]) for x in xs]
+    g_joint = _f32c(g_joint)
+    gxs = [torch.empty_like(x) for x in xs]
+    g_fw = torch.zeros(M, device=xs[0].device, dtype=torch.float32)
+    scratch = torch.empty(M, device=xs[0].device, dtype=torch.float32)
+    arr_p, arr_i = ctypes.c_void_p * M, ctypes.c_int * M
+    check(get_lib().sga_fuse_rows_bwd(arr_p(*[x.data_ptr() for x in xs]), arr_i(*dims), M, _ptr(_f32c(fusion_w).reshape(-1)), N,
+                                      _ptr(g_joint), g_joint.shape[1], arr_p(*[g.data_ptr() for g in gxs]), _ptr(g_fw), _ptr(scratch),
+                                      _stream()), 'sga_fuse_rows_bwd')
+    _count(2)
+    return gxs, g_fw
+
+
+def nca_loss_forward_backward(emb, e1, e2, alpha: float, beta: float, ep: float, want_grad: bool, normalize: bool = True):
+    """NCALoss(F.normalize(emb)[e1], F.normalize(emb)[e2]) (losses.py:161-176,189-200) and, if asked, its gradient
+    w.r.t. ``emb`` [N,D] (``normalize=False``: the rows are used as they are).  Score matrix and both gradient products on the tf32x3 tensor-core GEMM (row gathers and
+    the 1/norm scaling in its loaders, scatter-add of the rows in its epilogue)."""
+    emb = _f32c(emb)
+    N, D = emb.shape
+    A = int(e1.numel())
+    dev = emb.device
+    norms = row_l2norm(emb) if normalize else None
+    S = gemm_tf32x3(emb, emb, A, A, D, a_idx=e1, b_idx=e2, a_div=norms, b_div=norms)
+    rs = torch.empty(A, device=dev, dtype=torch.float32)
+    cs = torch.empty(A, device=dev, dtype=torch.float32)
+    dg = torch.empty(A, device=dev, dtype=torch.float32)
+    loss = torch.empty(1, device=dev, dtype=torch.float32)
+    lib = get_lib()
+    check(lib.sga_nca_forward(_ptr(S), A, float(alpha), float(beta), float(ep), _ptr(rs), _ptr(cs), _ptr(dg), _ptr(loss), _stream()),
+          'sga_nca_forward')
+    _count(3)
+    if not want_grad:
+        return loss[0], None
+    check(lib.sga_nca_coef(_ptr(S), A, float(alpha), float(beta), float(ep), _ptr(rs), _ptr(cs), _stream()), 'sga_nca_coef')
+    _count(1)
+    g = torch.zeros((N, D), device=dev, dtype=torch.float32)
+    # d/dP = dS Q^ (rows scattered to e1), d/dQ = dS^T P^ (rows scattered to e2)
+    gemm_tf32x3(S, emb, A, D, A, b_mn=True, b_idx=e2, b_div=norms, out=g, c_idx=e1)
+    gemm_tf32x3(S, emb, A, D, A, a_mn=True, b_mn=True, b_idx=e1, b_div=norms, out=g, c_idx=e2)
+    if normalize:
+        normalize_backward_rows_(emb, norms, g)
+    return loss[0], g
+
+
 # --------------------------------------------------------------------------------- optimiser
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
     check(get_lib().sga_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), lr, beta1, beta2,

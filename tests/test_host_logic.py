@@ -145,3 +145,27 @@ def test_loss_host_side_accounting_and_partition_check():
     assert not _index_tensors(dict(d), torch.device('cpu')).partition
     d['e1j'] = np.array([2, 2])          # repeated node
     assert not _index_tensors(dict(d), torch.device('cpu')).partition
+
+
+def test_eva_module_surface_matches_reference_key_set():
+    """EVA: constructor signature of eva.py:10, the reference's exact state_dict key set and
+    shapes (frozen in tests/golden/eva_ref.npz from the unmodified module), NCA loss classes exported like losses.py,
+    and a CPU batch raises instead of falling back."""
+    import os
+    import numpy as np
+    import pytest
+    import torch
+    from sgaligner_b200.eva import EVA
+    from sgaligner_b200 import losses
+    from tests.util import GOLD
+    z = np.load(os.path.join(GOLD, 'eva_ref.npz'))
+    ref = {k[2:]: tuple(z[k].shape) for k in z.files if k.startswith('p/')}
+    m = EVA(modules=['gcn', 'point', 'rel', 'attr'], rel_dim=41, attr_dim=164)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == ref
+    m.load_state_dict({k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('p/')}, strict=True)
+    assert m.modules == ['gcn', 'point', 'rel', 'attr'] and m.n_units == [3, 200, 400]
+    assert {'NCALoss', 'OverallNCALoss'} <= set(losses.__all__)
+    fn = losses.OverallNCALoss(['gcn', 'point'], 'cpu')
+    assert set(fn.criterion_dict) == {'gcn', 'point', 'joint'} and fn.criterion_dict['joint'].alpha == 1
+    with pytest.raises(RuntimeError):
+        m({'tot_obj_pts': torch.zeros(2, 8, 3)})
