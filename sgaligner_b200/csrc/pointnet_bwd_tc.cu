@@ -9,11 +9,17 @@
 //   S    gather x_r = pts[n, p_r], g_r = grad_out if out > 0;  h1 = relu(W1 x + b1) -> A1{hi,lo} [128 x 64]
 //   MMA2 D2[r x k2]   = A1 W2^T                           (conv2 recomputed for the 128 argmax points)
 //   E2   z2 = D2 + b2; h2 = relu(z2);  dW3[c_r,:] += g_r h2[r,:]   (thread-private: a thread owns a row)
-//        dz2[r,:] = (z2 > 0) g_r W3[c_r,:]  -> DZ2{hi,lo} [128 x 128];  db2 += sum_r dz2  (warp transpose-reduce)
+//        dz2[r,:] = (z2 > 0) g_r W3[c_r,:]  -> DZ2{hi,lo} [128 x 128]
 //   MMA5 D5[k2 x k1] += DZ2^T A1     (dW2: both operands read MN-major from the tiles above; the accumulator
 //                                      lives in TMEM for the whole kernel)
+//   MMA8 D8[k2 x 16]  += DZ2^T 1     (db2 = column sums of dz2 as a product with a tile of ones: the same MN-major
+//                                      DZ2 operand, N = 16, accumulator resident in TMEM -- replaces four 16-value
+//                                      warp transpose-reduces per thread and tile, 19 % of the samples before)
 //   MMA6 D6[r x k1]   = DZ2 W2       (dh1)
 //   E1   dz1 = (h1 > 0) D6;  dW1 += dz1^T x, db1 += sum_r dz1         (warp transpose-reduce)
+// Tile pipeline: A1 and the instance table are double-buffered, and a compute thread does S(t+1) (gather, conv1,
+// A1 store) between handing DZ2(t) to the tensor pipe and reading D6(t) back, so MMA5/8/6(t) and MMA2(t+1) run
+// under CUDA-core work instead of in front of a waiting CTA.
 // The reference-equivalent SIMT kernel (pointnet_bwd.cu) stays as the path for C3 % 128 != 0 and as the
 // on-GPU cross-check.
 #include "common.cuh"
@@ -31,22 +37,22 @@ constexpr uint32_t W2HI = 0;                   // [128 k2 rows][64 k1]  K-major:
 constexpr uint32_t W2LO = W2HI + kBlk;
 constexpr uint32_t W2THI = W2LO + kBlk;        // 2 blocks (k2 halves) of [64 k1 rows][64 k2]  K-major: B of MMA6
 constexpr uint32_t W2TLO = W2THI + kBlk;       //   (a block is 64 rows x 128 B = 8 KiB)
-constexpr uint32_t A1HI = W2TLO + kBlk;        // [128 r][64 k1]
-constexpr uint32_t A1LO = A1HI + kBlk;
-constexpr uint32_t DZHI = A1LO + kBlk;         // 2 blocks (k2 halves) of [128 r][64 k2]
+constexpr uint32_t A1HI = W2TLO + kBlk;        // 2 buffers (tile parity) of [128 r][64 k1]
+constexpr uint32_t A1LO = A1HI + 2 * kBlk;
+constexpr uint32_t DZHI = A1LO + 2 * kBlk;     // 2 blocks (k2 halves) of [128 r][64 k2]
 constexpr uint32_t DZLO = DZHI + 2 * kBlk;
-constexpr uint32_t SMALL = DZLO + 2 * kBlk;    // 163840
+constexpr uint32_t ONES = DZLO + 2 * kBlk;     // 196608: [16 rows][64 x bf16 1.0]: B operand of the db2 column-sum MMA
+constexpr uint32_t SMALL = ONES + 2048;
 constexpr uint32_t W1B1 = SMALL;               // float4[64] = {w0,w1,w2,b}
 constexpr uint32_t B2 = W1B1 + 1024;           // float[128]
-constexpr uint32_t XS = B2 + 512;              // float4[128] = {x0,x1,x2,g} of the current tile
-constexpr uint32_t W2F = XS + 2048;             // float[128][64]: fp32 W2 for the exact recompute at the ReLU kink
-constexpr uint32_t BARS = W2F + 32768;
+constexpr uint32_t XS = B2 + 512;              // 2 buffers of float4[128] = {x0,x1,x2,g} of a tile
+constexpr uint32_t BARS = XS + 2 * 2048;
 constexpr uint32_t TMEMPTR = BARS + 64;
 constexpr uint32_t SMEM_USED = TMEMPTR + 16;
 constexpr uint32_t SMEM_BYTES = SMEM_USED + 1024;
 
-constexpr uint32_t D2_COL = 0, D5_COL = 128, D6_COL = 192;
-constexpr int kTmemCols = 256;
+constexpr uint32_t D2_COL = 0, D5_COL = 128, D6_COL = 192, D8_COL = 256;
+constexpr int kTmemCols = 512;
 
 enum { BAR_A1_FULL = 0, BAR_D2_FULL = 1, BAR_DZ_FULL = 2, BAR_D6_FULL = 3 };
 
@@ -147,7 +153,7 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
   for (int i = tid; i < 64; i += kThreads)
     reinterpret_cast<float4*>(sm + W1B1)[i] = make_float4(W1[i * 3], W1[i * 3 + 1], W1[i * 3 + 2], b1[i]);
   for (int i = tid; i < 128; i += kThreads) reinterpret_cast<float*>(sm + B2)[i] = b2[i];
-  for (int i = tid; i < 128 * 16; i += kThreads) reinterpret_cast<float4*>(sm + W2F)[i] = reinterpret_cast<const float4*>(W2)[i];
+  for (int i = tid; i < 2048 / 4; i += kThreads) reinterpret_cast<uint32_t*>(sm + ONES)[i] = 0x3F803F80u;   // bf16 1.0 pairs
   if (tid == 0) {
     ptx::mbar_init(&bars[BAR_A1_FULL], kComputeThreads);
     ptx::mbar_init(&bars[BAR_D2_FULL], 1);
@@ -176,14 +182,17 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
     const uint64_t mDZhi = desc_mn_sw128(sm_base + DZHI, kBlk), mDZlo = desc_mn_sw128(sm_base + DZLO, kBlk);
     const uint64_t mA1hi = desc_mn_sw128(sm_base + A1HI, kBlk), mA1lo = desc_mn_sw128(sm_base + A1LO, kBlk);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t idesc8 = ptx::make_idesc(1, 128, 16) | (1u << 15);               // A (DZ2) MN-major, B (ones) K-major
+    const uint64_t dOnes = ptx::smem_desc_sw128(sm_base + ONES);
     for (int64_t t = 0; t < ntile; ++t) {
       const uint32_t ph = (uint32_t)(t & 1);
+      const uint64_t abuf = (uint64_t)(ph * (kBlk >> 4));                            // A1 buffer of this tile
       ptx::mbar_wait(&bars[BAR_A1_FULL], ph);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
-          const uint64_t ab = (pass == 1) ? dA1lo : dA1hi;
+          const uint64_t ab = ((pass == 1) ? dA1lo : dA1hi) + abuf;
           const uint64_t bb = (pass == 2) ? dW2lo : dW2hi;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
@@ -199,10 +208,18 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
           const uint64_t ab = (pass == 1) ? mDZlo : mDZhi;
-          const uint64_t bb = (pass == 2) ? mA1lo : mA1hi;
+          const uint64_t bb = ((pass == 2) ? mA1lo : mA1hi) + abuf;
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
             ptx::umma_bf16(tmem_u + D5_COL, ab + (uint64_t)(ks * 128), bb + (uint64_t)(ks * 128), idesc5, (t | pass | ks) != 0);
+        }
+        // MMA8: D8[k2 x 16] += sum_r dz2[r,k2] * 1   (db2; every B element is 1.0, so one 32-byte slice serves all steps)
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          const uint64_t ab = (pass == 1) ? mDZlo : mDZhi;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            ptx::umma_bf16(tmem_u + D8_COL, ab + (uint64_t)(ks * 128), dOnes, idesc8, (t | pass | ks) != 0);
         }
         // MMA6: D6[r x k1] = sum_k2 dz2[r,k2] W2[k2,k1]   (K = 128 channels: 2 blocks x 4 steps of 32 B)
 #pragma unroll
@@ -232,7 +249,6 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
 #pragma unroll
     for (int j = 0; j < 64; ++j) acc3[j] = 0.f;
     float accb3 = 0.f;                                   // db3[cb0 + row]  (wh == 0)
-    float accb2[4] = {0.f, 0.f, 0.f, 0.f};               // db2[64*wh + 16*c + e16(lane)]
     float accw1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // [16-chunk cc][d = 0,1,2 | bias] of k1 = 32*wh + 16*cc + e16(lane)
     const float* w3row = W3 + (int64_t)(cb0 + row) * 128 + 64 * wh;
 
@@ -257,20 +273,17 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
         ng = po > 0.f ? pgo : 0.f;
       }
     };
-    load_raw(0);
-    gather(0);
-    load_raw(1);
-
-    for (int64_t t = 0; t < ntile; ++t) {
-      const uint32_t ph = (uint32_t)(t & 1);
-      // ---- S: instance table, conv1 -> A1
-      if (tid < 128) xs[tid] = make_float4(nx0, nx1, nx2, ng);
+    // ---- S(k): instance table + conv1 -> A1, both in the buffers of tile parity k & 1; then the prefetch chain moves on
+    auto stage_s = [&](int64_t k) {
+      const uint32_t buf = (uint32_t)(k & 1);
+      float4* xb = xs + 128 * buf;
+      if (tid < 128) xb[tid] = make_float4(nx0, nx1, nx2, ng);
       compute_barrier();
-      gather(t + 1);
-      load_raw(t + 2);
+      gather(k + 1);
+      load_raw(k + 2);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 xr = xs[pg + 32 * i];
+        const float4 xr = xb[pg + 32 * i];
         float f[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -280,15 +293,23 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
         }
         uint4 hi, lo;
         split8(f, hi, lo);
-        uint32_t off = ptx::sw128_offset(pg + 32 * i, cg);
+        uint32_t off = buf * kBlk + ptx::sw128_offset(pg + 32 * i, cg);
         st_chunk(sm_base, A1HI + off, hi);
         st_chunk(sm_base, A1LO + off, lo);
       }
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(&bars[BAR_A1_FULL]);
+    };
 
+    load_raw(0);
+    gather(0);
+    load_raw(1);
+    if (ntile > 0) stage_s(0);
+
+    for (int64_t t = 0; t < ntile; ++t) {
+      const uint32_t ph = (uint32_t)(t & 1);
       // ---- E2
-      const float4 me = xs[row];
+      const float4 me = xs[128 * ph + row];
       const float g = me.w;
       if (wh == 0) accb3 += g;
       const float tau = 3e-5f * (1.f + fabsf(me.x) + fabsf(me.y) + fabsf(me.z));
@@ -314,26 +335,30 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
         uint32_t near = 0;
 #pragma unroll
         for (int e = 0; e < 16; ++e) near |= (fabsf(z[e]) < tau) ? (1u << e) : 0u;
-        if (__any_sync(0xffffffffu, near != 0)) {      // one vote per chunk; ~10 % of the chunks go on
-          const uint32_t wnear = __reduce_or_sync(0xffffffffu, near);
+        // ~10 % of the chunks have one: the WARP evaluates it together (lane k takes conv1 channels k and k + 32 of the
+        // flagged instance, one shuffle reduction per element) instead of every lane running the 64-term sum
+        uint32_t flagged = __ballot_sync(0xffffffffu, near != 0);
+        while (flagged) {                                // warp-uniform
+          const int L = __ffs(flagged) - 1;
+          flagged &= flagged - 1;
+          uint32_t nb = __shfl_sync(0xffffffffu, near, L);
+          const float mx = __shfl_sync(0xffffffffu, me.x, L), my = __shfl_sync(0xffffffffu, me.y, L), mz = __shfl_sync(0xffffffffu, me.z, L);
+          const float4 wa = w1b1[lane], wb = w1b1[lane + 32];
+          float ha = fmaf(wa.x, mx, fmaf(wa.y, my, fmaf(wa.z, mz, wa.w)));
+          float hb = fmaf(wb.x, mx, fmaf(wb.y, my, fmaf(wb.z, mz, wb.w)));
+          ha = ha > 0.f ? ha : 0.f;
+          hb = hb > 0.f ? hb : 0.f;
+          while (nb) {
+            const int e = __ffs(nb) - 1;
+            nb &= nb - 1;
+            const int k2 = 64 * wh + 16 * c + e;
+            float part = fmaf(ha, __ldg(W2 + k2 * 64 + lane), hb * __ldg(W2 + k2 * 64 + lane + 32));
+            part = warp_sum(part);
+            const float zz = part + b2s[k2];
+            if (lane == L) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {                // unrolled: z / bb stay in registers
-            if (wnear & (1u << e)) {                    // warp-uniform
-              const int k2 = 64 * wh + 16 * c + e;
-              const float4* wrow = reinterpret_cast<const float4*>(sm + W2F) + k2 * 16;
-              float zz = bb[e];
-#pragma unroll 4
-              for (int k4 = 0; k4 < 16; ++k4) {
-                const float4 wv = wrow[k4];
-                const float wk[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const float4 w1 = w1b1[4 * k4 + u];
-                  const float hv = fmaf(w1.x, me.x, fmaf(w1.y, me.y, fmaf(w1.z, me.z, w1.w)));
-                  zz = fmaf(hv > 0.f ? hv : 0.f, wk[u], zz);
-                }
-              }
-              if (near & (1u << e)) z[e] = zz;
+              for (int ee = 0; ee < 16; ++ee)
+                if (ee == e) z[ee] = zz;
             }
           }
         }
@@ -355,11 +380,14 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
         st_chunk(sm_base, DZHI + o1, h1);
         st_chunk(sm_base, DZLO + o0, l0);
         st_chunk(sm_base, DZLO + o1, l1);
-        accb2[c] += transpose_reduce16(dz, lane);
       }
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bars[BAR_DZ_FULL]);
+
+      // ---- S(t+1) while the tensor pipe works through MMA5/8/6(t): the other A1 / instance-table buffers were last
+      //      read by the MMAs and threads of tile t-1, all complete once D6_FULL(t-1) was observed
+      if (t + 1 < ntile) stage_s(t + 1);
 
       // ---- E1: dz1 = (h1 > 0) dh1;  dW1 / db1 partial sums over the 32 instances of this warp
       ptx::mbar_wait(&bars[BAR_D6_FULL], ph);
@@ -390,9 +418,7 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
           accw1[4 * cc + 3] += transpose_reduce16(dz1, lane);
         }
       }
-      // No barrier needed here: the next tile's S only starts once D6_FULL(t) has fired, which needs DZ_FULL(t)
-      // from every compute thread, i.e. everyone is past its reads of xs / A1; tcgen05.ld above is ordered
-      // before the next MMA6 by the tcgen05.fence in the next E2.
+      // tcgen05.ld above is ordered before the next MMA6 by the tcgen05.fence in the next E2.
     }
 
     // ---------------- flush
@@ -402,8 +428,6 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
       if (wh == 0) atomicAdd(&gb3[cb0 + row], accb3);
       if ((lane & 1) == 0) {      // transpose_reduce16: lanes 2j, 2j+1 hold the same total
 #pragma unroll
-        for (int c = 0; c < 4; ++c) atomicAdd(&gb2[64 * wh + 16 * c + e16(lane)], accb2[c]);
-#pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           const int k1 = 32 * wh + 16 * cc + e16(lane);
           atomicAdd(&gW1[k1 * 3 + 0], accw1[4 * cc + 0]);
@@ -412,8 +436,14 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
           atomicAdd(&gb1[k1], accw1[4 * cc + 3]);
         }
       }
-      // dW2 from the TMEM accumulator: lane = k2, columns = k1
+      // dW2 and db2 from the TMEM accumulators: lane = k2, columns = k1 (D5) / 16 identical column sums (D8)
       ptx::tc_fence_after();
+      if (wh == 0) {
+        uint32_t b[16];
+        ptx::tmem_ld16(tmem + lane_addr + D8_COL, b);
+        ptx::tmem_ld_wait();
+        atomicAdd(&gb2[row], __uint_as_float(b[0]));
+      }
       uint32_t v[32];
       ptx::tmem_ld32(tmem + lane_addr + D5_COL + 32 * wh, v);
       ptx::tmem_ld_wait();
