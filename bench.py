@@ -292,8 +292,44 @@ def run_ours(args, out=sys.stdout):
     cap = CapturedInference(model, data, k=6)
     assert cap.launches_per_replay == launches_per_step, (cap.launches_per_replay, launches_per_step)
     tot_ms, _, _ = timed(cap.replay, args.steps, args.warmup)
-    ms_step = tot_ms / args.steps
+    graph_ms_step = tot_ms / args.steps
+    # ---- (1c) the headline `value`: EXACTLY `steps` device-resident steps as a serving loop runs them -- consecutive
+    #      steps replayed on two alternating streams (serving.PipelinedServing.submit_resident), rotating through input
+    #      slots whose buffers together exceed L2 (no flush inside the timed region: the slots ARE the "inputs larger
+    #      than L2"), one event pair around the whole loop.  The short latency-bound tail of step k then runs beside
+    #      the point encoder of step k+1 instead of in front of an idle chip.
+    from sgaligner_b200.serving import PipelinedServing
+    from sgaligner_b200.data import h2d_bytes as _h2d_bytes
+    KEYS0 = needed_keys(MODULES)
+    res_slots = int(max(3, min(8, -(-(160 << 20) // max(1, _h2d_bytes(host, KEYS0))))))
+    rpipe = PipelinedServing(model, data, k=6, n_slots=res_slots, compute_streams=2)
+    for s_ in range(res_slots):
+        rpipe.load_resident(s_, data)
+
+    def resident_loop(steps):
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        rpipe.fork_resident()
+        for k_ in range(steps):
+            rpipe.submit_resident(k_ % res_slots)
+        rpipe.sync_resident()
+        t1.record()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1)
+
+    resident_loop(max(args.warmup, res_slots))
+    barrier()
+    t = torch.tensor([resident_loop(args.steps)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    barrier()
+    ms_step = float(t.item()) / args.steps
     value = world * PAIRS_PER_GPU / (ms_step * 1e-3)
+    r0 = rpipe.slots[(args.steps - 1) % res_slots].out
+    chk_topk, chk_pos = r0['topk_idx'].clone(), r0['anchor_pos'].clone()
+    del rpipe
+    torch.cuda.empty_cache()
     launches = launches_per_step * args.steps
 
     # ---- (2) end to end through the public API with HOST buffers (pinned): H2D + step + D2H
@@ -357,6 +393,7 @@ def run_ours(args, out=sys.stdout):
     g = cap.replay()
     torch.cuda.synchronize()
     assert torch.equal(g['topk_idx'], tk) and torch.equal(g['anchor_pos'], pos), 'graph replay differs from the eager step'
+    assert torch.equal(chk_topk, tk) and torch.equal(chk_pos, pos), 'two-stream resident loop differs from the eager step'
     del cap
 
     # ---- (2b) steady-state host-to-host loop: step k+1's H2D copy under step k's compute (serving.PipelinedServing).
@@ -580,11 +617,12 @@ def run_ours(args, out=sys.stdout):
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32 (PointNet convs: bf16x3 split-operand tcgen05, fp32 accumulate)', 'data': 'synthetic',
             'config': shared_config(),
-            'arm': {'l2': 'flushed between timed steps (512 MiB memset, untimed); the pipelined e2e loop rotates through input slots larger than L2 instead',
-                    'timing': 'per-step CUDA events, max over ranks',
-                    'launch': 'one CUDA-graph replay per step (serving.CapturedInference: graph branch on a forked stream, 16 SMs left to it); eager_ms_per_step = same kernels issued from Python on one stream',
+            'arm': {'l2': 'value and e2e loops rotate through input slots that together exceed L2 (no flush inside a timed loop); the single-stream / eager / config legs flush L2 between timed steps (512 MiB memset, untimed)',
+                    'timing': 'value and e2e: one CUDA-event pair around the K-step loop (barrier + synchronize on both sides), max over ranks; the other legs: per-step CUDA events',
+                    'launch': 'one CUDA-graph replay per step (serving.CapturedInference: graph branch on a forked stream, 16 SMs left to it), consecutive steps on two alternating streams over %d rotating input slots (serving.PipelinedServing.submit_resident), one event pair around exactly `steps` steps; single_stream_graph_ms_per_step = the same graph replayed on one stream with an L2 flush between steps (step latency); eager_ms_per_step = same kernels issued from Python on one stream' % res_slots,
                     'numa': numa_info},
             'eager_ms_per_step': eager_ms_step,
+            'single_stream_graph_ms_per_step': graph_ms_step,
             'roofline': {'kernel': 'pointnet_fwd_tc_kernel', 'bound': 'tensor', 'achieved': achieved, 'peak': tf_peak, 'unit': 'TFLOP/s',
                          'frac': (achieved / tf_peak) if achieved else None, 'traffic': PROFILED_TRAFFIC_BYTES, 'peak_source': peak_src,
                          'kernel_ms': k_ms, 'algorithmic_flops_per_launch': flops,

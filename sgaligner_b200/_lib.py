@@ -116,7 +116,7 @@ def get_lib():
     if _LIB is not None:
         return _LIB
     from . import build
-    path = build.LIB
+    path = os.environ.get('SGA_LIB_PATH') or build.LIB      # SGA_LIB_PATH: A/B runs against another build of the library
     if not os.path.exists(path):
         try:
             build.build()

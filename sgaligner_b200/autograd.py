@@ -12,7 +12,7 @@ class PointNetFeat(torch.autograd.Function):
     the saved per-channel argmax of the max-pool."""
 
     @staticmethod
-    def forward(ctx, pts, W1, b1, W2, b2, W3, b3, mode, chunks=None, want_stats=False, grad_mode=True):
+    def forward(ctx, pts, W1, b1, W2, b2, W3, b3, mode, chunks=None, want_stats=False, grad_mode=True, cta_cap=0):
         """Returns (pooled feature, moments); moments (f64, non-differentiable) is None unless want_stats.
         ``grad_mode``: torch.is_grad_enabled() at the call site -- inside forward() autograd is always off and
         needs_input_grad mirrors requires_grad of the parameters even under torch.no_grad(), so without it the
@@ -30,6 +30,7 @@ class PointNetFeat(torch.autograd.Function):
             ctx.save_for_backward(pts, W1, b1, W2, b2, W3, b3, out, arg)
             ctx.mode = mode if W3.shape[0] % 128 == 0 else ops.POINTNET_SIMT
             ctx.params = (W1, b1, W2, b2, W3, b3)
+            ctx.cta_cap = cta_cap       # SMs left to a concurrent branch in the forward are left to its backward too
         if mom is not None:
             ctx.mark_non_differentiable(mom)
         return out, mom
@@ -38,9 +39,15 @@ class PointNetFeat(torch.autograd.Function):
     def backward(ctx, gout, _gmom=None):
         pts, W1, b1, W2, b2, W3, b3, out, arg = ctx.saved_tensors
         into = [ops.grad_target(p) if need else None for p, need in zip(ctx.params, ctx.needs_input_grad[1:7])]
-        g = ops.pointnet_backward(pts, W1, b1, W2, b2, W3, b3, out, arg, gout.contiguous(), mode=ctx.mode, into=into)
+        if ctx.cta_cap:
+            ops.pointnet_set_max_ctas(ctx.cta_cap)
+        try:
+            g = ops.pointnet_backward(pts, W1, b1, W2, b2, W3, b3, out, arg, gout.contiguous(), mode=ctx.mode, into=into)
+        finally:
+            if ctx.cta_cap:
+                ops.pointnet_set_max_ctas(0)
         g = [None if t is None else t.view_as(p) for t, p in zip(g, ctx.params)]     # None: accumulated into p.grad
-        return (None, *g, None, None, None, None)
+        return (None, *g, None, None, None, None, None)
 
 
 class GATLayer(torch.autograd.Function):

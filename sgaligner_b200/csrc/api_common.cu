@@ -27,6 +27,16 @@ int sm_count() {
   return cached;
 }
 
+// Upper bound on the CTAs (= SMs) the persistent one-CTA-per-SM PointNet kernels (forward, Gram statistics, backward)
+// occupy; 0 = all.  A step that runs the graph branch concurrently on a second stream leaves it a few SMs this way
+// (serving.CapturedInference, the training forward / backward of MultiModalEncoder).
+static int g_persistent_cta_cap = 0;
+void set_persistent_cta_cap(int n) { g_persistent_cta_cap = n > 0 ? n : 0; }
+int persistent_ctas() {
+  const int sms = sm_count();
+  return (g_persistent_cta_cap > 0 && g_persistent_cta_cap < sms) ? g_persistent_cta_cap : sms;
+}
+
 }  // namespace sga
 
 extern "C" {

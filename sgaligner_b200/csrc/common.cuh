@@ -32,6 +32,8 @@ void set_error(const char* fmt, ...);
 #define SGA_LAUNCH_CHECK() SGA_CUDA(cudaGetLastError())
 
 int sm_count();
+int persistent_ctas();              // sm_count() capped by sga_pointnet_set_max_ctas
+void set_persistent_cta_cap(int n);
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -51,7 +51,7 @@ constexpr uint32_t TMEMPTR = BARS + 64;
 constexpr uint32_t SMEM_USED = TMEMPTR + 16;
 constexpr uint32_t SMEM_BYTES = SMEM_USED + 1024;
 
-constexpr uint32_t D2_COL = 0, D5_COL = 128, D6_COL = 192, D8_COL = 256;
+constexpr uint32_t D2_COL = 0, D5_COL = 128, D6_COL = 192, D8_COL = 256, W3_COL = 288;   // W3_COL: 128 columns, fp32 W3[cb0 + lane][:]
 constexpr int kTmemCols = 512;
 
 enum { BAR_A1_FULL = 0, BAR_D2_FULL = 1, BAR_DZ_FULL = 2, BAR_D6_FULL = 3 };
@@ -74,6 +74,13 @@ __device__ __forceinline__ void split8(const float (&f)[8], uint4& hi, uint4& lo
 }
 __device__ __forceinline__ void st_chunk(uint32_t smem_base, uint32_t off, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_base + off), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// 16-byte shared-memory load on a 32-bit shared address (pointers derived from the re-aligned dynamic shared memory
+// base are generic to the compiler: LD.E instead of LDS, and a float4 read came out as 8 + 4 bytes with 4x the wavefronts)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -168,6 +175,27 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  // W3[cb0 + r][0..127] (fp32) -> tensor memory, lane r: dz2 = g W3 reads 64 of them per thread and tile; from global
+  // memory those loads missed the (shared-memory-squeezed) L1 every tile and the epilogue waited on L2
+  if (warp < 4) {
+    const int r = 32 * warp + lane;
+    const float4* src = reinterpret_cast<const float4*>(W3 + (int64_t)(cb0 + r) * 128);
+#pragma unroll 1
+    for (int grp = 0; grp < 8; ++grp) {
+      uint32_t w[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 a = src[grp * 4 + j];
+        w[4 * j] = __float_as_uint(a.x); w[4 * j + 1] = __float_as_uint(a.y); w[4 * j + 2] = __float_as_uint(a.z); w[4 * j + 3] = __float_as_uint(a.w);
+      }
+      ptx::tmem_st16(tmem + ((uint32_t)(32 * warp) << 16) + W3_COL + grp * 16, w);
+    }
+    ptx::tmem_st_wait();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+
   const int64_t ntile = (N > (int64_t)blockIdx.x) ? (N - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (warp == 8) {
@@ -250,7 +278,6 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
     for (int j = 0; j < 64; ++j) acc3[j] = 0.f;
     float accb3 = 0.f;                                   // db3[cb0 + row]  (wh == 0)
     float accw1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // [16-chunk cc][d = 0,1,2 | bias] of k1 = 32*wh + 16*cc + e16(lane)
-    const float* w3row = W3 + (int64_t)(cb0 + row) * 128 + 64 * wh;
 
     // instance prefetch (threads < 128: one instance each): raw (argmax, out, grad_out) two tiles ahead of
     // their use, the gathered point one tile ahead
@@ -283,11 +310,11 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
       load_raw(k + 2);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 xr = xb[pg + 32 * i];
+        const float4 xr = lds128(sm_base + XS + (128 * buf + pg + 32 * i) * 16);
         float f[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const float4 w = w1b1[8 * cg + e];     // broadcast LDS: registers are the scarce resource here (acc3)
+          const float4 w = lds128(sm_base + W1B1 + (8 * cg + e) * 16);     // broadcast LDS: registers are the scarce resource here (acc3)
           float v = fmaf(w.x, xr.x, fmaf(w.y, xr.y, fmaf(w.z, xr.z, w.w)));
           f[e] = v > 0.f ? v : 0.f;
         }
@@ -309,7 +336,7 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
     for (int64_t t = 0; t < ntile; ++t) {
       const uint32_t ph = (uint32_t)(t & 1);
       // ---- E2
-      const float4 me = xs[128 * ph + row];
+      const float4 me = lds128(sm_base + XS + (128 * ph + row) * 16);
       const float g = me.w;
       if (wh == 0) accb3 += g;
       const float tau = 3e-5f * (1.f + fabsf(me.x) + fabsf(me.y) + fabsf(me.z));
@@ -319,11 +346,10 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
       for (int c = 0; c < 4; ++c) {
         uint32_t v[16];
         ptx::tmem_ld16(tmem + lane_addr + D2_COL + 64 * wh + 16 * c, v);
-        const float4* wq = reinterpret_cast<const float4*>(w3row + 16 * c);
-        const float4 w0 = __ldg(wq), w1 = __ldg(wq + 1), w2 = __ldg(wq + 2), w3 = __ldg(wq + 3);
-        const float ww[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
-        const float4* bq = reinterpret_cast<const float4*>(b2s + 64 * wh + 16 * c);
-        const float4 q0 = bq[0], q1 = bq[1], q2 = bq[2], q3 = bq[3];
+        uint32_t wwu[16];                      // W3[c_r][64 wh + 16 c ..]: resident in tensor memory (lane = row), see setup
+        ptx::tmem_ld16(tmem + lane_addr + W3_COL + 64 * wh + 16 * c, wwu);
+        const uint32_t bq = sm_base + B2 + (64 * wh + 16 * c) * 4;
+        const float4 q0 = lds128(bq), q1 = lds128(bq + 16), q2 = lds128(bq + 32), q3 = lds128(bq + 48);
         const float bb[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
         ptx::tmem_ld_wait();
         float z[16];
@@ -343,7 +369,7 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
           flagged &= flagged - 1;
           uint32_t nb = __shfl_sync(0xffffffffu, near, L);
           const float mx = __shfl_sync(0xffffffffu, me.x, L), my = __shfl_sync(0xffffffffu, me.y, L), mz = __shfl_sync(0xffffffffu, me.z, L);
-          const float4 wa = w1b1[lane], wb = w1b1[lane + 32];
+          const float4 wa = lds128(sm_base + W1B1 + lane * 16), wb = lds128(sm_base + W1B1 + (lane + 32) * 16);
           float ha = fmaf(wa.x, mx, fmaf(wa.y, my, fmaf(wa.z, mz, wa.w)));
           float hb = fmaf(wb.x, mx, fmaf(wb.y, my, fmaf(wb.z, mz, wb.w)));
           ha = ha > 0.f ? ha : 0.f;
@@ -367,7 +393,7 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
         for (int e = 0; e < 16; ++e) {
           const bool on = z[e] > 0.f;
           acc3[16 * c + e] = fmaf(g, on ? z[e] : 0.f, acc3[16 * c + e]);
-          dz[e] = on ? g * ww[e] : 0.f;
+          dz[e] = on ? g * __uint_as_float(wwu[e]) : 0.f;
         }
         const float f0[8] = {dz[0], dz[1], dz[2], dz[3], dz[4], dz[5], dz[6], dz[7]};
         const float f1[8] = {dz[8], dz[9], dz[10], dz[11], dz[12], dz[13], dz[14], dz[15]};
@@ -401,7 +427,7 @@ pointnet_bwd_tc_kernel(const float* __restrict__ pts, int64_t N, int P,
           float dz1[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const float4 w = w1b1[32 * wh + 16 * cc + e];
+            const float4 w = lds128(sm_base + W1B1 + (32 * wh + 16 * cc + e) * 16);
             const float z1 = fmaf(w.x, me.x, fmaf(w.y, me.y, fmaf(w.z, me.z, w.w)));
             dz1[e] = z1 > 0.f ? __uint_as_float(v[16 * cc + e]) : 0.f;
           }
@@ -467,7 +493,7 @@ int pointnet_bwd_tc(const float* pts, int64_t N, int P, const float* W1, const f
     attr_done = true;
   }
   const int nby = C3 / 128;
-  int gx = sm_count() / nby;
+  int gx = persistent_ctas() / nby;
   if (gx < 1) gx = 1;
   if ((int64_t)gx > N) gx = (int)N;
   dim3 grid(gx, nby);

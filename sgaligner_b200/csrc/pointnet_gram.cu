@@ -384,7 +384,7 @@ int pointnet_gram_moments(const float* pts, int64_t N, int P, const float* W1, c
     SGA_CUDA(cudaFuncSetAttribute(pointnet_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     attr_done = true;
   }
-  int grid = sm_count();
+  int grid = persistent_ctas();
   if ((int64_t)grid > N) grid = (int)N;
   unsigned char* ws = (unsigned char*)scratch;
   float* partial = (float*)ws;

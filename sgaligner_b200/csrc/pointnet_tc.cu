@@ -774,10 +774,7 @@ int debug_tie_stats(unsigned long long* host_out2, int reset) {
 
 size_t pointnet_tc_raw_doubles(int C3) { return (size_t)RAW_S3 + 2 * (size_t)C3; }
 
-// Upper bound on the CTAs (= SMs) the persistent forward kernel occupies; 0 = all.  A serving step that runs
-// the graph branch concurrently on a second stream leaves it a few SMs this way (serving.CapturedInference).
-static int g_max_ctas = 0;
-void pointnet_tc_set_max_ctas(int n) { g_max_ctas = n > 0 ? n : 0; }
+void pointnet_tc_set_max_ctas(int n) { set_persistent_cta_cap(n); }
 
 // raw != nullptr: also accumulate the BatchNorm batch statistics (raw: zeroed scratch of
 // pointnet_tc_raw_doubles(C3) doubles) and add them into moments[2*(64+128+C3)].
@@ -795,9 +792,7 @@ int pointnet_fwd_tc(const float* pts, int64_t N, int P, const float* W1, const f
     attr_done = true;
   }
   const int nby = (C3 + 255) / 256;
-  int sms = sm_count();
-  if (g_max_ctas > 0 && g_max_ctas < sms) sms = g_max_ctas;
-  int gx = sms / nby;
+  int gx = persistent_ctas() / nby;
   if (gx < 1) gx = 1;
   if ((int64_t)gx > N) gx = (int)N;
   dim3 grid(gx, nby);

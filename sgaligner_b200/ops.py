@@ -7,6 +7,7 @@ stream and never synchronise.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -73,6 +74,25 @@ def pointnet_set_max_ctas(n: int):
     check(get_lib().sga_pointnet_set_max_ctas(int(n)), 'sga_pointnet_set_max_ctas')
 
 
+_SIDE_STREAMS = []      # side streams that carry work of the current training step (see sg_aligner.MultiModalEncoder.forward)
+
+
+def note_side_stream(stream):
+    if stream is not None and all(stream is not s_ for s_ in _SIDE_STREAMS):
+        _SIDE_STREAMS.append(stream)
+
+
+def join_side_streams():
+    """The current stream waits for every side stream noted since the last join.  Autograd orders its own tensors
+    across streams, but a backward kernel that accumulates straight into ``p.grad`` (direct gradient accumulation)
+    is invisible to it: whoever consumes those buffers (``FlatAdam.allreduce_grads`` / ``step``) joins first."""
+    if _SIDE_STREAMS:
+        cur = torch.cuda.current_stream()
+        for s_ in _SIDE_STREAMS:
+            cur.wait_stream(s_)
+        del _SIDE_STREAMS[:]
+
+
 def sm_count() -> int:
     sm, maj, mnr = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
     check(get_lib().sga_device_info(ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mnr)), 'sga_device_info')
@@ -90,8 +110,9 @@ def _pointnet_args(pts, W1, b1, W2, b2, W3, b3, mode):
 
 
 def pointnet_forward(pts, W1, b1, W2, b2, W3, b3, want_argmax: bool, mode: int = POINTNET_TC, chunks=None, out=None):
-    """chunks: optional [(obj_start, obj_end, cuda_event)] -- the object ranges of ``pts`` become valid
-    when their event fires (streamed H2D copy, ``data.to_cuda_streamed``); one launch per range.
+    """chunks: optional [(obj_start, obj_end, cuda_event or None)] -- one launch per object range; a range with an
+    event becomes valid when it fires (streamed H2D copy, ``data.to_cuda_streamed``), ranges without one only cut the
+    encoder into shorter launches (finer-grained SM sharing between concurrent serving steps).
     ``out``: optional preallocated [N, C3] f32 result buffer (a static buffer a captured graph reads)."""
     pts, w = _pointnet_args(pts, W1, b1, W2, b2, W3, b3, mode)
     N, P, _ = pts.shape
@@ -105,7 +126,8 @@ def pointnet_forward(pts, W1, b1, W2, b2, W3, b3, want_argmax: bool, mode: int =
     if chunks:
         cur = torch.cuda.current_stream()
         for (s, e, ev) in chunks:
-            cur.wait_event(ev)
+            if ev is not None:
+                cur.wait_event(ev)
             check(lib.sga_pointnet_fwd(ctypes.c_void_p(pts.data_ptr() + s * P * 12), e - s, P, *[_ptr(t) for t in w], C3,
                                        ctypes.c_void_p(out.data_ptr() + s * C3 * 4),
                                        ctypes.c_void_p(0 if arg is None else arg.data_ptr() + s * C3 * 4), mode, _stream()),

@@ -24,10 +24,13 @@ _COUNT_KEYS = ('graph_per_obj_count', 'graph_per_edge_count', 'e1i', 'e2i')
 
 
 class CapturedInference:
-    def __init__(self, model, example: Dict, k: int = 6, want_sim: bool = True, graph_branch_sms: int = 16):
+    def __init__(self, model, example: Dict, k: int = 6, want_sim: bool = True, graph_branch_sms: int = 16, point_chunks: int = 1):
         """``graph_branch_sms`` > 0: the point encoder (one persistent CTA per SM) leaves that many SMs free and the
         graph branch (CSR build + two GAT layers) is captured on a forked stream, so the two branches of the
-        encoder run concurrently inside the graph; 0: one stream, everything back to back."""
+        encoder run concurrently inside the graph; 0: one stream, everything back to back.
+        ``point_chunks`` > 1: the point encoder is cut into that many launches over object ranges (each a static
+        partition over its CTAs): when several steps are in flight on different streams (``PipelinedServing``) the
+        shorter launches let the hardware scheduler pack the steps' CTAs tightly instead of in whole-step blocks."""
         pts = example['tot_obj_pts']
         if not (torch.is_tensor(pts) and pts.is_cuda):
             raise RuntimeError('CapturedInference needs a device-resident example batch (no CPU fallback)')
@@ -42,6 +45,15 @@ class CapturedInference:
             per = -(-n_obj // max(1, sms - graph_branch_sms))
             self.pointnet_ctas = min(sms - 1, -(-n_obj // per))
             self.side = torch.cuda.Stream(device=self.dev)
+        self.point_ranges = None
+        if point_chunks > 1 and 'point' in self.modules:
+            n_obj = int(pts.shape[0])
+            per = -(-n_obj // point_chunks)
+            self.point_ranges = [(lo, min(n_obj, lo + per), None) for lo in range(0, n_obj, per)]
+            if self.pointnet_ctas:            # the balanced CTA count is per launch now
+                sms = ops.sm_count()
+                per_cta = -(-per // max(1, sms - graph_branch_sms))
+                self.pointnet_ctas = min(sms - 1, -(-per // per_cta))
         self.static = {}
         for key, v in example.items():
             if key.startswith('_sga'):
@@ -77,6 +89,8 @@ class CapturedInference:
             d = dict(self.static)
             if self.graph_layout is not None:
                 d['_sga_graph_layout'] = self.graph_layout
+            if self.point_ranges is not None:
+                d['_sga_point_ranges'] = self.point_ranges
             if self.side is not None:
                 d['_sga_side_stream'] = self.side
                 ops.pointnet_set_max_ctas(self.pointnet_ctas)
@@ -363,12 +377,19 @@ class PipelinedServing:
     replaces: ``inference_align_reg.py:98-145`` (synchronous per-batch ``to_cuda`` + model call + per-pair matching).
     """
 
-    def __init__(self, model, example: Dict, k: int = 6, n_slots: int = 2):
+    def __init__(self, model, example: Dict, k: int = 6, n_slots: int = 2, compute_streams: int = 2, **capture_kw):
+        """``compute_streams`` > 1: consecutive steps are replayed on alternating streams, so the short tail of step k
+        (projection, matching head, anchor positions: latency-bound launches that leave most SMs idle) runs on the SMs
+        the point encoder of step k+1 does not occupy, and that encoder's CTAs start as soon as the previous one's
+        retire -- steady-state throughput approaches the SM time of the point encoder instead of the latency of a step."""
         from .data import needed_keys
-        assert n_slots >= 2
+        assert n_slots >= 2 and compute_streams >= 1
         self.dev = example['tot_obj_pts'].device
-        self.slots = [CapturedInference(model, example, k=k) for _ in range(n_slots)]
+        self.slots = [CapturedInference(model, example, k=k, **capture_kw) for _ in range(n_slots)]
         self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.cstreams = [torch.cuda.Stream(device=self.dev) for _ in range(compute_streams)]
+        self.n_submitted = 0
+        self.d2h_stream = torch.cuda.Stream(device=self.dev)      # results leave on their own stream: the next graph replay does not queue behind them
         c0 = self.slots[0]
         keys = [k_ for k_ in needed_keys(c0.modules) if k_ in c0.static and torch.is_tensor(c0.static[k_])]
         self.keys = keys
@@ -380,6 +401,7 @@ class PipelinedServing:
             if c.out['anchor_pos'] is not None:
                 c.p_out['anchor_pos'] = torch.empty(c.out['anchor_pos'].shape, dtype=torch.int32).pin_memory()
             c.ev_in = torch.cuda.Event()
+            c.ev_graph = torch.cuda.Event()
             c.ev_done = torch.cuda.Event()
             c.in_flight = False
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in c0.p_in.values()) + 8 * c0.n_anchor
@@ -412,12 +434,22 @@ class PipelinedServing:
                 c.e1.copy_(c.p_e1, non_blocking=True)
                 c.e2.copy_(c.p_e2, non_blocking=True)
             c.ev_in.record(cs)
-        cur.wait_event(c.ev_in)
-        c.graph.replay()
-        c.p_out['topk_idx'].copy_(c.out['topk_idx'], non_blocking=True)
-        if 'anchor_pos' in c.p_out:
-            c.p_out['anchor_pos'].copy_(c.out['anchor_pos'], non_blocking=True)
-        c.ev_done.record(cur)
+        st = self.cstreams[self.n_submitted % len(self.cstreams)]
+        self.n_submitted += 1
+        st.wait_stream(cur)                 # whatever the caller enqueued before this submit
+        st.wait_event(c.ev_in)
+        if c.in_flight:
+            st.wait_event(c.ev_done)        # the slot's previous results have left its output buffers
+        with torch.cuda.stream(st):
+            c.graph.replay()
+            c.ev_graph.record(st)
+        ds = self.d2h_stream
+        ds.wait_event(c.ev_graph)
+        with torch.cuda.stream(ds):
+            c.p_out['topk_idx'].copy_(c.out['topk_idx'], non_blocking=True)
+            if 'anchor_pos' in c.p_out:
+                c.p_out['anchor_pos'].copy_(c.out['anchor_pos'], non_blocking=True)
+            c.ev_done.record(ds)
         c.in_flight = True
 
     def wait(self, slot: int) -> Dict:
@@ -425,6 +457,35 @@ class PipelinedServing:
         if c.in_flight:
             c.ev_done.synchronize()
         return c.p_out
+
+    # ---- device-resident variant (inputs already in the slots' static buffers, results stay on the device)
+    def load_resident(self, slot: int, device_batch: Dict):
+        self.slots[slot].load(device_batch)
+
+    def submit_resident(self, slot: int):
+        """Replay slot ``slot`` on the next compute stream; no host traffic.  ``sync_resident`` joins the streams."""
+        c = self.slots[slot]
+        st = self.cstreams[self.n_submitted % len(self.cstreams)]
+        self.n_submitted += 1
+        if getattr(c, 'resident_busy', False):
+            st.wait_event(c.ev_graph)       # a slot never overlaps with itself (static output buffers)
+        with torch.cuda.stream(st):
+            c.graph.replay()
+            c.ev_graph.record(st)
+        c.resident_busy = True
+        return c.out
+
+    def fork_resident(self, stream=None):
+        """Make every compute stream wait for the work already enqueued on ``stream`` (default: the current one)."""
+        cur = stream or torch.cuda.current_stream(self.dev)
+        for st in self.cstreams:
+            st.wait_stream(cur)
+
+    def sync_resident(self, stream=None):
+        """Make ``stream`` (default: the current one) wait for every compute stream."""
+        cur = stream or torch.cuda.current_stream(self.dev)
+        for st in self.cstreams:
+            cur.wait_stream(st)
 
 
 class LayoutCache:

@@ -91,9 +91,10 @@ class PointNetfeat(nn.Module):
                 nn.init.xavier_normal_(conv.weight.data, gain=1)
                 nn.init.constant_(conv.bias.data, 0.0)
 
-    def forward(self, pts_npc: torch.Tensor, chunks=None) -> torch.Tensor:
+    def forward(self, pts_npc: torch.Tensor, chunks=None, cta_cap: int = 0) -> torch.Tensor:
         """``pts_npc``: [N, P, 3] (the collated layout; the reference permutes to [N,3,P] first).
-        ``chunks``: readiness events of a streamed host-to-device copy (``data.to_cuda_streamed``)."""
+        ``chunks``: readiness events of a streamed host-to-device copy (``data.to_cuda_streamed``).
+        ``cta_cap``: SMs this encoder's backward may occupy (0 = all); the caller caps the forward itself."""
         want_stats = self.use_batch_norm and self.training and self.track_bn_stats
         gram = want_stats and self.kernel_mode == ops.POINTNET_TC and self.bn_stats_mode == 'gram' and self.conv3.weight.shape[1] == 128
         fused = want_stats and self.kernel_mode == ops.POINTNET_TC and not gram
@@ -115,7 +116,7 @@ class PointNetfeat(nn.Module):
                                           self.conv3.weight, self.conv3.bias)
             self._update_bn_running_stats(mom, float(pts_npc.shape[0] * pts_npc.shape[1]))
         out, mom = ag.PointNetFeat.apply(pts_npc, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
-                                         self.conv3.weight, self.conv3.bias, self.kernel_mode, chunks, fused, torch.is_grad_enabled())
+                                         self.conv3.weight, self.conv3.bias, self.kernel_mode, chunks, fused, torch.is_grad_enabled(), cta_cap)
         if fused:                           # statistics came out of the forward launch itself
             self._update_bn_running_stats(mom, float(pts_npc.shape[0] * pts_npc.shape[1]))
         return out
@@ -188,6 +189,9 @@ class MultiGAT(nn.Module):
         return x
 
 
+_TRAIN_SIDE = {}      # device -> side stream of the training step's graph branch (not a module attribute: modules get deep-copied / pickled)
+
+
 class MultiModalEncoder(nn.Module):
     """``sg_aligner.py:37-137``."""
 
@@ -220,6 +224,7 @@ class MultiModalEncoder(nn.Module):
         self.structure_encoder = MultiGAT(n_units=self.hidden_units, n_heads=self.heads, dropout=self.dropout)
         self.structure_embedding = nn.Linear(256, self.emb_dim)
         self.fusion = MultiModalFusion(modal_num=self.inner_view_num, with_weight=1)
+        self.train_overlap = os.environ.get('SGA_TRAIN_OVERLAP', '1') != '0'
 
     def forward(self, data_dict):
         pts = data_dict['tot_obj_pts']
@@ -237,10 +242,24 @@ class MultiModalEncoder(nn.Module):
         # fork has to precede the point-encoder launch, or the side stream would wait for it
         side = data_dict.get('_sga_side_stream') if ('point' in self.modules and 'gat' in self.modules and ready is None) else None
         cur = torch.cuda.current_stream()
+        # Training: the same fork for the whole step.  The graph branch runs on a side stream, and because autograd replays
+        # every node on the stream of its forward, so does its backward -- next to the point encoder's backward, whose
+        # persistent kernel leaves it 16 SMs.
+        cta_cap = 0
+        if (side is None and self.train_overlap and self.training and torch.is_grad_enabled() and ready is None
+                and 'point' in self.modules and 'gat' in self.modules and not torch.cuda.is_current_stream_capturing()):
+            side = _TRAIN_SIDE.get(pts.device)
+            if side is None:
+                side = _TRAIN_SIDE[pts.device] = torch.cuda.Stream(device=pts.device)
+            cta_cap = max(1, ops.sm_count() - 16)
+            ops.note_side_stream(side)
         if side is not None:
             side.wait_stream(cur)
         if 'point' in self.modules and ready is None:
-            point_x = self.object_encoder(pts, None)
+            # the cap is handed to the BACKWARD only: in the forward the point encoder is 10 % faster on all SMs than on
+            # 132, which is more than hiding the 0.1 ms graph branch gains; the 0.3 ms backward of the graph branch is
+            # worth the 16 SMs (measured: tools/train_stages.py)
+            point_x = self.object_encoder(pts, data_dict.get('_sga_point_ranges'), cta_cap)
         elif 'pct' in self.modules:
             if ready is not None:
                 for (_, _, ev) in ready['pts']:

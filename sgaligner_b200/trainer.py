@@ -81,6 +81,7 @@ class FlatAdam:
 
     def allreduce_grads(self, group=None):
         """The one collective of the data-parallel path: sum the flat gradient over all ranks."""
+        ops.join_side_streams()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=group)
             return dist.get_world_size(group)
@@ -94,6 +95,7 @@ class FlatAdam:
         receives gradients in some steps and none in others)."""
         g = self.param_groups[0]
         self.step_count += 1
+        ops.join_side_streams()
         ops.adam_step_segments(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self._seg_off, self._seg_active,
                                float(g['lr']), g['betas'][0], g['betas'][1], g['eps'], g['weight_decay'], self.step_count, grad_scale)
 

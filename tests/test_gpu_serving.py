@@ -118,6 +118,34 @@ def test_pipelined_serving_overlaps_slots_and_matches_eager(dev):
         assert torch.equal(got['topk_idx'], want[b][0]) and torch.equal(got['anchor_pos'], want[b][1])
 
 
+def test_resident_two_stream_loop_matches_eager(dev):
+    """Device-resident serving loop on two alternating streams: 4 slots with different batches, 11 back-to-back
+    replays without any synchronisation in between; every slot ends with the eager results of its batch."""
+    from sgaligner_b200 import synthetic, to_cuda
+    from sgaligner_b200.serving import PipelinedServing
+    from sgaligner_b200.sg_aligner import MultiModalEncoder
+    torch.manual_seed(0)
+    model = MultiModalEncoder(modules=['point', 'gat'], rel_dim=41, attr_dim=164).to(dev).eval()
+    ns, nr, na = [40, 12, 64, 30], [33, 8, 64, 25], [5, 6, 30, 12]
+    hosts = [synthetic.make_batch(ns, nr, na, n_points=512, edge_mode='kout', k_out=5, seed=60 + i) for i in range(4)]
+    devs = [to_cuda(dict(h), dev) for h in hosts]
+    want = []
+    for d in devs:
+        _, res, pos = _eager(model, d, 6)
+        want.append((res['topk_idx'].clone(), pos.clone()))
+    pipe = PipelinedServing(model, devs[0], k=6, n_slots=4, compute_streams=2)
+    for s in range(4):
+        pipe.load_resident(s, devs[s])
+    pipe.fork_resident()
+    for step in range(11):
+        pipe.submit_resident(step % 4)
+    pipe.sync_resident()
+    torch.cuda.synchronize()
+    for s in range(4):
+        out = pipe.slots[s].out
+        assert torch.equal(out['topk_idx'], want[s][0]) and torch.equal(out['anchor_pos'], want[s][1]), s
+
+
 def test_layout_cache_serves_ragged_batches(dev):
     """Ragged stream: batches of three different layouts interleaved; a layout is served eagerly at first, from its
     own captured graph from the second time on -- identical results throughout."""

@@ -1,6 +1,6 @@
 """Aggregate ncu stall samples per CUDA source line (joins the ncu SASS page with nvdisasm line info).
     python tools/ncu_lines.py REP.ncu-rep CUBIN 'kernel-substring' [top-n]
-The cubin comes from `cuobjdump -xelf all libsga_b200.so`."""
+The cubin comes from `cuobjdump -xelf all libsga_b200.so`.  NCU_FILTER='-k regex:name -c 1' selects the kernel in a multi-kernel report."""
 import collections, csv, io, re, subprocess, sys
 rep, cubin, pat = sys.argv[1], sys.argv[2], sys.argv[3]
 topn = int(sys.argv[4]) if len(sys.argv) > 4 else 40
@@ -25,7 +25,8 @@ for l in dis[start + 1:]:
         continue
     if re.match(r'/\*[0-9a-f]{4,}\*/', s):
         ins.append((cur, tuple(inl), s))
-out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout.splitlines()
+import os
+out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'] + os.environ.get('NCU_FILTER', '').split(), capture_output=True, text=True).stdout.splitlines()
 h = next(i for i, l in enumerate(out) if l.startswith('"Address"'))
 rows = list(csv.DictReader(io.StringIO('\n'.join(out[h:]))))
 print('sass instrs: nvdisasm', len(ins), 'ncu', len(rows))

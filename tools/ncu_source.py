@@ -3,7 +3,8 @@
 import csv, io, subprocess, sys
 rep = sys.argv[1]
 topn = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+import os
+out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'] + os.environ.get('NCU_FILTER', '').split(), capture_output=True, text=True).stdout
 lines = out.splitlines()
 # the first line is the kernel name record; then header
 start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
