@@ -309,17 +309,78 @@ int sga_pct_attn_stats(const float* k, int64_t N, int P, float* c2, void* stream
 int sga_pct_attn(const float* k, const float* v, const float* c2, int64_t N, int P, float* xs, void* stream);
 /* cat(x1..x4) -> Conv1d(512,1024,bias=False) (pct.py:285-289,306-308) with x4 = x3 + relu(a4 t4 + b4) formed on the fly.
  * WL [1024,512].  Per object and channel only max_p z and min_p z are kept (zmax/zmin [N,2,1024]: the two 64-point
- * column halves of the tiles separately) plus the statistics [2048] of z: BN + LeakyReLU + max commute with them. */
+ * column halves of the tiles separately) plus the statistics [2048] of z: BN + LeakyReLU + max commute with them.
+ * imax/imin [N,2,1024] (both or neither; training): the point index that holds each maximum / minimum. */
 int sga_pct_cat_linear(const float* x1, const float* x2, const float* x3, const float* t4, const float* a4,
                        const float* b4, int64_t N, int P, const float* WL, float* zmax, float* zmin,
-                       double* stats, void* stream);
-/* pooled [N,1024] = LeakyReLU_0.2(a * (a >= 0 ? max : min) + b) = max_p LeakyReLU(BN(z)) (pct.py:310) */
-int sga_pct_pool_act(const float* zmax, const float* zmin, const float* a, const float* b, int64_t N, int P,
-                     float* out, void* stream);
+                       double* stats, int32_t* imax, int32_t* imin, void* stream);
+/* pooled [N,1024] = LeakyReLU_0.2(a * (a >= 0 ? max : min) + b) = max_p LeakyReLU(BN(z)) (pct.py:310); with imax/imin
+ * also pstar [N,1024] (the arg-max point, torch.max's index) and zsel [N,1024] (the selected z); NULL to skip. */
+int sga_pct_pool_act(const float* zmax, const float* zmin, const int32_t* imax, const int32_t* imin, const float* a,
+                     const float* b, int64_t N, int P, float* out, int32_t* pstar, float* zsel, void* stream);
 /* head (pct.py:311-316): column statistics of x [N,C] over the objects; out = relu(a x + b) * (mask ? mask*scale : 1) */
 int sga_col_stats(const float* x, int64_t N, int C, double* stats, void* stream);
 int sga_bn_act_rows(const float* x, const float* a, const float* b, const float* mask, float scale, int64_t N, int C,
                     float* out, void* stream);
+
+/* ---- backward of the NaivePCT encoder (autograd of pct.py:275-317; host orchestration in sgaligner_b200/pct.py).
+ * Every BatchNorm is differentiated in closed form: with gy = upstream * activation' (and dropout mask),
+ * S1 = sum gy, S2 = sum gy y over the batch,  d y = a gy - e - f y  (train mode: the batch-statistics terms; eval: e = f = 0). */
+/* sums [2C] (f64, zeroed by the caller) += {sum gy, sum gy*y} per column of g, y [rows, C]; gy = g * (mask ? mask*scale : 1)
+ * * (a y + b > 0 ? 1 : slope).  C in {128, 256, 512, 1024}. */
+int sga_bn_bwd_stats(const float* g, const float* y, const float* a, const float* b, const float* mask, float scale,
+                     float slope, int64_t rows, int C, double* sums, void* stream);
+/* per channel from the sums: d gamma, d beta, and the (e, f, mean) of  dy = a gy - e - f (y - mean).  stats = forward batch statistics
+ * {sum y, sum y^2} over cnt elements (training) or NULL (eval: running statistics, lin_bias = the bias folded into BN). */
+int sga_bn_bwd_coef(const double* sums, const double* stats, double cnt, const float* lin_bias, const float* gamma,
+                    const float* running_mean, const float* running_var, int training, float eps, int C, float* e,
+                    float* f, float* mean, float* dgamma, float* dbeta, void* stream);
+/* out [rows, C] = a gy - e - f (y - mean)  (e, f, mean may all be NULL = 0) */
+int sga_bn_bwd_apply(const float* g, const float* y, const float* a, const float* b, const float* mask, float scale,
+                     float slope, const float* e, const float* f, const float* mean, int64_t rows, int C, float* out,
+                     void* stream);
+/* Per-object power-of-two scale of a gradient operand (the backward's tensor-core products split their operands into
+ * fp16 pairs; gradients are far below that range): scale [N,2] = {s, 1/s}, s = 2^floor(log2(target / (max|x_n| max|y_n|)))
+ * over the `per` elements of object n (y may be NULL). */
+int sga_pct_pow2_scale(const float* x, const float* y, int64_t N, int64_t per, float target, float* scale, void* stream);
+/* SA backward, attention part (pct.py:217-224): dv [N,P,128] = attention dxs;  dk halves, see csrc/pct_attn.cu.
+ * scale = sga_pct_pow2_scale(dxs, v, ...) */
+int sga_pct_attn_bwd_dv(const float* k, const float* dxs, const float* c2, const float* scale, int64_t N, int P, float* dv,
+                        void* stream);
+int sga_pct_attn_bwd_dk(const float* k, const float* fixed, const float* streamed, const float* c2, float* delta,
+                        const float* scale, int64_t N, int P, int by_col, float* dk_out, void* stream);
+/* dX = dY Wt^T on the tensor cores: src [N,P,128] (scaled per object by scale [N,2]), Wt [128,128] (pass W^T), out [N,P,128] */
+int sga_pct_pointwise_scaled(const float* src, const float* scale, int64_t N, int P, const float* Wt, float* out, void* stream);
+/* gradient of an SA layer's input: out = gx (+ gcat) + dxv + (dk1 + dk2) Wk;  dk1 <- dk1 + dk2.  [rows,128] / [rows,32] */
+int sga_pct_sa_input_grad(const float* gx, const float* gcat, const float* dxv, float* dk1, const float* dk2,
+                          const float* Wk, int64_t rows, float* out, void* stream);
+/* a1 [rows,128] = relu(a (W1 p) + b)  (Embedding.conv1 + bn1 + ReLU, pct.py:122, re-materialised for the weight gradient) */
+int sga_pct_embed_a1(const float* pts, const float* W1, const float* a, const float* b, int64_t rows, float* out, void* stream);
+/* sums5 [5*128] (f64, zeroed) += per channel {sum gy, sum gy z1, sum gy p_x, sum gy p_y, sum gy p_z}, gy = g * [a z1 + b > 0] */
+int sga_pct_embed1_bwd_stats(const float* g, const float* pts, const float* W1, const float* a, const float* b,
+                             int64_t rows, double* sums5, void* stream);
+/* dW1 [128,3] = a T - e m1 - f (W1 M2 - mean m1) from the sums above and the 9 point moments (cnt = number of points) */
+int sga_pct_embed1_wgrad(const double* sums5, const double* mom9, double cnt, const float* W1, const float* a, const float* e,
+                         const float* f, float* dW1, void* stream);
+/* backward through concat -> conv(512,1024) -> BN -> LeakyReLU -> max (pct.py:306-310).  Dense half: g_x[a] = -u[a] - (M (xcat - xbar))[a]
+ * (M [512,512] symmetric, u, xbar [512]; overwrites g1..g4 [N,P,128]); sparse half: coef [N,1024] = a_c gy routed to the arg-max
+ * point pstar [N,1024]:  g_x[n,pstar,:] += coef WL[c,:]  and  dWL[c,:] += coef xcat[n,pstar,:]. */
+int sga_pct_cat_dense_bwd(const float* x1, const float* x2, const float* x3, const float* x4, int64_t N, int P,
+                          const float* M, const float* scale /* [2] = sga_pct_pow2_scale(M) */, const float* u,
+                          const float* xbar, float* g1, float* g2, float* g3, float* g4, void* stream);
+int sga_pct_cat_sparse_bwd_x(const float* coef, const int32_t* pstar, const float* WL, int64_t N, int P, float* g1,
+                             float* g2, float* g3, float* g4, void* stream);
+int sga_pct_cat_sparse_bwd_w(const float* coef, const int32_t* pstar, const float* x1, const float* x2, const float* x3,
+                             const float* x4, int64_t N, int P, float* dWL, void* stream);
+/* out [rows,128] = x + relu(a t + b)  (x4, re-materialised for the backward) */
+int sga_pct_residual(const float* x, const float* t, const float* a, const float* b, int64_t rows, float* out, void* stream);
+/* dst [R,C] = alpha * dst + beta * rowscale[r] * src[r,c] + gamma * rowscale2[r] * colvec[c]  (small weight-gradient algebra) */
+int sga_axpby_rows(float* dst, float alpha, const float* src, float beta, const float* rowscale, float gamma,
+                   const float* rowscale2, const double* colvec, int64_t R, int C, void* stream);
+/* Grouped weight-gradient products on sga_gemm_tf32x3 (both operands MN-major, split-K, atomic accumulation):
+ * C_i [M_i,N_i] += A_i^T B_i with A_i [K,M_i] (row stride lda_i) and B_i [K,N_i]; C must hold the value to add to. */
+int sga_wgrad_group(const float* const* A, const int64_t* lda, const int* M, const float* const* B, const int64_t* ldb,
+                    const int* Nn, float* const* C, const int64_t* ldc, int n, int64_t K, void* stream);
 
 /* ==== 8(f)4: EVA baseline path (src/aligner/eva.py:9-96; MultiGCN, src/aligner/networks/gat.py:6-25, over
  * torch_geometric 2.2.0 GCNConv; NCALoss / OverallNCALoss, src/aligner/losses.py:154-205).  The dense products of this

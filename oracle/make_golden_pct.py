@@ -55,6 +55,36 @@ def main():
         blob['after/' + k] = v.numpy()
     blob['y_train'] = y_train.numpy()
     blob['train_seed'] = np.array(123)
+    # ---- parameter gradients of the UNMODIFIED reference module in train mode (same seed -> same dropout masks):
+    # loss = sum(y * R) for a fixed random R.  Tensors above 20k elements are stored as every 17th element + their norm.
+    m.load_state_dict(params0, strict=True)
+    m.train()
+    R = torch.randn(y_train.shape, generator=torch.Generator().manual_seed(29))
+    torch.manual_seed(123)
+    y_g = m(x)
+    assert torch.equal(y_g.detach(), y_train)
+    (y_g * R).sum().backward()
+    po = {k: v.clone().requires_grad_(v.is_floating_point() and 'running' not in k) for k, v in params0.items()}
+    for sa in ('sa1', 'sa2', 'sa3', 'sa4'):
+        po[sa + '.q_conv.weight'] = po[sa + '.k_conv.weight']
+    torch.manual_seed(123)
+    (pct_oracle.naive_pct(x, po, training=True) * R).sum().backward()
+    blob['grad_R'] = R.numpy()
+    worst = 0.0
+    gmax = max(float(prm.grad.abs().max()) for prm in m.parameters())
+    for name, prm in m.named_parameters():
+        g = prm.grad
+        key = name.replace('q_conv', 'k_conv')
+        go = po[key].grad
+        # trans_conv.bias / linear2.bias (a bias in front of a train-mode BatchNorm) and, on this input, linear.1.bias have
+        # mathematically zero gradients: both sides hold rounding noise there (3e-7 of the largest gradient in fp32) -> floor the denominator
+        worst = max(worst, float((go - g).abs().max() / g.abs().max().clamp_min(1e-3 * gmax)))
+        flat = g.reshape(-1)
+        blob['gnorm/' + key] = np.array(float(flat.double().norm()))
+        blob['grad/' + key] = (flat[::17] if flat.numel() > 20000 else flat).numpy()
+    blob['grad_max'] = np.array(gmax)
+    assert worst < 2e-3, worst           # fp32 autograd of two differently ordered evaluations
+    print('oracle-vs-reference gradient mismatch (fp32 both): %.2e' % worst)
     np.savez_compressed(os.path.join(GOLD, 'pct_ref.npz'), **blob)
     print('eval err %.2e  train err %.2e  out %s  params %d  GFLOP/object@512 %.3f' % (
         err, err_t, tuple(y_eval.shape), sum(p_.numel() for p_ in m.parameters()),

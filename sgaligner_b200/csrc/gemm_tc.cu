@@ -531,3 +531,33 @@ extern "C" int sga_gemm_tf32x3(const float* A, int64_t lda, int a_mn_major, cons
   P.ksplit = c_idx ? ksplit : 1;
   return sga::launch_gemm_tc(P, (cudaStream_t)stream);
 }
+
+// Grouped weight-gradient products (NaivePCT backward): C_i [M_i,N_i] += A_i^T B_i, A_i [K,M_i], B_i [K,N_i] row-major --
+// both operands MN-major, the contraction runs over all K rows (points of the batch), cut into slices that add their
+// partial products atomically.  All problems of the call share one persistent launch per 16.
+extern "C" int sga_wgrad_group(const float* const* A, const int64_t* lda, const int* M, const float* const* B, const int64_t* ldb,
+                               const int* Nn, float* const* C, const int64_t* ldc, int n, int64_t K, void* stream) {
+  if (n <= 0 || K <= 0) return SGA_OK;
+  SGA_REQUIRE(A && lda && M && B && ldb && Nn && C && ldc && K < (int64_t)1 << 31, "sga_wgrad_group: bad arguments");
+  SGA_REQUIRE(n <= 64, "sga_wgrad_group: at most 64 problems per call (%d)", n);
+  sga::GemmParams ps[64];
+  int tiles = 0;
+  for (int i = 0; i < n; ++i) tiles += ((M[i] + 127) / 128) * ((Nn[i] + 127) / 128);
+  const int chunks = (int)((K + 31) / 32);
+  int want = (3 * sga::sm_count() + tiles - 1) / tiles;
+  const int cap = chunks / 4;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  for (int i = 0; i < n; ++i) {
+    SGA_REQUIRE(A[i] && B[i] && C[i], "sga_wgrad_group: null operand %d", i);
+    sga::GemmParams& P = ps[i];
+    memset(&P, 0, sizeof(P));
+    P.A = {A[i], lda[i], nullptr, nullptr, 1};
+    P.B = {B[i], ldb[i], nullptr, nullptr, 1};
+    P.M = M[i]; P.N = Nn[i]; P.K = (int)K;
+    P.C = C[i]; P.ldc = ldc[i];
+    P.mode = 2;
+    P.ksplit = want;
+  }
+  return sga::launch_gemm_tc_group(ps, n, (cudaStream_t)stream);
+}

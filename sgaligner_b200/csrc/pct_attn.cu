@@ -181,10 +181,17 @@ constexpr uint32_t S_COL = 0, O_COL = 256, EHI_COL = 384, ELO_COL = 448;
 enum { BAR_K_FULL = 0, BAR_V_FULL = 1 /*,2*/, BAR_S_FULL = 3 /*,4*/, BAR_S_FREE = 5 /*,6*/, BAR_E_FULL = 7, BAR_PV_DONE = 8, BAR_O_FREE = 9, kNumBars = 10 };
 }  // namespace at
 
+// kDv = false: the forward above.  kDv = true: the FIRST backward product, same structure with the roles of the two
+// indices swapped --  dv[i, :] = sum_j attention[i, j] dxs[j, :]  (x_s[:, j] = sum_i x_v[:, i] attention[i, j], pct.py:224):
+// work item (object, ROW block i), loop over the column blocks j, E[i, j] normalised by ITS OWN row (lane) instead of by
+// the contracted index, `v` = dxs -- a gradient operand, multiplied by the object's power-of-two scale[n][0] before the
+// fp16 split, the result by scale[n][1] (pct_common.cuh).
+template <bool kDv>
 __global__ void __launch_bounds__(kThreads, 1)
 pct_attn_kernel(const float* __restrict__ k, const float* __restrict__ v, const float* __restrict__ c2, int64_t N, int P,
-                float* __restrict__ xs) {
+                float* __restrict__ xs, const float* __restrict__ scale) {
   using namespace at;
+  constexpr int F = 0;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sm_base = ptx::smem_u32(sm);
@@ -216,7 +223,7 @@ pct_attn_kernel(const float* __restrict__ k, const float* __restrict__ v, const 
   if (warp == 8) {
     // =============================== MMA issuer ===============================
     const uint32_t idesc_s = ptx::make_idesc(kFmt, 128, 128);
-    const uint32_t idesc_pv = ptx::make_idesc(kFmt, 128, 128) | (1u << 16);      // B (= V tile) read MN-major
+    const uint32_t idesc_pv = ptx::make_idesc(F, 128, 128) | (1u << 16);         // B (= V tile) read MN-major
     const uint64_t dK = ptx::smem_desc_sw128(sm_base + KIMG);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
     uint32_t u = 0, wi = 0;                          // running i-block counter, work-item counter
@@ -293,9 +300,14 @@ pct_attn_kernel(const float* __restrict__ k, const float* __restrict__ v, const 
 #pragma unroll
         for (int qq = 0; qq < 2; ++qq) {
           const int row = r0 + 16 * (bt * 2 + qq);
-          const float f[8] = {x[qq][0].x, x[qq][0].y, x[qq][0].z, x[qq][0].w, x[qq][1].x, x[qq][1].y, x[qq][1].z, x[qq][1].w};
+          float f[8] = {x[qq][0].x, x[qq][0].y, x[qq][0].z, x[qq][0].w, x[qq][1].x, x[qq][1].y, x[qq][1].z, x[qq][1].w};
+          if (kDv) {
+            const float sc = __ldg(scale + 2 * n);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] *= sc;
+          }
           uint4 hi, lo;
-          split8(f, hi, lo);
+          split8f<F>(f, hi, lo);
           const uint32_t off = blk_off + ptx::sw128_offset(row, cc & 7);
           st_chunk(sm_base + VHI + off, hi);
           st_chunk(sm_base + VLO + off, lo);
@@ -329,13 +341,12 @@ pct_attn_kernel(const float* __restrict__ k, const float* __restrict__ v, const 
           ptx::tmem_ld_wait();
           const float* cp = c2s + it * kTile + hc * 64 + h * 32;
           const float* cl = cp + kMaxT * kTile;
+          const float cpr = c2s[jt * kTile + 32 * q + lane], clr = c2s[kMaxT * kTile + jt * kTile + 32 * q + lane];   // own row (kDv)
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
-            const float e0 = ex2(fmaf(__uint_as_float(sv[e]), kAlpha, -cp[e]) - cl[e]);
-            const float e1 = ex2(fmaf(__uint_as_float(sv[e + 1]), kAlpha, -cp[e + 1]) - cl[e + 1]);
-            const uint32_t hw = pack2(e0, e1);
-            eh[h * 16 + e / 2] = hw;
-            el[h * 16 + e / 2] = pack2(e0 - bf_lo(hw), e1 - bf_hi(hw));
+            const float e0 = ex2(fmaf(__uint_as_float(sv[e]), kAlpha, kDv ? -cpr : -cp[e]) - (kDv ? clr : cl[e]));
+            const float e1 = ex2(fmaf(__uint_as_float(sv[e + 1]), kAlpha, kDv ? -cpr : -cp[e + 1]) - (kDv ? clr : cl[e + 1]));
+            split2f<F>(e0, e1, eh[h * 16 + e / 2], el[h * 16 + e / 2]);
           }
         }
         ptx::tc_fence_before();
@@ -359,13 +370,292 @@ pct_attn_kernel(const float* __restrict__ k, const float* __restrict__ v, const 
         ptx::tmem_ld16(tmem + lane_addr + O_COL + (uint32_t)(hc * 64 + ch * 16), ov);
         ptx::tmem_ld_wait();
         float f[16];
+        const float osc = kDv ? __ldg(scale + 2 * n + 1) : 1.f;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(ov[e]);
+        for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(ov[e]) * osc;
         float s = 0.f, qv = 0.f;
         stage_store16(stage, f, xs + (rowbase + 32 * q) * 128 + hc * 64 + ch * 16, 128, nvalid, lane, s, qv, false);
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bars[BAR_O_FREE]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) ptx::tmem_dealloc<512>(tmem);
+}
+
+
+// =====================================================================================================================
+// Second backward product of the SA layer: the gradient of the shared q / k projection output.
+//   energy = k k^T / sqrt(32) (symmetric),  A[i,j] = softmax_j,  dA[i,j] = v_i . dxs_j,  delta_i = sum_j A[i,j] dA[i,j] = v_i . dv_i
+//   dS[i,j] = A[i,j] (dA[i,j] - delta_i)                     dk_i = (1/sqrt(32)) sum_j (dS[i,j] + dS[j,i]) k_j
+// Both halves are produced in "row i" orientation, so nothing is transposed or scattered:
+//   kCol = false:  T[i,j] = exp2(S a - M_i) (v_i . dxs_j - delta_i)        fixed rows = v,   streamed rows = dxs
+//   kCol = true :  T[i,j] = exp2(S a - M_j) (dxs_i . v_j - delta_j)        fixed rows = dxs, streamed rows = v   (= dS[j,i])
+// and dk_i += T[i, block b] k_b.  Work item = (object, row block); per column block b the tensor pipe computes S (fp16
+// pairs, four partial products: exponent) and the 128-deep product (fp16 pairs, three passes; the dxs rows scaled by the
+// object's power of two) into tensor memory, the
+// compute warps form T, split it into fp16 pairs BACK INTO TENSOR MEMORY as the A operand of the last product, whose B
+// operand is the [hi | lo] image of k_b read MN-major with N = 64: columns 0-31 of the accumulator collect T k.hi,
+// columns 32-63 T k.lo (two passes: T.hi, T.lo), added in the epilogue.  Single-buffered: correctness first.
+// delta_i.  Mathematically v_i . dv_i, but it must NOT be computed that way: with a peaked softmax (A[i,j*] ~ 1)
+// dA[i,j*] - delta_i is a small difference of two numbers that each carry the 1e-5 error of a split-operand product, and
+// only if delta is summed from the SAME dA values the kernel subtracts it from do those errors cancel (the error of the
+// difference is then eps (1 - A), not eps).  So the kCol = false kernel runs the S / dA products twice per work item:
+// a first sweep over the column blocks accumulates delta_i = sum_j E[i,j] dA[i,j] thread-locally (and writes it out
+// for the kCol = true launch, whose dA[j,i] = v_j . dxs_i is the same set of partial products), the second forms T.
+namespace dk {
+constexpr uint32_t KA = 0;                               // own block's k rows, fp16 [hi | lo]
+constexpr uint32_t KB16 = KA + kBlk;                     // block b's k rows, fp16 [hi | lo]
+constexpr uint32_t FHI = KB16 + kBlk;                    // fixed 128-channel rows (2 channel blocks), fp16 hi / lo
+constexpr uint32_t FLO = FHI + 2 * kBlk;
+constexpr uint32_t GHI = FLO + 2 * kBlk;                 // streamed rows
+constexpr uint32_t GLO = GHI + 2 * kBlk;
+constexpr uint32_t STAGE = GLO + 2 * kBlk;               // 163840
+constexpr uint32_t NRM = STAGE + 8 * kStageFloats * 4;   // float[3][512]: max * a, log2 sum, delta
+constexpr uint32_t XCH = NRM + 3 * kMaxT * kTile * 4;     // float[2][128]
+constexpr uint32_t BARS = XCH + 2 * 128 * 4;
+constexpr uint32_t TMEMPTR = BARS + 64;
+constexpr uint32_t SMEM_BYTES = TMEMPTR + 16 + 1024;
+constexpr uint32_t S_COL = 0, DA_COL = 128, THI_COL = 256, TLO_COL = 320, DK_COL = 384;
+enum { BAR_F_FULL = 0, BAR_G_FULL = 1, BAR_SD_FULL = 2, BAR_T_FULL = 3, BAR_DK_DONE = 4, kNumBars = 5 };
+}  // namespace dk
+
+// one tile of 128 rows x 32 channels of k -> [hi | lo] image (format kF)
+template <int kF>
+__device__ __forceinline__ void load_k_tile(const float* __restrict__ k, int64_t rowbase, int valid, uint32_t addr, int tid) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int idx = tid + 256 * u;
+    const int row = idx >> 2, j = idx & 3;
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (row < valid) {
+      const float4* src = reinterpret_cast<const float4*>(k + (rowbase + row) * 32 + j * 8);
+      const float4 x = __ldg(src), y = __ldg(src + 1);
+      f[0] = x.x; f[1] = x.y; f[2] = x.z; f[3] = x.w; f[4] = y.x; f[5] = y.y; f[6] = y.z; f[7] = y.w;
+    }
+    uint4 hi, lo;
+    split8f<kF>(f, hi, lo);
+    st_chunk(addr + ptx::sw128_offset(row, j), hi);
+    st_chunk(addr + ptx::sw128_offset(row, 4 + j), lo);
+  }
+}
+
+// one tile of 128 rows x 128 channels -> K-major hi / lo images (2 channel blocks each), format kF
+template <int kF>
+__device__ __forceinline__ void load_tile128(const float* __restrict__ src, int64_t rowbase, int valid, uint32_t hi_addr, uint32_t lo_addr,
+                                             int tid, float mul) {
+  const int cc = tid & 15, r0 = tid >> 4;
+  const uint32_t blk_off = (uint32_t)(cc >> 3) * kBlk;
+#pragma unroll 1
+  for (int bt = 0; bt < 4; ++bt) {
+    float4 x[2][2];
+#pragma unroll
+    for (int qq = 0; qq < 2; ++qq) {
+      const int row = r0 + 16 * (bt * 2 + qq);
+      const float4* p = reinterpret_cast<const float4*>(src + (rowbase + row) * 128 + cc * 8);
+      const bool ok = row < valid;
+      x[qq][0] = ok ? __ldg(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+      x[qq][1] = ok ? __ldg(p + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int qq = 0; qq < 2; ++qq) {
+      const int row = r0 + 16 * (bt * 2 + qq);
+      const float f[8] = {x[qq][0].x * mul, x[qq][0].y * mul, x[qq][0].z * mul, x[qq][0].w * mul,
+                          x[qq][1].x * mul, x[qq][1].y * mul, x[qq][1].z * mul, x[qq][1].w * mul};
+      uint4 hi, lo;
+      split8f<kF>(f, hi, lo);
+      const uint32_t off = blk_off + ptx::sw128_offset(row, cc & 7);
+      st_chunk(hi_addr + off, hi);
+      st_chunk(lo_addr + off, lo);
+    }
+  }
+}
+
+template <bool kCol>
+__global__ void __launch_bounds__(kThreads, 1)
+pct_attn_dk_kernel(const float* __restrict__ k, const float* __restrict__ fixed, const float* __restrict__ streamed,
+                   const float* __restrict__ c2, const float* __restrict__ delta_in, float* __restrict__ delta_out,
+                   const float* __restrict__ scale, int64_t N, int P, float* __restrict__ dk_out) {
+  using namespace dk;
+  constexpr int kPhases = kCol ? 1 : 2;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sm_base = ptx::smem_u32(sm);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + BARS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + TMEMPTR);
+  float* nrm = reinterpret_cast<float*>(sm + NRM);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = (P + kTile - 1) / kTile;
+  const int Ppad = T * kTile;
+  if (tid == 0) {
+    ptx::mbar_init(&bars[BAR_F_FULL], kComputeThreads);
+    ptx::mbar_init(&bars[BAR_G_FULL], kComputeThreads);
+    ptx::mbar_init(&bars[BAR_SD_FULL], 1);
+    ptx::mbar_init(&bars[BAR_T_FULL], kComputeThreads);
+    ptx::mbar_init(&bars[BAR_DK_DONE], 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 8) ptx::tmem_alloc<512>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int64_t W = N * T;
+
+  if (warp == 8) {
+    // =============================== MMA issuer ===============================
+    const uint32_t idesc_s = ptx::make_idesc(0, 128, 128);
+    const uint32_t idesc_da = ptx::make_idesc(0, 128, 128);
+    const uint32_t idesc_dk = ptx::make_idesc(0, 128, 64) | (1u << 16);          // B (= k_b image) read MN-major
+    const uint64_t dKA = ptx::smem_desc_sw128(sm_base + KA), dKB = ptx::smem_desc_sw128(sm_base + KB16);
+    const uint64_t dFhi = ptx::smem_desc_sw128(sm_base + FHI), dFlo = ptx::smem_desc_sw128(sm_base + FLO);
+    const uint64_t dGhi = ptx::smem_desc_sw128(sm_base + GHI), dGlo = ptx::smem_desc_sw128(sm_base + GLO);
+    const uint64_t mKB = desc_mn_sw128(sm_base + KB16, kBlk);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    uint32_t u = 0, ud = 0, wi = 0;
+    for (int64_t w = blockIdx.x; w < W; w += gridDim.x, ++wi) {
+      ptx::mbar_wait(&bars[BAR_F_FULL], wi & 1);
+      for (int ph = 0; ph < kPhases; ++ph) {
+        const bool dk_phase = kCol || ph == 1;
+        for (int b = 0; b < T; ++b, ++u) {
+          ptx::mbar_wait(&bars[BAR_G_FULL], u & 1);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            issue_s_block(tmem_u + S_COL, dKA, dKB, idesc_s);
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint64_t ad = (pass == 1) ? dFlo : dFhi;
+              const uint64_t bd = (pass == 2) ? dGlo : dGhi;
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {
+                const uint64_t o = (uint64_t)((ks >> 2) * (kBlk >> 4) + (ks & 3) * 2);
+                ptx::umma_bf16(tmem_u + DA_COL, ad + o, bd + o, idesc_da, (pass | ks) != 0);
+              }
+            }
+            ptx::umma_commit(&bars[BAR_SD_FULL]);
+          }
+          __syncwarp();
+          if (!dk_phase) continue;
+          ptx::mbar_wait(&bars[BAR_T_FULL], ud & 1);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+              const uint32_t a_tm = tmem_u + (pass ? TLO_COL : THI_COL);
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                ptx::umma_bf16_ts(tmem_u + DK_COL, a_tm + (uint32_t)(ks * 8), mKB + (uint64_t)(ks * 128), idesc_dk, (b | pass | ks) != 0);
+            }
+            ptx::umma_commit(&bars[BAR_DK_DONE]);
+          }
+          __syncwarp();
+          ++ud;
+        }
+      }
+    }
+  } else {
+    // =============================== compute warps ===============================
+    const int q = warp & 3, hc = warp >> 2;
+    const int row = 32 * q + lane;
+    const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+    float* stage = reinterpret_cast<float*>(sm + STAGE) + warp * kStageFloats;
+    const float* ma_s = nrm;
+    const float* lg_s = nrm + kMaxT * kTile;
+    const float* de_s = nrm + 2 * kMaxT * kTile;
+    float* xch = reinterpret_cast<float*>(sm + XCH);
+    uint32_t u = 0, ud = 0;
+    for (int64_t w = blockIdx.x; w < W; w += gridDim.x) {
+      const int64_t n = w / T;
+      const int a = (int)(w - n * T);
+      const int64_t obase = n * (int64_t)P;
+      // every MMA of the previous item has completed (its last DK_DONE was waited for in the epilogue)
+      load_k_tile<0>(k, obase + (int64_t)a * kTile, min(kTile, P - a * kTile), sm_base + KA, tid);
+      const float gsc = __ldg(scale + 2 * n), ginv = __ldg(scale + 2 * n + 1);     // the dxs operand carries gsc
+      load_tile128<0>(fixed, obase + (int64_t)a * kTile, min(kTile, P - a * kTile), sm_base + FHI, sm_base + FLO, tid, kCol ? gsc : 1.f);
+      for (int i = tid; i < Ppad; i += kComputeThreads) {
+        nrm[i] = c2[(n * 2) * Ppad + i];
+        nrm[kMaxT * kTile + i] = c2[(n * 2 + 1) * Ppad + i];
+        if (kCol) nrm[2 * kMaxT * kTile + i] = (i < P) ? delta_in[obase + i] : 0.f;
+      }
+      ptx::fence_proxy_async_smem();
+      compute_barrier();
+      ptx::mbar_arrive(&bars[BAR_F_FULL]);
+      const float mr = ma_s[a * kTile + row], lr = lg_s[a * kTile + row];
+      float dr = 0.f;                                   // delta of this thread's row (kCol = false: from the first sweep)
+      for (int ph = 0; ph < kPhases; ++ph) {
+        const bool dk_phase = kCol || ph == 1;
+        float dacc = 0.f;
+        for (int b = 0; b < T; ++b, ++u) {
+          if (dk_phase && b >= 1) ptx::mbar_wait(&bars[BAR_DK_DONE], (ud - 1) & 1);      // k_b images, G and T are free again
+          const int validb = min(kTile, P - b * kTile);
+          load_k_tile<0>(k, obase + (int64_t)b * kTile, validb, sm_base + KB16, tid);
+          load_tile128<0>(streamed, obase + (int64_t)b * kTile, validb, sm_base + GHI, sm_base + GLO, tid, kCol ? 1.f : gsc);
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive(&bars[BAR_G_FULL]);
+          ptx::mbar_wait(&bars[BAR_SD_FULL], u & 1);
+          ptx::tc_fence_after();
+          uint32_t th[32], tl[32];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t sv[32], dv[32];
+            ptx::tmem_ld32(tmem + lane_addr + S_COL + (uint32_t)(hc * 64 + h * 32), sv);
+            ptx::tmem_ld32(tmem + lane_addr + DA_COL + (uint32_t)(hc * 64 + h * 32), dv);
+            ptx::tmem_ld_wait();
+            const int cb = b * kTile + hc * 64 + h * 32;
+            if (!dk_phase) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                dacc = fmaf(ex2(fmaf(__uint_as_float(sv[e]), kAlpha, -mr) - lr), __uint_as_float(dv[e]), dacc);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; e += 2) {
+                float t0, t1;
+                if (kCol) {
+                  t0 = ex2(fmaf(__uint_as_float(sv[e]), kAlpha, -ma_s[cb + e]) - lg_s[cb + e]) * (__uint_as_float(dv[e]) - de_s[cb + e]);
+                  t1 = ex2(fmaf(__uint_as_float(sv[e + 1]), kAlpha, -ma_s[cb + e + 1]) - lg_s[cb + e + 1]) * (__uint_as_float(dv[e + 1]) - de_s[cb + e + 1]);
+                } else {
+                  t0 = ex2(fmaf(__uint_as_float(sv[e]), kAlpha, -mr) - lr) * (__uint_as_float(dv[e]) - dr);
+                  t1 = ex2(fmaf(__uint_as_float(sv[e + 1]), kAlpha, -mr) - lr) * (__uint_as_float(dv[e + 1]) - dr);
+                }
+                split2f<0>(t0, t1, th[h * 16 + e / 2], tl[h * 16 + e / 2]);
+              }
+            }
+          }
+          if (!dk_phase) {
+            ptx::tc_fence_before();         // the next G_FULL arrival orders the next S / dA products after these reads
+            continue;
+          }
+          ptx::tmem_st32(tmem + lane_addr + THI_COL + (uint32_t)(hc * 32), th);
+          ptx::tmem_st32(tmem + lane_addr + TLO_COL + (uint32_t)(hc * 32), tl);
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&bars[BAR_T_FULL]);
+          ++ud;
+        }
+        if (!dk_phase) {                    // delta_i: the two column halves of the row
+          xch[hc * 128 + row] = dacc;
+          compute_barrier();
+          dr = xch[row] + xch[128 + row];
+          if (hc == 0 && a * kTile + row < P) delta_out[obase + (int64_t)a * kTile + row] = dr;
+          compute_barrier();                // xch is rewritten by the next item
+        }
+      }
+      // ---- dk rows of this block: (T k.hi) + (T k.lo), scaled by 1/sqrt(32)
+      ptx::mbar_wait(&bars[BAR_DK_DONE], (ud - 1) & 1);
+      ptx::tc_fence_after();
+      uint32_t d0[16], d1[16];
+      ptx::tmem_ld16(tmem + lane_addr + DK_COL + (uint32_t)(hc * 16), d0);
+      ptx::tmem_ld16(tmem + lane_addr + DK_COL + (uint32_t)(32 + hc * 16), d1);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      float f[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) f[e] = (__uint_as_float(d0[e]) + __uint_as_float(d1[e])) * (0.17677669529663687f * ginv);
+      const int nvalid = max(0, min(32, P - a * kTile - 32 * q));
+      float s_ = 0.f, q_ = 0.f;
+      stage_store16(stage, f, dk_out + (obase + (int64_t)a * kTile + 32 * q) * 32 + hc * 16, 32, nvalid, lane, s_, q_, false);
     }
   }
   ptx::tc_fence_before();
@@ -401,14 +691,61 @@ extern "C" int sga_pct_attn(const float* k, const float* v, const float* c2, int
   using namespace sga::pct;
   static bool attr_done = false;
   if (!attr_done) {
-    SGA_CUDA(cudaFuncSetAttribute(pct_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at::SMEM_BYTES));
+    SGA_CUDA(cudaFuncSetAttribute(pct_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at::SMEM_BYTES));
     attr_done = true;
   }
   const int T = (P + kTile - 1) / kTile;
   int64_t W = N * T;
   int grid = sga::sm_count();
   if ((int64_t)grid > W) grid = (int)W;
-  pct_attn_kernel<<<grid, kThreads, at::SMEM_BYTES, (cudaStream_t)stream>>>(k, v, c2, N, P, xs);
+  pct_attn_kernel<false><<<grid, kThreads, at::SMEM_BYTES, (cudaStream_t)stream>>>(k, v, c2, N, P, xs, nullptr);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+/* dv [N,P,128] = attention dxs per object (first product of the SA backward; see pct_attn_kernel<true>) */
+extern "C" int sga_pct_attn_bwd_dv(const float* k, const float* dxs, const float* c2, const float* scale, int64_t N, int P, float* dv,
+                                   void* stream) {
+  if (N <= 0) return SGA_OK;
+  SGA_REQUIRE(k && dxs && c2 && dv && scale && P >= 1 && P <= sga::pct::kMaxT * sga::pct::kTile, "sga_pct_attn_bwd_dv: P=%d (1..512)", P);
+  SGA_REQUIRE((((uintptr_t)k | (uintptr_t)dxs) & 15) == 0, "sga_pct_attn_bwd_dv: k / dxs must be 16-byte aligned");
+  using namespace sga::pct;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SGA_CUDA(cudaFuncSetAttribute(pct_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int T = (P + kTile - 1) / kTile;
+  int64_t W = N * T;
+  int grid = sga::sm_count();
+  if ((int64_t)grid > W) grid = (int)W;
+  pct_attn_kernel<true><<<grid, kThreads, at::SMEM_BYTES, (cudaStream_t)stream>>>(k, dxs, c2, N, P, dv, scale);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+/* dk halves of the SA backward (see pct_attn_dk_kernel): by_col = 0: fixed = v, streamed = dxs (row half; also WRITES
+ * delta [N,P], in units of the object's scale); by_col = 1: fixed = dxs, streamed = v (column half; READS delta).
+ * scale [N,2] = sga_pct_pow2_scale(dxs, v).  dk_out [N,P,32] is overwritten. */
+extern "C" int sga_pct_attn_bwd_dk(const float* k, const float* fixed, const float* streamed, const float* c2, float* delta,
+                                   const float* scale, int64_t N, int P, int by_col, float* dk_out, void* stream) {
+  if (N <= 0) return SGA_OK;
+  SGA_REQUIRE(k && fixed && streamed && c2 && delta && scale && dk_out && P >= 1 && P <= sga::pct::kMaxT * sga::pct::kTile,
+              "sga_pct_attn_bwd_dk: P=%d (1..512)", P);
+  SGA_REQUIRE((((uintptr_t)k | (uintptr_t)fixed | (uintptr_t)streamed) & 15) == 0, "sga_pct_attn_bwd_dk: operands must be 16-byte aligned");
+  using namespace sga::pct;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SGA_CUDA(cudaFuncSetAttribute(pct_attn_dk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dk::SMEM_BYTES));
+    SGA_CUDA(cudaFuncSetAttribute(pct_attn_dk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dk::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int T = (P + kTile - 1) / kTile;
+  int64_t W = N * T;
+  int grid = sga::sm_count();
+  if ((int64_t)grid > W) grid = (int)W;
+  if (by_col) pct_attn_dk_kernel<true><<<grid, kThreads, dk::SMEM_BYTES, (cudaStream_t)stream>>>(k, fixed, streamed, c2, delta, nullptr, scale, N, P, dk_out);
+  else pct_attn_dk_kernel<false><<<grid, kThreads, dk::SMEM_BYTES, (cudaStream_t)stream>>>(k, fixed, streamed, c2, nullptr, delta, scale, N, P, dk_out);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }

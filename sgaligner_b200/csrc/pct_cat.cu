@@ -21,19 +21,35 @@ namespace ct {
 constexpr uint32_t WLO = 0;                               // 8 blocks (kc * 2 + blk) x 16 KiB
 constexpr uint32_t RING = WLO + 8 * kBlk;                 // 3 slots x {hi 16 KiB, lo 16 KiB}
 constexpr uint32_t SLOT = 2 * kBlk;
-constexpr uint32_t AB4 = RING + 3 * SLOT;                 // a4[128], b4[128]
-constexpr uint32_t BARS = AB4 + 1024;
+constexpr uint32_t AB4 = RING + 3 * SLOT;                 // a4[128], b4[128]  (mode 2: xbar[512])
+constexpr uint32_t BARS = AB4 + 2048;
 constexpr uint32_t TMEMPTR = BARS + 128;
 constexpr uint32_t SMEM_BYTES = TMEMPTR + 16 + 1024;
 constexpr uint32_t D_COL = 0, WHI_COL = 256;
 enum { BAR_FULL = 0 /*..2*/, BAR_FREE = 3 /*..5*/, BAR_D_FULL = 6 /*,7*/, BAR_D_FREE = 8 /*,9*/, kNumBars = 10 };
 }  // namespace ct
 
+// kMode 0: the forward above.  kMode 1: the training forward -- the epilogue also tracks WHICH point holds the maximum /
+// minimum of every (object, channel) (the backward routes the pooled gradient there).  kMode 2: the dense half of the
+// backward through this layer, as the same streaming product with another weight and another epilogue:
+//     g_x[a][n, p, :] = -u[a] - (M (xcat[n, p, :] - xbar))[a-th block of 128 channels],   M = W^T diag(f) W  (512 x 512, symmetric)
+// (xbar = the batch mean of xcat, subtracted in the loader BEFORE the split: M xcat and M xbar would cancel digits)
+// (train-mode BatchNorm sends a gradient -e_c - f_c z[n,p,c] to EVERY point; W^T of that is a 512 -> 512 pointwise map of
+// the concatenated activations -- see sgaligner_b200/pct.py).  The fourth source is the plain x4 then (`t4`); M is of
+// gradient magnitude, so it is multiplied by the power of two scale[0] before the fp16 split and the product by scale[1]
+// (sga_pct_pow2_scale); grid.y = 4, and a thread stores its channel's 32 points per TMEM load: a warp writes 32
+// consecutive channels of one point = one 128-byte line per instruction.
+struct CatBwdOut { float* g[4]; const float* u; const float* scale; const float* xbar; };
+
+template <int kMode>
 __global__ void __launch_bounds__(kThreads, 1)
 pct_cat_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const float* __restrict__ x3,
                const float* __restrict__ t4, const float* __restrict__ a4, const float* __restrict__ b4, int64_t N, int P,
-               const float* __restrict__ WL, float* __restrict__ zmax, float* __restrict__ zmin, double* __restrict__ stats) {
+               const float* __restrict__ WL, float* __restrict__ zmax, float* __restrict__ zmin, double* __restrict__ stats,
+               int32_t* __restrict__ imax, int32_t* __restrict__ imin, const CatBwdOut bo) {
   using namespace ct;
+  constexpr int F = 0;
+  const float wsc = (kMode == 2) ? bo.scale[0] : 1.f;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sm_base = ptx::smem_u32(sm);
@@ -48,14 +64,18 @@ pct_cat_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const
     const int r = i >> 6, j = i & 63;
     const float4* src = reinterpret_cast<const float4*>(WL + (int64_t)(cb0 + r) * 512 + j * 8);
     const float4 x = src[0], y = src[1];
-    const float f[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+    const float f[8] = {x.x * wsc, x.y * wsc, x.z * wsc, x.w * wsc, y.x * wsc, y.y * wsc, y.z * wsc, y.w * wsc};
     uint4 hi, lo;
-    split8(f, hi, lo);
+    split8f<F>(f, hi, lo);
     st_chunk(sm_base + WLO + (uint32_t)(j >> 3) * kBlk + ptx::sw128_offset(r, j & 7), lo);
   }
-  for (int i = tid; i < 128; i += kThreads) {
-    ab4[i] = a4[i];
-    ab4[128 + i] = b4[i];
+  if (kMode != 2) {
+    for (int i = tid; i < 128; i += kThreads) {
+      ab4[i] = a4[i];
+      ab4[128 + i] = b4[i];
+    }
+  } else {
+    for (int i = tid; i < 512; i += kThreads) ab4[i] = bo.xbar[i];
   }
   if (tid == 0) {
     for (int s = 0; s < 3; ++s) {
@@ -83,8 +103,8 @@ pct_cat_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 a = src[grp * 8 + j];
-        w[2 * j] = pack2(a.x, a.y);
-        w[2 * j + 1] = pack2(a.z, a.w);
+        w[2 * j] = pack2f<F>(a.x * wsc, a.y * wsc);
+        w[2 * j + 1] = pack2f<F>(a.z * wsc, a.w * wsc);
       }
       ptx::tmem_st16(tmem + ((uint32_t)(32 * warp) << 16) + WHI_COL + grp * 16, w);
     }
@@ -100,7 +120,7 @@ pct_cat_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const
 
   if (warp == 8) {
     // =============================== MMA issuer ===============================
-    const uint32_t idesc = ptx::make_idesc(kFmt, 128, 128);
+    const uint32_t idesc = ptx::make_idesc(F, 128, 128);
     const uint64_t dWlo = ptx::smem_desc_sw128(sm_base + WLO);
     const uint64_t dRing = ptx::smem_desc_sw128(sm_base + RING);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
@@ -136,6 +156,10 @@ pct_cat_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const
     const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
     const int ch = cb0 + 32 * q + lane;
     float vmax = -INFINITY, vmin = INFINITY;
+    int pmax = 0, pmin = 0;
+    const float u_ch = (kMode == 2) ? bo.u[ch] : 0.f;
+    const float winv = (kMode == 2) ? bo.scale[1] : 1.f;
+    float* const gout = (kMode == 2) ? bo.g[blockIdx.y] : nullptr;
     double dsum = 0, dsq = 0;
     uint32_t hg = 0;
     int e_t = 0;                                           // epilogue cursor: tile within object
@@ -152,15 +176,28 @@ pct_cat_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const
         uint32_t v[32];
         ptx::tmem_ld32(tmem + lane_addr + D_COL + b * 128 + (uint32_t)(hc * 64 + h * 32), v);
         ptx::tmem_ld_wait();
+        if (kMode == 2) {
+          float* dst = gout + (e_n * (int64_t)P + (int64_t)e_t * kTile + hc * 64 + h * 32) * 128 + (32 * q + lane);
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float f = __uint_as_float(v[e]);
-          const bool ok = h * 32 + e < valid;
-          vmax = fmaxf(vmax, ok ? f : -INFINITY);
-          vmin = fminf(vmin, ok ? f : INFINITY);
-          const float g0 = ok ? f : 0.f;
-          s += g0;
-          sq = fmaf(g0, g0, sq);
+          for (int e = 0; e < 32; ++e)
+            if (h * 32 + e < valid) dst[(int64_t)e * 128] = -fmaf(__uint_as_float(v[e]), winv, u_ch);
+        } else {
+          const int pt0 = e_t * kTile + hc * 64 + h * 32;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float f = __uint_as_float(v[e]);
+            const bool ok = h * 32 + e < valid;
+            if (kMode == 1) {
+              if (ok && f > vmax) { vmax = f; pmax = pt0 + e; }
+              if (ok && f < vmin) { vmin = f; pmin = pt0 + e; }
+            } else {
+              vmax = fmaxf(vmax, ok ? f : -INFINITY);
+              vmin = fminf(vmin, ok ? f : INFINITY);
+            }
+            const float g0 = ok ? f : 0.f;
+            s += g0;
+            sq = fmaf(g0, g0, sq);
+          }
         }
       }
       ptx::tc_fence_before();
@@ -168,8 +205,14 @@ pct_cat_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const
       dsum += (double)s;
       dsq += (double)sq;
       if (++e_t == T) {                                    // object complete: this half's max / min
-        zmax[(e_n * 2 + hc) * 1024 + ch] = vmax;
-        zmin[(e_n * 2 + hc) * 1024 + ch] = vmin;
+        if (kMode != 2) {
+          zmax[(e_n * 2 + hc) * 1024 + ch] = vmax;
+          zmin[(e_n * 2 + hc) * 1024 + ch] = vmin;
+          if (kMode == 1) {
+            imax[(e_n * 2 + hc) * 1024 + ch] = pmax;
+            imin[(e_n * 2 + hc) * 1024 + ch] = pmin;
+          }
+        }
         vmax = -INFINITY;
         vmin = INFINITY;
         e_t = 0;
@@ -186,7 +229,7 @@ pct_cat_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const
       for (int h = 0; h < 8; ++h, ++hg) {
         const int kc = h >> 1;
         const uint32_t slot = hg % 3;
-        const float* src = (kc == 0) ? x1 : (kc == 1) ? x2 : x3;
+        const float* src = (kc == 0) ? x1 : (kc == 1) ? x2 : (kMode == 2 && kc == 3) ? t4 : x3;
         const int chb = (h & 1) * 64 + cc * 8;             // channel of this thread's chunk inside the 128-channel source
         float4 u[4][2], w[4][2];
 #pragma unroll
@@ -196,7 +239,7 @@ pct_cat_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const
           const float4* s1 = reinterpret_cast<const float4*>(src + (rowbase + row) * 128 + chb);
           u[qq][0] = ok ? __ldg(s1) : make_float4(0.f, 0.f, 0.f, 0.f);
           u[qq][1] = ok ? __ldg(s1 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-          if (kc == 3) {
+          if (kMode != 2 && kc == 3) {
             const float4* s2 = reinterpret_cast<const float4*>(t4 + (rowbase + row) * 128 + chb);
             w[qq][0] = ok ? __ldg(s2) : make_float4(0.f, 0.f, 0.f, 0.f);
             w[qq][1] = ok ? __ldg(s2 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -207,7 +250,12 @@ pct_cat_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const
         for (int qq = 0; qq < 4; ++qq) {
           const int row = r0 + 32 * qq;
           float f[8] = {u[qq][0].x, u[qq][0].y, u[qq][0].z, u[qq][0].w, u[qq][1].x, u[qq][1].y, u[qq][1].z, u[qq][1].w};
-          if (kc == 3) {
+          if (kMode == 2) {
+            const bool okr = row < valid;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = okr ? f[e] - ab4[kc * 128 + chb + e] : 0.f;
+          }
+          if (kMode != 2 && kc == 3) {
             const float tv[8] = {w[qq][0].x, w[qq][0].y, w[qq][0].z, w[qq][0].w, w[qq][1].x, w[qq][1].y, w[qq][1].z, w[qq][1].w};
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -220,7 +268,7 @@ pct_cat_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const
             }
           }
           uint4 hi, lo;
-          split8(f, hi, lo);
+          split8f<F>(f, hi, lo);
           const uint32_t off = RING + slot * SLOT + ptx::sw128_offset(row, cc);
           st_chunk(sm_base + off, hi);
           st_chunk(sm_base + off + kBlk, lo);
@@ -235,62 +283,100 @@ pct_cat_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const
       }
     }
     if (G > 0) epilogue(G - 1);
-    atomicAdd(&stats[ch], dsum);
-    atomicAdd(&stats[1024 + ch], dsq);
+    if (kMode != 2) {
+      atomicAdd(&stats[ch], dsum);
+      atomicAdd(&stats[1024 + ch], dsq);
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 8) ptx::tmem_dealloc<512>(tmem);
 }
 
-// pooled[n, c] = lrelu_0.2(a_c * (a_c >= 0 ? max : min) + b_c), the two column halves combined (pct.py:288-289, :310)
-__global__ void pct_pool_act_kernel(const float* __restrict__ zmax, const float* __restrict__ zmin, const float* __restrict__ a,
-                                    const float* __restrict__ b, int64_t N, int P, float* __restrict__ out) {
+// pooled[n, c] = lrelu_0.2(a_c * (a_c >= 0 ? max : min) + b_c), the two column halves combined (pct.py:288-289, :310);
+// with the tracked indices also the point that holds it (pstar) and the selected pre-BatchNorm value (zsel)
+__global__ void pct_pool_act_kernel(const float* __restrict__ zmax, const float* __restrict__ zmin, const int32_t* __restrict__ imax,
+                                    const int32_t* __restrict__ imin, const float* __restrict__ a, const float* __restrict__ b,
+                                    int64_t N, int P, float* __restrict__ out, int32_t* __restrict__ pstar, float* __restrict__ zsel) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * 1024) return;
   const int64_t n = i >> 10;
   const int c = (int)(i & 1023);
-  float mx = zmax[(n * 2) * 1024 + c], mn = zmin[(n * 2) * 1024 + c];
+  const int64_t i0 = (n * 2) * 1024 + c, i1 = i0 + 1024;
+  float mx = zmax[i0], mn = zmin[i0];
+  int px = imax ? imax[i0] : 0, pn = imin ? imin[i0] : 0;
   if (P > 64) {                                           // the second column half holds points only then
-    mx = fmaxf(mx, zmax[(n * 2 + 1) * 1024 + c]);
-    mn = fminf(mn, zmin[(n * 2 + 1) * 1024 + c]);
+    const float mx1 = zmax[i1], mn1 = zmin[i1];
+    if (mx1 > mx || (imax && mx1 == mx && imax[i1] < px)) { mx = mx1; if (imax) px = imax[i1]; }
+    if (mn1 < mn || (imin && mn1 == mn && imin[i1] < pn)) { mn = mn1; if (imin) pn = imin[i1]; }
   }
   const float ac = a[c];
-  const float y = fmaf(ac, ac >= 0.f ? mx : mn, b[c]);
+  const float z = ac >= 0.f ? mx : mn;
+  const float y = fmaf(ac, z, b[c]);
   out[i] = y > 0.f ? y : 0.2f * y;
+  if (pstar) pstar[i] = ac >= 0.f ? px : pn;
+  if (zsel) zsel[i] = z;
 }
 
 }  // namespace
 }  // namespace pct
 }  // namespace sga
 
-extern "C" int sga_pct_cat_linear(const float* x1, const float* x2, const float* x3, const float* t4, const float* a4,
-                                  const float* b4, int64_t N, int P, const float* WL, float* zmax, float* zmin,
-                                  double* stats, void* stream) {
-  if (N <= 0) return SGA_OK;
-  SGA_REQUIRE(x1 && x2 && x3 && t4 && a4 && b4 && WL && zmax && zmin && stats && P >= 1, "sga_pct_cat_linear: bad arguments");
-  SGA_REQUIRE((((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)x3 | (uintptr_t)t4 | (uintptr_t)WL) & 15) == 0,
-              "sga_pct_cat_linear: activations / weights must be 16-byte aligned");
+static int cat_launch(int mode, const float* x1, const float* x2, const float* x3, const float* t4, const float* a4, const float* b4,
+                      int64_t N, int P, const float* WL, float* zmax, float* zmin, double* stats, int32_t* imax, int32_t* imin,
+                      const sga::pct::CatBwdOut& bo, void* stream) {
   using namespace sga::pct;
   static bool attr_done = false;
   if (!attr_done) {
-    SGA_CUDA(cudaFuncSetAttribute(pct_cat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct::SMEM_BYTES));
+    SGA_CUDA(cudaFuncSetAttribute(pct_cat_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct::SMEM_BYTES));
+    SGA_CUDA(cudaFuncSetAttribute(pct_cat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct::SMEM_BYTES));
+    SGA_CUDA(cudaFuncSetAttribute(pct_cat_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct::SMEM_BYTES));
     attr_done = true;
   }
-  int gx = sga::sm_count() / 8;
+  const int gy = mode == 2 ? 4 : 8;
+  int gx = sga::sm_count() / gy;
   if (gx < 1) gx = 1;
   if ((int64_t)gx > N) gx = (int)N;
-  pct_cat_kernel<<<dim3(gx, 8), kThreads, ct::SMEM_BYTES, (cudaStream_t)stream>>>(x1, x2, x3, t4, a4, b4, N, P, WL, zmax, zmin, stats);
+  const dim3 grid(gx, gy);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 0) pct_cat_kernel<0><<<grid, kThreads, ct::SMEM_BYTES, st>>>(x1, x2, x3, t4, a4, b4, N, P, WL, zmax, zmin, stats, imax, imin, bo);
+  else if (mode == 1) pct_cat_kernel<1><<<grid, kThreads, ct::SMEM_BYTES, st>>>(x1, x2, x3, t4, a4, b4, N, P, WL, zmax, zmin, stats, imax, imin, bo);
+  else pct_cat_kernel<2><<<grid, kThreads, ct::SMEM_BYTES, st>>>(x1, x2, x3, t4, a4, b4, N, P, WL, zmax, zmin, stats, imax, imin, bo);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }
 
-extern "C" int sga_pct_pool_act(const float* zmax, const float* zmin, const float* a, const float* b, int64_t N, int P,
-                                float* out, void* stream) {
+extern "C" int sga_pct_cat_linear(const float* x1, const float* x2, const float* x3, const float* t4, const float* a4,
+                                  const float* b4, int64_t N, int P, const float* WL, float* zmax, float* zmin,
+                                  double* stats, int32_t* imax, int32_t* imin, void* stream) {
+  if (N <= 0) return SGA_OK;
+  SGA_REQUIRE(x1 && x2 && x3 && t4 && a4 && b4 && WL && zmax && zmin && stats && P >= 1, "sga_pct_cat_linear: bad arguments");
+  SGA_REQUIRE((imax == nullptr) == (imin == nullptr), "sga_pct_cat_linear: imax / imin come together");
+  SGA_REQUIRE((((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)x3 | (uintptr_t)t4 | (uintptr_t)WL) & 15) == 0,
+              "sga_pct_cat_linear: activations / weights must be 16-byte aligned");
+  sga::pct::CatBwdOut bo{};
+  return cat_launch(imax ? 1 : 0, x1, x2, x3, t4, a4, b4, N, P, WL, zmax, zmin, stats, imax, imin, bo, stream);
+}
+
+extern "C" int sga_pct_cat_dense_bwd(const float* x1, const float* x2, const float* x3, const float* x4, int64_t N, int P,
+                                     const float* M, const float* scale, const float* u, const float* xbar, float* g1, float* g2,
+                                     float* g3, float* g4, void* stream) {
+  if (N <= 0) return SGA_OK;
+  SGA_REQUIRE(x1 && x2 && x3 && x4 && M && scale && u && xbar && g1 && g2 && g3 && g4 && P >= 1, "sga_pct_cat_dense_bwd: bad arguments");
+  SGA_REQUIRE((((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)x3 | (uintptr_t)x4 | (uintptr_t)M) & 15) == 0,
+              "sga_pct_cat_dense_bwd: activations / weights must be 16-byte aligned");
+  sga::pct::CatBwdOut bo{};
+  bo.g[0] = g1; bo.g[1] = g2; bo.g[2] = g3; bo.g[3] = g4; bo.u = u; bo.scale = scale; bo.xbar = xbar;
+  return cat_launch(2, x1, x2, x3, x4, nullptr, nullptr, N, P, M, nullptr, nullptr, nullptr, nullptr, nullptr, bo, stream);
+}
+
+extern "C" int sga_pct_pool_act(const float* zmax, const float* zmin, const int32_t* imax, const int32_t* imin, const float* a,
+                                const float* b, int64_t N, int P, float* out, int32_t* pstar, float* zsel, void* stream) {
   if (N <= 0) return SGA_OK;
   SGA_REQUIRE(zmax && zmin && a && b && out, "sga_pct_pool_act: null pointer");
   const int64_t total = N * 1024;
-  sga::pct::pct_pool_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(zmax, zmin, a, b, N, P, out);
+  sga::pct::pct_pool_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(zmax, zmin, imax, imin, a, b, N, P, out,
+                                                                                                  pstar, zsel);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }

@@ -42,9 +42,10 @@ struct PwArgs {
   int64_t N; int P;
   const float* W; const float* bias; int Cout; int c0;
   float* out_x; float* out0; float* out1; double* stats;
+  const float* scale;                                                 // backward: [N,2] per-object {s, 1/s}: X is multiplied by s on the way in, Y by 1/s on the way out
 };
 
-template <bool kEmbed>
+template <bool kEmbed, bool kScaled>
 __global__ void __launch_bounds__(kThreads, 1) pct_pw_kernel(const PwArgs A) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -206,6 +207,11 @@ __global__ void __launch_bounds__(kThreads, 1) pct_pw_kernel(const PwArgs A) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = 0.f;
           }
+          if (kScaled) {
+            const float sc = __ldg(A.scale + 2 * n);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] *= sc;
+          }
           if (!kEmbed && A.out_x && ok) {
             float4* ox = reinterpret_cast<float4*>(A.out_x + (rowbase + row) * 128 + ch0);
             ox[0] = make_float4(f[0], f[1], f[2], f[3]);
@@ -233,8 +239,9 @@ __global__ void __launch_bounds__(kThreads, 1) pct_pw_kernel(const PwArgs A) {
         ptx::tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, v);
         ptx::tmem_ld_wait();
         float f[16];
+        const float osc = kScaled ? __ldg(A.scale + 2 * n + 1) : 1.f;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]) + bias_s[col0 + e];
+        for (int e = 0; e < 16; ++e) f[e] = kScaled ? __uint_as_float(v[e]) * osc : __uint_as_float(v[e]) + bias_s[col0 + e];
         float* dst;
         int64_t ld;
         if (col0 < A.c0) {
@@ -277,16 +284,18 @@ __global__ void __launch_bounds__(kThreads, 1) pct_pw_kernel(const PwArgs A) {
 int pw_launch(const PwArgs& a, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    SGA_CUDA(cudaFuncSetAttribute(pct_pw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    SGA_CUDA(cudaFuncSetAttribute(pct_pw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    SGA_CUDA(cudaFuncSetAttribute(pct_pw_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    SGA_CUDA(cudaFuncSetAttribute(pct_pw_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    SGA_CUDA(cudaFuncSetAttribute(pct_pw_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     attr_done = true;
   }
   const int T = (a.P + kTile - 1) / kTile;
   int64_t G = a.N * T;
   int grid = sm_count();
   if ((int64_t)grid > G) grid = (int)G;
-  if (a.pts) pct_pw_kernel<true><<<grid, kThreads, SMEM_BYTES, st>>>(a);
-  else pct_pw_kernel<false><<<grid, kThreads, SMEM_BYTES, st>>>(a);
+  if (a.pts) pct_pw_kernel<true, false><<<grid, kThreads, SMEM_BYTES, st>>>(a);
+  else if (a.scale) pct_pw_kernel<false, true><<<grid, kThreads, SMEM_BYTES, st>>>(a);
+  else pct_pw_kernel<false, false><<<grid, kThreads, SMEM_BYTES, st>>>(a);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }
@@ -303,9 +312,9 @@ static int check_pw_common(const char* who, int64_t N, int P, const float* W, in
   return SGA_OK;
 }
 
-extern "C" int sga_pct_pointwise(const float* src1, const float* a1, const float* b1, const float* src2, const float* a2,
-                                 const float* b2, int64_t N, int P, const float* W, const float* bias, int Cout, int c0,
-                                 float* out_x, float* out0, float* out1, double* stats, void* stream) {
+static int pct_pointwise_impl(const float* src1, const float* a1, const float* b1, const float* src2, const float* a2,
+                              const float* b2, int64_t N, int P, const float* W, const float* bias, int Cout, int c0,
+                              float* out_x, float* out0, float* out1, double* stats, const float* scale, void* stream) {
   if (N <= 0) return SGA_OK;
   int rc = check_pw_common("sga_pct_pointwise", N, P, W, Cout);
   if (rc) return rc;
@@ -319,8 +328,23 @@ extern "C" int sga_pct_pointwise(const float* src1, const float* a1, const float
   a.src2 = src2; a.a2 = a2; a.b2 = b2; a.mode2 = src2 ? (a2 ? 2 : 1) : 0;
   a.pts = nullptr; a.w1 = nullptr;
   a.N = N; a.P = P; a.W = W; a.bias = bias; a.Cout = Cout; a.c0 = c0;
-  a.out_x = out_x; a.out0 = out0; a.out1 = out1; a.stats = stats;
+  a.out_x = out_x; a.out0 = out0; a.out1 = out1; a.stats = stats; a.scale = scale;
   return sga::pct::pw_launch(a, (cudaStream_t)stream);
+}
+
+extern "C" int sga_pct_pointwise(const float* src1, const float* a1, const float* b1, const float* src2, const float* a2,
+                                 const float* b2, int64_t N, int P, const float* W, const float* bias, int Cout, int c0,
+                                 float* out_x, float* out0, float* out1, double* stats, void* stream) {
+  return pct_pointwise_impl(src1, a1, b1, src2, a2, b2, N, P, W, bias, Cout, c0, out_x, out0, out1, stats, nullptr, stream);
+}
+
+// The same kernel for the input-gradient products of the backward (dX = dY W: pass W^T as the weight): the operand is a
+// gradient, so it is multiplied by the object's power-of-two scale[n][0] before the fp16 split and the result by
+// scale[n][1] = 1 / scale[n][0] (sga_pct_pow2_scale).
+extern "C" int sga_pct_pointwise_scaled(const float* src, const float* scale, int64_t N, int P, const float* Wt, float* out, void* stream) {
+  SGA_REQUIRE(scale, "sga_pct_pointwise_scaled: null scale");
+  return pct_pointwise_impl(src, nullptr, nullptr, nullptr, nullptr, nullptr, N, P, Wt, nullptr, 128, 128, nullptr, out, nullptr,
+                            nullptr, scale, stream);
 }
 
 extern "C" int sga_pct_embed(const float* pts, int64_t N, int P, const float* W1, const float* a1, const float* b1,

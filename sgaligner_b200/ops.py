@@ -346,7 +346,7 @@ def pct_pointwise(src1, ab1, src2, ab2, W, bias, c0: int, want_x: bool, want_sta
     return out0, out1, out_x, stats
 
 
-def pct_attention(k, v):
+def pct_attention(k, v, want_c2: bool = False):
     """x_s = torch.bmm(x_v, softmax(x_k^T x_k / sqrt(32), -1)) for every object (pct.py:217-224), [N,P,128]."""
     N, P, _ = k.shape
     Ppad = (P + 127) // 128 * 128
@@ -358,28 +358,216 @@ def pct_attention(k, v):
     with _timed('pct_attn'):
         check(lib.sga_pct_attn(_ptr(k), _ptr(v), _ptr(c2), N, P, _ptr(xs), _stream()), 'sga_pct_attn')
     _count(2)
-    return xs
+    return (xs, c2) if want_c2 else xs
 
 
-def pct_cat_linear(x1, x2, x3, t4, ab4, WL):
+def pct_cat_linear(x1, x2, x3, t4, ab4, WL, track: bool = False):
+    """-> (zmax, zmin, stats, imax, imin); the index tensors only with ``track`` (training: the backward needs the arg-max)."""
     N, P, _ = x1.shape
     dev = x1.device
     zmax = torch.empty((N, 2, 1024), device=dev, dtype=torch.float32)
     zmin = torch.empty((N, 2, 1024), device=dev, dtype=torch.float32)
+    imax = torch.empty((N, 2, 1024), device=dev, dtype=torch.int32) if track else None
+    imin = torch.empty((N, 2, 1024), device=dev, dtype=torch.int32) if track else None
     stats = _f64z(2048, dev)
     with _timed('pct_cat_linear'):
         check(get_lib().sga_pct_cat_linear(_ptr(x1), _ptr(x2), _ptr(x3), _ptr(t4), _ptr(ab4[0]), _ptr(ab4[1]), N, P, _ptr(WL), _ptr(zmax),
-                                           _ptr(zmin), _ptr(stats), _stream()), 'sga_pct_cat_linear')
+                                           _ptr(zmin), _ptr(stats), _ptr(imax), _ptr(imin), _stream()), 'sga_pct_cat_linear')
     _count(1)
-    return zmax, zmin, stats
+    return zmax, zmin, stats, imax, imin
 
 
-def pct_pool_act(zmax, zmin, a, b, P: int):
+def pct_pool_act(zmax, zmin, a, b, P: int, imax=None, imin=None):
+    """pooled [N,1024]; with the tracked indices -> (pooled, pstar [N,1024] int32, zsel [N,1024])."""
     N = zmax.shape[0]
-    out = torch.empty((N, 1024), device=zmax.device, dtype=torch.float32)
-    check(get_lib().sga_pct_pool_act(_ptr(zmax), _ptr(zmin), _ptr(a), _ptr(b), N, int(P), _ptr(out), _stream()), 'sga_pct_pool_act')
+    dev = zmax.device
+    out = torch.empty((N, 1024), device=dev, dtype=torch.float32)
+    pstar = torch.empty((N, 1024), device=dev, dtype=torch.int32) if imax is not None else None
+    zsel = torch.empty((N, 1024), device=dev, dtype=torch.float32) if imax is not None else None
+    check(get_lib().sga_pct_pool_act(_ptr(zmax), _ptr(zmin), _ptr(imax), _ptr(imin), _ptr(a), _ptr(b), N, int(P), _ptr(out), _ptr(pstar),
+                                     _ptr(zsel), _stream()), 'sga_pct_pool_act')
+    _count(1)
+    return out if imax is None else (out, pstar, zsel)
+
+
+# ---- NaivePCT backward building blocks (csrc/pct_bwd.cu, pct_attn.cu, pct_cat.cu)
+def bn_backward(g, y, ab, bn, stats, cnt: float, training: bool, mask=None, scale: float = 1.0, slope: float = 0.0, lin_bias=None,
+                want_dy: bool = True):
+    """Backward of  act(BN(y + lin_bias)) (* mask * scale)  for the STORED y [rows, C]: (dy or None, dgamma, dbeta, (e, f, mean))
+    with dy = a gy - e - f (y - mean).
+    act = ReLU (slope 0) or LeakyReLU(slope); ``stats`` = the forward's batch statistics {sum y, sum y^2} (training)."""
+    C = y.shape[-1]
+    rows = y.numel() // C
+    dev = y.device
+    lib = get_lib()
+    sums = _f64z(2 * C, dev)
+    check(lib.sga_bn_bwd_stats(_ptr(g), _ptr(y), _ptr(ab[0]), _ptr(ab[1]), _ptr(mask), float(scale), float(slope), rows, C, _ptr(sums),
+                               _stream()), 'sga_bn_bwd_stats')
+    e = torch.empty(C, device=dev, dtype=torch.float32)
+    f = torch.empty(C, device=dev, dtype=torch.float32)
+    mean = torch.empty(C, device=dev, dtype=torch.float32)
+    dgamma = torch.empty(C, device=dev, dtype=torch.float32)
+    dbeta = torch.empty(C, device=dev, dtype=torch.float32)
+    check(lib.sga_bn_bwd_coef(_ptr(sums), _ptr(stats if training else None), float(cnt), _ptr(lin_bias), _ptr(bn.weight), _ptr(bn.running_mean),
+                              _ptr(bn.running_var), 1 if training else 0, float(bn.eps), C, _ptr(e), _ptr(f), _ptr(mean), _ptr(dgamma),
+                              _ptr(dbeta), _stream()), 'sga_bn_bwd_coef')
+    dy = None
+    if want_dy:
+        dy = torch.empty_like(y)
+        check(lib.sga_bn_bwd_apply(_ptr(g), _ptr(y), _ptr(ab[0]), _ptr(ab[1]), _ptr(mask), float(scale), float(slope), _ptr(e), _ptr(f),
+                                   _ptr(mean), rows, C, _ptr(dy), _stream()), 'sga_bn_bwd_apply')
+    _count(3 if want_dy else 2)
+    return dy, dgamma, dbeta, (e, f, mean)
+
+
+def bn_backward_apply(g, y, ab, slope: float = 0.0):
+    """a * g * act'(a y + b)  (the BatchNorm scale and the activation mask only; no batch-statistics terms)."""
+    C = y.shape[-1]
+    out = torch.empty_like(y)
+    check(get_lib().sga_bn_bwd_apply(_ptr(g), _ptr(y), _ptr(ab[0]), _ptr(ab[1]), None, 1.0, float(slope), None, None, None, y.numel() // C, C,
+                                     _ptr(out), _stream()), 'sga_bn_bwd_apply')
     _count(1)
     return out
+
+
+def pct_pow2_scale(x, y=None, target: float = 4096.0, per_object: bool = True):
+    """[N,2] = {s, 1/s}: per-object (or, ``per_object=False``, whole-tensor) power-of-two scale of a gradient operand."""
+    N = x.shape[0] if per_object else 1
+    per = x.numel() // N
+    scale = torch.empty((N, 2), device=x.device, dtype=torch.float32)
+    check(get_lib().sga_pct_pow2_scale(_ptr(x), _ptr(y), N, per, float(target), _ptr(scale), _stream()), 'sga_pct_pow2_scale')
+    _count(1)
+    return scale
+
+
+def pct_attention_backward(k, v, c2, dxs):
+    """(dk_row, dk_col [N,P,32] -- their sum is d k --, dv [N,P,128]) of x_s = bmm(x_v, softmax(k^T k / sqrt(32)))."""
+    N, P, _ = k.shape
+    lib = get_lib()
+    # |v_i . dxs_j| <= 128 max|v| max|dxs|: the scaled products (and T = E (dA - delta)) stay below 2^15 < 65504
+    scale = pct_pow2_scale(dxs, v, target=16384.0 / 128.0)
+    dv = torch.empty_like(v)
+    with _timed('pct_attn_bwd_dv'):
+        check(lib.sga_pct_attn_bwd_dv(_ptr(k), _ptr(dxs), _ptr(c2), _ptr(scale), N, P, _ptr(dv), _stream()), 'sga_pct_attn_bwd_dv')
+    delta = torch.empty((N, P), device=k.device, dtype=torch.float32)      # sum_j A[i,j] dA[i,j], written by the row half
+    dk1 = torch.empty_like(k)
+    dk2 = torch.empty_like(k)
+    with _timed('pct_attn_bwd_dk'):
+        check(lib.sga_pct_attn_bwd_dk(_ptr(k), _ptr(v), _ptr(dxs), _ptr(c2), _ptr(delta), _ptr(scale), N, P, 0, _ptr(dk1), _stream()),
+              'sga_pct_attn_bwd_dk')
+        check(lib.sga_pct_attn_bwd_dk(_ptr(k), _ptr(dxs), _ptr(v), _ptr(c2), _ptr(delta), _ptr(scale), N, P, 1, _ptr(dk2), _stream()),
+              'sga_pct_attn_bwd_dk')
+    _count(3)
+    return dk1, dk2, dv
+
+
+def pct_pointwise_grad(src, Wt):
+    """src [N,P,128] @ Wt^T (Wt [128,128] contiguous): the input-gradient products; src is scaled per object into the fp16
+    range on the way in, the result scaled back."""
+    N, P, _ = src.shape
+    out = torch.empty_like(src)
+    scale = pct_pow2_scale(src)
+    with _timed('pct_pointwise_bwd'):
+        check(get_lib().sga_pct_pointwise_scaled(_ptr(src), _ptr(scale), N, P, _ptr(Wt), _ptr(out), _stream()), 'sga_pct_pointwise_scaled')
+    _count(1)
+    return out
+
+
+def pct_sa_input_grad(gx, gcat, dxv, dk1, dk2, Wk):
+    """gx (+ gcat) + dxv + (dk1 + dk2) Wk -> [N,P,128]; dk1 becomes dk1 + dk2 (in place)."""
+    out = torch.empty_like(gx)
+    check(get_lib().sga_pct_sa_input_grad(_ptr(gx), _ptr(gcat), _ptr(dxv), _ptr(dk1), _ptr(dk2), _ptr(Wk), gx.numel() // 128, _ptr(out),
+                                          _stream()), 'sga_pct_sa_input_grad')
+    _count(1)
+    return out
+
+
+def pct_residual(x, t, ab):
+    out = torch.empty_like(x)
+    check(get_lib().sga_pct_residual(_ptr(x), _ptr(t), _ptr(ab[0]), _ptr(ab[1]), x.numel() // 128, _ptr(out), _stream()), 'sga_pct_residual')
+    _count(1)
+    return out
+
+
+def pct_embed_a1(pts, W1, ab1):
+    N, P, _ = pts.shape
+    out = torch.empty((N, P, 128), device=pts.device, dtype=torch.float32)
+    check(get_lib().sga_pct_embed_a1(_ptr(pts), _ptr(W1), _ptr(ab1[0]), _ptr(ab1[1]), N * P, _ptr(out), _stream()), 'sga_pct_embed_a1')
+    _count(1)
+    return out
+
+
+def pct_embed1_backward(g, pts, W1, ab1, bn, stats, mom, cnt: float, training: bool):
+    """(dW1 [128,3], dgamma, dbeta) of relu(bn1(conv1(points))) given g = d/d(that activation) [N,P,128]."""
+    dev = g.device
+    lib = get_lib()
+    sums5 = _f64z(5 * 128, dev)
+    check(lib.sga_pct_embed1_bwd_stats(_ptr(g), _ptr(pts), _ptr(W1), _ptr(ab1[0]), _ptr(ab1[1]), g.numel() // 128, _ptr(sums5), _stream()),
+          'sga_pct_embed1_bwd_stats')
+    e = torch.empty(128, device=dev, dtype=torch.float32)
+    f = torch.empty(128, device=dev, dtype=torch.float32)
+    mean = torch.empty(128, device=dev, dtype=torch.float32)
+    dgamma = torch.empty(128, device=dev, dtype=torch.float32)
+    dbeta = torch.empty(128, device=dev, dtype=torch.float32)
+    check(lib.sga_bn_bwd_coef(_ptr(sums5), _ptr(stats if training else None), float(cnt), None, _ptr(bn.weight), _ptr(bn.running_mean),
+                              _ptr(bn.running_var), 1 if training else 0, float(bn.eps), 128, _ptr(e), _ptr(f), _ptr(mean), _ptr(dgamma),
+                              _ptr(dbeta), _stream()), 'sga_bn_bwd_coef')
+    dW1 = torch.empty((128, 3), device=dev, dtype=torch.float32)
+    check(lib.sga_pct_embed1_wgrad(_ptr(sums5), _ptr(mom), float(cnt), _ptr(W1), _ptr(ab1[0]), _ptr(e), _ptr(f), _ptr(dW1), _stream()),
+          'sga_pct_embed1_wgrad')
+    _count(3)
+    return dW1, dgamma, dbeta
+
+
+def pct_cat_dense_backward(x1, x2, x3, x4, M, u, xbar):
+    """g_x[a] = -u[a] - (M (xcat - xbar))[a]  for the four 128-channel blocks of the concatenation."""
+    N, P, _ = x1.shape
+    gs = [torch.empty_like(x1) for _ in range(4)]
+    scale = pct_pow2_scale(M, per_object=False)
+    with _timed('pct_cat_dense_bwd'):
+        check(get_lib().sga_pct_cat_dense_bwd(_ptr(x1), _ptr(x2), _ptr(x3), _ptr(x4), N, P, _ptr(M), _ptr(scale), _ptr(u), _ptr(xbar),
+                                              *[_ptr(g) for g in gs], _stream()), 'sga_pct_cat_dense_bwd')
+    _count(1)
+    return gs
+
+
+def pct_cat_sparse_backward(coef, pstar, WL, xs4, gs, dWL):
+    """gs[a][n, pstar, :] += coef WL[c, a-th block]  and  dWL[c, :] += coef xcat[n, pstar, :]."""
+    N, P, _ = xs4[0].shape
+    lib = get_lib()
+    check(lib.sga_pct_cat_sparse_bwd_x(_ptr(coef), _ptr(pstar), _ptr(WL), N, P, *[_ptr(g) for g in gs], _stream()), 'sga_pct_cat_sparse_bwd_x')
+    check(lib.sga_pct_cat_sparse_bwd_w(_ptr(coef), _ptr(pstar), *[_ptr(x) for x in xs4], N, P, _ptr(dWL), _stream()), 'sga_pct_cat_sparse_bwd_w')
+    _count(2)
+
+
+def axpby_rows(dst, alpha, src=None, beta=0.0, rowscale=None, gamma=0.0, rowscale2=None, colvec=None):
+    R, C = dst.shape
+    check(get_lib().sga_axpby_rows(_ptr(dst), float(alpha), _ptr(src), float(beta), _ptr(rowscale), float(gamma), _ptr(rowscale2), _ptr(colvec),
+                                   R, C, _stream()), 'sga_axpby_rows')
+    _count(1)
+    return dst
+
+
+def wgrad_group(problems):
+    """``problems``: list of (A [K,M], B [K,N], C [M,N]); C += A^T B on the tensor cores, one grouped launch per 16."""
+    n = len(problems)
+    if n == 0:
+        return
+    K = problems[0][0].shape[0]
+    arr_p, arr_l, arr_i = ctypes.c_void_p * n, ctypes.c_int64 * n, ctypes.c_int * n
+    A = arr_p(*[a.data_ptr() for a, _, _ in problems])
+    B = arr_p(*[b.data_ptr() for _, b, _ in problems])
+    C = arr_p(*[c.data_ptr() for _, _, c in problems])
+    lda = arr_l(*[a.stride(0) for a, _, _ in problems])
+    ldb = arr_l(*[b.stride(0) for _, b, _ in problems])
+    ldc = arr_l(*[c.stride(0) for _, _, c in problems])
+    M = arr_i(*[a.shape[1] for a, _, _ in problems])
+    Nn = arr_i(*[b.shape[1] for _, b, _ in problems])
+    for a, b, c in problems:
+        assert a.shape[0] == K and b.shape[0] == K and c.shape == (a.shape[1], b.shape[1])
+    with _timed('pct_wgrad'):
+        check(get_lib().sga_wgrad_group(A, lda, M, B, ldb, Nn, C, ldc, n, K, _stream()), 'sga_wgrad_group')
+    _count((n + 15) // 16)
 
 
 def col_stats(x):

@@ -120,7 +120,7 @@ def test_cat_linear_pooling(N, P, dev):
     x1, x2, x3, t4 = [_rand((N, P, 128), dev, 1 + i) for i in range(4)]
     a4, b4 = _rand((128,), dev, 7, 0.7), _rand((128,), dev, 8, 0.3)
     WL = _rand((1024, 512), dev, 9, 1 / math.sqrt(512))
-    zmax, zmin, st = ops.pct_cat_linear(x1, x2, x3, t4, (a4, b4), WL)
+    zmax, zmin, st, _, _ = ops.pct_cat_linear(x1, x2, x3, t4, (a4, b4), WL)
     x4 = x3.double() + torch.relu(a4.double() * t4.double() + b4.double())
     Z = torch.cat([x1.double(), x2.double(), x3.double(), x4], dim=2) @ WL.double().t()      # [N, P, 1024]
     aL, bL = _rand((1024,), dev, 11, 0.8), _rand((1024,), dev, 12, 0.3)
@@ -130,6 +130,17 @@ def test_cat_linear_pooling(N, P, dev):
     assert rel_inf(pooled, ref) < 3e-5
     flat = Z.reshape(-1, 1024)
     assert rel_inf(st[:1024], flat.sum(0)) < 1e-5 and rel_inf(st[1024:], (flat * flat).sum(0)) < 1e-5
+    # training forward: the same values plus the arg-max point of every (object, channel) -- torch.max's index
+    zmax2, zmin2, st2, imax, imin = ops.pct_cat_linear(x1, x2, x3, t4, (a4, b4), WL, track=True)
+    pooled2, pstar, zsel = ops.pct_pool_act(zmax2, zmin2, aL, bL, P, imax, imin)
+    torch.cuda.synchronize()
+    assert torch.equal(pooled2, pooled) and torch.equal(zmax2, zmax) and torch.equal(zmin2, zmin)
+    Y = F.leaky_relu(aL.double() * Z + bL.double(), 0.2)
+    ref_idx = Y.max(dim=1).indices
+    picked = torch.gather(Y, 1, pstar.long()[:, None, :])[:, 0]
+    assert rel_inf(picked, ref) < 3e-5                                          # the tracked point attains the maximum
+    assert float((pstar.long() == ref_idx).float().mean()) > 0.999              # (near-ties may resolve differently)
+    assert rel_inf(zsel, torch.gather(Z, 1, pstar.long()[:, None, :])[:, 0]) < 3e-5
 
 
 def _gold():
@@ -231,11 +242,3 @@ def test_encoder_with_pct_vs_reference(dev):
     for key in z.files:
         if key.startswith('after/') and 'running' in key:
             assert rel_inf(after[key[6:]], torch.from_numpy(z[key])) < 1e-4, key
-
-
-def test_pct_backward_fails_loudly(dev):
-    from sgaligner_b200.pct import NaivePCT
-    m = NaivePCT().to(dev).train()
-    y = m(torch.randn(4, 64, 3, device=dev))
-    with pytest.raises(NotImplementedError):
-        y.sum().backward()

@@ -1,0 +1,236 @@
+"""GPU parity of the NaivePCT BACKWARD (autograd of src/aligner/networks/pct.py:275-317): the building
+blocks against fp64 autograd of the same formulas, and every parameter gradient of the encoder against (i) the gradients
+of the UNMODIFIED reference module (tests/golden/pct_ref.npz: train mode, recorded dropout seed) and (ii) fp64 autograd of
+the oracle at shapes with several point tiles, in train() and eval().  Gate: 1e-3 of the tensor's largest gradient
+(tensors whose gradient is mathematically zero -- a bias in front of a train-mode BatchNorm -- against 1e-3 of the largest
+gradient of the model instead: both sides hold rounding noise there)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import pct_oracle
+from tests.util import GOLD, rel_inf
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device('cuda:0')
+
+
+def _rand(shape, dev, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dev)
+
+
+@pytest.mark.parametrize('rows,C,masked,slope', [(1000, 128, False, 0.0), (77, 512, True, 0.0), (33, 1024, False, 0.2), (5000, 256, True, 0.0)])
+@pytest.mark.parametrize('training', [True, False])
+def test_bn_backward_vs_autograd(rows, C, masked, slope, training, dev):
+    from sgaligner_b200 import ops
+    y = _rand((rows, C), dev, 1) * 2 + 0.3
+    g = _rand((rows, C), dev, 2, 1e-4)                      # gradient-sized values
+    bn = torch.nn.BatchNorm1d(C).to(dev)
+    with torch.no_grad():
+        bn.weight.copy_(_rand((C,), dev, 3, 0.3) + 1)
+        bn.bias.copy_(_rand((C,), dev, 4, 0.2))
+        bn.running_mean.copy_(_rand((C,), dev, 5, 0.2))
+        bn.running_var.copy_(torch.rand(C, device=dev) + 0.5)
+    lin_bias = _rand((C,), dev, 6, 0.1)
+    mask = (torch.rand(rows, C, device=dev) < 0.5).float() if masked else None
+    # reference: fp64 autograd
+    yd = y.double().requires_grad_(True)
+    w = bn.weight.detach().double().requires_grad_(True)
+    b = bn.bias.detach().double().requires_grad_(True)
+    z = F.batch_norm(yd + lin_bias.double(), bn.running_mean.double().clone(), bn.running_var.double().clone(), w, b, training, 0.1, bn.eps)
+    act = F.leaky_relu(z, slope) if slope else F.relu(z)
+    if masked:
+        act = act * mask.double() * 2.0
+    (act * g.double()).sum().backward()
+    # ours
+    stats = ops.col_stats(y) if training else None
+    ab = ops.bn_fold(bn, stats, float(rows), training, lin_bias=lin_bias)
+    dy, dga, dbe, _ = ops.bn_backward(g, y, ab, bn, stats, float(rows), training, mask=mask, scale=2.0, slope=slope, lin_bias=lin_bias)
+    torch.cuda.synchronize()
+    assert rel_inf(dy, yd.grad) < 2e-5
+    assert rel_inf(dga, w.grad) < 2e-5 and rel_inf(dbe, b.grad) < 2e-5
+
+
+@pytest.mark.parametrize('N,P', [(3, 96), (5, 128), (4, 300), (20, 512)])
+def test_attention_backward_vs_autograd(N, P, dev):
+    from sgaligner_b200 import ops
+    k = _rand((N, P, 32), dev, 1, 1.2)
+    v = _rand((N, P, 128), dev, 2)
+    dxs = _rand((N, P, 128), dev, 3, 1e-5)                  # far below the fp16 range on purpose
+    xs, c2 = ops.pct_attention(k, v, want_c2=True)
+    dk1, dk2, dv = ops.pct_attention_backward(k, v, c2, dxs)
+    torch.cuda.synchronize()
+    kd = k.double().requires_grad_(True)
+    vd = v.double().requires_grad_(True)
+    A = torch.softmax(kd @ kd.transpose(1, 2) / math.sqrt(32), dim=-1)
+    ref = A.transpose(1, 2) @ vd                             # xs[j] = sum_i A[i, j] v[i]
+    assert rel_inf(xs, ref) < 2e-5
+    (ref * dxs.double()).sum().backward()
+    e_dv, e_dk = rel_inf(dv, vd.grad), rel_inf(dk1 + dk2, kd.grad)
+    print('attention backward N=%d P=%d: dv %.2e  dk %.2e' % (N, P, e_dv, e_dk))
+    assert e_dv < 1e-4 and e_dk < 1e-4
+
+
+@pytest.mark.parametrize('N,P', [(2, 96), (3, 300), (150, 512)])
+def test_cat_stage_backward_pieces(N, P, dev):
+    from sgaligner_b200 import ops
+    xs4 = [_rand((N, P, 128), dev, 10 + i) for i in range(4)]
+    M = _rand((512, 512), dev, 20, 1e-6)
+    M = (M + M.t()).contiguous()
+    u = _rand((512,), dev, 21, 1e-6)
+    xbar = _rand((512,), dev, 24, 0.5)
+    gs = ops.pct_cat_dense_backward(*xs4, M, u, xbar)
+    xcat = torch.cat(xs4, dim=-1).double()
+    ref = -((xcat - xbar.double()) @ M.double().t()) - u.double()
+    torch.cuda.synchronize()
+    got = torch.cat(gs, dim=-1)
+    assert rel_inf(got, ref) < 1e-5, rel_inf(got, ref)
+    # sparse half
+    WL = _rand((1024, 512), dev, 22, 1 / math.sqrt(512))
+    coef = _rand((N, 1024), dev, 23, 1e-5)
+    coef[:, ::7] = 0
+    pstar = torch.randint(0, P, (N, 1024), device=dev, dtype=torch.int32)
+    dWL = torch.zeros_like(WL)
+    base = [g.clone() for g in gs]
+    ops.pct_cat_sparse_backward(coef, pstar, WL, xs4, gs, dWL)
+    torch.cuda.synchronize()
+    D = torch.zeros(N, P, 1024, dtype=torch.float64, device=dev)
+    D.scatter_(1, pstar.long()[:, None, :], coef.double()[:, None, :])        # D[n, pstar[n,c], c] = coef[n,c]
+    ref_g = torch.cat(base, dim=-1).double() + D @ WL.double()
+    ref_w = torch.einsum('npc,npk->ck', D, xcat)
+    assert rel_inf(torch.cat(gs, dim=-1), ref_g) < 1e-5
+    assert rel_inf(dWL, ref_w) < 1e-5
+    # Gram matrix of the concatenated activations through the grouped weight-gradient GEMM
+    G = torch.zeros((512, 512), device=dev)
+    ops.wgrad_group([(xs4[a].reshape(-1, 128), xs4[b].reshape(-1, 128), G[128 * a:128 * a + 128, 128 * b:128 * b + 128])
+                     for a in range(4) for b in range(a, 4)])
+    dWk = torch.zeros((32, 128), device=dev)
+    small = _rand((N, P, 32), dev, 30, 1e-6)
+    ops.wgrad_group([(small.reshape(-1, 32), xs4[0].reshape(-1, 128), dWk)])
+    torch.cuda.synchronize()
+    Gr = (xcat.reshape(-1, 512).t() @ xcat.reshape(-1, 512))
+    for a in range(4):
+        for b in range(a, 4):
+            blk = (slice(128 * a, 128 * a + 128), slice(128 * b, 128 * b + 128))
+            assert rel_inf(G[blk], Gr[blk]) < 5e-5
+    assert rel_inf(dWk, small.double().reshape(-1, 32).t() @ xs4[0].double().reshape(-1, 128)) < 5e-5
+
+
+def _grad_report(named, ref_of, gmax, tol=1e-3):
+    worst, lines = 0.0, []
+    for name, p in named:
+        ref = ref_of(name)
+        if ref is None:
+            continue
+        got = p.grad
+        assert got is not None, name
+        got = got.detach().double().cpu().reshape(-1)
+        if ref.numel() != got.numel():
+            got = got[::17]
+        err = float((got - ref.double().reshape(-1)).abs().max() / max(float(ref.abs().max()), 1e-3 * gmax))
+        lines.append('%-28s %.2e' % (name, err))
+        worst = max(worst, err)
+    return worst, lines
+
+
+def test_param_grads_vs_reference_golden(dev):
+    """Train mode, the reference's recorded dropout seed: gradients of the unmodified reference module."""
+    from sgaligner_b200.pct import NaivePCT
+    z = np.load(os.path.join(GOLD, 'pct_ref.npz'))
+    m = NaivePCT()
+    m.load_state_dict(pct_oracle.random_params(int(z['param_seed'])), strict=True)
+    m = m.to(dev).train()
+    m.dropout_rng = 'cpu'
+    x = torch.from_numpy(z['x']).permute(0, 2, 1).contiguous().to(dev)
+    R = torch.from_numpy(z['grad_R']).to(dev)
+    torch.manual_seed(int(z['train_seed']))
+    y = m(x)
+    assert rel_inf(y, torch.from_numpy(z['y_train'])) < 1e-4
+    (y * R).sum().backward()
+    torch.cuda.synchronize()
+
+    def ref_of(name):
+        key = 'grad/' + name.replace('q_conv', 'k_conv')
+        return torch.from_numpy(z[key]) if key in z.files else None
+
+    worst, lines = _grad_report(list(m.named_parameters()), ref_of, float(z['grad_max']))
+    print('\n'.join(lines))
+    print('NaivePCT parameter gradients vs the reference module: worst %.2e' % worst)
+    assert worst < 1e-3
+
+
+@pytest.mark.parametrize('N,P,training', [(5, 300, True), (4, 200, False), (9, 512, True)])
+def test_param_grads_vs_oracle_autograd(N, P, training, dev):
+    from sgaligner_b200.pct import NaivePCT
+    p = pct_oracle.random_params(13)
+    m = NaivePCT()
+    m.load_state_dict(p, strict=True)
+    m = m.to(dev).train(training)
+    m.dropout_rng = 'cpu'
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(N, P, 3, generator=g) * 0.7 + torch.rand(N, 1, 3, generator=g) * 2 - 1
+    R = torch.randn(N, 256, generator=g)
+    torch.manual_seed(77)
+    y = m(x.to(dev))
+    (y * R.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    def oracle_grads(dt):
+        po = {k: (v.clone().to(dt).requires_grad_('running' not in k) if v.is_floating_point() else v.clone()) for k, v in p.items()}
+        for sa in ('sa1', 'sa2', 'sa3', 'sa4'):
+            po[sa + '.q_conv.weight'] = po[sa + '.k_conv.weight']
+        torch.manual_seed(77)
+        yo = pct_oracle.naive_pct(x.permute(0, 2, 1).to(dt), po, training=training)
+        (yo * R.to(dt)).sum().backward()
+        return yo.detach(), po
+
+    yo, po = oracle_grads(torch.float64)
+    assert rel_inf(y, yo) < 1e-4
+    _, p32 = oracle_grads(torch.float32)                  # what fp32 autograd itself loses on this input
+    gmax = max(float(v.grad.abs().max()) for k, v in po.items() if v.is_floating_point() and v.grad is not None)
+
+    def ref_of(name):
+        return po[name.replace('q_conv', 'k_conv')].grad
+
+    worst, lines = _grad_report(list(m.named_parameters()), ref_of, gmax)
+
+    class _P:      # the fp32 oracle's gradients in the shape _grad_report expects
+        def __init__(self, g):
+            self.grad = g
+    worst32, lines32 = _grad_report([(n, _P(p32[n.replace('q_conv', 'k_conv')].grad)) for n, _ in m.named_parameters()], ref_of, gmax)
+    print('\n'.join('%s   (fp32 autograd: %s)' % (a, b.split()[-1]) for a, b in zip(lines, lines32)))
+    print('NaivePCT parameter gradients vs fp64 oracle autograd (N=%d P=%d train=%s): worst %.2e (fp32 torch autograd: %.2e)'
+          % (N, P, training, worst, worst32))
+    assert worst < max(1e-3, 4 * worst32)
+
+
+def test_encoder_with_pct_trains(dev):
+    """MultiModalEncoder(['pct','gat','rel','attr']) -- the module list of the shipped config
+    (configs/scan3r/scan3r_ground_truth.yaml:5) -- through OverallLoss, backward and Adam: finite gradients on every
+    parameter of the point encoder and a decreasing loss."""
+    from sgaligner_b200 import synthetic, to_cuda
+    from sgaligner_b200.losses import CustomMultiLossLayer, OverallLoss
+    from sgaligner_b200.sg_aligner import MultiModalEncoder
+    from sgaligner_b200.trainer import FlatAdam, train_step
+    torch.manual_seed(1)
+    modules = ['pct', 'gat', 'rel', 'attr']
+    data = to_cuda(synthetic.make_batch([10] * 4, [12] * 4, [6] * 4, n_points=160, edge_mode='complete', seed=3), dev)
+    model = MultiModalEncoder(modules=modules, rel_dim=41, attr_dim=164).to(dev).train()
+    li, lc = CustomMultiLossLayer(4).to(dev), CustomMultiLossLayer(4).to(dev)
+    fn = OverallLoss(li, lc, dev, {'zoom': 0.1, 'wt_align_loss': 1.0, 'wt_contrastive_loss': 1.0, 'modules': modules})
+    opt = FlatAdam(list(model.parameters()) + list(li.parameters()) + list(lc.parameters()), lr=1e-3, weight_decay=1e-6)
+    losses = [float(train_step(model, fn, opt, data)['loss']) for _ in range(10)]
+    for name, p in model.object_encoder.named_parameters():
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), name
+    print('pct training losses', ['%.3f' % l for l in losses])
+    assert all(np.isfinite(losses))
+    assert min(losses[-3:]) < losses[0]
