@@ -507,9 +507,10 @@ def run_ours(args, out=sys.stdout):
                                workload='BASELINE configs[4] per-GPU share: 8 pairs x (256+256) objects x 1024 pts, pt_out 512, emb 128 (joint 512-d)')
 
     # ---- (2c') the module list of the reference's SHIPPED config (scan3r_ground_truth.yaml:5): NaivePCT object encoder
-    #       + gat + rel + attr on the C2 shapes.  Serving only (the PCT backward is not built);
-    #      per-kernel times of the PCT launches, and on rank 0 the reference's NaivePCT op sequence in PyTorch eager
-    #      on this GPU (cuBLAS / cuDNN fp32) as the kernel-to-beat.
+    #       + gat + rel + attr on the C2 shapes: serving, and the full training step (forward with
+    #      batch statistics + OverallLoss + backward + Adam); per-kernel times of the PCT launches, and on rank 0 the
+    #      reference's NaivePCT op sequence in PyTorch eager on this GPU (cuBLAS / cuDNN fp32) as the kernel-to-beat
+    #      (forward, and forward + autograd backward).
     def run_pct_config():
         import collections
         PCT = ['pct', 'gat', 'rel', 'attr']
@@ -539,9 +540,29 @@ def run_ours(args, out=sys.stdout):
         flop_obj = (2 * Pp * (3 * 128 + 128 * 128) + 4 * (2 * Pp * (128 * 32 + 2 * 128 * 128) + 2 * Pp * Pp * 160) + 2 * Pp * 512 * 1024
                     + 2 * (1024 * 512 + 512 * 256))
         k_tot = sum(agg.values())
+        # training step of the shipped module list
+        l_i, l_c = CustomMultiLossLayer(4).to(dev), CustomMultiLossLayer(4).to(dev)
+        lf = OverallLoss(l_i, l_c, dev, {'zoom': 0.1, 'wt_align_loss': 1.0, 'wt_contrastive_loss': 1.0, 'modules': PCT})
+        mdl.train()
+        op = FlatAdam(list(mdl.parameters()) + list(l_i.parameters()) + list(l_c.parameters()), lr=1e-3, weight_decay=1e-6)
+        pct_steps = max(2, min(cfg_steps, 4))
+        tr_ms, _, _ = timed(lambda: train_step(mdl, lf, op, d), pct_steps, 2)
+        tr_ms /= pct_steps
+        ops.KERNEL_EVENTS = []
+        train_step(mdl, lf, op, d)
+        torch.cuda.synchronize()
+        agg_t = collections.OrderedDict()
+        for nme, a_, b_ in ops.KERNEL_EVENTS:
+            if nme.startswith('pct_'):
+                agg_t[nme] = agg_t.get(nme, 0.0) + a_.elapsed_time(b_)
+        ops.KERNEL_EVENTS = None
+        peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+        del op, lf, l_i, l_c
+        mdl.eval()
         res = {'pairs_per_gpu': PAIRS_PER_GPU, 'objects_per_gpu': n_obj, 'modules': '+'.join(PCT),
                'serve_ms_per_step': sv_ms, 'serve_pairs_per_s': world * PAIRS_PER_GPU / (sv_ms * 1e-3),
-               'train_ms_per_step': None, 'train': 'not built: the NaivePCT backward raises NotImplementedError',
+               'train_ms_per_step': tr_ms, 'train_pairs_per_s': world * PAIRS_PER_GPU / (tr_ms * 1e-3),
+               'train_pct_kernel_ms': {k_: round(v_, 4) for k_, v_ in agg_t.items()}, 'train_peak_mem_gib': round(peak_mem, 2),
                'pct_kernel_ms': {k_: round(v_, 4) for k_, v_ in agg.items()}, 'pct_kernels_total_ms': k_tot,
                'pct_flop_per_object': flop_obj,
                'pct_algorithmic_tflops': flop_obj * n_obj / (k_tot * 1e-3) / 1e12 if k_tot else None,
@@ -572,6 +593,25 @@ def run_ours(args, out=sys.stdout):
                         'same points and weights, 512 objects per call',
                 'ms': a_.elapsed_time(b_) / 3, 'matmul_allow_tf32': bool(torch.backends.cuda.matmul.allow_tf32),
                 'max_rel_diff_ours_vs_eager': float((y_our - y_ref).abs().max() / y_ref.abs().max())}
+            # forward + autograd backward of the encoder alone in eager PyTorch (train mode, 512 objects per call: the
+            # [B, 512, 512] attention maps of four layers and the [B, 1024, 512] activation are kept for the backward)
+            try:
+                pg = {k_: (v_.detach().clone().requires_grad_(v_.is_floating_point() and 'running' not in k_)) for k_, v_ in pp.items()}
+
+                def eager_train():
+                    for i in range(0, n_obj, 512):
+                        PO.naive_pct(xin[i:i + 512], pg, True).sum().backward()
+                eager_train()
+                torch.cuda.synchronize()
+                a_.record()
+                eager_train()
+                b_.record()
+                torch.cuda.synchronize()
+                res['pct_gpu_eager_baseline']['train_fwd_bwd_ms'] = a_.elapsed_time(b_)
+                del pg
+            except RuntimeError as ex_:          # out of memory on a smaller card
+                res['pct_gpu_eager_baseline']['train_fwd_bwd_ms'] = None
+                res['pct_gpu_eager_baseline']['train_error'] = str(ex_)[:120]
         del mdl, d
         torch.cuda.empty_cache()
         return res

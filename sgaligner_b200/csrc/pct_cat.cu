@@ -21,8 +21,8 @@ namespace ct {
 constexpr uint32_t WLO = 0;                               // 8 blocks (kc * 2 + blk) x 16 KiB
 constexpr uint32_t RING = WLO + 8 * kBlk;                 // 3 slots x {hi 16 KiB, lo 16 KiB}
 constexpr uint32_t SLOT = 2 * kBlk;
-constexpr uint32_t AB4 = RING + 3 * SLOT;                 // a4[128], b4[128]  (mode 2: xbar[512])
-constexpr uint32_t BARS = AB4 + 2048;
+constexpr uint32_t AB4 = RING + 3 * SLOT;                 // a4[128], b4[128]
+constexpr uint32_t BARS = AB4 + 1024;
 constexpr uint32_t TMEMPTR = BARS + 128;
 constexpr uint32_t SMEM_BYTES = TMEMPTR + 16 + 1024;
 constexpr uint32_t D_COL = 0, WHI_COL = 256;
@@ -74,8 +74,6 @@ pct_cat_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const
       ab4[i] = a4[i];
       ab4[128 + i] = b4[i];
     }
-  } else {
-    for (int i = tid; i < 512; i += kThreads) ab4[i] = bo.xbar[i];
   }
   if (tid == 0) {
     for (int s = 0; s < 3; ++s) {
@@ -250,10 +248,13 @@ pct_cat_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const
         for (int qq = 0; qq < 4; ++qq) {
           const int row = r0 + 32 * qq;
           float f[8] = {u[qq][0].x, u[qq][0].y, u[qq][0].z, u[qq][0].w, u[qq][1].x, u[qq][1].y, u[qq][1].z, u[qq][1].w};
-          if (kMode == 2) {
+          if (kMode == 2) {         // centre: xbar (2 KB, L1 resident; shared memory is full)
             const bool okr = row < valid;
+            const float4 m0 = __ldg(reinterpret_cast<const float4*>(bo.xbar + kc * 128 + chb));
+            const float4 m1 = __ldg(reinterpret_cast<const float4*>(bo.xbar + kc * 128 + chb) + 1);
+            const float mb[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = okr ? f[e] - ab4[kc * 128 + chb + e] : 0.f;
+            for (int e = 0; e < 8; ++e) f[e] = okr ? f[e] - mb[e] : 0.f;
           }
           if (kMode != 2 && kc == 3) {
             const float tv[8] = {w[qq][0].x, w[qq][0].y, w[qq][0].z, w[qq][0].w, w[qq][1].x, w[qq][1].y, w[qq][1].z, w[qq][1].w};
