@@ -348,7 +348,9 @@ int sga_pct_pow2_scale(const float* x, const float* y, int64_t N, int64_t per, f
 int sga_pct_attn_bwd_dv(const float* k, const float* dxs, const float* c2, const float* scale, int64_t N, int P, float* dv,
                         void* stream);
 int sga_pct_attn_bwd_dk(const float* k, const float* fixed, const float* streamed, const float* c2, float* delta,
-                        const float* scale, int64_t N, int P, int by_col, float* dk_out, void* stream);
+                        const float* scale, int64_t N, int P, int by_col, int delta_sweep, float* dk_out, void* stream);
+/* delta [N,P] = scale[n][0] * sum_c x[n,p,c] y[n,p,c] (C = 128): the softmax-backward row term v_i . dv_i in scaled units */
+int sga_pct_rowdot_scaled(const float* x, const float* y, const float* scale, int64_t N, int P, float* out, void* stream);
 /* dX = dY Wt^T on the tensor cores: src [N,P,128] (scaled per object by scale [N,2]), Wt [128,128] (pass W^T), out [N,P,128] */
 int sga_pct_pointwise_scaled(const float* src, const float* scale, int64_t N, int P, const float* Wt, float* out, void* stream);
 /* gradient of an SA layer's input: out = gx (+ gcat) + dxv + (dk1 + dk2) Wk;  dk1 <- dk1 + dk2.  [rows,128] / [rows,32] */
@@ -377,6 +379,12 @@ int sga_pct_residual(const float* x, const float* t, const float* a, const float
 /* dst [R,C] = alpha * dst + beta * rowscale[r] * src[r,c] + gamma * rowscale2[r] * colvec[c]  (small weight-gradient algebra) */
 int sga_axpby_rows(float* dst, float alpha, const float* src, float beta, const float* rowscale, float gamma,
                    const float* rowscale2, const double* colvec, int64_t R, int C, void* stream);
+/* Weight gradients / Gram blocks as contractions over all R = N*P points (csrc/pct_wgrad.cu; tcgen05, bf16 operand pairs,
+ * accumulators resident in tensor memory):  C_b[m, n] += sum_r A[r, m] B_b[r, n]  for up to four B_b [R, nb_b] (nb_b = 128 or
+ * 32) that share A [R, 128]; transpose != 0 stores C_b[n * ldc_b + m] instead (dW = dY^T X with A = X).  C must hold the
+ * value to add to. */
+int sga_pct_wgrad(const float* A, int64_t R, const float* const* B, const int* nb, int nB, float* const* C,
+                  const int64_t* ldc, int transpose, void* stream);
 /* Grouped weight-gradient products on sga_gemm_tf32x3 (both operands MN-major, split-K, atomic accumulation):
  * C_i [M_i,N_i] += A_i^T B_i with A_i [K,M_i] (row stride lda_i) and B_i [K,N_i]; C must hold the value to add to. */
 int sga_wgrad_group(const float* const* A, const int64_t* lda, const int* M, const float* const* B, const int64_t* ldb,

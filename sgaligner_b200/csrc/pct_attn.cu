@@ -477,9 +477,9 @@ template <bool kCol>
 __global__ void __launch_bounds__(kThreads, 1)
 pct_attn_dk_kernel(const float* __restrict__ k, const float* __restrict__ fixed, const float* __restrict__ streamed,
                    const float* __restrict__ c2, const float* __restrict__ delta_in, float* __restrict__ delta_out,
-                   const float* __restrict__ scale, int64_t N, int P, float* __restrict__ dk_out) {
+                   const float* __restrict__ scale, int64_t N, int P, float* __restrict__ dk_out, int sweeps) {
   using namespace dk;
-  constexpr int kPhases = kCol ? 1 : 2;
+  const int kPhases = kCol ? 1 : sweeps;       // kCol = false: 2 = delta from a first sweep (written to delta_out), 1 = delta_in
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sm_base = ptx::smem_u32(sm);
@@ -518,7 +518,7 @@ pct_attn_dk_kernel(const float* __restrict__ k, const float* __restrict__ fixed,
     for (int64_t w = blockIdx.x; w < W; w += gridDim.x, ++wi) {
       ptx::mbar_wait(&bars[BAR_F_FULL], wi & 1);
       for (int ph = 0; ph < kPhases; ++ph) {
-        const bool dk_phase = kCol || ph == 1;
+        const bool dk_phase = ph == kPhases - 1;
         for (int b = 0; b < T; ++b, ++u) {
           ptx::mbar_wait(&bars[BAR_G_FULL], u & 1);
           ptx::tc_fence_after();
@@ -577,15 +577,15 @@ pct_attn_dk_kernel(const float* __restrict__ k, const float* __restrict__ fixed,
       for (int i = tid; i < Ppad; i += kComputeThreads) {
         nrm[i] = c2[(n * 2) * Ppad + i];
         nrm[kMaxT * kTile + i] = c2[(n * 2 + 1) * Ppad + i];
-        if (kCol) nrm[2 * kMaxT * kTile + i] = (i < P) ? delta_in[obase + i] : 0.f;
+        nrm[2 * kMaxT * kTile + i] = ((kCol || kPhases == 1) && i < P) ? delta_in[obase + i] : 0.f;
       }
       ptx::fence_proxy_async_smem();
       compute_barrier();
       ptx::mbar_arrive(&bars[BAR_F_FULL]);
       const float mr = ma_s[a * kTile + row], lr = lg_s[a * kTile + row];
-      float dr = 0.f;                                   // delta of this thread's row (kCol = false: from the first sweep)
+      float dr = de_s[a * kTile + row];                 // delta of this thread's row (two sweeps: replaced after the first)
       for (int ph = 0; ph < kPhases; ++ph) {
-        const bool dk_phase = kCol || ph == 1;
+        const bool dk_phase = ph == kPhases - 1;
         float dacc = 0.f;
         for (int b = 0; b < T; ++b, ++u) {
           if (dk_phase && b >= 1) ptx::mbar_wait(&bars[BAR_DK_DONE], (ud - 1) & 1);      // k_b images, G and T are free again
@@ -725,10 +725,11 @@ extern "C" int sga_pct_attn_bwd_dv(const float* k, const float* dxs, const float
 }
 
 /* dk halves of the SA backward (see pct_attn_dk_kernel): by_col = 0: fixed = v, streamed = dxs (row half; also WRITES
- * delta [N,P], in units of the object's scale); by_col = 1: fixed = dxs, streamed = v (column half; READS delta).
+ * delta [N,P], in units of the object's scale, when delta_sweep != 0 -- otherwise it READS it like by_col = 1 does);
+ * by_col = 1: fixed = dxs, streamed = v (column half; READS delta).
  * scale [N,2] = sga_pct_pow2_scale(dxs, v).  dk_out [N,P,32] is overwritten. */
 extern "C" int sga_pct_attn_bwd_dk(const float* k, const float* fixed, const float* streamed, const float* c2, float* delta,
-                                   const float* scale, int64_t N, int P, int by_col, float* dk_out, void* stream) {
+                                   const float* scale, int64_t N, int P, int by_col, int delta_sweep, float* dk_out, void* stream) {
   if (N <= 0) return SGA_OK;
   SGA_REQUIRE(k && fixed && streamed && c2 && delta && scale && dk_out && P >= 1 && P <= sga::pct::kMaxT * sga::pct::kTile,
               "sga_pct_attn_bwd_dk: P=%d (1..512)", P);
@@ -744,8 +745,8 @@ extern "C" int sga_pct_attn_bwd_dk(const float* k, const float* fixed, const flo
   int64_t W = N * T;
   int grid = sga::sm_count();
   if ((int64_t)grid > W) grid = (int)W;
-  if (by_col) pct_attn_dk_kernel<true><<<grid, kThreads, dk::SMEM_BYTES, (cudaStream_t)stream>>>(k, fixed, streamed, c2, delta, nullptr, scale, N, P, dk_out);
-  else pct_attn_dk_kernel<false><<<grid, kThreads, dk::SMEM_BYTES, (cudaStream_t)stream>>>(k, fixed, streamed, c2, nullptr, delta, scale, N, P, dk_out);
+  if (by_col) pct_attn_dk_kernel<true><<<grid, kThreads, dk::SMEM_BYTES, (cudaStream_t)stream>>>(k, fixed, streamed, c2, delta, nullptr, scale, N, P, dk_out, 1);
+  else pct_attn_dk_kernel<false><<<grid, kThreads, dk::SMEM_BYTES, (cudaStream_t)stream>>>(k, fixed, streamed, c2, delta, delta, scale, N, P, dk_out, delta_sweep ? 2 : 1);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }

@@ -128,6 +128,17 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------- small row kernels
+// delta[n, p] = scale[n][0] * sum_c v[n,p,c] dv[n,p,c]   (= sum_j A[i,j] dA[i,j] of the softmax backward, in scaled units)
+__global__ void __launch_bounds__(256) rowdot_scaled_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                            const float* __restrict__ scale, int64_t rows, int P, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float4 a = ld4(x + r * 128 + lane * 4), b = ld4(y + r * 128 + lane * 4);
+  const float s = warp_sum(a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w);
+  if (lane == 0) out[r] = s * __ldg(scale + 2 * (r / P));
+}
+
 // out = gx (+ gcat) + dxv + (dk1 + dk2) Wk; dk1 <- dk1 + dk2.  One warp per row, lane = 4 output channels.
 __global__ void __launch_bounds__(256) sa_input_grad_kernel(const float* __restrict__ gx, const float* __restrict__ gcat,
                                                             const float* __restrict__ dxv, float* __restrict__ dk1,
@@ -464,6 +475,15 @@ extern "C" int sga_bn_bwd_apply(const float* g, const float* y, const float* a, 
               "sga_bn_bwd_apply: 16-byte alignment");
   const int64_t total4 = rows * C / 4;
   bn_bwd_apply_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, y, a, b, mask, scale, slope, e, f, mean, total4, C, out);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+extern "C" int sga_pct_rowdot_scaled(const float* x, const float* y, const float* scale, int64_t N, int P, float* out, void* stream) {
+  if (N <= 0) return SGA_OK;
+  SGA_REQUIRE(x && y && scale && out && P >= 1, "sga_pct_rowdot_scaled: bad arguments");
+  const int64_t rows = N * P;
+  rowdot_scaled_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, y, scale, rows, P, out);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }

@@ -99,6 +99,48 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict_
   }
 }
 
+// the same for long tensors ([N*P, 128] activations / gradients of the NaivePCT backward): float4 rows, fp32 partial sums
+// over at most a few hundred rows per thread, fp64 across threads -- HBM bound instead of FP64-latency bound
+__global__ void __launch_bounds__(256) col_stats_long_kernel(const float* __restrict__ x, int64_t N, int C, double* __restrict__ stats) {
+  const int tpr = C >> 2, rpi = 256 / tpr;
+  const int col4 = threadIdx.x % tpr, rslot = threadIdx.x / tpr;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  double ds[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
+  int run = 0;
+  for (int64_t r = (int64_t)blockIdx.x * rpi + rslot; r < N; r += (int64_t)gridDim.x * rpi) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * C + col4 * 4));
+    s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]); q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
+    if (++run == 64) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        ds[i] += (double)s[i]; dq[i] += (double)q[i];
+        s[i] = 0.f; q[i] = 0.f;
+      }
+      run = 0;
+    }
+  }
+  __shared__ double red[256][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    red[threadIdx.x][i] = ds[i] + (double)s[i];
+    red[threadIdx.x][4 + i] = dq[i] + (double)q[i];
+  }
+  __syncthreads();
+  if (rslot == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double t1 = 0, t2 = 0;
+      for (int k = 0; k < rpi; ++k) {
+        t1 += red[k * tpr + col4][i];
+        t2 += red[k * tpr + col4][4 + i];
+      }
+      atomicAdd(&stats[col4 * 4 + i], t1);
+      atomicAdd(&stats[C + col4 * 4 + i], t2);
+    }
+  }
+}
+
 // out = relu(a_c x + b_c) * (mask ? mask * scale : 1)        (BatchNorm + ReLU + nn.Dropout, pct.py:312-316)
 __global__ void bn_act_rows_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
                                    const float* __restrict__ mask, float scale, int64_t total, int C, float* __restrict__ out) {
@@ -147,6 +189,15 @@ extern "C" int sga_bn_fold(const double* stats, double cnt, const float* lin_bia
 extern "C" int sga_col_stats(const float* x, int64_t N, int C, double* stats, void* stream) {
   if (N <= 0) return SGA_OK;
   SGA_REQUIRE(x && stats && C >= 1, "sga_col_stats: bad arguments");
+  if (N >= 8192 && (C == 128 || C == 256 || C == 512 || C == 1024) && ((uintptr_t)x & 15) == 0) {
+    const int rpi = 256 / (C / 4);
+    int64_t blocks = (N + (int64_t)rpi * 16 - 1) / ((int64_t)rpi * 16);
+    const int64_t cap = (int64_t)sga::sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    sga::pct::col_stats_long_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, N, C, stats);
+    SGA_LAUNCH_CHECK();
+    return SGA_OK;
+  }
   int gy = (int)((N + 63) / 64);
   if (gy > 64) gy = 64;
   sga::pct::col_stats_kernel<<<dim3((C + 31) / 32, gy), 256, 0, (cudaStream_t)stream>>>(x, N, C, stats);

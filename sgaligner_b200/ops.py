@@ -449,13 +449,20 @@ def pct_attention_backward(k, v, c2, dxs):
     dv = torch.empty_like(v)
     with _timed('pct_attn_bwd_dv'):
         check(lib.sga_pct_attn_bwd_dv(_ptr(k), _ptr(dxs), _ptr(c2), _ptr(scale), N, P, _ptr(dv), _stream()), 'sga_pct_attn_bwd_dv')
-    delta = torch.empty((N, P), device=k.device, dtype=torch.float32)      # sum_j A[i,j] dA[i,j], written by the row half
+    # delta_i = sum_j A[i,j] dA[i,j] (in scaled units): summed by the row half from ITS OWN dA values in a first sweep, so
+    # that the errors of dA and delta cancel in (dA - delta) where the softmax is peaked.  SGA_PCT_DELTA=dot takes the
+    # mathematically equal v_i . dv_i from the FMA pipe instead (one S / dA sweep less, -9 ms at 4096 x 512): measured
+    # 10x worse on d k_conv.weight at peaked attention (2e-3 .. 2e-2 vs fp64, tools/dbg_pct_attn_bwd.py) -- not the default.
+    sweep = os.environ.get('SGA_PCT_DELTA', 'sweep') != 'dot'
+    delta = torch.empty((N, P), device=k.device, dtype=torch.float32)
+    if not sweep:
+        check(lib.sga_pct_rowdot_scaled(_ptr(v), _ptr(dv), _ptr(scale), N, P, _ptr(delta), _stream()), 'sga_pct_rowdot_scaled')
     dk1 = torch.empty_like(k)
     dk2 = torch.empty_like(k)
     with _timed('pct_attn_bwd_dk'):
-        check(lib.sga_pct_attn_bwd_dk(_ptr(k), _ptr(v), _ptr(dxs), _ptr(c2), _ptr(delta), _ptr(scale), N, P, 0, _ptr(dk1), _stream()),
-              'sga_pct_attn_bwd_dk')
-        check(lib.sga_pct_attn_bwd_dk(_ptr(k), _ptr(dxs), _ptr(v), _ptr(c2), _ptr(delta), _ptr(scale), N, P, 1, _ptr(dk2), _stream()),
+        check(lib.sga_pct_attn_bwd_dk(_ptr(k), _ptr(v), _ptr(dxs), _ptr(c2), _ptr(delta), _ptr(scale), N, P, 0, 1 if sweep else 0, _ptr(dk1),
+                                      _stream()), 'sga_pct_attn_bwd_dk')
+        check(lib.sga_pct_attn_bwd_dk(_ptr(k), _ptr(dxs), _ptr(v), _ptr(c2), _ptr(delta), _ptr(scale), N, P, 1, 0, _ptr(dk2), _stream()),
               'sga_pct_attn_bwd_dk')
     _count(3)
     return dk1, dk2, dv
@@ -546,6 +553,23 @@ def axpby_rows(dst, alpha, src=None, beta=0.0, rowscale=None, gamma=0.0, rowscal
                                    R, C, _stream()), 'sga_axpby_rows')
     _count(1)
     return dst
+
+
+def pct_wgrad(A, Bs, Cs, transpose: bool = False):
+    """C_b[m, n] += sum_r A[r, m] B_b[r, n]  (transpose: C_b[n, m]) for up to four B_b [R, 128 | 32] sharing A [R, 128]; the
+    contraction runs over all R rows on the tensor cores (csrc/pct_wgrad.cu)."""
+    n = len(Bs)
+    R = A.shape[0]
+    assert A.shape[1] == 128 and A.is_contiguous() and 1 <= n <= 4
+    for b, c in zip(Bs, Cs):
+        assert b.shape[0] == R and b.is_contiguous() and b.shape[1] in (128, 32) and c.stride(1) == 1
+        assert tuple(c.shape) == ((b.shape[1], 128) if transpose else (128, b.shape[1]))
+    arr_p, arr_l, arr_i = ctypes.c_void_p * n, ctypes.c_int64 * n, ctypes.c_int * n
+    with _timed('pct_wgrad'):
+        check(get_lib().sga_pct_wgrad(_ptr(A), R, arr_p(*[b.data_ptr() for b in Bs]), arr_i(*[b.shape[1] for b in Bs]), n,
+                                      arr_p(*[c.data_ptr() for c in Cs]), arr_l(*[c.stride(0) for c in Cs]), 1 if transpose else 0,
+                                      _stream()), 'sga_pct_wgrad')
+    _count(1)
 
 
 def wgrad_group(problems):

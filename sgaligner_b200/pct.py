@@ -173,7 +173,7 @@ class NaivePCT(nn.Module):
         """d(loss)/d(parameter) for every parameter, keyed by ``id(parameter)``; ``g_out`` [N,256] = d(loss)/d(output).
 
         Head and SA layers: plain chain rule, BatchNorm in closed form (``ops.bn_backward``), weight gradients as grouped
-        contractions over all N*P points (``ops.wgrad_group``), input gradients on the pointwise tensor-core kernel (fp16 pairs, per-object power-of-two scaling of the gradient operand).
+        contractions over all N*P points (``ops.pct_wgrad``), input gradients on the pointwise tensor-core kernel (fp16 pairs, per-object power-of-two scaling of the gradient operand).
 
         Concat stage (pct.py:306-310): z = WL xcat is never stored.  With gy = d/d(BN output) -- non-zero only at the
         arg-max point p*(n, c) -- the BatchNorm formula gives  dz[n,p,c] = a_c gy [p = p*] - e_c - f_c (z[n,p,c] - mean_c),
@@ -225,8 +225,9 @@ class NaivePCT(nn.Module):
         dWL = torch.zeros_like(WL)
         ops.pct_cat_sparse_backward(coef, S['pstar'], WL, xs4, gcat, dWL)
         G = torch.zeros((512, 512), device=dev, dtype=torch.float32)
-        ops.wgrad_group([(xs4[a].reshape(-1, 128), xs4[b].reshape(-1, 128), G[128 * a:128 * a + 128, 128 * b:128 * b + 128])
-                         for a in range(4) for b in range(a, 4)])
+        for a in range(4):      # row block a of the Gram matrix: x_a against x_a .. x_4, accumulators resident in tensor memory
+            ops.pct_wgrad(xs4[a].reshape(-1, 128), [xs4[b].reshape(-1, 128) for b in range(a, 4)],
+                          [G[128 * a:128 * a + 128, 128 * b:128 * b + 128] for b in range(a, 4)])
         for a in range(4):
             for b in range(a + 1, 4):
                 G[128 * b:128 * b + 128, 128 * a:128 * a + 128] = G[128 * a:128 * a + 128, 128 * b:128 * b + 128].t()
@@ -242,7 +243,9 @@ class NaivePCT(nn.Module):
             Lr = L[li]
             dt, dga, dbe, _ = ops.bn_backward(gx, Lr['t'], Lr['abt'], sa.after_norm, Lr['stt'], cnt, tr)
             put(sa.after_norm.weight, dga); put(sa.after_norm.bias, dbe)
-            put(sa.trans_conv.bias, colsum(dt, 128))
+            # a bias in front of a batch-statistics BatchNorm has gradient sum_r dt = 0 identically (the reference's autograd
+            # returns rounding noise of 1e-7 of the largest gradient there): no pass over dt in train()
+            put(sa.trans_conv.bias, torch.zeros(128, device=dev) if tr else colsum(dt, 128))
             Wt = sa.trans_conv.weight.reshape(128, 128)
             dxs = ops.pct_pointwise_grad(dt, Wt.t().contiguous())
             dk1, dk2, dv = ops.pct_attention_backward(Lr['k'], Lr['v'], Lr['c2'], dxs)
@@ -257,8 +260,8 @@ class NaivePCT(nn.Module):
             dWv = torch.zeros((128, 128), device=dev, dtype=torch.float32)
             dWk = torch.zeros((32, 128), device=dev, dtype=torch.float32)
             xin = Lr['x_in'].reshape(-1, 128)
-            ops.wgrad_group([(dt.reshape(-1, 128), Lr['x_s'].reshape(-1, 128), dWt), (dv.reshape(-1, 128), xin, dWv),
-                             (dk1.reshape(-1, 32), xin, dWk)])
+            ops.pct_wgrad(dt.reshape(-1, 128), [Lr['x_s'].reshape(-1, 128)], [dWt])
+            ops.pct_wgrad(xin, [dv.reshape(-1, 128), dk1.reshape(-1, 32)], [dWv, dWk], transpose=True)      # one pass over x_in
             put(sa.trans_conv.weight, dWt); put(sa.v_conv.weight, dWv); put(sa.k_conv.weight, dWk)
             del dt, dv, dk1
             L[li] = None
@@ -269,7 +272,7 @@ class NaivePCT(nn.Module):
         W1 = ops._f32c(emb.conv1.weight.reshape(128, 3))
         a1 = ops.pct_embed_a1(pts, W1, S['ab1'])
         dW2 = torch.zeros((128, 128), device=dev, dtype=torch.float32)
-        ops.wgrad_group([(dz2.reshape(-1, 128), a1.reshape(-1, 128), dW2)])
+        ops.pct_wgrad(dz2.reshape(-1, 128), [a1.reshape(-1, 128)], [dW2])
         put(emb.conv2.weight, dW2)
         del a1
         da1 = ops.pct_pointwise_grad(dz2, emb.conv2.weight.reshape(128, 128).t().contiguous())

@@ -117,12 +117,24 @@ def test_cat_stage_backward_pieces(N, P, dev):
     dWk = torch.zeros((32, 128), device=dev)
     small = _rand((N, P, 32), dev, 30, 1e-6)
     ops.wgrad_group([(small.reshape(-1, 32), xs4[0].reshape(-1, 128), dWk)])
+    # ... and through the dedicated kernel (accumulators resident in tensor memory, bf16 pairs), plus the transposed
+    # [128 | 32]-wide form of d W_v, d W_k
+    G2 = torch.zeros((512, 512), device=dev)
+    for a in range(4):
+        ops.pct_wgrad(xs4[a].reshape(-1, 128), [xs4[b].reshape(-1, 128) for b in range(a, 4)],
+                      [G2[128 * a:128 * a + 128, 128 * b:128 * b + 128] for b in range(a, 4)])
+    dWv2, dWk2 = torch.zeros((128, 128), device=dev), torch.zeros((32, 128), device=dev)
+    gv = _rand((N, P, 128), dev, 31, 1e-6)
+    ops.pct_wgrad(xs4[0].reshape(-1, 128), [gv.reshape(-1, 128), small.reshape(-1, 32)], [dWv2, dWk2], transpose=True)
     torch.cuda.synchronize()
     Gr = (xcat.reshape(-1, 512).t() @ xcat.reshape(-1, 512))
     for a in range(4):
         for b in range(a, 4):
             blk = (slice(128 * a, 128 * a + 128), slice(128 * b, 128 * b + 128))
             assert rel_inf(G[blk], Gr[blk]) < 5e-5
+            assert rel_inf(G2[blk], Gr[blk]) < 5e-5, (a, b, rel_inf(G2[blk], Gr[blk]))
+    assert rel_inf(dWk2, small.double().reshape(-1, 32).t() @ xs4[0].double().reshape(-1, 128)) < 5e-5
+    assert rel_inf(dWv2, gv.double().reshape(-1, 128).t() @ xs4[0].double().reshape(-1, 128)) < 5e-5
     assert rel_inf(dWk, small.double().reshape(-1, 32).t() @ xs4[0].double().reshape(-1, 128)) < 5e-5
 
 
