@@ -25,18 +25,29 @@ constexpr float kAlpha = 1.4426950408889634f * 0.17677669529663687f;   // log2(e
 
 // ---- K image: per tile of 128 points one 16 KiB block of 128-byte rows [k.hi (32 fp16) | k.lo (32 fp16)]
 __device__ __forceinline__ void load_k_image(const float* __restrict__ k, int64_t rowbase0, int P, int T, uint32_t kimg_addr, int tid) {
-  for (int t = 0; t < T; ++t) {
+  // loads of all tiles first (the asm stores below are ordering barriers for the compiler: interleaved, every tile
+  // would pay its own DRAM latency)
+  float4 x[kMaxT][2][2];
+#pragma unroll
+  for (int t = 0; t < kMaxT; ++t) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int idx = tid + 256 * u;
       const int row = idx >> 2, j = idx & 3;
-      const bool ok = t * kTile + row < P;
-      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (ok) {
-        const float4* src = reinterpret_cast<const float4*>(k + (rowbase0 + (int64_t)t * kTile + row) * 32 + j * 8);
-        const float4 x = __ldg(src), y = __ldg(src + 1);
-        f[0] = x.x; f[1] = x.y; f[2] = x.z; f[3] = x.w; f[4] = y.x; f[5] = y.y; f[6] = y.z; f[7] = y.w;
-      }
+      const bool ok = t < T && t * kTile + row < P;
+      const float4* src = reinterpret_cast<const float4*>(k + (rowbase0 + (int64_t)t * kTile + row) * 32 + j * 8);
+      x[t][u][0] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+      x[t][u][1] = ok ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < kMaxT; ++t) {
+    if (t >= T) break;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int idx = tid + 256 * u;
+      const int row = idx >> 2, j = idx & 3;
+      const float f[8] = {x[t][u][0].x, x[t][u][0].y, x[t][u][0].z, x[t][u][0].w, x[t][u][1].x, x[t][u][1].y, x[t][u][1].z, x[t][u][1].w};
       uint4 hi, lo;
       split8(f, hi, lo);
       const uint32_t base = kimg_addr + (uint32_t)t * kBlk;
@@ -286,32 +297,27 @@ pct_attn_kernel(const float* __restrict__ k, const float* __restrict__ v, const 
       const int64_t rowbase = n * (int64_t)P + (int64_t)it * kTile;
       const int valid = min(kTile, P - it * kTile);
       const uint32_t blk_off = (uint32_t)(b * 2 + (cc >> 3)) * kBlk;
-#pragma unroll 1
-      for (int bt = 0; bt < 4; ++bt) {
-        float4 x[2][2];
+      // all 16 loads of the thread in flight together: the tile comes from DRAM / L2 and a thread that waits for it does
+      // nothing else (two warps per scheduler), so what the loop pays is ONE latency instead of four
+      float4 x[8][2];
 #pragma unroll
-        for (int qq = 0; qq < 2; ++qq) {
-          const int row = r0 + 16 * (bt * 2 + qq);
-          const float4* src = reinterpret_cast<const float4*>(v + (rowbase + row) * 128 + cc * 8);
-          const bool ok = row < valid;
-          x[qq][0] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
-          x[qq][1] = ok ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+      for (int i = 0; i < 8; ++i) {
+        const int row = r0 + 16 * i;
+        const float4* src = reinterpret_cast<const float4*>(v + (rowbase + row) * 128 + cc * 8);
+        const bool ok = row < valid;
+        x[i][0] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[i][1] = ok ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      const float sc = kDv ? __ldg(scale + 2 * n) : 1.f;
 #pragma unroll
-        for (int qq = 0; qq < 2; ++qq) {
-          const int row = r0 + 16 * (bt * 2 + qq);
-          float f[8] = {x[qq][0].x, x[qq][0].y, x[qq][0].z, x[qq][0].w, x[qq][1].x, x[qq][1].y, x[qq][1].z, x[qq][1].w};
-          if (kDv) {
-            const float sc = __ldg(scale + 2 * n);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] *= sc;
-          }
-          uint4 hi, lo;
-          split8f<F>(f, hi, lo);
-          const uint32_t off = blk_off + ptx::sw128_offset(row, cc & 7);
-          st_chunk(sm_base + VHI + off, hi);
-          st_chunk(sm_base + VLO + off, lo);
-        }
+      for (int i = 0; i < 8; ++i) {
+        const int row = r0 + 16 * i;
+        const float f[8] = {x[i][0].x * sc, x[i][0].y * sc, x[i][0].z * sc, x[i][0].w * sc, x[i][1].x * sc, x[i][1].y * sc, x[i][1].z * sc, x[i][1].w * sc};
+        uint4 hi, lo;
+        split8f<F>(f, hi, lo);
+        const uint32_t off = blk_off + ptx::sw128_offset(row, cc & 7);
+        st_chunk(sm_base + VHI + off, hi);
+        st_chunk(sm_base + VLO + off, lo);
       }
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(&bars[BAR_V_FULL + b]);
@@ -425,16 +431,21 @@ enum { BAR_F_FULL = 0, BAR_G_FULL = 1, BAR_SD_FULL = 2, BAR_T_FULL = 3, BAR_DK_D
 // one tile of 128 rows x 32 channels of k -> [hi | lo] image (format kF)
 template <int kF>
 __device__ __forceinline__ void load_k_tile(const float* __restrict__ k, int64_t rowbase, int valid, uint32_t addr, int tid) {
+  float4 x[2][2];
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     const int idx = tid + 256 * u;
     const int row = idx >> 2, j = idx & 3;
-    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (row < valid) {
-      const float4* src = reinterpret_cast<const float4*>(k + (rowbase + row) * 32 + j * 8);
-      const float4 x = __ldg(src), y = __ldg(src + 1);
-      f[0] = x.x; f[1] = x.y; f[2] = x.z; f[3] = x.w; f[4] = y.x; f[5] = y.y; f[6] = y.z; f[7] = y.w;
-    }
+    const float4* src = reinterpret_cast<const float4*>(k + (rowbase + row) * 32 + j * 8);
+    const bool ok = row < valid;
+    x[u][0] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+    x[u][1] = ok ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int idx = tid + 256 * u;
+    const int row = idx >> 2, j = idx & 3;
+    const float f[8] = {x[u][0].x, x[u][0].y, x[u][0].z, x[u][0].w, x[u][1].x, x[u][1].y, x[u][1].z, x[u][1].w};
     uint4 hi, lo;
     split8f<kF>(f, hi, lo);
     st_chunk(addr + ptx::sw128_offset(row, j), hi);
@@ -442,34 +453,32 @@ __device__ __forceinline__ void load_k_tile(const float* __restrict__ k, int64_t
   }
 }
 
-// one tile of 128 rows x 128 channels -> K-major hi / lo images (2 channel blocks each), format kF
+// one tile of 128 rows x 128 channels -> K-major hi / lo images (2 channel blocks each), format kF; the 16 loads of a
+// thread are all in flight together (the tile usually comes from L2: latency, not bandwidth, is what the loop pays)
 template <int kF>
 __device__ __forceinline__ void load_tile128(const float* __restrict__ src, int64_t rowbase, int valid, uint32_t hi_addr, uint32_t lo_addr,
                                              int tid, float mul) {
   const int cc = tid & 15, r0 = tid >> 4;
   const uint32_t blk_off = (uint32_t)(cc >> 3) * kBlk;
-#pragma unroll 1
-  for (int bt = 0; bt < 4; ++bt) {
-    float4 x[2][2];
+  float4 x[8][2];
 #pragma unroll
-    for (int qq = 0; qq < 2; ++qq) {
-      const int row = r0 + 16 * (bt * 2 + qq);
-      const float4* p = reinterpret_cast<const float4*>(src + (rowbase + row) * 128 + cc * 8);
-      const bool ok = row < valid;
-      x[qq][0] = ok ? __ldg(p) : make_float4(0.f, 0.f, 0.f, 0.f);
-      x[qq][1] = ok ? __ldg(p + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+  for (int i = 0; i < 8; ++i) {
+    const int row = r0 + 16 * i;
+    const float4* p = reinterpret_cast<const float4*>(src + (rowbase + row) * 128 + cc * 8);
+    const bool ok = row < valid;
+    x[i][0] = ok ? __ldg(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+    x[i][1] = ok ? __ldg(p + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 #pragma unroll
-    for (int qq = 0; qq < 2; ++qq) {
-      const int row = r0 + 16 * (bt * 2 + qq);
-      const float f[8] = {x[qq][0].x * mul, x[qq][0].y * mul, x[qq][0].z * mul, x[qq][0].w * mul,
-                          x[qq][1].x * mul, x[qq][1].y * mul, x[qq][1].z * mul, x[qq][1].w * mul};
-      uint4 hi, lo;
-      split8f<kF>(f, hi, lo);
-      const uint32_t off = blk_off + ptx::sw128_offset(row, cc & 7);
-      st_chunk(hi_addr + off, hi);
-      st_chunk(lo_addr + off, lo);
-    }
+  for (int i = 0; i < 8; ++i) {
+    const int row = r0 + 16 * i;
+    const float f[8] = {x[i][0].x * mul, x[i][0].y * mul, x[i][0].z * mul, x[i][0].w * mul,
+                        x[i][1].x * mul, x[i][1].y * mul, x[i][1].z * mul, x[i][1].w * mul};
+    uint4 hi, lo;
+    split8f<kF>(f, hi, lo);
+    const uint32_t off = blk_off + ptx::sw128_offset(row, cc & 7);
+    st_chunk(hi_addr + off, hi);
+    st_chunk(lo_addr + off, lo);
   }
 }
 

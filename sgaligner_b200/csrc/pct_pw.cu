@@ -14,6 +14,7 @@
 // drain the accumulator through a coalescing stage.  These convolutions are HBM bound (0.13-0.27 MB in+out per tile
 // against 0.5 us of MMAs), so the tile pipeline is kept simple: what matters is bytes, and those are minimal.
 #include "pct_common.cuh"
+#include <type_traits>
 
 namespace sga {
 namespace pct {
@@ -146,13 +147,15 @@ __global__ void __launch_bounds__(kThreads, 1) pct_pw_kernel(const PwArgs A) {
       const int64_t rowbase = n * A.P + (int64_t)t * kTile;
       const int valid = min(kTile, A.P - t * kTile);
       // ---- load + prologue + split -> A tile (the previous tile's MMAs have completed: D_FULL was waited for)
-#pragma unroll 1
-      for (int bt = 0; bt < 4; ++bt) {            // 4 batches of 2 rows: the loads of a batch are in flight together
-        float4 u[2][2], w[2][2];
-        float3 p3[2];
+      // The asm shared-memory stores are ordering barriers for the compiler, so the loads of a batch are issued before
+      // its first store: a batch = 8 rows of one source (16 loads of 16 bytes in flight per thread), or 4 rows of two.
+      auto batch = [&](auto rows_tag, int bt) {
+        constexpr int kRows = decltype(rows_tag)::value;
+        float4 u[kRows][2], w[kRows][2];
+        float3 p3[kRows];
 #pragma unroll
-        for (int qq = 0; qq < 2; ++qq) {
-          const int row = r0 + 16 * (bt * 2 + qq);
+        for (int qq = 0; qq < kRows; ++qq) {
+          const int row = r0 + 16 * (bt * kRows + qq);
           const bool ok = row < valid;
           if (kEmbed) {
             const float* pp = A.pts + (rowbase + row) * 3;
@@ -169,8 +172,8 @@ __global__ void __launch_bounds__(kThreads, 1) pct_pw_kernel(const PwArgs A) {
           }
         }
 #pragma unroll
-        for (int qq = 0; qq < 2; ++qq) {
-          const int row = r0 + 16 * (bt * 2 + qq);
+        for (int qq = 0; qq < kRows; ++qq) {
+          const int row = r0 + 16 * (bt * kRows + qq);
           const bool ok = row < valid;
           float f[8];
           if (kEmbed) {
@@ -223,6 +226,12 @@ __global__ void __launch_bounds__(kThreads, 1) pct_pw_kernel(const PwArgs A) {
           st_chunk(sm_base + AHI + off, hi);
           st_chunk(sm_base + ALO + off, lo);
         }
+      };
+      if (!kEmbed && A.mode2) {
+        batch(std::integral_constant<int, 4>{}, 0);
+        batch(std::integral_constant<int, 4>{}, 1);
+      } else {
+        batch(std::integral_constant<int, 8>{}, 0);
       }
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(&bars[BAR_A_FULL]);
