@@ -15,6 +15,7 @@
 // Split fp16 operands (pct_common.cuh), fp32 accumulate: three passes for x_v * attention, all four partial products for
 // the scores.  P <= 512 (the [128 x P] score block must fit the 512 columns of tensor memory).
 #include "pct_common.cuh"
+#include <stdlib.h>
 
 namespace sga {
 namespace pct {
@@ -676,6 +677,22 @@ pct_attn_dk_kernel(const float* __restrict__ k, const float* __restrict__ fixed,
 }  // namespace pct
 }  // namespace sga
 
+namespace sga {
+namespace pct {
+// pct_attn2.cu: two CTAs per SM (default); SGA_PCT_ATTN=v1 selects the kernels of this file
+int attn2_fwd(const float* k, const float* v, const float* c2, int64_t N, int P, float* xs, cudaStream_t st);
+int attn2_dv(const float* k, const float* dxs, const float* c2, const float* scale, int64_t N, int P, float* dv, cudaStream_t st);
+static bool attn_v1() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SGA_PCT_ATTN");
+    v = (e && e[0] == 'v' && e[1] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+}  // namespace pct
+}  // namespace sga
+
 extern "C" int sga_pct_attn_stats(const float* k, int64_t N, int P, float* c2, void* stream) {
   if (N <= 0) return SGA_OK;
   SGA_REQUIRE(k && c2 && P >= 1 && P <= sga::pct::kMaxT * sga::pct::kTile, "sga_pct_attn_stats: P=%d (1..512)", P);
@@ -698,6 +715,7 @@ extern "C" int sga_pct_attn(const float* k, const float* v, const float* c2, int
   SGA_REQUIRE(k && v && c2 && xs && P >= 1 && P <= sga::pct::kMaxT * sga::pct::kTile, "sga_pct_attn: P=%d (1..512)", P);
   SGA_REQUIRE((((uintptr_t)k | (uintptr_t)v) & 15) == 0, "sga_pct_attn: k / v must be 16-byte aligned");
   using namespace sga::pct;
+  if (!attn_v1()) return attn2_fwd(k, v, c2, N, P, xs, (cudaStream_t)stream);
   static bool attr_done = false;
   if (!attr_done) {
     SGA_CUDA(cudaFuncSetAttribute(pct_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at::SMEM_BYTES));
@@ -719,6 +737,7 @@ extern "C" int sga_pct_attn_bwd_dv(const float* k, const float* dxs, const float
   SGA_REQUIRE(k && dxs && c2 && dv && scale && P >= 1 && P <= sga::pct::kMaxT * sga::pct::kTile, "sga_pct_attn_bwd_dv: P=%d (1..512)", P);
   SGA_REQUIRE((((uintptr_t)k | (uintptr_t)dxs) & 15) == 0, "sga_pct_attn_bwd_dv: k / dxs must be 16-byte aligned");
   using namespace sga::pct;
+  if (!attn_v1()) return attn2_dv(k, dxs, c2, scale, N, P, dv, (cudaStream_t)stream);
   static bool attr_done = false;
   if (!attr_done) {
     SGA_CUDA(cudaFuncSetAttribute(pct_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at::SMEM_BYTES));
