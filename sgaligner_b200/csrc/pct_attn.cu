@@ -682,6 +682,8 @@ namespace pct {
 // pct_attn2.cu: two CTAs per SM (default); SGA_PCT_ATTN=v1 selects the kernels of this file
 int attn2_fwd(const float* k, const float* v, const float* c2, int64_t N, int P, float* xs, cudaStream_t st);
 int attn2_dv(const float* k, const float* dxs, const float* c2, const float* scale, int64_t N, int P, float* dv, cudaStream_t st);
+int attn2_dk(const float* k, const float* fixed, const float* streamed, const float* c2, float* delta, const float* scale, int64_t N,
+             int P, int by_col, int delta_sweep, float* dk_out, cudaStream_t st);
 static bool attn_v1() {
   static int v = -1;
   if (v < 0) {
@@ -763,6 +765,7 @@ extern "C" int sga_pct_attn_bwd_dk(const float* k, const float* fixed, const flo
               "sga_pct_attn_bwd_dk: P=%d (1..512)", P);
   SGA_REQUIRE((((uintptr_t)k | (uintptr_t)fixed | (uintptr_t)streamed) & 15) == 0, "sga_pct_attn_bwd_dk: operands must be 16-byte aligned");
   using namespace sga::pct;
+  if (!attn_v1()) return attn2_dk(k, fixed, streamed, c2, delta, scale, N, P, by_col, delta_sweep, dk_out, (cudaStream_t)stream);
   static bool attr_done = false;
   if (!attr_done) {
     SGA_CUDA(cudaFuncSetAttribute(pct_attn_dk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dk::SMEM_BYTES));

@@ -271,3 +271,344 @@ int attn2_dv(const float* k, const float* dxs, const float* c2, const float* sca
 
 }  // namespace pct
 }  // namespace sga
+
+// =====================================================================================================================
+// dk halves of the SA backward (see pct_attn.cu for the algebra), two CTAs per SM.  What had to shrink to fit (the first
+// kernel holds 160 KiB and 448 TMEM columns): column blocks of 64 (the streamed tile is 32 KiB, its k rows 8 KiB), the own
+// block's k rows live in TENSOR MEMORY as the A operand of the score product (32 columns), T is written over S and the
+// per-step product T k_b over dA, and dk is accumulated in REGISTERS (16 per thread) from the per-step product instead of
+// in a resident accumulator: 115 KiB, 192 columns, 96 registers.
+namespace sga {
+namespace pct {
+namespace {
+
+namespace d2 {
+constexpr uint32_t kHalf = kBlk / 2;                       // [64 rows x 128 B]
+constexpr uint32_t KB = 0;                                 // current block's k rows (64), fp16 [hi | lo]
+constexpr uint32_t FHI = KB + kHalf;                       // own block's 128-channel rows: 2 channel blocks hi, 2 lo
+constexpr uint32_t FLO = FHI + 2 * kBlk;
+constexpr uint32_t GHI = FLO + 2 * kBlk;                   // current block's rows (64): 2 channel half-blocks hi, 2 lo
+constexpr uint32_t GLO = GHI + 2 * kHalf;
+constexpr uint32_t NRM = GLO + 2 * kHalf;                  // float[3][512]: max * a, log2 sum, delta
+constexpr uint32_t XCH = NRM + 3 * kMaxT2 * kTile * 4;     // float[2][128]
+constexpr uint32_t BARS = XCH + 2 * 128 * 4;
+constexpr uint32_t TMEMPTR = BARS + 64;
+constexpr uint32_t SMEM_BYTES = TMEMPTR + 16 + 1024;       // 114768
+constexpr uint32_t KAH_COL = 0, KAL_COL = 16, ST_COL = 64, DA_COL = 128;
+enum { BAR_LD_FULL = 0, BAR_SD_FULL = 1, BAR_T_FULL = 2, BAR_DK_DONE = 3, kNumBars = 4 };
+static_assert(8 * kStageFloats * 4 <= 4 * kHalf, "the output staging patch must fit the streamed tile");
+}  // namespace d2
+
+template <bool kCol>
+__global__ void __launch_bounds__(kThreads, 2)
+pct_attn2_dk_kernel(const float* __restrict__ k, const float* __restrict__ fixed, const float* __restrict__ streamed,
+                    const float* __restrict__ c2, const float* __restrict__ delta_in, float* __restrict__ delta_out,
+                    const float* __restrict__ scale, int64_t N, int P, float* __restrict__ dk_out, int sweeps) {
+  using namespace d2;
+  const int kPhases = kCol ? 1 : sweeps;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sm_base = ptx::smem_u32(sm);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + BARS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + TMEMPTR);
+  float* nrm = reinterpret_cast<float*>(sm + NRM);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = (P + kTile - 1) / kTile;                   // own blocks of 128 rows
+  const int Tb = (P + 63) / 64;                            // column blocks of 64
+  const int Ppad = T * kTile;
+  if (tid == 0) {
+    ptx::mbar_init(&bars[BAR_LD_FULL], kComputeThreads);
+    ptx::mbar_init(&bars[BAR_SD_FULL], 1);
+    ptx::mbar_init(&bars[BAR_T_FULL], kComputeThreads);
+    ptx::mbar_init(&bars[BAR_DK_DONE], 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 8) ptx::tmem_alloc<256>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int64_t W = N * T;
+
+  if (warp == 8) {
+    // =============================== MMA issuer ===============================
+    const uint32_t idesc_s = ptx::make_idesc(kFmt, 128, 64);
+    const uint32_t idesc_da = ptx::make_idesc(kFmt, 128, 64);
+    const uint32_t idesc_dk = ptx::make_idesc(kFmt, 128, 64) | (1u << 16);        // B (= k_b image) read MN-major
+    const uint64_t dKB = ptx::smem_desc_sw128(sm_base + KB);
+    const uint64_t dFhi = ptx::smem_desc_sw128(sm_base + FHI), dFlo = ptx::smem_desc_sw128(sm_base + FLO);
+    const uint64_t dGhi = ptx::smem_desc_sw128(sm_base + GHI), dGlo = ptx::smem_desc_sw128(sm_base + GLO);
+    const uint64_t mKB = desc_mn_sw128(sm_base + KB, kHalf);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    uint32_t u = 0, ud = 0;
+    for (int64_t w = blockIdx.x; w < W; w += gridDim.x) {
+      for (int ph = 0; ph < kPhases; ++ph) {
+        const bool dk_phase = ph == kPhases - 1;
+        for (int b = 0; b < Tb; ++b, ++u) {
+          ptx::mbar_wait(&bars[BAR_LD_FULL], u & 1);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            // S[128 x 64] = k_a k_b^T: A from tensor memory (hi / lo, K = 32 = 2 steps of 8 columns), four partial products
+#pragma unroll
+            for (int pass = 0; pass < 4; ++pass) {
+              const uint32_t a_tm = tmem_u + ((pass >= 2) ? KAL_COL : KAH_COL);
+              const uint64_t bo = (pass & 1) ? 4 : 0;
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks)
+                ptx::umma_bf16_ts(tmem_u + ST_COL, a_tm + (uint32_t)(ks * 8), dKB + bo + (uint64_t)(ks * 2), idesc_s, (pass | ks) != 0);
+            }
+            // dA[128 x 64] = F_a G_b^T, K = 128 channels
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint64_t ad = (pass == 1) ? dFlo : dFhi;
+              const uint64_t bd = (pass == 2) ? dGlo : dGhi;
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {
+                const uint64_t ao = (uint64_t)((ks >> 2) * (kBlk >> 4) + (ks & 3) * 2);
+                const uint64_t bo = (uint64_t)((ks >> 2) * (kHalf >> 4) + (ks & 3) * 2);
+                ptx::umma_bf16(tmem_u + DA_COL, ad + ao, bd + bo, idesc_da, (pass | ks) != 0);
+              }
+            }
+            ptx::umma_commit(&bars[BAR_SD_FULL]);
+          }
+          __syncwarp();
+          ptx::mbar_wait(&bars[BAR_T_FULL], u & 1);          // S / dA have been read (and, in the dk sweep, T is in place)
+          if (!dk_phase) continue;
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            // D[128 x 64] = T [k_b.hi | k_b.lo], K = 64 rows of the block: written over dA
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                ptx::umma_bf16_ts(tmem_u + DA_COL, tmem_u + ST_COL + (uint32_t)((ks >> 1) * 32 + (ks & 1) * 8 + pass * 16),
+                                  mKB + (uint64_t)(ks * 128), idesc_dk, (pass | ks) != 0);
+            }
+            ptx::umma_commit(&bars[BAR_DK_DONE]);
+          }
+          __syncwarp();
+          ++ud;
+        }
+      }
+    }
+  } else {
+    // =============================== compute warps ===============================
+    const int q = warp & 3, hc = warp >> 2;
+    const int row = 32 * q + lane;
+    const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+    const uint32_t c0 = (uint32_t)(hc * 32);
+    float* stage = reinterpret_cast<float*>(sm + GHI) + warp * kStageFloats;      // reuses the streamed tile at the end of an item
+    float* xch = reinterpret_cast<float*>(sm + XCH);
+    const float* ma_s = nrm;
+    const float* lg_s = nrm + kMaxT2 * kTile;
+    const float* de_s = nrm + 2 * kMaxT2 * kTile;
+    uint32_t u = 0, ud = 0;
+    for (int64_t w = blockIdx.x; w < W; w += gridDim.x) {
+      const int64_t n = w / T;
+      const int a = (int)(w - n * T);
+      const int64_t obase = n * (int64_t)P;
+      const int valida = min(kTile, P - a * kTile);
+      const float gsc = __ldg(scale + 2 * n), ginv = __ldg(scale + 2 * n + 1);
+      // every product of the previous item has completed and its rows are stored by THIS warp; the barrier below covers the others
+      {   // own block: k rows -> tensor memory (hc == 0 warps, one per lane quarter), fixed tile -> shared memory, statistics
+        if (hc == 0) {
+          float4 kx[8];
+          const float4* src = reinterpret_cast<const float4*>(k + (obase + (int64_t)a * kTile + row) * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) kx[j] = (row < valida) ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          uint32_t kh[16], kl[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            split2f<0>(kx[j].x, kx[j].y, kh[2 * j], kl[2 * j]);
+            split2f<0>(kx[j].z, kx[j].w, kh[2 * j + 1], kl[2 * j + 1]);
+          }
+          ptx::tmem_st16(tmem + lane_addr + KAH_COL, kh);
+          ptx::tmem_st16(tmem + lane_addr + KAL_COL, kl);
+          ptx::tmem_st_wait();
+        }
+        const int cc = tid & 15, r0 = tid >> 4;
+        float4 x[8][2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = r0 + 16 * i;
+          const float4* src = reinterpret_cast<const float4*>(fixed + (obase + (int64_t)a * kTile + r) * 128 + cc * 8);
+          const bool ok = r < valida;
+          x[i][0] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+          x[i][1] = ok ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float mul = kCol ? gsc : 1.f;
+        const uint32_t blk_off = (uint32_t)(cc >> 3) * kBlk;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = r0 + 16 * i;
+          const float f[8] = {x[i][0].x * mul, x[i][0].y * mul, x[i][0].z * mul, x[i][0].w * mul,
+                              x[i][1].x * mul, x[i][1].y * mul, x[i][1].z * mul, x[i][1].w * mul};
+          uint4 hi, lo;
+          split8(f, hi, lo);
+          const uint32_t off = blk_off + ptx::sw128_offset(r, cc & 7);
+          st_chunk(sm_base + FHI + off, hi);
+          st_chunk(sm_base + FLO + off, lo);
+        }
+        for (int i = tid; i < Ppad; i += kComputeThreads) {
+          nrm[i] = c2[(n * 2) * Ppad + i];
+          nrm[kMaxT2 * kTile + i] = c2[(n * 2 + 1) * Ppad + i];
+          nrm[2 * kMaxT2 * kTile + i] = ((kCol || kPhases == 1) && i < P) ? delta_in[obase + i] : 0.f;
+        }
+      }
+      compute_barrier();                               // statistics visible; every warp is past its output stores (staging patch = G)
+      const float mr = ma_s[a * kTile + row], lr = lg_s[a * kTile + row];
+      float dr = de_s[a * kTile + row];
+      float acc[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+      // the per-step product T k_b of step x: added to this thread's 16 dk channels (hi and lo halves of the k image)
+      auto drain_dk = [&](uint32_t x) {
+        ptx::mbar_wait(&bars[BAR_DK_DONE], x & 1);
+        ptx::tc_fence_after();
+        uint32_t d0[16], d1[16];
+        ptx::tmem_ld16(tmem + lane_addr + DA_COL + (uint32_t)(hc * 16), d0);
+        ptx::tmem_ld16(tmem + lane_addr + DA_COL + (uint32_t)(32 + hc * 16), d1);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[e] += __uint_as_float(d0[e]) + __uint_as_float(d1[e]);
+      };
+      for (int ph = 0; ph < kPhases; ++ph) {
+        const bool dk_phase = ph == kPhases - 1;
+        float dacc = 0.f;
+        for (int b = 0; b < Tb; ++b, ++u) {
+          if (dk_phase && b >= 1) drain_dk(ud - 1);           // also: k_b / G / the S and dA columns are free again
+          const int validb = min(64, P - b * 64);
+          {   // k rows (64 x 32) and streamed rows (64 x 128) of block b; all loads in flight before the first store
+            const int64_t rb = obase + (int64_t)b * 64;
+            const int krow = tid >> 2, kj = tid & 3;
+            const float4* ks = reinterpret_cast<const float4*>(k + (rb + krow) * 32 + kj * 8);
+            const bool kok = krow < validb;
+            const float4 k0 = kok ? __ldg(ks) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 k1 = kok ? __ldg(ks + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int cc = tid & 15, r0 = tid >> 4;
+            float4 x[4][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = r0 + 16 * i;
+              const float4* src = reinterpret_cast<const float4*>(streamed + (rb + r) * 128 + cc * 8);
+              const bool ok = r < validb;
+              x[i][0] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+              x[i][1] = ok ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            {
+              const float f[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+              uint4 hi, lo;
+              split8(f, hi, lo);
+              st_chunk(sm_base + KB + ptx::sw128_offset(krow, kj), hi);
+              st_chunk(sm_base + KB + ptx::sw128_offset(krow, 4 + kj), lo);
+            }
+            const float mul = kCol ? 1.f : gsc;
+            const uint32_t blk_off = (uint32_t)(cc >> 3) * kHalf;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = r0 + 16 * i;
+              const float f[8] = {x[i][0].x * mul, x[i][0].y * mul, x[i][0].z * mul, x[i][0].w * mul,
+                                  x[i][1].x * mul, x[i][1].y * mul, x[i][1].z * mul, x[i][1].w * mul};
+              uint4 hi, lo;
+              split8(f, hi, lo);
+              const uint32_t off = blk_off + ptx::sw128_offset(r, cc & 7);
+              st_chunk(sm_base + GHI + off, hi);
+              st_chunk(sm_base + GLO + off, lo);
+            }
+          }
+          ptx::fence_proxy_async_smem();
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&bars[BAR_LD_FULL]);
+          ptx::mbar_wait(&bars[BAR_SD_FULL], u & 1);
+          ptx::tc_fence_after();
+          // this thread: row `row`, the 32 columns [c0, c0 + 32) of the block, in two halves of 16 (second half first, so
+          // that T can be written over S: [c0, c0+16) = T.hi of the 32 columns, [c0+16, c0+32) = T.lo)
+          uint32_t th1[8], tl1[8];
+#pragma unroll
+          for (int h = 1; h >= 0; --h) {
+            uint32_t sv[16], dv[16];
+            ptx::tmem_ld16(tmem + lane_addr + ST_COL + c0 + (uint32_t)(h * 16), sv);
+            ptx::tmem_ld16(tmem + lane_addr + DA_COL + c0 + (uint32_t)(h * 16), dv);
+            ptx::tmem_ld_wait();
+            const int cb = b * 64 + (int)c0 + h * 16;
+            if (!dk_phase) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                dacc = fmaf(ex2(fmaf(__uint_as_float(sv[e]), kAlpha2, -mr) - lr), __uint_as_float(dv[e]), dacc);
+            } else {
+              uint32_t th[8], tl[8];
+#pragma unroll
+              for (int e = 0; e < 16; e += 2) {
+                float t0, t1;
+                if (kCol) {
+                  t0 = ex2(fmaf(__uint_as_float(sv[e]), kAlpha2, -ma_s[cb + e]) - lg_s[cb + e]) * (__uint_as_float(dv[e]) - de_s[cb + e]);
+                  t1 = ex2(fmaf(__uint_as_float(sv[e + 1]), kAlpha2, -ma_s[cb + e + 1]) - lg_s[cb + e + 1]) * (__uint_as_float(dv[e + 1]) - de_s[cb + e + 1]);
+                } else {
+                  t0 = ex2(fmaf(__uint_as_float(sv[e]), kAlpha2, -mr) - lr) * (__uint_as_float(dv[e]) - dr);
+                  t1 = ex2(fmaf(__uint_as_float(sv[e + 1]), kAlpha2, -mr) - lr) * (__uint_as_float(dv[e + 1]) - dr);
+                }
+                split2f<0>(t0, t1, th[e / 2], tl[e / 2]);
+              }
+              if (h == 1) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { th1[e] = th[e]; tl1[e] = tl[e]; }
+              } else {           // both halves of S are in registers now: write T over them
+                ptx::tmem_st8(tmem + lane_addr + ST_COL + c0, th);
+                ptx::tmem_st8(tmem + lane_addr + ST_COL + c0 + 8, th1);
+                ptx::tmem_st8(tmem + lane_addr + ST_COL + c0 + 16, tl);
+                ptx::tmem_st8(tmem + lane_addr + ST_COL + c0 + 24, tl1);
+                ptx::tmem_st_wait();
+              }
+            }
+          }
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&bars[BAR_T_FULL]);
+          if (dk_phase) ++ud;
+        }
+        if (!dk_phase) {                    // delta_i: the two column halves of the row
+          xch[hc * 128 + row] = dacc;
+          compute_barrier();
+          dr = xch[row] + xch[128 + row];
+          if (hc == 0 && a * kTile + row < P) delta_out[obase + (int64_t)a * kTile + row] = dr;
+          compute_barrier();
+        }
+      }
+      drain_dk(ud - 1);
+      // ---- dk rows of this block, scaled by 1/sqrt(32) and back from the object's scale; staging patch = the streamed tile
+      compute_barrier();                               // every warp has drained the last product (which read k_b) before G is reused
+      float f[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) f[e] = acc[e] * (0.17677669529663687f * ginv);
+      const int nvalid = max(0, min(32, P - a * kTile - 32 * q));
+      float s_ = 0.f, q_ = 0.f;
+      stage_store16(stage, f, dk_out + (obase + (int64_t)a * kTile + 32 * q) * 32 + hc * 16, 32, nvalid, lane, s_, q_, false);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) ptx::tmem_dealloc<256>(tmem);
+}
+
+}  // namespace
+
+int attn2_dk(const float* k, const float* fixed, const float* streamed, const float* c2, float* delta, const float* scale, int64_t N,
+             int P, int by_col, int delta_sweep, float* dk_out, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    SGA_CUDA(cudaFuncSetAttribute(pct_attn2_dk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2::SMEM_BYTES));
+    SGA_CUDA(cudaFuncSetAttribute(pct_attn2_dk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int T = (P + kTile - 1) / kTile;
+  const int64_t W = N * T;
+  int64_t grid = 2 * (int64_t)sm_count();
+  if (grid > W) grid = W;
+  if (by_col) pct_attn2_dk_kernel<true><<<(unsigned)grid, kThreads, d2::SMEM_BYTES, st>>>(k, fixed, streamed, c2, delta, nullptr, scale, N, P, dk_out, 1);
+  else pct_attn2_dk_kernel<false><<<(unsigned)grid, kThreads, d2::SMEM_BYTES, st>>>(k, fixed, streamed, c2, delta, delta, scale, N, P, dk_out, delta_sweep ? 2 : 1);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+}  // namespace pct
+}  // namespace sga
