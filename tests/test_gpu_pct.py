@@ -80,7 +80,7 @@ def test_embed_stage(N, P, dev):
     assert rel_inf(s1[:128], z1.sum(0)) < 1e-9 + 1e-6 and rel_inf(s1[128:], (z1 * z1).sum(0)) < 1e-6
 
 
-@pytest.mark.parametrize('N,P', [(3, 96), (4, 128), (5, 300), (9, 512), (160, 512)])
+@pytest.mark.parametrize('N,P', [(3, 96), (4, 128), (5, 300), (9, 512), (160, 512), (6, 40), (5, 200), (450, 512)])
 def test_attention_vs_fp64(N, P, dev):
     """x_s = bmm(x_v, softmax(x_k^T x_k / sqrt(32), -1)) (pct.py:217-224) vs fp64, ragged point counts included."""
     from sgaligner_b200 import ops
