@@ -149,7 +149,8 @@ def _grad_report(named, ref_of, gmax, tol=1e-3):
         got = got.detach().double().cpu().reshape(-1)
         if ref.numel() != got.numel():
             got = got[::17]
-        err = float((got - ref.double().reshape(-1)).abs().max() / max(float(ref.abs().max()), 1e-3 * gmax))
+        ref = ref.detach().double().cpu().reshape(-1)
+        err = float((got - ref).abs().max() / max(float(ref.abs().max()), 1e-3 * gmax))
         lines.append('%-28s %.2e' % (name, err))
         worst = max(worst, err)
     return worst, lines
@@ -242,6 +243,81 @@ def test_param_grads_vs_oracle_autograd(N, P, training, dev):
     print('NaivePCT parameter gradients vs fp64 oracle autograd (N=%d P=%d train=%s): worst per seed %s'
           % (N, P, training, ['%.2e' % w for w in worsts]))
     assert sorted(worsts)[1] < 1e-3 and max(worsts) < 2e-2
+
+
+@pytest.mark.parametrize('init', ['torch_default', 'stress'])
+def test_param_grads_mid_size_vs_eager_cuda(init, dev):
+    """512 objects x 512 points (1024 attention work items, 262 k rows in every batch-wide reduction, several work items per
+    persistent CTA in every kernel): against the oracle's op sequence evaluated in FP64 on the same GPU (torch eager) -- the
+    size the CPU oracle cannot reach in a test -- with the same sequence in fp32 (TF32 off) beside it to show what fp32
+    autograd itself loses at this size.
+      torch_default: the initialisation training starts from (reference: NaivePCT() as constructed, pct.py:276-297);
+                     gate: every tensor within max(2e-3, twice fp32 eager's own worst) of fp64 (measured: ours 1.1e-3 on one
+                     BatchNorm bias -- a ReLU decision --, fp32 eager 9.4e-4 on another), median tensor < 2e-4 (measured 3e-5).
+      stress:        the seeded recipe of the goldens, whose BatchNorm affine parameters and unnormalised attention output
+                     (columns of the softmax do not sum to one, pct.py:224) drive the layer-4 energies to 4.5e4: the forward's
+                     7e-6 on k (22-bit operand pairs, compounding over four layers; fp32: 1e-6) is a 2e-4 error on x_s there
+                     (`tools/dbg_pct_bwd_chain.py 512 512 1 gpu 21`), and the chain through the peaked softmax multiplies it:
+                     the gradients are REPORTED (fp32 eager beside them) with a loose gate -- worst tensor 5e-2, median 5e-3."""
+    import torch.nn.functional as F_
+    from sgaligner_b200.pct import NaivePCT
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    orig_dropout = F_.dropout
+    try:
+        N, P = 512, 512
+        m = NaivePCT()
+        if init == 'stress':
+            m.load_state_dict(pct_oracle.random_params(21), strict=True)
+        else:
+            torch.manual_seed(4)
+            m = NaivePCT()
+        p = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        m = m.to(dev).train()
+        g = torch.Generator().manual_seed(8)
+        x = (torch.randn(N, P, 3, generator=g) * 0.7 + torch.rand(N, 1, 3, generator=g) * 2 - 1).to(dev)
+        R = torch.randn(N, 256, generator=g).to(dev)
+        masks = [(torch.rand(N, 512, generator=g) < 0.5).float().to(dev), (torch.rand(N, 256, generator=g) < 0.5).float().to(dev)]
+        it = iter(masks)
+        m._mask = lambda n, c, d: next(it)                     # the same dropout masks on both sides
+        y = m(x)
+        (y * R).sum().backward()
+        torch.cuda.synchronize()
+
+        def eager(dt):
+            po = {k: (v.clone().to(dev).to(dt).requires_grad_('running' not in k) if v.is_floating_point() else v.clone().to(dev))
+                  for k, v in p.items()}
+            for sa in ('sa1', 'sa2', 'sa3', 'sa4'):
+                po[sa + '.q_conv.weight'] = po[sa + '.k_conv.weight']
+            it2 = iter(masks)
+            F_.dropout = lambda t, pr, training: t * next(it2).to(t.dtype) * 2.0
+            yo = pct_oracle.naive_pct(x.permute(0, 2, 1).to(dt), po, training=True)
+            (yo * R.to(dt)).sum().backward()
+            return yo.detach(), po
+
+        yo, po = eager(torch.float64)
+        assert rel_inf(y, yo) < 2e-4
+        _, p32 = eager(torch.float32)
+        gmax = max(float(v.grad.abs().max()) for k, v in po.items() if v.is_floating_point() and v.grad is not None)
+        ref_of = lambda name: po[name.replace('q_conv', 'k_conv')].grad      # noqa: E731
+        worst, lines = _grad_report(list(m.named_parameters()), ref_of, gmax)
+
+        class _P:
+            def __init__(self, g_):
+                self.grad = g_
+        worst32, lines32 = _grad_report([(n, _P(p32[n.replace('q_conv', 'k_conv')].grad)) for n, _ in m.named_parameters()], ref_of, gmax)
+        errs = sorted(float(ln.split()[-1]) for ln in lines)
+        print('\n'.join('%s   (fp32 eager: %s)' % (a, b.split()[-1]) for a, b in zip(lines, lines32) if float(a.split()[-1]) > 5e-4))
+        print('NaivePCT 512 x 512 (%s) parameter gradients vs fp64 eager CUDA autograd: worst %.2e, median tensor %.2e  (fp32 eager: worst %.2e)'
+              % (init, worst, errs[len(errs) // 2], worst32))
+        if init == 'stress':
+            assert worst < 5e-2 and errs[len(errs) // 2] < 5e-3
+        else:
+            assert worst < max(2e-3, 2 * worst32) and errs[len(errs) // 2] < 2e-4
+    finally:
+        F_.dropout = orig_dropout
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
 
 
 def test_encoder_with_pct_trains(dev):

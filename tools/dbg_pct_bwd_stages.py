@@ -15,8 +15,9 @@ def rel(a, b):
 
 
 N, P, training = (int(sys.argv[1]), int(sys.argv[2]), sys.argv[3] == '1') if len(sys.argv) > 3 else (4, 200, False)
+PSEED = int(sys.argv[4]) if len(sys.argv) > 4 else 13
 dev = torch.device('cuda:0')
-p = pct_oracle.random_params(13)
+p = pct_oracle.random_params(PSEED)
 m = NaivePCT()
 m.load_state_dict(p, strict=True)
 m = m.to(dev).train(training)
