@@ -68,8 +68,9 @@ class _PCTFunction(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_out):
+        # ctx.saved is left intact: the reference calls loss.backward(retain_graph=True) (a second pass over the same graph
+        # must find its activations); autograd drops the node -- and with it the tensors -- when the graph is released
         grads = ctx.mod._backward(ctx.saved, g_out.contiguous(), ctx.training)
-        ctx.saved = None
         return (None, None) + tuple(grads.get(id(p)) if ctx.needs_input_grad[2 + i] else None for i, p in enumerate(ctx.params))
 
 
@@ -264,7 +265,6 @@ class NaivePCT(nn.Module):
             ops.pct_wgrad(xin, [dv.reshape(-1, 128), dk1.reshape(-1, 32)], [dWv, dWk], transpose=True)      # one pass over x_in
             put(sa.trans_conv.weight, dWt); put(sa.v_conv.weight, dWv); put(sa.k_conv.weight, dWk)
             del dt, dv, dk1
-            L[li] = None
         # ---- Embedding (pct.py:120-125): gx = d/d x0, x0 = relu(bn2(conv2(a1))), a1 = relu(bn1(conv1(points)))
         emb = self.embedding
         dz2, dga, dbe, _ = ops.bn_backward(gx, S['z2'], S['ab2'], emb.bn2, S['st2'], cnt, tr)

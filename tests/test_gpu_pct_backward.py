@@ -320,6 +320,26 @@ def test_param_grads_mid_size_vs_eager_cuda(init, dev):
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
 
 
+def test_backward_twice_with_retain_graph(dev):
+    """The reference's trainer calls ``loss.backward(retain_graph=True)``: a second pass over the same graph must find the
+    saved activations untouched and accumulate the same gradients again; frozen parameters receive none."""
+    from sgaligner_b200.pct import NaivePCT
+    torch.manual_seed(2)
+    m = NaivePCT().to(dev).train()
+    m.linear1.weight.requires_grad_(False)
+    x = torch.randn(6, 130, 3, device=dev)
+    y = m(x)
+    loss = (y * y).sum()
+    loss.backward(retain_graph=True)
+    g1 = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    loss.backward()
+    torch.cuda.synchronize()
+    assert 'linear1.weight' not in g1 and m.linear1.weight.grad is None
+    for n, p in m.named_parameters():
+        if n in g1:
+            assert rel_inf(p.grad, 2 * g1[n]) < 1e-5 or float(g1[n].abs().max()) == 0.0, n      # atomics: not bit-identical
+
+
 def test_encoder_with_pct_trains(dev):
     """MultiModalEncoder(['pct','gat','rel','attr']) -- the module list of the shipped config
     (configs/scan3r/scan3r_ground_truth.yaml:5) -- through OverallLoss, backward and Adam: finite gradients on every
