@@ -1,4 +1,4 @@
-"""One serving step + one training step of a configuration, eager launches (for ncu).  python tools/step_once.py [c2|c2all|c3]"""
+"""One serving step + one training step of a configuration, eager launches (for ncu).  python tools/step_once.py [c2|c2all|c3|c2pct]"""
 import os, sys
 sys.path.insert(0, os.getcwd())
 import torch
@@ -8,7 +8,7 @@ from sgaligner_b200.sg_aligner import MultiModalEncoder
 from sgaligner_b200.trainer import FlatAdam, train_step
 cfg = sys.argv[1] if len(sys.argv) > 1 else 'c2'
 dev = torch.device('cuda:0')
-mods = ['point', 'gat'] if cfg == 'c2' else ['point', 'gat', 'rel', 'attr']
+mods = ['point', 'gat'] if cfg == 'c2' else (['pct', 'gat', 'rel', 'attr'] if cfg == 'c2pct' else ['point', 'gat', 'rel', 'attr'])
 host = synthetic.config_c3(batch=128, seed=1) if cfg == 'c3' else synthetic.config_c2(batch=32, seed=100)
 data = to_cuda(dict(host), dev)
 torch.manual_seed(0)
