@@ -310,10 +310,15 @@ int sga_pct_attn(const float* k, const float* v, const float* c2, int64_t N, int
 /* cat(x1..x4) -> Conv1d(512,1024,bias=False) (pct.py:285-289,306-308) with x4 = x3 + relu(a4 t4 + b4) formed on the fly.
  * WL [1024,512].  Per object and channel only max_p z and min_p z are kept (zmax/zmin [N,2,1024]: the two 64-point
  * column halves of the tiles separately) plus the statistics [2048] of z: BN + LeakyReLU + max commute with them.
- * imax/imin [N,2,1024] (both or neither; training): the point index that holds each maximum / minimum. */
+ * imax/imin [N,2,1024] (both or neither; training): the point index that holds each maximum / minimum.
+ * img (may be NULL): the pre-split operand image written by sga_pct_cat_pack (sga_pct_cat_image_bytes bytes, 128-byte
+ * aligned); with it the kernel streams its operands with cp.async.bulk instead of converting them 8 times over. */
+size_t sga_pct_cat_image_bytes(int64_t N, int P);
+int sga_pct_cat_pack(const float* x1, const float* x2, const float* x3, const float* t4, const float* a4, const float* b4,
+                     int64_t N, int P, void* img, void* stream);
 int sga_pct_cat_linear(const float* x1, const float* x2, const float* x3, const float* t4, const float* a4,
                        const float* b4, int64_t N, int P, const float* WL, float* zmax, float* zmin,
-                       double* stats, int32_t* imax, int32_t* imin, void* stream);
+                       double* stats, int32_t* imax, int32_t* imin, const void* img, void* stream);
 /* pooled [N,1024] = LeakyReLU_0.2(a * (a >= 0 ? max : min) + b) = max_p LeakyReLU(BN(z)) (pct.py:310); with imax/imin
  * also pstar [N,1024] (the arg-max point, torch.max's index) and zsel [N,1024] (the selected z); NULL to skip. */
 int sga_pct_pool_act(const float* zmax, const float* zmin, const int32_t* imax, const int32_t* imin, const float* a,

@@ -74,7 +74,9 @@ def _declare(lib):
     sig('sga_pct_pointwise', c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p)
     sig('sga_pct_attn_stats', c_i, c_p, c_l, c_i, c_p, c_p)
     sig('sga_pct_attn', c_i, c_p, c_p, c_p, c_l, c_i, c_p, c_p)
-    sig('sga_pct_cat_linear', c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p)
+    sig('sga_pct_cat_linear', c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p)
+    sig('sga_pct_cat_image_bytes', c_size_t, c_l, c_i)
+    sig('sga_pct_cat_pack', c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_p, c_p)
     sig('sga_pct_pool_act', c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p)
     sig('sga_bn_bwd_stats', c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_l, c_i, c_p, c_p)
     sig('sga_bn_bwd_coef', c_i, c_p, c_p, c_d, c_p, c_p, c_p, c_p, c_i, c_f, c_i, c_p, c_p, c_p, c_p, c_p, c_p)
@@ -120,7 +122,7 @@ EXPORTS = ['sga_last_error', 'sga_version', 'sga_device_info', 'sga_pointnet_fwd
            'sga_match_sim', 'sga_match_topk_tc', 'sga_match_rank', 'sga_match_anchor_pos', 'sga_match_pair_metrics', 'sga_center_points', 'sga_loss_workspace_bytes', 'sga_loss_launch_count', 'sga_loss_set_gram_path', 'sga_bn_running_update', 'sga_pointnet_gram_scratch_bytes', 'sga_pointnet_bn_moments_gram',
            'sga_loss_fwd_bwd', 'sga_gemm_tf32x3', 'sga_adam_step', 'sga_adam_step_segments', 'sga_selftest_umma', 'sga_debug_set_trace', 'sga_debug_tie_stats',
            'sga_pct_point_moments', 'sga_pct_affine_stats', 'sga_bn_fold', 'sga_pct_embed', 'sga_pct_pointwise', 'sga_pct_attn_stats',
-           'sga_pct_attn', 'sga_pct_cat_linear', 'sga_pct_pool_act', 'sga_col_stats', 'sga_bn_act_rows',
+           'sga_pct_attn', 'sga_pct_cat_linear', 'sga_pct_cat_image_bytes', 'sga_pct_cat_pack', 'sga_pct_pool_act', 'sga_col_stats', 'sga_bn_act_rows',
            'sga_bn_bwd_stats', 'sga_bn_bwd_coef', 'sga_bn_bwd_apply', 'sga_pct_attn_bwd_dv', 'sga_pct_attn_bwd_dk', 'sga_pct_rowdot_scaled',
            'sga_pct_pointwise_scaled', 'sga_pct_pow2_scale', 'sga_pct_sa_input_grad', 'sga_pct_embed_a1', 'sga_pct_embed1_bwd_stats', 'sga_pct_embed1_wgrad',
            'sga_pct_cat_dense_bwd', 'sga_pct_cat_sparse_bwd_x', 'sga_pct_cat_sparse_bwd_w', 'sga_pct_residual', 'sga_axpby_rows',

@@ -41,13 +41,19 @@ enum { BAR_FULL = 0 /*..2*/, BAR_FREE = 3 /*..5*/, BAR_D_FULL = 6 /*,7*/, BAR_D_
 // consecutive channels of one point = one 128-byte line per instruction.
 struct CatBwdOut { float* g[4]; const float* u; const float* scale; const float* xbar; };
 
-template <int kMode>
-__global__ void __launch_bounds__(kThreads, 1)
+// kImg: the operand tiles come PRE-SPLIT from HBM (pct_cat_pack_kernel writes every [128 points x 64 channels] half-chunk
+// once, hi | lo, already in the swizzled image the MMA reads) and a producer warp streams them with cp.async.bulk (TMA,
+// 32 KiB per copy, completion on the slot's mbarrier): no registers, no conversion, no shared-memory stores in this
+// kernel.  Without it each of the 8 channel-block CTAs re-reads and re-converts the same activations -- 8x the
+// conversion work, and the first use of the loaded rows was 31 % of the stall samples (profiles/r2_ncu_pct_cat_lines.txt).
+template <int kMode, bool kImg>
+__global__ void __launch_bounds__(kImg ? kThreads + 32 : kThreads, 1)
 pct_cat_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const float* __restrict__ x3,
                const float* __restrict__ t4, const float* __restrict__ a4, const float* __restrict__ b4, int64_t N, int P,
                const float* __restrict__ WL, float* __restrict__ zmax, float* __restrict__ zmin, double* __restrict__ stats,
-               int32_t* __restrict__ imax, int32_t* __restrict__ imin, const CatBwdOut bo) {
+               int32_t* __restrict__ imax, int32_t* __restrict__ imin, const CatBwdOut bo, const unsigned char* __restrict__ img) {
   using namespace ct;
+  const int nthr = kImg ? kThreads + 32 : kThreads;
   constexpr int F = 0;
   const float wsc = (kMode == 2) ? bo.scale[0] : 1.f;
   extern __shared__ unsigned char smem_raw[];
@@ -60,7 +66,7 @@ pct_cat_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const
   const int cb0 = blockIdx.y * 128;                     // first output channel of this CTA
 
   // ---- setup: W.lo image, a4/b4, barriers, TMEM, W.hi -> TMEM
-  for (int i = tid; i < 128 * 64; i += kThreads) {        // [128 rows][64 chunks of 8 k]
+  for (int i = tid; i < 128 * 64; i += nthr) {        // [128 rows][64 chunks of 8 k]
     const int r = i >> 6, j = i & 63;
     const float4* src = reinterpret_cast<const float4*>(WL + (int64_t)(cb0 + r) * 512 + j * 8);
     const float4 x = src[0], y = src[1];
@@ -70,14 +76,14 @@ pct_cat_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const
     st_chunk(sm_base + WLO + (uint32_t)(j >> 3) * kBlk + ptx::sw128_offset(r, j & 7), lo);
   }
   if (kMode != 2) {
-    for (int i = tid; i < 128; i += kThreads) {
+    for (int i = tid; i < 128; i += nthr) {
       ab4[i] = a4[i];
       ab4[128 + i] = b4[i];
     }
   }
   if (tid == 0) {
     for (int s = 0; s < 3; ++s) {
-      ptx::mbar_init(&bars[BAR_FULL + s], kComputeThreads);
+      ptx::mbar_init(&bars[BAR_FULL + s], kImg ? 1 : kComputeThreads);
       ptx::mbar_init(&bars[BAR_FREE + s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -147,6 +153,27 @@ pct_cat_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const
         __syncwarp();
       }
     }
+  } else if (kImg && warp == 9) {
+    // =============================== producer: one lane streams the packed half-chunks ===============================
+    if (lane == 0) {
+      uint32_t hg = 0;
+      int64_t n = blockIdx.x;
+      int t = 0;
+      for (int64_t g = 0; g < G; ++g) {
+        const unsigned char* tile = img + ((n * T + t) * 8) * (int64_t)SLOT;
+        for (int h = 0; h < 8; ++h, ++hg) {
+          const uint32_t slot = hg % 3;
+          if (hg >= 3) ptx::mbar_wait(&bars[BAR_FREE + slot], (hg / 3 - 1) & 1);
+          ptx::mbar_arrive_expect_tx(&bars[BAR_FULL + slot], SLOT);
+          ptx::bulk_g2s(sm + RING + slot * SLOT, tile + (int64_t)h * SLOT, SLOT, &bars[BAR_FULL + slot]);
+        }
+        if (++t == T) {
+          t = 0;
+          n += gridDim.x;
+        }
+      }
+    }
+    __syncwarp();
   } else {
     // =============================== compute warps ===============================
     const int cc = tid & 7, r0 = tid >> 3;                 // loader: 8-channel chunk cc of rows r0 + 32 q
@@ -224,7 +251,7 @@ pct_cat_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const
       const int64_t rowbase = n * (int64_t)P + (int64_t)t * kTile;
       const int valid = min(kTile, P - t * kTile);
 #pragma unroll 1
-      for (int h = 0; h < 8; ++h, ++hg) {
+      for (int h = 0; h < (kImg ? 0 : 8); ++h, ++hg) {
         const int kc = h >> 1;
         const uint32_t slot = hg % 3;
         const float* src = (kc == 0) ? x1 : (kc == 1) ? x2 : (kMode == 2 && kc == 3) ? t4 : x3;
@@ -289,13 +316,17 @@ pct_cat_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&bars[BAR_FULL + slot]);
       }
+      if (kImg) {
+        epilogue(g);
+        continue;
+      }
       if (g > 0) epilogue(g - 1);
       if (++t == T) {
         t = 0;
         n += gridDim.x;
       }
     }
-    if (G > 0) epilogue(G - 1);
+    if (!kImg && G > 0) epilogue(G - 1);
     if (kMode != 2) {
       atomicAdd(&stats[ch], dsum);
       atomicAdd(&stats[1024 + ch], dsq);
@@ -304,6 +335,72 @@ pct_cat_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 8) ptx::tmem_dealloc<512>(tmem);
+}
+
+// The operand image of pct_cat_kernel<., true>: per point tile and half-chunk h (source kc = h / 2, channels (h & 1) * 64 ..)
+// one 32 KiB block [hi 16 KiB | lo 16 KiB] of 128-byte rows with the 128B swizzle -- exactly the bytes of a ring slot.
+// x4 = x3 + relu(a4 t4 + b4) is formed here; rows past the object's last point are zero.  One CTA per tile, HBM bound
+// (4 B in, 4 B out per element).
+__global__ void __launch_bounds__(256) pct_cat_pack_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
+                                                           const float* __restrict__ x3, const float* __restrict__ t4,
+                                                           const float* __restrict__ a4, const float* __restrict__ b4, int P, int T,
+                                                           unsigned char* __restrict__ img) {
+  const int64_t tile = blockIdx.x;
+  const int64_t n = tile / T;
+  const int t = (int)(tile - n * T);
+  const int64_t rowbase = n * (int64_t)P + (int64_t)t * kTile;
+  const int valid = min(kTile, P - t * kTile);
+  const int tid = threadIdx.x, cc = tid & 7, r0 = tid >> 3;
+  unsigned char* out = img + tile * 8 * (int64_t)ct::SLOT;
+#pragma unroll 1
+  for (int h = 0; h < 8; ++h) {
+    const int kc = h >> 1;
+    const float* src = (kc == 0) ? x1 : (kc == 1) ? x2 : x3;
+    const int chb = (h & 1) * 64 + cc * 8;
+    float4 u[4][2], w[4][2];
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+      const int row = r0 + 32 * qq;
+      const bool ok = row < valid;
+      const float4* s1 = reinterpret_cast<const float4*>(src + (rowbase + row) * 128 + chb);
+      u[qq][0] = ok ? __ldg(s1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      u[qq][1] = ok ? __ldg(s1 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kc == 3) {
+        const float4* s2 = reinterpret_cast<const float4*>(t4 + (rowbase + row) * 128 + chb);
+        w[qq][0] = ok ? __ldg(s2) : make_float4(0.f, 0.f, 0.f, 0.f);
+        w[qq][1] = ok ? __ldg(s2 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    float av[8], bv[8];
+    if (kc == 3) {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(a4 + chb)), a1 = __ldg(reinterpret_cast<const float4*>(a4 + chb) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(b4 + chb)), b1 = __ldg(reinterpret_cast<const float4*>(b4 + chb) + 1);
+      av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w; av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
+      bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+    }
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+      const int row = r0 + 32 * qq;
+      float f[8] = {u[qq][0].x, u[qq][0].y, u[qq][0].z, u[qq][0].w, u[qq][1].x, u[qq][1].y, u[qq][1].z, u[qq][1].w};
+      if (kc == 3) {
+        const float tv[8] = {w[qq][0].x, w[qq][0].y, w[qq][0].z, w[qq][0].w, w[qq][1].x, w[qq][1].y, w[qq][1].z, w[qq][1].w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float r = fmaf(av[e], tv[e], bv[e]);
+          f[e] += r > 0.f ? r : 0.f;
+        }
+        if (row >= valid) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = 0.f;
+        }
+      }
+      uint4 hi, lo;
+      split8(f, hi, lo);
+      unsigned char* dst = out + (int64_t)h * ct::SLOT + ptx::sw128_offset(row, cc);
+      *reinterpret_cast<uint4*>(dst) = hi;
+      *reinterpret_cast<uint4*>(dst + kBlk) = lo;
+    }
+  }
 }
 
 // pooled[n, c] = lrelu_0.2(a_c * (a_c >= 0 ? max : min) + b_c), the two column halves combined (pct.py:288-289, :310);
@@ -337,13 +434,15 @@ __global__ void pct_pool_act_kernel(const float* __restrict__ zmax, const float*
 
 static int cat_launch(int mode, const float* x1, const float* x2, const float* x3, const float* t4, const float* a4, const float* b4,
                       int64_t N, int P, const float* WL, float* zmax, float* zmin, double* stats, int32_t* imax, int32_t* imin,
-                      const sga::pct::CatBwdOut& bo, void* stream) {
+                      const sga::pct::CatBwdOut& bo, const unsigned char* img, void* stream) {
   using namespace sga::pct;
   static bool attr_done = false;
   if (!attr_done) {
-    SGA_CUDA(cudaFuncSetAttribute(pct_cat_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct::SMEM_BYTES));
-    SGA_CUDA(cudaFuncSetAttribute(pct_cat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct::SMEM_BYTES));
-    SGA_CUDA(cudaFuncSetAttribute(pct_cat_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct::SMEM_BYTES));
+    SGA_CUDA(cudaFuncSetAttribute(pct_cat_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct::SMEM_BYTES));
+    SGA_CUDA(cudaFuncSetAttribute(pct_cat_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct::SMEM_BYTES));
+    SGA_CUDA(cudaFuncSetAttribute(pct_cat_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct::SMEM_BYTES));
+    SGA_CUDA(cudaFuncSetAttribute(pct_cat_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct::SMEM_BYTES));
+    SGA_CUDA(cudaFuncSetAttribute(pct_cat_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct::SMEM_BYTES));
     attr_done = true;
   }
   const int gy = mode == 2 ? 4 : 8;
@@ -352,23 +451,43 @@ static int cat_launch(int mode, const float* x1, const float* x2, const float* x
   if ((int64_t)gx > N) gx = (int)N;
   const dim3 grid(gx, gy);
   cudaStream_t st = (cudaStream_t)stream;
-  if (mode == 0) pct_cat_kernel<0><<<grid, kThreads, ct::SMEM_BYTES, st>>>(x1, x2, x3, t4, a4, b4, N, P, WL, zmax, zmin, stats, imax, imin, bo);
-  else if (mode == 1) pct_cat_kernel<1><<<grid, kThreads, ct::SMEM_BYTES, st>>>(x1, x2, x3, t4, a4, b4, N, P, WL, zmax, zmin, stats, imax, imin, bo);
-  else pct_cat_kernel<2><<<grid, kThreads, ct::SMEM_BYTES, st>>>(x1, x2, x3, t4, a4, b4, N, P, WL, zmax, zmin, stats, imax, imin, bo);
+  if (img && mode == 0) pct_cat_kernel<0, true><<<grid, kThreads + 32, ct::SMEM_BYTES, st>>>(x1, x2, x3, t4, a4, b4, N, P, WL, zmax, zmin, stats, imax, imin, bo, img);
+  else if (img && mode == 1) pct_cat_kernel<1, true><<<grid, kThreads + 32, ct::SMEM_BYTES, st>>>(x1, x2, x3, t4, a4, b4, N, P, WL, zmax, zmin, stats, imax, imin, bo, img);
+  else if (mode == 0) pct_cat_kernel<0, false><<<grid, kThreads, ct::SMEM_BYTES, st>>>(x1, x2, x3, t4, a4, b4, N, P, WL, zmax, zmin, stats, imax, imin, bo, nullptr);
+  else if (mode == 1) pct_cat_kernel<1, false><<<grid, kThreads, ct::SMEM_BYTES, st>>>(x1, x2, x3, t4, a4, b4, N, P, WL, zmax, zmin, stats, imax, imin, bo, nullptr);
+  else pct_cat_kernel<2, false><<<grid, kThreads, ct::SMEM_BYTES, st>>>(x1, x2, x3, t4, a4, b4, N, P, WL, zmax, zmin, stats, imax, imin, bo, nullptr);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }
 
 extern "C" int sga_pct_cat_linear(const float* x1, const float* x2, const float* x3, const float* t4, const float* a4,
                                   const float* b4, int64_t N, int P, const float* WL, float* zmax, float* zmin,
-                                  double* stats, int32_t* imax, int32_t* imin, void* stream) {
+                                  double* stats, int32_t* imax, int32_t* imin, const void* img, void* stream) {
   if (N <= 0) return SGA_OK;
   SGA_REQUIRE(x1 && x2 && x3 && t4 && a4 && b4 && WL && zmax && zmin && stats && P >= 1, "sga_pct_cat_linear: bad arguments");
   SGA_REQUIRE((imax == nullptr) == (imin == nullptr), "sga_pct_cat_linear: imax / imin come together");
   SGA_REQUIRE((((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)x3 | (uintptr_t)t4 | (uintptr_t)WL) & 15) == 0,
               "sga_pct_cat_linear: activations / weights must be 16-byte aligned");
   sga::pct::CatBwdOut bo{};
-  return cat_launch(imax ? 1 : 0, x1, x2, x3, t4, a4, b4, N, P, WL, zmax, zmin, stats, imax, imin, bo, stream);
+  SGA_REQUIRE(((uintptr_t)img & 127) == 0, "sga_pct_cat_linear: img must be 128-byte aligned");
+  return cat_launch(imax ? 1 : 0, x1, x2, x3, t4, a4, b4, N, P, WL, zmax, zmin, stats, imax, imin, bo, (const unsigned char*)img, stream);
+}
+
+extern "C" size_t sga_pct_cat_image_bytes(int64_t N, int P) {
+  return (size_t)N * (size_t)((P + sga::pct::kTile - 1) / sga::pct::kTile) * 8 * sga::pct::ct::SLOT;
+}
+
+extern "C" int sga_pct_cat_pack(const float* x1, const float* x2, const float* x3, const float* t4, const float* a4, const float* b4,
+                                int64_t N, int P, void* img, void* stream) {
+  if (N <= 0) return SGA_OK;
+  SGA_REQUIRE(x1 && x2 && x3 && t4 && a4 && b4 && img && P >= 1, "sga_pct_cat_pack: bad arguments");
+  SGA_REQUIRE((((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)x3 | (uintptr_t)t4 | (uintptr_t)a4 | (uintptr_t)b4 | (uintptr_t)img) & 15) == 0,
+              "sga_pct_cat_pack: 16-byte alignment");
+  const int T = (P + sga::pct::kTile - 1) / sga::pct::kTile;
+  SGA_REQUIRE(N * T < ((int64_t)1 << 31), "sga_pct_cat_pack: too many tiles");
+  sga::pct::pct_cat_pack_kernel<<<(unsigned)(N * T), 256, 0, (cudaStream_t)stream>>>(x1, x2, x3, t4, a4, b4, P, T, (unsigned char*)img);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
 }
 
 extern "C" int sga_pct_cat_dense_bwd(const float* x1, const float* x2, const float* x3, const float* x4, int64_t N, int P,
@@ -380,7 +499,7 @@ extern "C" int sga_pct_cat_dense_bwd(const float* x1, const float* x2, const flo
               "sga_pct_cat_dense_bwd: activations / weights must be 16-byte aligned");
   sga::pct::CatBwdOut bo{};
   bo.g[0] = g1; bo.g[1] = g2; bo.g[2] = g3; bo.g[3] = g4; bo.u = u; bo.scale = scale; bo.xbar = xbar;
-  return cat_launch(2, x1, x2, x3, x4, nullptr, nullptr, N, P, M, nullptr, nullptr, nullptr, nullptr, nullptr, bo, stream);
+  return cat_launch(2, x1, x2, x3, x4, nullptr, nullptr, N, P, M, nullptr, nullptr, nullptr, nullptr, nullptr, bo, nullptr, stream);
 }
 
 extern "C" int sga_pct_pool_act(const float* zmax, const float* zmin, const int32_t* imax, const int32_t* imin, const float* a,

@@ -370,9 +370,18 @@ def pct_cat_linear(x1, x2, x3, t4, ab4, WL, track: bool = False):
     imax = torch.empty((N, 2, 1024), device=dev, dtype=torch.int32) if track else None
     imin = torch.empty((N, 2, 1024), device=dev, dtype=torch.int32) if track else None
     stats = _f64z(2048, dev)
+    lib = get_lib()
+    img = None
+    if os.environ.get('SGA_PCT_CAT', '') != 'v1':
+        # operands pre-split once into the image the MMA reads (the 8 channel-block CTAs then stream it with TMA copies)
+        img = _workspace_named('pct_cat_img', int(lib.sga_pct_cat_image_bytes(N, P)), dev)
+        with _timed('pct_cat_pack'):
+            check(lib.sga_pct_cat_pack(_ptr(x1), _ptr(x2), _ptr(x3), _ptr(t4), _ptr(ab4[0]), _ptr(ab4[1]), N, P, _ptr(img), _stream()),
+                  'sga_pct_cat_pack')
+        _count(1)
     with _timed('pct_cat_linear'):
-        check(get_lib().sga_pct_cat_linear(_ptr(x1), _ptr(x2), _ptr(x3), _ptr(t4), _ptr(ab4[0]), _ptr(ab4[1]), N, P, _ptr(WL), _ptr(zmax),
-                                           _ptr(zmin), _ptr(stats), _ptr(imax), _ptr(imin), _stream()), 'sga_pct_cat_linear')
+        check(lib.sga_pct_cat_linear(_ptr(x1), _ptr(x2), _ptr(x3), _ptr(t4), _ptr(ab4[0]), _ptr(ab4[1]), N, P, _ptr(WL), _ptr(zmax),
+                                     _ptr(zmin), _ptr(stats), _ptr(imax), _ptr(imin), _ptr(img), _stream()), 'sga_pct_cat_linear')
     _count(1)
     return zmax, zmin, stats, imax, imin
 
