@@ -15,6 +15,7 @@
 // against 0.5 us of MMAs), so the tile pipeline is kept simple: what matters is bytes, and those are minimal.
 #include "pct_common.cuh"
 #include <type_traits>
+#include <stdlib.h>
 
 namespace sga {
 namespace pct {
@@ -291,6 +292,232 @@ __global__ void __launch_bounds__(kThreads, 1) pct_pw_kernel(const PwArgs A) {
   if (warp == 8) ptx::tmem_dealloc<kTmemCols>(tmem);
 }
 
+
+// =====================================================================================================================
+// Second generation for Cout = 128 (the trans convolutions of the forward, every input-gradient product of the backward):
+// CHANNELS ON THE TMEM LANES and two co-resident CTAs per SM.
+//     D[ch, pt] = sum_k W[ch, k] X[pt, k]          A operand = W from TENSOR MEMORY (hi 64 + lo 64 columns, staged once per
+//                                                  CTA), B operand = the X tile's K-major image, N = 128 points
+// The first kernel keeps 64-80 KiB of weight images next to the 64 KiB tile and one serial chain load -> product -> store
+// per SM (ncu: issue slots 28 %, DRAM 26 %, long scoreboard on top).  With W in tensor memory a CTA needs the tile only
+// (66 KiB, 256 TMEM columns), so a second CTA's chain fills the gaps of the first.  The epilogue thread owns an output
+// channel: BatchNorm sums are thread-local, and a warp stores 32 consecutive channels of one point per instruction.
+namespace p2 {
+constexpr uint32_t AHI = 0;
+constexpr uint32_t ALO = AHI + 2 * kBlk;
+constexpr uint32_t BARS = ALO + 2 * kBlk;                  // 65536
+constexpr uint32_t TMEMPTR = BARS + 64;
+constexpr uint32_t SMEM_BYTES = TMEMPTR + 16 + 1024;
+constexpr uint32_t D_COL = 0, WHI_COL = 128, WLO_COL = 192;
+enum { BAR_A_FULL = 0, BAR_D_FULL = 1 };
+}  // namespace p2
+
+template <bool kScaled>
+__global__ void __launch_bounds__(kThreads, 2) pct_pw2_kernel(const PwArgs A) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sm_base = ptx::smem_u32(sm);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + p2::BARS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + p2::TMEMPTR);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    ptx::mbar_init(&bars[p2::BAR_A_FULL], kComputeThreads);
+    ptx::mbar_init(&bars[p2::BAR_D_FULL], 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 8) ptx::tmem_alloc<256>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp < 4) {       // W: output channel on the TMEM lane, 128 k packed two per 32-bit column, hi and lo
+    const int r = 32 * warp + lane;
+    const float4* src = reinterpret_cast<const float4*>(A.W + (int64_t)r * 128);
+#pragma unroll 1
+    for (int grp = 0; grp < 4; ++grp) {
+      uint32_t wh[16], wl[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 a = __ldg(src + grp * 8 + j);
+        split2f<0>(a.x, a.y, wh[2 * j], wl[2 * j]);
+        split2f<0>(a.z, a.w, wh[2 * j + 1], wl[2 * j + 1]);
+      }
+      ptx::tmem_st16(tmem + ((uint32_t)(32 * warp) << 16) + p2::WHI_COL + grp * 16, wh);
+      ptx::tmem_st16(tmem + ((uint32_t)(32 * warp) << 16) + p2::WLO_COL + grp * 16, wl);
+    }
+    ptx::tmem_st_wait();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+
+  const int T = (A.P + kTile - 1) / kTile;
+  const int64_t G = A.N * T;
+
+  if (warp == 8) {
+    // =============================== MMA issuer ===============================
+    const uint32_t idesc = ptx::make_idesc(kFmt, 128, 128);
+    const uint64_t dAhi = ptx::smem_desc_sw128(sm_base + p2::AHI), dAlo = ptx::smem_desc_sw128(sm_base + p2::ALO);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    uint32_t it = 0;
+    for (int64_t g = blockIdx.x; g < G; g += gridDim.x, ++it) {
+      ptx::mbar_wait(&bars[p2::BAR_A_FULL], it & 1);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+#pragma unroll
+        for (int pass = 0; pass < 4; ++pass) {          // (W.hi, X.hi) (W.hi, X.lo) (W.lo, X.hi) (W.lo, X.lo)
+          const uint32_t wcol = (pass & 2) ? p2::WLO_COL : p2::WHI_COL;
+          const uint64_t xd = (pass & 1) ? dAlo : dAhi;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            ptx::umma_bf16_ts(tmem_u + p2::D_COL, tmem_u + wcol + (uint32_t)(ks * 8), xd + (uint64_t)((ks >> 2) * (kBlk >> 4) + (ks & 3) * 2),
+                              idesc, (pass | ks) != 0);
+        }
+        ptx::umma_commit(&bars[p2::BAR_D_FULL]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // =============================== compute warps ===============================
+    const int cc = tid & 15, r0 = tid >> 4;          // loader: 8-channel chunk cc of rows r0 + 16 q
+    const int ch0 = cc * 8;
+    float pa1[8], pb1[8], pa2[8], pb2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      pa1[e] = (A.mode1 == 2) ? A.a1[ch0 + e] : 1.f;
+      pb1[e] = (A.mode1 == 2) ? A.b1[ch0 + e] : 0.f;
+      pa2[e] = (A.mode2 == 2) ? A.a2[ch0 + e] : 1.f;
+      pb2[e] = (A.mode2 == 2) ? A.b2[ch0 + e] : 0.f;
+    }
+    const uint32_t a_off_blk = (uint32_t)(cc >> 3) * kBlk;
+    const int q = warp & 3, hc = warp >> 2;           // epilogue: channel = 32 q + lane, point half hc
+    const int och = 32 * q + lane;
+    const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+    const float bias = A.bias ? A.bias[och] : 0.f;
+    const bool want_stats = A.stats != nullptr;
+    double ds = 0, dq = 0;
+
+    uint32_t it = 0;
+    for (int64_t g = blockIdx.x; g < G; g += gridDim.x, ++it) {
+      const int64_t n = g / T;
+      const int t = (int)(g - n * T);
+      const int64_t rowbase = n * A.P + (int64_t)t * kTile;
+      const int valid = min(kTile, A.P - t * kTile);
+      const float sc = kScaled ? __ldg(A.scale + 2 * n) : 1.f;
+      // ---- load + prologue + split -> X tile (the previous tile's products have completed: D_FULL was waited for)
+      auto batch = [&](auto rows_tag, int bt) {
+        constexpr int kRows = decltype(rows_tag)::value;
+        float4 u[kRows][2], w[kRows][2];
+#pragma unroll
+        for (int qq = 0; qq < kRows; ++qq) {
+          const int row = r0 + 16 * (bt * kRows + qq);
+          const bool ok = row < valid;
+          const float4* s1 = reinterpret_cast<const float4*>(A.src1 + (rowbase + row) * 128 + ch0);
+          u[qq][0] = ok ? __ldg(s1) : make_float4(0.f, 0.f, 0.f, 0.f);
+          u[qq][1] = ok ? __ldg(s1 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (A.mode2) {
+            const float4* s2 = reinterpret_cast<const float4*>(A.src2 + (rowbase + row) * 128 + ch0);
+            w[qq][0] = ok ? __ldg(s2) : make_float4(0.f, 0.f, 0.f, 0.f);
+            w[qq][1] = ok ? __ldg(s2 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int qq = 0; qq < kRows; ++qq) {
+          const int row = r0 + 16 * (bt * kRows + qq);
+          const bool ok = row < valid;
+          float f[8];
+          const float s1[8] = {u[qq][0].x, u[qq][0].y, u[qq][0].z, u[qq][0].w, u[qq][1].x, u[qq][1].y, u[qq][1].z, u[qq][1].w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float v = s1[e];
+            if (A.mode1 == 2) {
+              v = fmaf(pa1[e], v, pb1[e]);
+              v = v > 0.f ? v : 0.f;
+            }
+            f[e] = v;
+          }
+          if (A.mode2) {
+            const float s2[8] = {w[qq][0].x, w[qq][0].y, w[qq][0].z, w[qq][0].w, w[qq][1].x, w[qq][1].y, w[qq][1].z, w[qq][1].w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float v = s2[e];
+              if (A.mode2 == 2) {
+                v = fmaf(pa2[e], v, pb2[e]);
+                v = v > 0.f ? v : 0.f;
+              }
+              f[e] += v;
+            }
+          }
+          if (!ok) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = 0.f;
+          }
+          if (A.out_x && ok) {
+            float4* ox = reinterpret_cast<float4*>(A.out_x + (rowbase + row) * 128 + ch0);
+            ox[0] = make_float4(f[0], f[1], f[2], f[3]);
+            ox[1] = make_float4(f[4], f[5], f[6], f[7]);
+          }
+          if (kScaled) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] *= sc;
+          }
+          uint4 hi, lo;
+          split8(f, hi, lo);
+          const uint32_t off = a_off_blk + ptx::sw128_offset(row, cc & 7);
+          st_chunk(sm_base + p2::AHI + off, hi);
+          st_chunk(sm_base + p2::ALO + off, lo);
+        }
+      };
+      if (A.mode2) {          // 96 registers per thread (two CTAs per SM): smaller batches than the first kernel's
+#pragma unroll 1
+        for (int bt = 0; bt < 4; ++bt) batch(std::integral_constant<int, 2>{}, bt);
+      } else {
+#pragma unroll 1
+        for (int bt = 0; bt < 2; ++bt) batch(std::integral_constant<int, 4>{}, bt);
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&bars[p2::BAR_A_FULL]);
+
+      // ---- epilogue: this thread's channel, the 64 points of its half
+      ptx::mbar_wait(&bars[p2::BAR_D_FULL], it & 1);
+      ptx::tc_fence_after();
+      const float osc = kScaled ? __ldg(A.scale + 2 * n + 1) : 1.f;
+      float s = 0.f, sq = 0.f;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem + lane_addr + p2::D_COL + (uint32_t)(hc * 64 + h * 32), v);
+        ptx::tmem_ld_wait();
+        const int p0 = hc * 64 + h * 32;
+        float* dst = A.out0 + (rowbase + p0) * 128 + och;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          if (p0 + e < valid) {
+            const float y = kScaled ? __uint_as_float(v[e]) * osc : __uint_as_float(v[e]) + bias;
+            dst[(int64_t)e * 128] = y;
+            if (want_stats) {
+              s += y;
+              sq = fmaf(y, y, sq);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();     // the next A_FULL arrival orders the next tile's products after these TMEM reads
+      if (want_stats) {
+        ds += (double)s;
+        dq += (double)sq;
+      }
+    }
+    if (want_stats) {             // the two point halves of a channel
+      atomicAdd(&A.stats[och], ds);
+      atomicAdd(&A.stats[128 + och], dq);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) ptx::tmem_dealloc<256>(tmem);
+}
+
 }  // namespace
 
 int pw_launch(const PwArgs& a, cudaStream_t st) {
@@ -305,6 +532,21 @@ int pw_launch(const PwArgs& a, cudaStream_t st) {
   int64_t G = a.N * T;
   int grid = sm_count();
   if ((int64_t)grid > G) grid = (int)G;
+  static const bool v1 = [] { const char* e = getenv("SGA_PCT_PW"); return e && e[0] == 'v' && e[1] == '1'; }();
+  if (!a.pts && a.Cout == 128 && a.c0 == 128 && !v1) {       // second generation: channels on lanes, two CTAs per SM
+    static bool attr2 = false;
+    if (!attr2) {
+      SGA_CUDA(cudaFuncSetAttribute(pct_pw2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2::SMEM_BYTES));
+      SGA_CUDA(cudaFuncSetAttribute(pct_pw2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2::SMEM_BYTES));
+      attr2 = true;
+    }
+    int64_t g2 = 2 * (int64_t)sm_count();
+    if (g2 > G) g2 = G;
+    if (a.scale) pct_pw2_kernel<true><<<(unsigned)g2, kThreads, p2::SMEM_BYTES, st>>>(a);
+    else pct_pw2_kernel<false><<<(unsigned)g2, kThreads, p2::SMEM_BYTES, st>>>(a);
+    SGA_LAUNCH_CHECK();
+    return SGA_OK;
+  }
   if (a.pts) pct_pw_kernel<true, false><<<grid, kThreads, SMEM_BYTES, st>>>(a);
   else if (a.scale) pct_pw_kernel<false, true><<<grid, kThreads, SMEM_BYTES, st>>>(a);
   else pct_pw_kernel<false, false><<<grid, kThreads, SMEM_BYTES, st>>>(a);
