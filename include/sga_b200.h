@@ -351,7 +351,10 @@ int sga_pct_pow2_scale(const float* x, const float* y, int64_t N, int64_t per, f
 /* SA backward, attention part (pct.py:217-224): dv [N,P,128] = attention dxs;  dk halves, see csrc/pct_attn.cu.
  * scale = sga_pct_pow2_scale(dxs, v, ...) */
 int sga_pct_attn_bwd_dv(const float* k, const float* dxs, const float* c2, const float* scale, int64_t N, int P, float* dv,
+                        double* dv_colsum /* [128], zeroed; or NULL */, float* dv_absmax /* [N], zeroed; or NULL */,
                         void* stream);
+/* scale [N,2] = {s, 1/s}, s = 2^floor(log2(target / absmax[n])): the per-object scale from maxima a kernel recorded */
+int sga_pct_scale_from_absmax(const float* absmax, int64_t N, float target, float* scale, void* stream);
 int sga_pct_attn_bwd_dk(const float* k, const float* fixed, const float* streamed, const float* c2, float* delta,
                         const float* scale, int64_t N, int P, int by_col, int delta_sweep, float* dk_out, void* stream);
 /* delta [N,P] = scale[n][0] * sum_c x[n,p,c] y[n,p,c] (C = 128): the softmax-backward row term v_i . dv_i in scaled units */

@@ -681,7 +681,8 @@ namespace sga {
 namespace pct {
 // pct_attn2.cu: two CTAs per SM (default); SGA_PCT_ATTN=v1 selects the kernels of this file
 int attn2_fwd(const float* k, const float* v, const float* c2, int64_t N, int P, float* xs, cudaStream_t st);
-int attn2_dv(const float* k, const float* dxs, const float* c2, const float* scale, int64_t N, int P, float* dv, cudaStream_t st);
+int attn2_dv(const float* k, const float* dxs, const float* c2, const float* scale, int64_t N, int P, float* dv, double* colsum,
+             float* absmax, cudaStream_t st);
 int attn2_dk(const float* k, const float* fixed, const float* streamed, const float* c2, float* delta, const float* scale, int64_t N,
              int P, int by_col, int delta_sweep, float* dk_out, cudaStream_t st);
 static bool attn_v1() {
@@ -734,12 +735,13 @@ extern "C" int sga_pct_attn(const float* k, const float* v, const float* c2, int
 
 /* dv [N,P,128] = attention dxs per object (first product of the SA backward; see pct_attn_kernel<true>) */
 extern "C" int sga_pct_attn_bwd_dv(const float* k, const float* dxs, const float* c2, const float* scale, int64_t N, int P, float* dv,
-                                   void* stream) {
+                                   double* dv_colsum, float* dv_absmax, void* stream) {
   if (N <= 0) return SGA_OK;
   SGA_REQUIRE(k && dxs && c2 && dv && scale && P >= 1 && P <= sga::pct::kMaxT * sga::pct::kTile, "sga_pct_attn_bwd_dv: P=%d (1..512)", P);
   SGA_REQUIRE((((uintptr_t)k | (uintptr_t)dxs) & 15) == 0, "sga_pct_attn_bwd_dv: k / dxs must be 16-byte aligned");
   using namespace sga::pct;
-  if (!attn_v1()) return attn2_dv(k, dxs, c2, scale, N, P, dv, (cudaStream_t)stream);
+  if (!attn_v1()) return attn2_dv(k, dxs, c2, scale, N, P, dv, dv_colsum, dv_absmax, (cudaStream_t)stream);
+  SGA_REQUIRE(!dv_colsum && !dv_absmax, "sga_pct_attn_bwd_dv: the fused column sums / maxima need the two-CTA kernel (unset SGA_PCT_ATTN)");
   static bool attr_done = false;
   if (!attr_done) {
     SGA_CUDA(cudaFuncSetAttribute(pct_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at::SMEM_BYTES));

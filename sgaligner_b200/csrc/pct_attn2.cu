@@ -105,7 +105,7 @@ __device__ __forceinline__ void load_tiles2(const float* __restrict__ k, int64_t
 template <bool kDv>
 __global__ void __launch_bounds__(kThreads, 2)
 pct_attn2_kernel(const float* __restrict__ k, const float* __restrict__ v, const float* __restrict__ c2, int64_t N, int P,
-                 float* __restrict__ out, const float* __restrict__ scale) {
+                 float* __restrict__ out, const float* __restrict__ scale, double* __restrict__ colsum, float* __restrict__ absmax) {
   using namespace a2;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -172,6 +172,7 @@ pct_attn2_kernel(const float* __restrict__ k, const float* __restrict__ v, const
     const uint32_t c0 = (uint32_t)(hc * 64);
     float* stage = reinterpret_cast<float*>(sm + VHI) + warp * kStageFloats;     // reuses the V tile once the item's products are done
     uint32_t u = 0;
+    double dcs[4] = {0, 0, 0, 0};                      // kDv: column sums of dv (= d v_conv.bias), this lane's column of each chunk
     for (int64_t w = blockIdx.x; w < W; w += gridDim.x) {
       const int64_t n = w / T;
       const int a = (int)(w - n * T);
@@ -226,17 +227,35 @@ pct_attn2_kernel(const float* __restrict__ k, const float* __restrict__ v, const
       const int nvalid = max(0, min(32, P - a * kTile - 32 * q));
       const float osc = kDv ? __ldg(scale + 2 * n + 1) : 1.f;
 #pragma unroll 1
+      float amax = 0.f;
+      const bool stats = kDv && colsum != nullptr;
+#pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         uint32_t ov[16];
         ptx::tmem_ld16(tmem + lane_addr + O_COL + (uint32_t)(hc * 64 + ch * 16), ov);
         ptx::tmem_ld_wait();
         float f[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(ov[e]) * osc;
+        for (int e = 0; e < 16; ++e) {
+          f[e] = __uint_as_float(ov[e]) * osc;
+          if (kDv && lane < nvalid) amax = fmaxf(amax, fabsf(f[e]));
+        }
         float s = 0.f, qv = 0.f;
-        stage_store16(stage, f, out + (rowbase + 32 * q) * 128 + hc * 64 + ch * 16, 128, nvalid, lane, s, qv, false);
+        stage_store16(stage, f, out + (rowbase + 32 * q) * 128 + hc * 64 + ch * 16, 128, nvalid, lane, s, qv, stats);
+        if (stats) dcs[ch] += (double)s;
+      }
+      if (kDv && absmax != nullptr) {                  // the object's largest |dv|: the scale of the next product (dv W_v) comes from it
+        amax = warp_max(amax);
+        if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(absmax + n), __float_as_uint(amax));
       }
       ptx::tc_fence_before();
+    }
+    if (kDv && colsum != nullptr) {
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        const double t = dcs[ch] + __shfl_xor_sync(0xffffffffu, dcs[ch], 16);
+        if (lane < 16) atomicAdd(&colsum[hc * 64 + ch * 16 + lane], t);
+      }
     }
   }
   ptx::tc_fence_before();
@@ -245,7 +264,8 @@ pct_attn2_kernel(const float* __restrict__ k, const float* __restrict__ v, const
 }
 
 template <bool kDv>
-int attn2_launch(const float* k, const float* v, const float* c2, int64_t N, int P, float* out, const float* scale, cudaStream_t st) {
+int attn2_launch(const float* k, const float* v, const float* c2, int64_t N, int P, float* out, const float* scale, double* colsum,
+                 float* absmax, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
     SGA_CUDA(cudaFuncSetAttribute(pct_attn2_kernel<kDv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a2::SMEM_BYTES));
@@ -255,7 +275,7 @@ int attn2_launch(const float* k, const float* v, const float* c2, int64_t N, int
   const int64_t W = N * T;
   int64_t grid = 2 * (int64_t)sm_count();
   if (grid > W) grid = W;
-  pct_attn2_kernel<kDv><<<(unsigned)grid, kThreads, a2::SMEM_BYTES, st>>>(k, v, c2, N, P, out, scale);
+  pct_attn2_kernel<kDv><<<(unsigned)grid, kThreads, a2::SMEM_BYTES, st>>>(k, v, c2, N, P, out, scale, colsum, absmax);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }
@@ -263,10 +283,11 @@ int attn2_launch(const float* k, const float* v, const float* c2, int64_t N, int
 }  // namespace
 
 int attn2_fwd(const float* k, const float* v, const float* c2, int64_t N, int P, float* xs, cudaStream_t st) {
-  return attn2_launch<false>(k, v, c2, N, P, xs, nullptr, st);
+  return attn2_launch<false>(k, v, c2, N, P, xs, nullptr, nullptr, nullptr, st);
 }
-int attn2_dv(const float* k, const float* dxs, const float* c2, const float* scale, int64_t N, int P, float* dv, cudaStream_t st) {
-  return attn2_launch<true>(k, dxs, c2, N, P, dv, scale, st);
+int attn2_dv(const float* k, const float* dxs, const float* c2, const float* scale, int64_t N, int P, float* dv, double* colsum,
+             float* absmax, cudaStream_t st) {
+  return attn2_launch<true>(k, dxs, c2, N, P, dv, scale, colsum, absmax, st);
 }
 
 }  // namespace pct

@@ -427,6 +427,18 @@ __global__ void __launch_bounds__(256) pow2_scale_kernel(const float* __restrict
   }
 }
 
+// scale[n] = {s, 1/s}, s = 2^floor(log2(target / absmax[n])) -- the per-object scale from a maximum a producing kernel recorded
+__global__ void scale_from_absmax_kernel(const float* __restrict__ absmax, int64_t N, float target, float* __restrict__ scale) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float den = absmax[n];
+  int ex = 0;
+  if (den > 0.f && isfinite(den)) ex = (int)floorf(log2f(target / den));
+  ex = max(-100, min(100, ex));
+  scale[2 * n] = exp2f((float)ex);
+  scale[2 * n + 1] = exp2f((float)-ex);
+}
+
 inline unsigned grid_for(int64_t work_rows, int per_block) {
   int64_t blocks = (work_rows + per_block - 1) / per_block;
   const int64_t cap = (int64_t)sm_count() * 8;
@@ -565,6 +577,14 @@ extern "C" int sga_pct_pow2_scale(const float* x, const float* y, int64_t N, int
   SGA_REQUIRE(x && scale && per >= 4 && per % 4 == 0 && target > 0.f, "sga_pct_pow2_scale: bad arguments");
   SGA_REQUIRE((((uintptr_t)x | (uintptr_t)y) & 15) == 0, "sga_pct_pow2_scale: 16-byte alignment");
   pow2_scale_kernel<<<(unsigned)N, 256, 0, (cudaStream_t)stream>>>(x, y, per, target, scale);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+extern "C" int sga_pct_scale_from_absmax(const float* absmax, int64_t N, float target, float* scale, void* stream) {
+  if (N <= 0) return SGA_OK;
+  SGA_REQUIRE(absmax && scale && target > 0.f, "sga_pct_scale_from_absmax: bad arguments");
+  scale_from_absmax_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(absmax, N, target, scale);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }

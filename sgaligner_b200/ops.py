@@ -456,8 +456,12 @@ def pct_attention_backward(k, v, c2, dxs):
     # |v_i . dxs_j| <= 128 max|v| max|dxs|: the scaled products (and T = E (dA - delta)) stay below 2^15 < 65504
     scale = pct_pow2_scale(dxs, v, target=16384.0 / 128.0)
     dv = torch.empty_like(v)
+    fused = os.environ.get('SGA_PCT_ATTN', '') != 'v1'      # the two-CTA kernel also records sum_rows dv and max |dv| per object
+    dv_colsum = _f64z(128, k.device) if fused else None
+    dv_absmax = torch.zeros(N, device=k.device, dtype=torch.float32) if fused else None
     with _timed('pct_attn_bwd_dv'):
-        check(lib.sga_pct_attn_bwd_dv(_ptr(k), _ptr(dxs), _ptr(c2), _ptr(scale), N, P, _ptr(dv), _stream()), 'sga_pct_attn_bwd_dv')
+        check(lib.sga_pct_attn_bwd_dv(_ptr(k), _ptr(dxs), _ptr(c2), _ptr(scale), N, P, _ptr(dv), _ptr(dv_colsum), _ptr(dv_absmax), _stream()),
+              'sga_pct_attn_bwd_dv')
     # delta_i = sum_j A[i,j] dA[i,j] (in scaled units): summed by the row half from ITS OWN dA values in a first sweep, so
     # that the errors of dA and delta cancel in (dA - delta) where the softmax is peaked.  SGA_PCT_DELTA=dot takes the
     # mathematically equal v_i . dv_i from the FMA pipe instead (one S / dA sweep less, -9 ms at 4096 x 512): measured
@@ -474,15 +478,21 @@ def pct_attention_backward(k, v, c2, dxs):
         check(lib.sga_pct_attn_bwd_dk(_ptr(k), _ptr(dxs), _ptr(v), _ptr(c2), _ptr(delta), _ptr(scale), N, P, 1, 0, _ptr(dk2), _stream()),
               'sga_pct_attn_bwd_dk')
     _count(3)
-    return dk1, dk2, dv
+    return dk1, dk2, dv, dv_colsum, dv_absmax
 
 
-def pct_pointwise_grad(src, Wt):
+def pct_pointwise_grad(src, Wt, absmax=None):
     """src [N,P,128] @ Wt^T (Wt [128,128] contiguous): the input-gradient products; src is scaled per object into the fp16
-    range on the way in, the result scaled back."""
+    range on the way in, the result scaled back.  ``absmax`` [N]: max |src| per object if the producer recorded it (saves
+    the reduction pass)."""
     N, P, _ = src.shape
     out = torch.empty_like(src)
-    scale = pct_pow2_scale(src)
+    if absmax is not None:
+        scale = torch.empty((N, 2), device=src.device, dtype=torch.float32)
+        check(get_lib().sga_pct_scale_from_absmax(_ptr(absmax), N, 4096.0, _ptr(scale), _stream()), 'sga_pct_scale_from_absmax')
+        _count(1)
+    else:
+        scale = pct_pow2_scale(src)
     with _timed('pct_pointwise_bwd'):
         check(get_lib().sga_pct_pointwise_scaled(_ptr(src), _ptr(scale), N, P, _ptr(Wt), _ptr(out), _stream()), 'sga_pct_pointwise_scaled')
     _count(1)

@@ -249,14 +249,14 @@ class NaivePCT(nn.Module):
             put(sa.trans_conv.bias, torch.zeros(128, device=dev) if tr else colsum(dt, 128))
             Wt = sa.trans_conv.weight.reshape(128, 128)
             dxs = ops.pct_pointwise_grad(dt, Wt.t().contiguous())
-            dk1, dk2, dv = ops.pct_attention_backward(Lr['k'], Lr['v'], Lr['c2'], dxs)
+            dk1, dk2, dv, dv_colsum, dv_absmax = ops.pct_attention_backward(Lr['k'], Lr['v'], Lr['c2'], dxs)
             del dxs
             Wv = sa.v_conv.weight.reshape(128, 128)
             Wk = ops._f32c(sa.k_conv.weight.reshape(32, 128))
-            dxv = ops.pct_pointwise_grad(dv, Wv.t().contiguous())
+            dxv = ops.pct_pointwise_grad(dv, Wv.t().contiguous(), absmax=dv_absmax)
             gx = ops.pct_sa_input_grad(gx, gcat[li - 1] if li > 0 else None, dxv, dk1, dk2, Wk)      # dk1 <- dk
             del dxv, dk2
-            put(sa.v_conv.bias, colsum(dv, 128))
+            put(sa.v_conv.bias, dv_colsum.float() if dv_colsum is not None else colsum(dv, 128))
             dWt = torch.zeros((128, 128), device=dev, dtype=torch.float32)
             dWv = torch.zeros((128, 128), device=dev, dtype=torch.float32)
             dWk = torch.zeros((32, 128), device=dev, dtype=torch.float32)

@@ -68,7 +68,7 @@ def test_attention_backward_vs_autograd(N, P, dev):
     v = _rand((N, P, 128), dev, 2)
     dxs = _rand((N, P, 128), dev, 3, 1e-5)                  # far below the fp16 range on purpose
     xs, c2 = ops.pct_attention(k, v, want_c2=True)
-    dk1, dk2, dv = ops.pct_attention_backward(k, v, c2, dxs)
+    dk1, dk2, dv, dv_colsum, dv_absmax = ops.pct_attention_backward(k, v, c2, dxs)
     torch.cuda.synchronize()
     kd = k.double().requires_grad_(True)
     vd = v.double().requires_grad_(True)

@@ -22,7 +22,7 @@ for P in (200, 512):
             v = torch.randn(N, P, 128, generator=g).to(dev)
             dxs = (torch.randn(N, P, 128, generator=g) * 1e-5).to(dev)
             xs, c2 = ops.pct_attention(k, v, want_c2=True)
-            dk1, dk2, dv = ops.pct_attention_backward(k, v, c2, dxs)
+            dk1, dk2, dv, dv_colsum, dv_absmax = ops.pct_attention_backward(k, v, c2, dxs)
             torch.cuda.synchronize()
 
             def ref(dt):

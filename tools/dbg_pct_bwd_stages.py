@@ -30,7 +30,7 @@ orig_attn, orig_pw, orig_wg = ops.pct_attention_backward, ops.pct_pointwise_grad
 
 
 def attn(k, v, c2, dxs):
-    dk1, dk2, dv = orig_attn(k, v, c2, dxs)
+    dk1, dk2, dv, dvc, dvm = orig_attn(k, v, c2, dxs)
     torch.cuda.synchronize()
     with torch.enable_grad():
         kd = k.double().requires_grad_(True)
@@ -40,11 +40,11 @@ def attn(k, v, c2, dxs):
     print('attn_bwd: |k|max %.1f energy max %.0f  |dxs|max %.2e  dv %.1e dk %.1e  (|dk|max %.2e)' % (
         float(k.abs().max()), float((k.double() ** 2).sum(-1).max() / math.sqrt(32)), float(dxs.abs().max()), rel(dv, vd.grad),
         rel(dk1 + dk2, kd.grad), float(kd.grad.abs().max())))
-    return dk1, dk2, dv
+    return dk1, dk2, dv, dvc, dvm
 
 
-def pw(src, Wt):
-    out = orig_pw(src, Wt)
+def pw(src, Wt, absmax=None):
+    out = orig_pw(src, Wt, absmax)
     torch.cuda.synchronize()
     print('pointwise_grad: %.1e' % rel(out, src.double() @ Wt.double().t()))
     return out

@@ -17,12 +17,12 @@ v = torch.randn(N, P, 128, generator=g).to(dev)
 dxs = (torch.randn(N, P, 128, generator=g) * 1e-3).to(dev)
 for _ in range(reps):
     xs, c2 = ops.pct_attention(k, v, want_c2=True)
-    dk1, dk2, dv = ops.pct_attention_backward(k, v, c2, dxs)
+    dk1, dk2, dv, dv_colsum, dv_absmax = ops.pct_attention_backward(k, v, c2, dxs)
 torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ops.KERNEL_EVENTS = []
 xs, c2 = ops.pct_attention(k, v, want_c2=True)
-dk1, dk2, dv = ops.pct_attention_backward(k, v, c2, dxs)
+dk1, dk2, dv, dv_colsum, dv_absmax = ops.pct_attention_backward(k, v, c2, dxs)
 torch.cuda.synchronize()
 for nme, e0, e1 in ops.KERNEL_EVENTS:
     print('%-20s %.3f ms' % (nme, e0.elapsed_time(e1)))
