@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(256) rowdot_scaled_kernel(const float* __restr
   if (lane == 0) out[r] = s * __ldg(scale + 2 * (r / P));
 }
 
-// out = gx (+ gcat) + dxv + (dk1 + dk2) Wk; dk1 <- dk1 + dk2.  One warp per row, lane = 4 output channels.
+// out = gx (+ gcat) + dxv + (dk1 + dk2) Wk; dk1 <- dk1 + dk2.  One warp per row PAIR, lane = 4 output channels; the loads of
+// both rows are issued before the first use (the 32-step shuffle / FMA chain of one row runs under the other's loads).
 __global__ void __launch_bounds__(256) sa_input_grad_kernel(const float* __restrict__ gx, const float* __restrict__ gcat,
                                                             const float* __restrict__ dxv, float* __restrict__ dk1,
                                                             const float* __restrict__ dk2, const float* __restrict__ Wk, int64_t rows,
@@ -148,23 +149,40 @@ __global__ void __launch_bounds__(256) sa_input_grad_kernel(const float* __restr
   for (int i = threadIdx.x; i < 32 * 32; i += 256) ws[i >> 5][i & 31] = ld4(Wk + (int64_t)i * 4);
   __syncthreads();
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  for (int64_t r = (int64_t)blockIdx.x * 8 + wrp; r < rows; r += (int64_t)gridDim.x * 8) {
-    const float dks = dk1[r * 32 + lane] + dk2[r * 32 + lane];
-    dk1[r * 32 + lane] = dks;
-    float4 acc = ld4(gx + r * 128 + lane * 4);
-    const float4 dv = ld4(dxv + r * 128 + lane * 4);
-    acc.x += dv.x; acc.y += dv.y; acc.z += dv.z; acc.w += dv.w;
-    if (gcat) {
-      const float4 gc = ld4(gcat + r * 128 + lane * 4);
-      acc.x += gc.x; acc.y += gc.y; acc.z += gc.z; acc.w += gc.w;
+  constexpr int R = 2;
+  for (int64_t r0 = ((int64_t)blockIdx.x * 8 + wrp) * R; r0 < rows; r0 += (int64_t)gridDim.x * 8 * R) {
+    float dks[R];
+    float4 acc[R], dv[R], gc[R];
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const int64_t r = min(r0 + u, rows - 1);
+      dks[u] = dk1[r * 32 + lane] + dk2[r * 32 + lane];
+      acc[u] = ld4(gx + r * 128 + lane * 4);
+      dv[u] = ld4(dxv + r * 128 + lane * 4);
+      gc[u] = gcat ? ld4(gcat + r * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      acc[u].x += dv[u].x; acc[u].y += dv[u].y; acc[u].z += dv[u].z; acc[u].w += dv[u].w;
+      if (gcat) { acc[u].x += gc[u].x; acc[u].y += gc[u].y; acc[u].z += gc[u].z; acc[u].w += gc[u].w; }
     }
 #pragma unroll
     for (int kk = 0; kk < 32; ++kk) {
-      const float d = __shfl_sync(0xffffffffu, dks, kk);
       const float4 w = ws[kk][lane];
-      acc.x = fmaf(d, w.x, acc.x); acc.y = fmaf(d, w.y, acc.y); acc.z = fmaf(d, w.z, acc.z); acc.w = fmaf(d, w.w, acc.w);
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        const float d = __shfl_sync(0xffffffffu, dks[u], kk);
+        acc[u].x = fmaf(d, w.x, acc[u].x); acc[u].y = fmaf(d, w.y, acc[u].y); acc[u].z = fmaf(d, w.z, acc[u].z); acc[u].w = fmaf(d, w.w, acc[u].w);
+      }
     }
-    *reinterpret_cast<float4*>(out + r * 128 + lane * 4) = acc;
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const int64_t r = r0 + u;
+      if (r < rows) {
+        dk1[r * 32 + lane] = dks[u];
+        *reinterpret_cast<float4*>(out + r * 128 + lane * 4) = acc[u];
+      }
+    }
   }
 }
 
@@ -504,7 +522,7 @@ extern "C" int sga_pct_sa_input_grad(const float* gx, const float* gcat, const f
                                      const float* Wk, int64_t rows, float* out, void* stream) {
   if (rows <= 0) return SGA_OK;
   SGA_REQUIRE(gx && dxv && dk1 && dk2 && Wk && out, "sga_pct_sa_input_grad: null pointer");
-  sa_input_grad_kernel<<<grid_for(rows, 32), 256, 0, (cudaStream_t)stream>>>(gx, gcat, dxv, dk1, dk2, Wk, rows, out);
+  sa_input_grad_kernel<<<grid_for(rows, 64), 256, 0, (cudaStream_t)stream>>>(gx, gcat, dxv, dk1, dk2, Wk, rows, out);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }
