@@ -309,16 +309,25 @@ constexpr uint32_t BARS = ALO + 2 * kBlk;                  // 65536
 constexpr uint32_t TMEMPTR = BARS + 64;
 constexpr uint32_t SMEM_BYTES = TMEMPTR + 16 + 1024;
 constexpr uint32_t D_COL = 0, WHI_COL = 128, WLO_COL = 192;
+// fused k | v convolution (Cout = 32 + 128): W_v.lo and both halves of W_k are shared-memory images, D_k takes W_v.lo's columns
+constexpr uint32_t KV_WLO = ALO + 2 * kBlk;                // W_v.lo  [128 x 128] K-major, 2 blocks
+constexpr uint32_t KV_WKH = KV_WLO + 2 * kBlk;             // W_k.hi  [32 x 128]: 2 blocks of 4 KiB
+constexpr uint32_t KV_WKL = KV_WKH + 8192;
+constexpr uint32_t KV_BARS = KV_WKL + 8192;                // 114688
+constexpr uint32_t KV_TMEMPTR = KV_BARS + 64;
+constexpr uint32_t KV_SMEM_BYTES = KV_TMEMPTR + 16;        // 114768: no alignment slack (two CTAs per SM), the base is checked
+constexpr uint32_t DK_COL = 192;
 enum { BAR_A_FULL = 0, BAR_D_FULL = 1 };
 }  // namespace p2
 
-template <bool kScaled>
+template <bool kScaled, bool kKV>
 __global__ void __launch_bounds__(kThreads, 2) pct_pw2_kernel(const PwArgs A) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  if (kKV && sm != smem_raw) __trap();       // KV_SMEM_BYTES has no slack: the dynamic shared memory window must start 1 KiB aligned
   const uint32_t sm_base = ptx::smem_u32(sm);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + p2::BARS);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + p2::TMEMPTR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + (kKV ? p2::KV_BARS : p2::BARS));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (kKV ? p2::KV_TMEMPTR : p2::TMEMPTR));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     ptx::mbar_init(&bars[p2::BAR_A_FULL], kComputeThreads);
@@ -330,9 +339,10 @@ __global__ void __launch_bounds__(kThreads, 2) pct_pw2_kernel(const PwArgs A) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const float* Wmain = kKV ? A.W + 32 * 128 : A.W;       // k | v: rows 0..31 are W_k, 32..159 W_v
   if (warp < 4) {       // W: output channel on the TMEM lane, 128 k packed two per 32-bit column, hi and lo
     const int r = 32 * warp + lane;
-    const float4* src = reinterpret_cast<const float4*>(A.W + (int64_t)r * 128);
+    const float4* src = reinterpret_cast<const float4*>(Wmain + (int64_t)r * 128);
 #pragma unroll 1
     for (int grp = 0; grp < 4; ++grp) {
       uint32_t wh[16], wl[16];
@@ -343,10 +353,33 @@ __global__ void __launch_bounds__(kThreads, 2) pct_pw2_kernel(const PwArgs A) {
         split2f<0>(a.z, a.w, wh[2 * j + 1], wl[2 * j + 1]);
       }
       ptx::tmem_st16(tmem + ((uint32_t)(32 * warp) << 16) + p2::WHI_COL + grp * 16, wh);
-      ptx::tmem_st16(tmem + ((uint32_t)(32 * warp) << 16) + p2::WLO_COL + grp * 16, wl);
+      if (!kKV) {
+        ptx::tmem_st16(tmem + ((uint32_t)(32 * warp) << 16) + p2::WLO_COL + grp * 16, wl);
+      } else {          // 32 k = four 16-byte chunks of the K-major image
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const int chunk = grp * 4 + c4;
+          st_chunk(sm_base + p2::KV_WLO + (uint32_t)(chunk >> 3) * kBlk + ptx::sw128_offset(r, chunk & 7),
+                   make_uint4(wl[4 * c4], wl[4 * c4 + 1], wl[4 * c4 + 2], wl[4 * c4 + 3]));
+        }
+      }
     }
     ptx::tmem_st_wait();
+  } else if (kKV && warp < 8) {       // W_k: 32 rows x 16 chunks, four per thread
+#pragma unroll 1
+    for (int i = tid - 128; i < 32 * 16; i += 128) {
+      const int r = i >> 4, chunk = i & 15;
+      const float4* src = reinterpret_cast<const float4*>(A.W + (int64_t)r * 128 + chunk * 8);
+      const float4 x = __ldg(src), y = __ldg(src + 1);
+      const float f[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+      uint4 hi, lo;
+      split8(f, hi, lo);
+      const uint32_t off = (uint32_t)(chunk >> 3) * 4096 + ptx::sw128_offset(r, chunk & 7);
+      st_chunk(sm_base + p2::KV_WKH + off, hi);
+      st_chunk(sm_base + p2::KV_WKL + off, lo);
+    }
   }
+  if (kKV) ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -358,6 +391,9 @@ __global__ void __launch_bounds__(kThreads, 2) pct_pw2_kernel(const PwArgs A) {
     // =============================== MMA issuer ===============================
     const uint32_t idesc = ptx::make_idesc(kFmt, 128, 128);
     const uint64_t dAhi = ptx::smem_desc_sw128(sm_base + p2::AHI), dAlo = ptx::smem_desc_sw128(sm_base + p2::ALO);
+    const uint32_t idesc_k = ptx::make_idesc(kFmt, 128, 32);
+    const uint64_t dWlo = ptx::smem_desc_sw128(sm_base + p2::KV_WLO);
+    const uint64_t dWkh = ptx::smem_desc_sw128(sm_base + p2::KV_WKH), dWkl = ptx::smem_desc_sw128(sm_base + p2::KV_WKL);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
     uint32_t it = 0;
     for (int64_t g = blockIdx.x; g < G; g += gridDim.x, ++it) {
@@ -369,9 +405,22 @@ __global__ void __launch_bounds__(kThreads, 2) pct_pw2_kernel(const PwArgs A) {
           const uint32_t wcol = (pass & 2) ? p2::WLO_COL : p2::WHI_COL;
           const uint64_t xd = (pass & 1) ? dAlo : dAhi;
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            ptx::umma_bf16_ts(tmem_u + p2::D_COL, tmem_u + wcol + (uint32_t)(ks * 8), xd + (uint64_t)((ks >> 2) * (kBlk >> 4) + (ks & 3) * 2),
-                              idesc, (pass | ks) != 0);
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t koff = (uint64_t)((ks >> 2) * (kBlk >> 4) + (ks & 3) * 2);
+            if (kKV && (pass & 2)) ptx::umma_bf16(tmem_u + p2::D_COL, dWlo + koff, xd + koff, idesc, 1);
+            else ptx::umma_bf16_ts(tmem_u + p2::D_COL, tmem_u + wcol + (uint32_t)(ks * 8), xd + koff, idesc, (pass | ks) != 0);
+          }
+        }
+        if (kKV) {        // k = X W_k^T with the POINTS on the lanes: the X tile is the A operand of this one
+#pragma unroll
+          for (int pass = 0; pass < 4; ++pass) {
+            const uint64_t xd = (pass & 1) ? dAlo : dAhi;
+            const uint64_t wd = (pass & 2) ? dWkl : dWkh;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              ptx::umma_bf16(tmem_u + p2::DK_COL, xd + (uint64_t)((ks >> 2) * (kBlk >> 4) + (ks & 3) * 2),
+                             wd + (uint64_t)((ks >> 2) * (4096 >> 4) + (ks & 3) * 2), idesc_k, (pass | ks) != 0);
+          }
         }
         ptx::umma_commit(&bars[p2::BAR_D_FULL]);
       }
@@ -393,7 +442,8 @@ __global__ void __launch_bounds__(kThreads, 2) pct_pw2_kernel(const PwArgs A) {
     const int q = warp & 3, hc = warp >> 2;           // epilogue: channel = 32 q + lane, point half hc
     const int och = 32 * q + lane;
     const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
-    const float bias = A.bias ? A.bias[och] : 0.f;
+    const float bias = A.bias ? A.bias[(kKV ? 32 : 0) + och] : 0.f;
+    float* const out_main = kKV ? A.out1 : A.out0;
     const bool want_stats = A.stats != nullptr;
     double ds = 0, dq = 0;
 
@@ -489,7 +539,7 @@ __global__ void __launch_bounds__(kThreads, 2) pct_pw2_kernel(const PwArgs A) {
         ptx::tmem_ld32(tmem + lane_addr + p2::D_COL + (uint32_t)(hc * 64 + h * 32), v);
         ptx::tmem_ld_wait();
         const int p0 = hc * 64 + h * 32;
-        float* dst = A.out0 + (rowbase + p0) * 128 + och;
+        float* dst = out_main + (rowbase + p0) * 128 + och;
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
           if (p0 + e < valid) {
@@ -499,6 +549,24 @@ __global__ void __launch_bounds__(kThreads, 2) pct_pw2_kernel(const PwArgs A) {
               s += y;
               sq = fmaf(y, y, sq);
             }
+          }
+        }
+      }
+      if (kKV) {                  // k: this thread's point (lane 32 q + lane), 16 of the 32 channels
+        uint32_t v[16];
+        ptx::tmem_ld16(tmem + lane_addr + p2::DK_COL + (uint32_t)(hc * 16), v);
+        ptx::tmem_ld_wait();
+        const int pt = 32 * q + lane;
+        if (pt < valid) {
+          float4* dk = reinterpret_cast<float4*>(A.out0 + (rowbase + pt) * 32 + hc * 16);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float4 o = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3]));
+            if (A.bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(A.bias + hc * 16 + 4 * e));
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            dk[e] = o;
           }
         }
       }
@@ -533,17 +601,21 @@ int pw_launch(const PwArgs& a, cudaStream_t st) {
   int grid = sm_count();
   if ((int64_t)grid > G) grid = (int)G;
   static const bool v1 = [] { const char* e = getenv("SGA_PCT_PW"); return e && e[0] == 'v' && e[1] == '1'; }();
-  if (!a.pts && a.Cout == 128 && a.c0 == 128 && !v1) {       // second generation: channels on lanes, two CTAs per SM
+  const bool plain = !a.pts && a.Cout == 128 && a.c0 == 128;
+  const bool kv = !a.pts && a.Cout == 160 && a.c0 == 32 && !a.scale && !a.stats;
+  if ((plain || kv) && !v1) {       // second generation: channels on lanes, two CTAs per SM
     static bool attr2 = false;
     if (!attr2) {
-      SGA_CUDA(cudaFuncSetAttribute(pct_pw2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2::SMEM_BYTES));
-      SGA_CUDA(cudaFuncSetAttribute(pct_pw2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2::SMEM_BYTES));
+      SGA_CUDA(cudaFuncSetAttribute(pct_pw2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2::SMEM_BYTES));
+      SGA_CUDA(cudaFuncSetAttribute(pct_pw2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2::SMEM_BYTES));
+      SGA_CUDA(cudaFuncSetAttribute(pct_pw2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2::KV_SMEM_BYTES));
       attr2 = true;
     }
     int64_t g2 = 2 * (int64_t)sm_count();
     if (g2 > G) g2 = G;
-    if (a.scale) pct_pw2_kernel<true><<<(unsigned)g2, kThreads, p2::SMEM_BYTES, st>>>(a);
-    else pct_pw2_kernel<false><<<(unsigned)g2, kThreads, p2::SMEM_BYTES, st>>>(a);
+    if (kv) pct_pw2_kernel<false, true><<<(unsigned)g2, kThreads, p2::KV_SMEM_BYTES, st>>>(a);
+    else if (a.scale) pct_pw2_kernel<true, false><<<(unsigned)g2, kThreads, p2::SMEM_BYTES, st>>>(a);
+    else pct_pw2_kernel<false, false><<<(unsigned)g2, kThreads, p2::SMEM_BYTES, st>>>(a);
     SGA_LAUNCH_CHECK();
     return SGA_OK;
   }

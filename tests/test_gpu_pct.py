@@ -46,6 +46,16 @@ def test_pointwise_conv_prologues_and_stats(N, P, dev):
     assert rel_inf(k, Y[..., :32]) < 2e-5 and rel_inf(v, Y[..., 32:]) < 2e-5
     flat = Y.reshape(-1, 160)
     assert rel_inf(st[:160], flat.sum(0)) < 1e-5 and rel_inf(st[160:], (flat * flat).sum(0)) < 1e-5
+    # the same k | v product without statistics (what the encoder launches: the two-CTA kernel with the points on the lanes
+    # for k), two sources and one source
+    k2, v2, x2, _ = ops.pct_pointwise(s1, (a1, b1), s2, (a2, b2), W, bias, 32, want_x=True, want_stats=False)
+    torch.cuda.synchronize()
+    assert rel_inf(x2, X) < 1e-6
+    assert rel_inf(k2, Y[..., :32]) < 2e-5 and rel_inf(v2, Y[..., 32:]) < 2e-5
+    k3, v3, _, _ = ops.pct_pointwise(s1, None, None, None, W, None, 32, want_x=False, want_stats=False)
+    Y3 = s1.double() @ W.double().t()
+    torch.cuda.synchronize()
+    assert rel_inf(k3, Y3[..., :32]) < 2e-5 and rel_inf(v3, Y3[..., 32:]) < 2e-5
     # identity prologue, one source, Cout = 128
     W2 = W[:128].contiguous()
     y, _, _, st2 = ops.pct_pointwise(s1, None, None, None, W2, bias[:128].contiguous(), 128, want_x=False, want_stats=True)
