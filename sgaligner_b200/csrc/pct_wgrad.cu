@@ -4,7 +4,7 @@
 // activations that the train-mode BatchNorm of the 512 -> 1024 convolution needs (sgaligner_b200/pct.py, concat stage).
 // HBM bound by construction (128 KiB of operands per 1536 tensor cycles), so: one persistent CTA per SM walks row tiles
 // of 128 points, the 8 compute warps turn the fp32 rows into bf16 hi / lo images (16 loads of 16 bytes in flight per
-// thread), both operands are read MN-major (the contraction index is the ROW of the 128B-swizzled image, the same bytes
+// thread, the NEXT operand's while this one is converted), both operands are read MN-major (the contraction index is the ROW of the 128B-swizzled image, the same bytes
 // a K-major read of the activations uses), the accumulators of up to four B operands that share one A tile stay in
 // tensor memory for the whole launch and are added to C atomically at the end (148 x 16 K atomics per operand).
 // bf16 pairs, three passes (hi hi + lo hi + hi lo): no scaling needed -- bf16 has the fp32 range -- and the 2^-17
@@ -38,12 +38,12 @@ struct WgArgs {
   int64_t R;
 };
 
-// 128 rows x 128 channels -> bf16 hi / lo images (2 channel blocks each); all 16 loads of a thread in flight together
-__device__ __forceinline__ void wg_load128(const float* __restrict__ src, int64_t rowbase, int valid, uint32_t hi_addr, uint32_t lo_addr,
-                                           int tid) {
+// 128 rows x 128 channels -> bf16 hi / lo images (2 channel blocks each).  Two halves: all 16 loads of a thread go out
+// (wg_issue128), the conversion + shared-memory stores happen one operand later (wg_store128), so the next operand's rows are
+// in flight while this one is converted -- inline-asm shared stores are ordering barriers for the compiler, the loads
+// have to precede them in program order.
+__device__ __forceinline__ void wg_issue128(const float* __restrict__ src, int64_t rowbase, int valid, int tid, float4 (&x)[8][2]) {
   const int cc = tid & 15, r0 = tid >> 4;
-  const uint32_t blk_off = (uint32_t)(cc >> 3) * kBlk;
-  float4 x[8][2];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int row = r0 + 16 * i;
@@ -52,6 +52,10 @@ __device__ __forceinline__ void wg_load128(const float* __restrict__ src, int64_
     x[i][0] = ok ? __ldg(p) : make_float4(0.f, 0.f, 0.f, 0.f);
     x[i][1] = ok ? __ldg(p + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+}
+__device__ __forceinline__ void wg_store128(const float4 (&x)[8][2], uint32_t hi_addr, uint32_t lo_addr, int tid) {
+  const int cc = tid & 15, r0 = tid >> 4;
+  const uint32_t blk_off = (uint32_t)(cc >> 3) * kBlk;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int row = r0 + 16 * i;
@@ -64,9 +68,8 @@ __device__ __forceinline__ void wg_load128(const float* __restrict__ src, int64_
   }
 }
 
-// 128 rows x 32 channels -> one block of [hi (32) | lo (32)] rows
-__device__ __forceinline__ void wg_load32(const float* __restrict__ src, int64_t rowbase, int valid, uint32_t addr, int tid) {
-  float4 x[2][2];
+// 128 rows x 32 channels -> one block of [hi (32) | lo (32)] rows (registers x[0..1] of the operand buffer)
+__device__ __forceinline__ void wg_issue32(const float* __restrict__ src, int64_t rowbase, int valid, int tid, float4 (&x)[8][2]) {
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     const int idx = tid + 256 * u;
@@ -76,6 +79,8 @@ __device__ __forceinline__ void wg_load32(const float* __restrict__ src, int64_t
     x[u][0] = ok ? __ldg(p) : make_float4(0.f, 0.f, 0.f, 0.f);
     x[u][1] = ok ? __ldg(p + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+}
+__device__ __forceinline__ void wg_store32(const float4 (&x)[8][2], uint32_t addr, int tid) {
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     const int idx = tid + 256 * u;
@@ -160,22 +165,47 @@ __global__ void __launch_bounds__(kThreads, 1) pct_wgrad_kernel(const WgArgs W) 
     }
   } else {
     // =============================== loaders / epilogue ===============================
-    uint32_t u = 0;
-    for (int64_t t = 0; t < ntile; ++t) {
+    // flat sequence of operands: item = t * (nB + 1) + op, op 0 = the A tile, op b + 1 = B_b.  Item i + 1 is loaded into the
+    // other register buffer before item i is converted.
+    const int per = nB + 1;
+    const int64_t items = ntile * per;
+    auto issue = [&](int64_t item, float4 (&x)[8][2]) {
+      const int64_t t = item / per;
+      const int op = (int)(item - t * per);
       const int64_t rowbase = ((int64_t)blockIdx.x + t * gridDim.x) * kTile;
       const int valid = (int)min((int64_t)kTile, W.R - rowbase);
-      if (t >= 1) ptx::mbar_wait(&bars[BAR_A_FREE], (uint32_t)((t - 1) & 1));
-      wg_load128(W.A, rowbase, valid, sm_base + AHI, sm_base + ALO, tid);
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&bars[BAR_A_FULL]);
-      for (int b = 0; b < nB; ++b, ++u) {
+      if (op == 0) wg_issue128(W.A, rowbase, valid, tid, x);
+      else if (W.nb[op - 1] == 128) wg_issue128(W.B[op - 1], rowbase, valid, tid, x);
+      else wg_issue32(W.B[op - 1], rowbase, valid, tid, x);
+    };
+    auto store = [&](int64_t item, const float4 (&x)[8][2]) {
+      const int64_t t = item / per;
+      const int op = (int)(item - t * per);
+      if (op == 0) {
+        if (t >= 1) ptx::mbar_wait(&bars[BAR_A_FREE], (uint32_t)((t - 1) & 1));
+        wg_store128(x, sm_base + AHI, sm_base + ALO, tid);
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&bars[BAR_A_FULL]);
+      } else {
+        const uint32_t u = (uint32_t)(t * nB + (op - 1));
         const uint32_t slot = u & 1;
         if (u >= 2) ptx::mbar_wait(&bars[BAR_B_FREE + slot], ((u - 2) >> 1) & 1);
         const uint32_t sb = sm_base + BRING + slot * BSLOT;
-        if (W.nb[b] == 128) wg_load128(W.B[b], rowbase, valid, sb, sb + 2 * kBlk, tid);
-        else wg_load32(W.B[b], rowbase, valid, sb, tid);
+        if (W.nb[op - 1] == 128) wg_store128(x, sb, sb + 2 * kBlk, tid);
+        else wg_store32(x, sb, tid);
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&bars[BAR_B_FULL + slot]);
+      }
+    };
+    float4 X0[8][2], X1[8][2];
+    if (items > 0) issue(0, X0);
+#pragma unroll 1
+    for (int64_t i = 0; i < items; i += 2) {
+      if (i + 1 < items) issue(i + 1, X1);
+      store(i, X0);
+      if (i + 1 < items) {
+        if (i + 2 < items) issue(i + 2, X0);
+        store(i + 1, X1);
       }
     }
     if (ntile > 0) {
