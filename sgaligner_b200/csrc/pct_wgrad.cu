@@ -35,6 +35,7 @@ struct WgArgs {
   float* C[4];
   int64_t ldc[4];
   int transpose;
+  int alias;          // 1: a B operand that IS the A tensor reuses the A images (diagonal Gram blocks)
   int64_t R;
 };
 
@@ -129,15 +130,19 @@ __global__ void __launch_bounds__(kThreads, 1) pct_wgrad_kernel(const WgArgs W) 
     uint32_t u = 0;
     for (int64_t t = 0; t < ntile; ++t) {
       ptx::mbar_wait(&bars[BAR_A_FULL], (uint32_t)(t & 1));
-      for (int b = 0; b < nB; ++b, ++u) {
+      for (int b = 0; b < nB; ++b) {
+        const bool self = W.alias && W.B[b] == W.A;        // a diagonal Gram block: the A images are the B operand too, nothing is loaded
         const uint32_t slot = u & 1;
-        ptx::mbar_wait(&bars[BAR_B_FULL + slot], (u >> 1) & 1);
+        if (!self) {
+          ptx::mbar_wait(&bars[BAR_B_FULL + slot], (u >> 1) & 1);
+          ++u;
+        }
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint32_t sb = sm_base + BRING + slot * BSLOT;
           const uint32_t d = tmem_u + (uint32_t)b * 128;
           if (W.nb[b] == 128) {
-            const uint64_t mBhi = desc_mn_sw128(sb, kBlk), mBlo = desc_mn_sw128(sb + 2 * kBlk, kBlk);
+            const uint64_t mBhi = self ? mAhi : desc_mn_sw128(sb, kBlk), mBlo = self ? mAlo : desc_mn_sw128(sb + 2 * kBlk, kBlk);
 #pragma unroll
             for (int pass = 0; pass < 3; ++pass) {
               const uint64_t ad = (pass == 1) ? mAlo : mAhi;
@@ -156,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 1) pct_wgrad_kernel(const WgArgs W) 
                 ptx::umma_bf16(d, ad + (uint64_t)(ks * 128), mB + (uint64_t)(ks * 128), idesc64, (t | pass | ks) != 0);
             }
           }
-          ptx::umma_commit(&bars[BAR_B_FREE + slot]);
+          if (!self) ptx::umma_commit(&bars[BAR_B_FREE + slot]);
           if (b == nB - 1) ptx::umma_commit(&bars[BAR_A_FREE]);
           if (b == nB - 1 && t == ntile - 1) ptx::umma_commit(&bars[BAR_ACC]);
         }
@@ -167,20 +172,27 @@ __global__ void __launch_bounds__(kThreads, 1) pct_wgrad_kernel(const WgArgs W) 
     // =============================== loaders / epilogue ===============================
     // flat sequence of operands: item = t * (nB + 1) + op, op 0 = the A tile, op b + 1 = B_b.  Item i + 1 is loaded into the
     // other register buffer before item i is converted.
-    const int per = nB + 1;
+    uint32_t lmap = 0;                          // the B operands that are loaded (B_b == A reuses the A images), 2 bits each
+    int nL = 0;
+    for (int b = 0; b < nB; ++b)
+      if (!(W.alias && W.B[b] == W.A)) lmap |= (uint32_t)b << (2 * nL++);
+    const int per = nL + 1;
     const int64_t items = ntile * per;
     auto issue = [&](int64_t item, float4 (&x)[8][2]) {
       const int64_t t = item / per;
       const int op = (int)(item - t * per);
       const int64_t rowbase = ((int64_t)blockIdx.x + t * gridDim.x) * kTile;
       const int valid = (int)min((int64_t)kTile, W.R - rowbase);
-      if (op == 0) wg_issue128(W.A, rowbase, valid, tid, x);
-      else if (W.nb[op - 1] == 128) wg_issue128(W.B[op - 1], rowbase, valid, tid, x);
-      else wg_issue32(W.B[op - 1], rowbase, valid, tid, x);
+      if (op == 0) { wg_issue128(W.A, rowbase, valid, tid, x); return; }
+      const int b = (int)((lmap >> (2 * (op - 1))) & 3u);
+      if (W.nb[b] == 128) wg_issue128(W.B[b], rowbase, valid, tid, x);
+      else wg_issue32(W.B[b], rowbase, valid, tid, x);
     };
     auto store = [&](int64_t item, const float4 (&x)[8][2]) {
       const int64_t t = item / per;
       const int op = (int)(item - t * per);
+      const int nB = nL;                        // ring position counts loaded operands only
+      const int bsel = op == 0 ? 0 : (int)((lmap >> (2 * (op - 1))) & 3u);
       if (op == 0) {
         if (t >= 1) ptx::mbar_wait(&bars[BAR_A_FREE], (uint32_t)((t - 1) & 1));
         wg_store128(x, sm_base + AHI, sm_base + ALO, tid);
@@ -191,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) pct_wgrad_kernel(const WgArgs W) 
         const uint32_t slot = u & 1;
         if (u >= 2) ptx::mbar_wait(&bars[BAR_B_FREE + slot], ((u - 2) >> 1) & 1);
         const uint32_t sb = sm_base + BRING + slot * BSLOT;
-        if (W.nb[op - 1] == 128) wg_store128(x, sb, sb + 2 * kBlk, tid);
+        if (W.nb[bsel] == 128) wg_store128(x, sb, sb + 2 * kBlk, tid);
         else wg_store32(x, sb, tid);
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&bars[BAR_B_FULL + slot]);
@@ -259,9 +271,12 @@ extern "C" int sga_pct_wgrad(const float* A, int64_t R, const float* const* B, c
   using namespace sga::pct;
   WgArgs W{};
   W.A = A; W.R = R; W.nB = nB; W.transpose = transpose;
+  static const bool no_alias = [] { const char* e = getenv("SGA_PCT_WGRAD_ALIAS"); return e && e[0] == '0'; }();
+  W.alias = no_alias ? 0 : 1;
   SGA_REQUIRE(((uintptr_t)A & 15) == 0, "sga_pct_wgrad: A must be 16-byte aligned");
   for (int b = 0; b < nB; ++b) {
     SGA_REQUIRE(B[b] && C[b] && (nb[b] == 128 || nb[b] == 32) && ((uintptr_t)B[b] & 15) == 0, "sga_pct_wgrad: operand %d", b);
+    SGA_REQUIRE(B[b] != A || nb[b] == 128, "sga_pct_wgrad: operand %d aliases A with another width", b);
     W.B[b] = B[b]; W.nb[b] = nb[b]; W.C[b] = C[b]; W.ldc[b] = ldc[b];
   }
   static bool attr_done = false;
