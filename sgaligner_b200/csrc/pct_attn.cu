@@ -132,6 +132,9 @@ pct_attn_stats_kernel(const float* __restrict__ k, int64_t N, int P, float* __re
       load_k_image(k, n * (int64_t)P, P, T, sm_base + KIMG, tid);
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(&bars[BAR_K_FULL]);
+      if (n + gridDim.x < N) {        // the next object's k (P rows of 128 B) -> L2 under this object's score blocks
+        for (int r = tid; r < P; r += kComputeThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(k + ((n + gridDim.x) * (int64_t)P + r) * 32));
+      }
       for (int it = 0; it < T; ++it, ++blk) {
         ptx::mbar_wait(&bars[BAR_S_FULL], blk & 1);
         ptx::tc_fence_after();

@@ -100,6 +100,8 @@ __device__ __forceinline__ void load_tiles2(const float* __restrict__ k, int64_t
   }
 }
 
+__device__ int g_attn2_pf = 1;
+
 // kDv = false: xs[a, :] = sum_b softmax(energy)[b, a] v[b, :]     (lanes = own block a, normaliser of the CONTRACTED row b)
 // kDv = true : dv[a, :] = sum_b softmax(energy)[a, b] dxs[b, :]   (normaliser of the own row a; `v` = dxs, scaled per object)
 template <bool kDv>
@@ -189,6 +191,21 @@ pct_attn2_kernel(const float* __restrict__ k, const float* __restrict__ v, const
         load_tiles2<true>(k, obase + (int64_t)b * kTile, min(kTile, P - b * kTile), sm_base + KB, v, sm_base + VHI, sm_base + VLO, gsc, tid);
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&bars[BAR_LD_FULL]);
+        if (g_attn2_pf) {      // the next step's k / V tile -> L2 while this step's products and exponentials run
+          int64_t nb = obase + (int64_t)(b + 1) * kTile;
+          int nvalid = min(kTile, P - (b + 1) * kTile);
+          if (b + 1 == T) {
+            const int64_t wn = w + gridDim.x;
+            nb = (wn / T) * (int64_t)P;
+            nvalid = (wn < W) ? min(kTile, P) : 0;
+          }
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int line = tid + 256 * j;           // 512 lines of 128 B: row = line / 4
+            if ((line >> 2) < nvalid) asm volatile("prefetch.global.L2 [%0];" ::"l"(v + (nb + (line >> 2)) * 128 + (line & 3) * 32));
+          }
+          if (tid < nvalid) asm volatile("prefetch.global.L2 [%0];" ::"l"(k + (nb + tid) * 32));
+        }
         ptx::mbar_wait(&bars[BAR_S_FULL], u & 1);
         ptx::tc_fence_after();
         // ---- E = exp2(S a - normaliser) for this thread's row and its 64 columns, written over S:
@@ -275,6 +292,13 @@ int attn2_launch(const float* k, const float* v, const float* c2, int64_t N, int
   const int64_t W = N * T;
   int64_t grid = 2 * (int64_t)sm_count();
   if (grid > W) grid = W;
+  static const bool pf_init = [] {
+    const char* e = getenv("SGA_PCT_ATTN_PF");
+    const int on = (e && e[0] == '0') ? 0 : 1;
+    cudaMemcpyToSymbol(g_attn2_pf, &on, sizeof(int));
+    return true;
+  }();
+  (void)pf_init;
   pct_attn2_kernel<kDv><<<(unsigned)grid, kThreads, a2::SMEM_BYTES, st>>>(k, v, c2, N, P, out, scale, colsum, absmax);
   SGA_LAUNCH_CHECK();
   return SGA_OK;

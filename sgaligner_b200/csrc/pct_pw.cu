@@ -320,6 +320,11 @@ constexpr uint32_t DK_COL = 192;
 enum { BAR_A_FULL = 0, BAR_D_FULL = 1 };
 }  // namespace p2
 
+__device__ __forceinline__ void ld8(const float* __restrict__ p, float (&o)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+
 template <bool kScaled, bool kKV>
 __global__ void __launch_bounds__(kThreads, 2) pct_pw2_kernel(const PwArgs A) {
   extern __shared__ unsigned char smem_raw[];
@@ -430,14 +435,6 @@ __global__ void __launch_bounds__(kThreads, 2) pct_pw2_kernel(const PwArgs A) {
     // =============================== compute warps ===============================
     const int cc = tid & 15, r0 = tid >> 4;          // loader: 8-channel chunk cc of rows r0 + 16 q
     const int ch0 = cc * 8;
-    float pa1[8], pb1[8], pa2[8], pb2[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      pa1[e] = (A.mode1 == 2) ? A.a1[ch0 + e] : 1.f;
-      pb1[e] = (A.mode1 == 2) ? A.b1[ch0 + e] : 0.f;
-      pa2[e] = (A.mode2 == 2) ? A.a2[ch0 + e] : 1.f;
-      pb2[e] = (A.mode2 == 2) ? A.b2[ch0 + e] : 0.f;
-    }
     const uint32_t a_off_blk = (uint32_t)(cc >> 3) * kBlk;
     const int q = warp & 3, hc = warp >> 2;           // epilogue: channel = 32 q + lane, point half hc
     const int och = 32 * q + lane;
@@ -454,22 +451,33 @@ __global__ void __launch_bounds__(kThreads, 2) pct_pw2_kernel(const PwArgs A) {
       const int64_t rowbase = n * A.P + (int64_t)t * kTile;
       const int valid = min(kTile, A.P - t * kTile);
       const float sc = kScaled ? __ldg(A.scale + 2 * n) : 1.f;
-      // ---- load + prologue + split -> X tile (the previous tile's products have completed: D_FULL was waited for)
-      auto batch = [&](auto rows_tag, int bt) {
+      // ---- load + prologue + split -> X tile (the previous tile's products have completed: D_FULL was waited for).
+      auto issue = [&](auto rows_tag, int bt, int64_t rb, int vld, float4 (&u)[4][2], float4 (&w)[4][2]) {
         constexpr int kRows = decltype(rows_tag)::value;
-        float4 u[kRows][2], w[kRows][2];
 #pragma unroll
         for (int qq = 0; qq < kRows; ++qq) {
           const int row = r0 + 16 * (bt * kRows + qq);
-          const bool ok = row < valid;
-          const float4* s1 = reinterpret_cast<const float4*>(A.src1 + (rowbase + row) * 128 + ch0);
+          const bool ok = row < vld;
+          const float4* s1 = reinterpret_cast<const float4*>(A.src1 + (rb + row) * 128 + ch0);
           u[qq][0] = ok ? __ldg(s1) : make_float4(0.f, 0.f, 0.f, 0.f);
           u[qq][1] = ok ? __ldg(s1 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
           if (A.mode2) {
-            const float4* s2 = reinterpret_cast<const float4*>(A.src2 + (rowbase + row) * 128 + ch0);
+            const float4* s2 = reinterpret_cast<const float4*>(A.src2 + (rb + row) * 128 + ch0);
             w[qq][0] = ok ? __ldg(s2) : make_float4(0.f, 0.f, 0.f, 0.f);
             w[qq][1] = ok ? __ldg(s2 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
+        }
+      };
+      auto finish = [&](auto rows_tag, int bt, const float4 (&u)[4][2], const float4 (&w)[4][2]) {
+        constexpr int kRows = decltype(rows_tag)::value;
+        float pa1[8], pb1[8], pa2[8], pb2[8];        // fetched per batch (L1 hits): 32 registers not held across the epilogue
+        if (A.mode1 == 2) {
+          ld8(A.a1 + ch0, pa1);
+          ld8(A.b1 + ch0, pb1);
+        }
+        if (A.mode2 == 2) {
+          ld8(A.a2 + ch0, pa2);
+          ld8(A.b2 + ch0, pb2);
         }
 #pragma unroll
         for (int qq = 0; qq < kRows; ++qq) {
@@ -487,7 +495,8 @@ __global__ void __launch_bounds__(kThreads, 2) pct_pw2_kernel(const PwArgs A) {
             f[e] = v;
           }
           if (A.mode2) {
-            const float s2[8] = {w[qq][0].x, w[qq][0].y, w[qq][0].z, w[qq][0].w, w[qq][1].x, w[qq][1].y, w[qq][1].z, w[qq][1].w};
+            const float s2[8] = {w[qq][0].x, w[qq][0].y, w[qq][0].z, w[qq][0].w,
+                                 w[qq][1].x, w[qq][1].y, w[qq][1].z, w[qq][1].w};
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               float v = s2[e];
@@ -518,15 +527,40 @@ __global__ void __launch_bounds__(kThreads, 2) pct_pw2_kernel(const PwArgs A) {
           st_chunk(sm_base + p2::ALO + off, lo);
         }
       };
+      using I2 = std::integral_constant<int, 2>;
+      using I4 = std::integral_constant<int, 4>;
       if (A.mode2) {          // 96 registers per thread (two CTAs per SM): smaller batches than the first kernel's
+        float4 u[4][2], w[4][2];
 #pragma unroll 1
-        for (int bt = 0; bt < 4; ++bt) batch(std::integral_constant<int, 2>{}, bt);
+        for (int bt = 0; bt < 4; ++bt) {
+          issue(I2{}, bt, rowbase, valid, u, w);
+          finish(I2{}, bt, u, w);
+        }
       } else {
+        float4 u[4][2];
 #pragma unroll 1
-        for (int bt = 0; bt < 2; ++bt) batch(std::integral_constant<int, 4>{}, bt);
+        for (int bt = 0; bt < 2; ++bt) {
+          issue(I4{}, bt, rowbase, valid, u, u);
+          finish(I4{}, bt, u, u);
+        }
       }
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(&bars[p2::BAR_A_FULL]);
+      if (g + gridDim.x < G) {          // next tile -> L2 while this one's products and epilogue run (2 lines per thread and source):
+                                        // the loader then pays an L2 hit instead of a DRAM round trip per batch
+        const int64_t gn = g + gridDim.x;
+        const int64_t nn = gn / T;
+        const int64_t rb = nn * A.P + (gn - nn * T) * kTile;
+        const int vld = min(kTile, A.P - (int)(gn - nn * T) * kTile);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int line = tid + 256 * j;           // 512 lines of 128 B: row = line / 4
+          if ((line >> 2) < vld) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(A.src1 + (rb + (line >> 2)) * 128 + (line & 3) * 32));
+            if (A.mode2) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.src2 + (rb + (line >> 2)) * 128 + (line & 3) * 32));
+          }
+        }
+      }
 
       // ---- epilogue: this thread's channel, the 64 points of its half
       ptx::mbar_wait(&bars[p2::BAR_D_FULL], it & 1);
@@ -534,14 +568,14 @@ __global__ void __launch_bounds__(kThreads, 2) pct_pw2_kernel(const PwArgs A) {
       const float osc = kScaled ? __ldg(A.scale + 2 * n + 1) : 1.f;
       float s = 0.f, sq = 0.f;
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        uint32_t v[32];
-        ptx::tmem_ld32(tmem + lane_addr + p2::D_COL + (uint32_t)(hc * 64 + h * 32), v);
+      for (int h = 0; h < 4; ++h) {           // 16 points at a time: the prefetched rows of the next tile stay in registers
+        uint32_t v[16];
+        ptx::tmem_ld16(tmem + lane_addr + p2::D_COL + (uint32_t)(hc * 64 + h * 16), v);
         ptx::tmem_ld_wait();
-        const int p0 = hc * 64 + h * 32;
+        const int p0 = hc * 64 + h * 16;
         float* dst = out_main + (rowbase + p0) * 128 + och;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
+        for (int e = 0; e < 16; ++e) {
           if (p0 + e < valid) {
             const float y = kScaled ? __uint_as_float(v[e]) * osc : __uint_as_float(v[e]) + bias;
             dst[(int64_t)e * 128] = y;
