@@ -15,13 +15,14 @@ if 'offset' in sys.argv[1:]:
     pts = pts + (torch.rand(4096, 1, 3, device=dev) * 4 - 2)
 w = [net.conv1.weight, net.conv1.bias, net.conv2.weight, net.conv2.bias, net.conv3.weight, net.conv3.bias]
 stats = 'stats' in sys.argv[1:]
+argmax = 'argmax' in sys.argv[1:]      # the training forward of the default path (arg-max tracking, no moments)
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev) if 'flush' in sys.argv[1:] else None
 with torch.no_grad():
     for _ in range(3):
         if stats:
             ops.pointnet_forward_stats(pts, *w, want_argmax=True)
         else:
-            ops.pointnet_forward(pts, *w, want_argmax=False)
+            ops.pointnet_forward(pts, *w, want_argmax=argmax)
     torch.cuda.synchronize()
     ts = []
     for _ in range(10):
@@ -32,7 +33,7 @@ with torch.no_grad():
         if stats:
             ops.pointnet_forward_stats(pts, *w, want_argmax=True)
         else:
-            ops.pointnet_forward(pts, *w, want_argmax=False)
+            ops.pointnet_forward(pts, *w, want_argmax=argmax)
         b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
