@@ -54,18 +54,48 @@ class CapturedInference:
                 sms = ops.sm_count()
                 per_cta = -(-per // max(1, sms - graph_branch_sms))
                 self.pointnet_ctas = min(sms - 1, -(-per // per_cta))
+        # Static input buffers.  Everything a host-fed step copies besides the points (edges, poses, bag-of-words rows, the
+        # anchor indices) lives in ONE device arena, so that a serving loop moves it with a single H2D copy from a pinned
+        # mirror (``arena_bytes`` / ``arena_slices``) instead of one small copy -- one DMA latency -- per tensor.
+        from .data import needed_keys
+        need = needed_keys(self.modules)
+        self.n_anchor = int(np.asarray(example['e1i']).size)
+        e1_host = torch.as_tensor(np.asarray(example['e1i']).astype(np.int32))
+        e2_host = torch.as_tensor(np.asarray(example['e2i']).astype(np.int32))
+        plan, off = [], 0
+        for key, v in example.items():
+            if torch.is_tensor(v) and not key.startswith('_sga') and key in need and key != 'tot_obj_pts':
+                plan.append((key, off, v))
+                off += (v.numel() * v.element_size() + 255) & ~255
+        for key, v in (('e1i', e1_host), ('e2i', e2_host)):
+            plan.append((key, off, v))
+            off += (v.numel() * v.element_size() + 255) & ~255
+        self.arena_bytes = off
+        self.arena = torch.empty(max(off, 256), dtype=torch.uint8, device=self.dev)
+        self.arena_slices = {key: (o, tuple(v.shape), v.dtype) for key, o, v in plan}
+
+        def arena_view(buf, key):
+            o, shape, dtype = self.arena_slices[key]
+            n = int(np.prod(shape)) if len(shape) else 1
+            return buf[o:o + n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(shape)
+        self.arena_view = arena_view
         self.static = {}
         for key, v in example.items():
             if key.startswith('_sga'):
                 continue
-            self.static[key] = v.clone() if torch.is_tensor(v) else v
+            if torch.is_tensor(v) and key in self.arena_slices:
+                self.static[key] = arena_view(self.arena, key)
+                self.static[key].copy_(v)
+            else:
+                self.static[key] = v.clone() if torch.is_tensor(v) else v
         self.oc = np.asarray(example['graph_per_obj_count']).copy()
         self.ec = np.asarray(example['graph_per_edge_count']).copy()
         self.graph_layout = ops.GraphLayout(self.oc, self.ec, self.dev) if 'gat' in self.modules else None
         self.pair_layout = ops.PairLayout(self.oc, self.dev)
-        self.n_anchor = int(np.asarray(example['e1i']).size)
-        self.e1 = torch.as_tensor(np.asarray(example['e1i']).astype(np.int32)).to(self.dev)
-        self.e2 = torch.as_tensor(np.asarray(example['e2i']).astype(np.int32)).to(self.dev)
+        self.e1 = arena_view(self.arena, 'e1i')
+        self.e2 = arena_view(self.arena, 'e2i')
+        self.e1.copy_(e1_host)
+        self.e2.copy_(e2_host)
         was_training = model.training
         model.eval()
         cur = torch.cuda.current_stream(self.dev)
@@ -393,10 +423,15 @@ class PipelinedServing:
         c0 = self.slots[0]
         keys = [k_ for k_ in needed_keys(c0.modules) if k_ in c0.static and torch.is_tensor(c0.static[k_])]
         self.keys = keys
+        self.small_stream = torch.cuda.Stream(device=self.dev)     # the arena copy runs beside the points copy, not behind it
         for c in self.slots:
-            c.p_in = {k_: torch.empty(c.static[k_].shape, dtype=c.static[k_].dtype).pin_memory() for k_ in keys}
-            c.p_e1 = torch.empty(c.n_anchor, dtype=torch.int32).pin_memory()
-            c.p_e2 = torch.empty(c.n_anchor, dtype=torch.int32).pin_memory()
+            # pinned mirror of the slot's device arena: the small tensors and the anchor indices are views into it
+            c.p_arena = torch.empty(max(c.arena_bytes, 256), dtype=torch.uint8).pin_memory()
+            c.p_in = {k_: (c.arena_view(c.p_arena, k_) if k_ in c.arena_slices
+                           else torch.empty(c.static[k_].shape, dtype=c.static[k_].dtype).pin_memory()) for k_ in keys}
+            c.p_e1 = c.arena_view(c.p_arena, 'e1i')
+            c.p_e2 = c.arena_view(c.p_arena, 'e2i')
+            c.ev_small = torch.cuda.Event()
             c.p_out = {'topk_idx': torch.empty(c.out['topk_idx'].shape, dtype=torch.int32).pin_memory()}
             if c.out['anchor_pos'] is not None:
                 c.p_out['anchor_pos'] = torch.empty(c.out['anchor_pos'].shape, dtype=torch.int32).pin_memory()
@@ -404,7 +439,8 @@ class PipelinedServing:
             c.ev_graph = torch.cuda.Event()
             c.ev_done = torch.cuda.Event()
             c.in_flight = False
-        self.h2d_bytes = sum(t.numel() * t.element_size() for t in c0.p_in.values()) + 8 * c0.n_anchor
+        self.big_keys = [k_ for k_ in keys if k_ not in c0.arena_slices]
+        self.h2d_bytes = sum(c0.p_in[k_].numel() * c0.p_in[k_].element_size() for k_ in self.big_keys) + c0.arena_bytes
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in c0.p_out.values())
 
     def staging(self, slot: int) -> Dict:
@@ -427,13 +463,8 @@ class PipelinedServing:
         cs = self.copy_stream
         if c.in_flight:
             cs.wait_event(c.ev_done)        # the slot's previous compute has read its static buffers
-        with torch.cuda.stream(cs):
-            for k_ in self.keys:
-                c.static[k_].copy_(c.p_in[k_], non_blocking=True)
-            if c.n_anchor:
-                c.e1.copy_(c.p_e1, non_blocking=True)
-                c.e2.copy_(c.p_e2, non_blocking=True)
-            c.ev_in.record(cs)
+            self.small_stream.wait_event(c.ev_done)
+        self.h2d(c)
         st = self.cstreams[self.n_submitted % len(self.cstreams)]
         self.n_submitted += 1
         st.wait_stream(cur)                 # whatever the caller enqueued before this submit
@@ -451,6 +482,20 @@ class PipelinedServing:
                 c.p_out['anchor_pos'].copy_(c.out['anchor_pos'], non_blocking=True)
             c.ev_done.record(ds)
         c.in_flight = True
+
+    def h2d(self, c):
+        """One step's host-to-device traffic: the points (and any other large tensor) on the copy stream, the slot's arena
+        (every small tensor + the anchor indices) as ONE copy on a second stream; ``c.ev_in`` fires when both have landed."""
+        with torch.cuda.stream(self.small_stream):
+            if c.arena_bytes:
+                c.arena.copy_(c.p_arena, non_blocking=True)
+            c.ev_small.record(self.small_stream)
+        cs = self.copy_stream
+        with torch.cuda.stream(cs):
+            for k_ in self.big_keys:
+                c.static[k_].copy_(c.p_in[k_], non_blocking=True)
+            cs.wait_event(c.ev_small)
+            c.ev_in.record(cs)
 
     def wait(self, slot: int) -> Dict:
         c = self.slots[slot]
