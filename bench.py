@@ -439,8 +439,8 @@ def run_ours(args, out=sys.stdout):
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
-        pipe.copy_stream.wait_event(t0)
-        pipe.small_stream.wait_event(t0)
+        for st_ in [pipe.copy_stream, pipe.small_stream] + list(pipe.extra_copy_streams):
+            st_.wait_event(t0)
         for k_ in range(steps):
             pipe.h2d(pipe.slots[k_ % n_slots])       # exactly the copies submit() issues
         torch.cuda.current_stream().wait_stream(pipe.copy_stream)
@@ -452,6 +452,7 @@ def run_ours(args, out=sys.stdout):
         pipe.wait(s_)
     copy_only(n_slots)
     e2e_copy_floor_ms = copy_only(pipe_steps)
+    pipe_copy_split = pipe.copy_split
     got = pipe.wait(0)
     assert torch.equal(got['topk_idx'], tk_e) and torch.equal(got['anchor_pos'], pos_e), 'pipelined step differs from the eager e2e step'
     del pipe
@@ -700,7 +701,7 @@ def run_ours(args, out=sys.stdout):
             'e2e': {'value': world * PAIRS_PER_GPU / (min(e2e_ms, e2e_pipe_ms) * 1e-3), 'unit': UNIT,
                     'ms_per_step': min(e2e_ms, e2e_pipe_ms),
                     'pipelined_ms_per_step': e2e_pipe_ms, 'pipelined_slots': n_slots, 'pipelined_steps_timed': pipe_steps,
-                    'pipelined_copy_only_floor_ms_per_step': e2e_copy_floor_ms,
+                    'pipelined_copy_only_floor_ms_per_step': e2e_copy_floor_ms, 'pipelined_h2d_streams': pipe_copy_split,
                     'pipelined_api': 'serving.PipelinedServing: per step H2D from pinned staging (copy stream) -> graph replay -> D2H to pinned '
                                      'results; graph replays on three alternating compute streams, up to 3 steps in flight, the host reads step '
                                      'k-3 before submitting step k; steady-state throughput = 1 / max(copy, compute): on this workload the loop '

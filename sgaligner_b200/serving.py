@@ -15,12 +15,31 @@ from __future__ import annotations
 
 from typing import Dict, Optional
 
+import contextlib
+import gc
+
 import numpy as np
 import torch
 
 from . import matching, ops
 
 _COUNT_KEYS = ('graph_per_obj_count', 'graph_per_edge_count', 'e1i', 'e2i')
+
+
+@contextlib.contextmanager
+def _capture(graph):
+    """``torch.cuda.graph`` with the cyclic garbage collector parked: an unreachable CUDA graph / tensor of an earlier instance
+    that is collected in the middle of a capture frees device memory, which is not permitted while a stream is capturing and
+    invalidates the capture (seen as a sporadic ``cudaErrorStreamCaptureInvalidated``)."""
+    gc.collect()
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        with torch.cuda.graph(graph):
+            yield
+    finally:
+        if was:
+            gc.enable()
 
 
 class CapturedInference:
@@ -74,11 +93,7 @@ class CapturedInference:
         self.arena = torch.empty(max(off, 256), dtype=torch.uint8, device=self.dev)
         self.arena_slices = {key: (o, tuple(v.shape), v.dtype) for key, o, v in plan}
 
-        def arena_view(buf, key):
-            o, shape, dtype = self.arena_slices[key]
-            n = int(np.prod(shape)) if len(shape) else 1
-            return buf[o:o + n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(shape)
-        self.arena_view = arena_view
+        arena_view = self.arena_view
         self.static = {}
         for key, v in example.items():
             if key.startswith('_sga'):
@@ -108,11 +123,19 @@ class CapturedInference:
         torch.cuda.synchronize(self.dev)
         l0 = ops.LAUNCHES
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with _capture(self.graph):
             self.out = self._step()
         self.launches_per_replay = ops.LAUNCHES - l0
         if was_training:
             model.train()
+
+    def arena_view(self, buf, key):
+        """The tensor ``key`` of the arena layout as a typed view into ``buf`` (the device arena or a pinned mirror).  A method,
+        not a stored closure: a reference cycle through ``self`` would leave dropped instances (and their CUDA graphs) to the
+        cyclic collector, which may then free them in the middle of a later capture and invalidate it."""
+        o, shape, dtype = self.arena_slices[key]
+        n = int(np.prod(shape)) if len(shape) else 1
+        return buf[o:o + n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(shape)
 
     def _step(self):
         with torch.no_grad():
@@ -232,7 +255,7 @@ class CapturedInference:
         cur.wait_stream(side)
         torch.cuda.synchronize(self.dev)
         self.graph_host = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_host):
+        with _capture(self.graph_host):
             self.out_host = body()
         if was_training:
             self.model.train()
@@ -317,10 +340,10 @@ class CapturedInference:
         self.hy_gat = None
         if has_gat:
             self.hy_graph_a = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.hy_graph_a):
+            with _capture(self.hy_graph_a):
                 self.hy_gat = graph_branch()
         self.hy_graph_b = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.hy_graph_b):
+        with _capture(self.hy_graph_b):
             self.hy_tail_out = tail(self.hy_gat)
         if was_training:
             m.train()
@@ -424,6 +447,11 @@ class PipelinedServing:
         keys = [k_ for k_ in needed_keys(c0.modules) if k_ in c0.static and torch.is_tensor(c0.static[k_])]
         self.keys = keys
         self.small_stream = torch.cuda.Stream(device=self.dev)     # the arena copy runs beside the points copy, not behind it
+        # On some hosts one DMA stream tops out near 35 GB/s where two concurrent copies reach the 54 GB/s of the link
+        # (tools/h2d_split_probe.py); where one stream already does, splitting only adds events and jitter (measured: 0.486 ->
+        # 0.52-0.62 ms per step).  So the split is chosen from a 2 ms measurement on slot 0's own buffers (below).
+        self.copy_split = 1
+        self.extra_copy_streams = [torch.cuda.Stream(device=self.dev)]
         for c in self.slots:
             # pinned mirror of the slot's device arena: the small tensors and the anchor indices are views into it
             c.p_arena = torch.empty(max(c.arena_bytes, 256), dtype=torch.uint8).pin_memory()
@@ -432,6 +460,7 @@ class PipelinedServing:
             c.p_e1 = c.arena_view(c.p_arena, 'e1i')
             c.p_e2 = c.arena_view(c.p_arena, 'e2i')
             c.ev_small = torch.cuda.Event()
+            c.ev_part = [torch.cuda.Event() for _ in self.extra_copy_streams]
             c.p_out = {'topk_idx': torch.empty(c.out['topk_idx'].shape, dtype=torch.int32).pin_memory()}
             if c.out['anchor_pos'] is not None:
                 c.p_out['anchor_pos'] = torch.empty(c.out['anchor_pos'].shape, dtype=torch.int32).pin_memory()
@@ -440,6 +469,7 @@ class PipelinedServing:
             c.ev_done = torch.cuda.Event()
             c.in_flight = False
         self.big_keys = [k_ for k_ in keys if k_ not in c0.arena_slices]
+        self.copy_split = self._pick_copy_split(c0)
         self.h2d_bytes = sum(c0.p_in[k_].numel() * c0.p_in[k_].element_size() for k_ in self.big_keys) + c0.arena_bytes
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in c0.p_out.values())
 
@@ -464,6 +494,8 @@ class PipelinedServing:
         if c.in_flight:
             cs.wait_event(c.ev_done)        # the slot's previous compute has read its static buffers
             self.small_stream.wait_event(c.ev_done)
+            for xs in self.extra_copy_streams:
+                xs.wait_event(c.ev_done)
         self.h2d(c)
         st = self.cstreams[self.n_submitted % len(self.cstreams)]
         self.n_submitted += 1
@@ -491,11 +523,46 @@ class PipelinedServing:
                 c.arena.copy_(c.p_arena, non_blocking=True)
             c.ev_small.record(self.small_stream)
         cs = self.copy_stream
+        streams = ([cs] + self.extra_copy_streams)[:self.copy_split]
+        for i, st in enumerate(streams):
+            with torch.cuda.stream(st):
+                for k_ in self.big_keys:
+                    dst, src = c.static[k_], c.p_in[k_]
+                    rows = dst.shape[0]
+                    per = -(-rows // len(streams))
+                    lo, hi = min(rows, i * per), min(rows, (i + 1) * per)
+                    if hi > lo:
+                        dst[lo:hi].copy_(src[lo:hi], non_blocking=True)
+                if i > 0:
+                    c.ev_part[i - 1].record(st)
         with torch.cuda.stream(cs):
-            for k_ in self.big_keys:
-                c.static[k_].copy_(c.p_in[k_], non_blocking=True)
+            for ev in c.ev_part[:self.copy_split - 1]:
+                cs.wait_event(ev)
             cs.wait_event(c.ev_small)
             c.ev_in.record(cs)
+
+    def _pick_copy_split(self, c) -> int:
+        """1 or 2 concurrent H2D streams for the large tensors: whichever moves slot 0's staging buffers faster (best of 3
+        passes each; 2 only if it wins by more than 10 %)."""
+        if not self.big_keys:
+            return 1
+        best = {}
+        for split in (1, 2):
+            self.copy_split = split
+            ts = []
+            for _ in range(4):
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                cur = torch.cuda.current_stream(self.dev)
+                t0.record(cur)
+                for st in [self.copy_stream, self.small_stream] + self.extra_copy_streams:
+                    st.wait_event(t0)
+                self.h2d(c)
+                cur.wait_event(c.ev_in)
+                t1.record(cur)
+                t1.synchronize()
+                ts.append(t0.elapsed_time(t1))
+            best[split] = min(ts[1:])
+        return 2 if best[2] < 0.9 * best[1] else 1
 
     def wait(self, slot: int) -> Dict:
         c = self.slots[slot]
