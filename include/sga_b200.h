@@ -300,6 +300,11 @@ int sga_pct_embed(const float* pts, int64_t N, int P, const float* W1, const flo
 int sga_pct_pointwise(const float* src1, const float* a1, const float* b1, const float* src2, const float* a2,
                       const float* b2, int64_t N, int P, const float* W, const float* bias, int Cout, int c0,
                       float* out_x, float* out0, float* out1, double* stats, void* stream);
+/* The fused k | v convolution (Cout = 32 + 128, W rows 0..31 = k_conv = q_conv, pct.py:197-200) that also records
+ * v_absmax [N] (zeroed by the caller) = max |v| per object, which the backward's operand scale needs. */
+int sga_pct_pointwise_kv(const float* src1, const float* a1, const float* b1, const float* src2, const float* a2,
+                         const float* b2, int64_t N, int P, const float* W, const float* bias, float* out_x, float* k,
+                         float* v, float* v_absmax, void* stream);
 /* SA attention (pct.py:217-224), q and k share one weight: k [N,P,32], v [N,P,128].
  * sga_pct_attn_stats: c2 [N, 2, Ppad] (Ppad = P rounded up to 128) = log2-domain softmax normaliser of every row i of
  * energy = k k^T / sqrt(32), in two parts that are never added in fp32: [n,0,i] = row max * log2e/sqrt(32) (+inf for
@@ -344,6 +349,11 @@ int sga_bn_bwd_coef(const double* sums, const double* stats, double cnt, const f
 int sga_bn_bwd_apply(const float* g, const float* y, const float* a, const float* b, const float* mask, float scale,
                      float slope, const float* e, const float* f, const float* mean, int64_t rows, int C, float* out,
                      void* stream);
+/* ... recording absmax [rows / rows_per_object] (zeroed by the caller) = max |out| per object, the operand scale of the
+ * tensor-core product that consumes `out` */
+int sga_bn_bwd_apply_absmax(const float* g, const float* y, const float* a, const float* b, const float* mask, float scale,
+                            float slope, const float* e, const float* f, const float* mean, int64_t rows, int C, float* out,
+                            int64_t rows_per_object, float* absmax, void* stream);
 /* Per-object power-of-two scale of a gradient operand (the backward's tensor-core products split their operands into
  * fp16 pairs; gradients are far below that range): scale [N,2] = {s, 1/s}, s = 2^floor(log2(target / (max|x_n| max|y_n|)))
  * over the `per` elements of object n (y may be NULL). */
@@ -355,12 +365,18 @@ int sga_pct_attn_bwd_dv(const float* k, const float* dxs, const float* c2, const
                         void* stream);
 /* scale [N,2] = {s, 1/s}, s = 2^floor(log2(target / absmax[n])): the per-object scale from maxima a kernel recorded */
 int sga_pct_scale_from_absmax(const float* absmax, int64_t N, float target, float* scale, void* stream);
+/* the same from two maxima: s = 2^floor(log2(target / (absmax_x[n] * absmax_y[n]))) (= sga_pct_pow2_scale(x, y, ...)) */
+int sga_pct_scale_from_absmax_pair(const float* absmax_x, const float* absmax_y, int64_t N, float target, float* scale,
+                                   void* stream);
 int sga_pct_attn_bwd_dk(const float* k, const float* fixed, const float* streamed, const float* c2, float* delta,
                         const float* scale, int64_t N, int P, int by_col, int delta_sweep, float* dk_out, void* stream);
 /* delta [N,P] = scale[n][0] * sum_c x[n,p,c] y[n,p,c] (C = 128): the softmax-backward row term v_i . dv_i in scaled units */
 int sga_pct_rowdot_scaled(const float* x, const float* y, const float* scale, int64_t N, int P, float* out, void* stream);
 /* dX = dY Wt^T on the tensor cores: src [N,P,128] (scaled per object by scale [N,2]), Wt [128,128] (pass W^T), out [N,P,128] */
 int sga_pct_pointwise_scaled(const float* src, const float* scale, int64_t N, int P, const float* Wt, float* out, void* stream);
+/* ... recording out_absmax [N] (zeroed by the caller) = max |out| per object on the way out */
+int sga_pct_pointwise_scaled_absmax(const float* src, const float* scale, int64_t N, int P, const float* Wt, float* out,
+                                    float* out_absmax, void* stream);
 /* gradient of an SA layer's input: out = gx (+ gcat) + dxv + (dk1 + dk2) Wk;  dk1 <- dk1 + dk2.  [rows,128] / [rows,32] */
 int sga_pct_sa_input_grad(const float* gx, const float* gcat, const float* dxv, float* dk1, const float* dk2,
                           const float* Wk, int64_t rows, float* out, void* stream);

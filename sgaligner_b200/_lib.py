@@ -81,12 +81,16 @@ def _declare(lib):
     sig('sga_bn_bwd_stats', c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_l, c_i, c_p, c_p)
     sig('sga_bn_bwd_coef', c_i, c_p, c_p, c_d, c_p, c_p, c_p, c_p, c_i, c_f, c_i, c_p, c_p, c_p, c_p, c_p, c_p)
     sig('sga_bn_bwd_apply', c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_p, c_p, c_p, c_l, c_i, c_p, c_p)
+    sig('sga_bn_bwd_apply_absmax', c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_p, c_p, c_p, c_l, c_i, c_p, c_l, c_p, c_p)
     sig('sga_pct_pow2_scale', c_i, c_p, c_p, c_l, c_l, c_f, c_p, c_p)
     sig('sga_pct_attn_bwd_dv', c_i, c_p, c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p)
     sig('sga_pct_scale_from_absmax', c_i, c_p, c_l, c_f, c_p, c_p)
     sig('sga_pct_attn_bwd_dk', c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_i, c_p, c_p)
     sig('sga_pct_rowdot_scaled', c_i, c_p, c_p, c_p, c_l, c_i, c_p, c_p)
     sig('sga_pct_pointwise_scaled', c_i, c_p, c_p, c_l, c_i, c_p, c_p, c_p)
+    sig('sga_pct_pointwise_scaled_absmax', c_i, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p)
+    sig('sga_pct_pointwise_kv', c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p)
+    sig('sga_pct_scale_from_absmax_pair', c_i, c_p, c_p, c_l, c_f, c_p, c_p)
     sig('sga_pct_sa_input_grad', c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_p, c_p)
     sig('sga_pct_embed_a1', c_i, c_p, c_p, c_p, c_p, c_l, c_p, c_p)
     sig('sga_pct_embed1_bwd_stats', c_i, c_p, c_p, c_p, c_p, c_p, c_l, c_p, c_p)
@@ -124,8 +128,8 @@ EXPORTS = ['sga_last_error', 'sga_version', 'sga_device_info', 'sga_pointnet_fwd
            'sga_loss_fwd_bwd', 'sga_gemm_tf32x3', 'sga_adam_step', 'sga_adam_step_segments', 'sga_selftest_umma', 'sga_debug_set_trace', 'sga_debug_tie_stats',
            'sga_pct_point_moments', 'sga_pct_affine_stats', 'sga_bn_fold', 'sga_pct_embed', 'sga_pct_pointwise', 'sga_pct_attn_stats',
            'sga_pct_attn', 'sga_pct_cat_linear', 'sga_pct_cat_image_bytes', 'sga_pct_cat_pack', 'sga_pct_pool_act', 'sga_col_stats', 'sga_bn_act_rows',
-           'sga_bn_bwd_stats', 'sga_bn_bwd_coef', 'sga_bn_bwd_apply', 'sga_pct_attn_bwd_dv', 'sga_pct_scale_from_absmax', 'sga_pct_attn_bwd_dk', 'sga_pct_rowdot_scaled',
-           'sga_pct_pointwise_scaled', 'sga_pct_pow2_scale', 'sga_pct_sa_input_grad', 'sga_pct_embed_a1', 'sga_pct_embed1_bwd_stats', 'sga_pct_embed1_wgrad',
+           'sga_bn_bwd_stats', 'sga_bn_bwd_coef', 'sga_bn_bwd_apply', 'sga_bn_bwd_apply_absmax', 'sga_pct_attn_bwd_dv', 'sga_pct_scale_from_absmax', 'sga_pct_attn_bwd_dk', 'sga_pct_rowdot_scaled',
+           'sga_pct_pointwise_scaled', 'sga_pct_pow2_scale', 'sga_pct_pointwise_scaled_absmax', 'sga_pct_pointwise_kv', 'sga_pct_scale_from_absmax_pair', 'sga_pct_sa_input_grad', 'sga_pct_embed_a1', 'sga_pct_embed1_bwd_stats', 'sga_pct_embed1_wgrad',
            'sga_pct_cat_dense_bwd', 'sga_pct_cat_sparse_bwd_x', 'sga_pct_cat_sparse_bwd_w', 'sga_pct_residual', 'sga_axpby_rows',
            'sga_wgrad_group', 'sga_pct_wgrad',
            'sga_gcn_aggregate', 'sga_linear_smallk', 'sga_wgrad_smallk', 'sga_relu_mask', 'sga_colsum_rows', 'sga_row_l2norm',

@@ -95,36 +95,69 @@ __global__ void bn_bwd_coef_kernel(const double* __restrict__ sums, const double
   mean_out[c] = (float)mean;
 }
 
+constexpr int kApplyPer = 4;       // float4 per thread: a CTA covers 1024 float4 (4096 elements)
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ y,
                                                            const float* __restrict__ a, const float* __restrict__ b,
                                                            const float* __restrict__ mask, float scale, float slope,
                                                            const float* __restrict__ e, const float* __restrict__ f,
                                                            const float* __restrict__ mean, int64_t total4, int C,
-                                                           float* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (i >= total4) return;
-  const int c = (int)((i * 4) % C);
-  const float4 gv = ld4(g + i * 4), yv = ld4(y + i * 4), av = ld4(a + c), bv = ld4(b + c);
-  float gg[4] = {gv.x, gv.y, gv.z, gv.w};
-  const float yy[4] = {yv.x, yv.y, yv.z, yv.w}, aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
-  float ee[4] = {0.f, 0.f, 0.f, 0.f}, ff[4] = {0.f, 0.f, 0.f, 0.f}, mm[4] = {0.f, 0.f, 0.f, 0.f};
-  if (e) {
-    const float4 ev = ld4(e + c), fv = ld4(f + c), mv = ld4(mean + c);
-    ee[0] = ev.x; ee[1] = ev.y; ee[2] = ev.z; ee[3] = ev.w;
-    ff[0] = fv.x; ff[1] = fv.y; ff[2] = fv.z; ff[3] = fv.w;
-    mm[0] = mv.x; mm[1] = mv.y; mm[2] = mv.z; mm[3] = mv.w;
-  }
-  if (mask) {
-    const float4 mv = ld4(mask + i * 4);
-    gg[0] *= mv.x * scale; gg[1] *= mv.y * scale; gg[2] *= mv.z * scale; gg[3] *= mv.w * scale;
-  }
-  float o[4];
+                                                           float* __restrict__ out, int64_t per_obj4, float* __restrict__ absmax) {
+  const int64_t i0 = (int64_t)blockIdx.x * (256 * kApplyPer);
+  const int64_t i1 = min(i0 + 256 * kApplyPer - 1, total4 - 1);
+  // max |out| per object (the operand scale of the next tensor-core product): one atomic per CTA when its 4096 elements
+  // belong to one object (always, when P * C is a multiple of 4096), one per thread and element group in a CTA that straddles two
+  const bool one_obj = absmax != nullptr && (i0 / per_obj4 == i1 / per_obj4);
+  float amax = 0.f;
+  float4 gv[kApplyPer], yv[kApplyPer];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float gy = gg[k] * (fmaf(aa[k], yy[k], bb[k]) > 0.f ? 1.f : slope);
-    o[k] = fmaf(aa[k], gy, -ee[k]) - ff[k] * (yy[k] - mm[k]);
+  for (int u = 0; u < kApplyPer; ++u) {
+    const int64_t i = i0 + u * 256 + threadIdx.x;
+    if (i < total4) {
+      gv[u] = ld4(g + i * 4);
+      yv[u] = ld4(y + i * 4);
+    }
   }
-  *reinterpret_cast<float4*>(out + i * 4) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+  for (int u = 0; u < kApplyPer; ++u) {
+    const int64_t i = i0 + u * 256 + threadIdx.x;
+    if (i >= total4) continue;
+    const int c = (int)((i * 4) % C);
+    const float4 av = ld4(a + c), bv = ld4(b + c);
+    float gg[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+    const float yy[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w}, aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+    float ee[4] = {0.f, 0.f, 0.f, 0.f}, ff[4] = {0.f, 0.f, 0.f, 0.f}, mm[4] = {0.f, 0.f, 0.f, 0.f};
+    if (e) {
+      const float4 ev = ld4(e + c), fv = ld4(f + c), mv = ld4(mean + c);
+      ee[0] = ev.x; ee[1] = ev.y; ee[2] = ev.z; ee[3] = ev.w;
+      ff[0] = fv.x; ff[1] = fv.y; ff[2] = fv.z; ff[3] = fv.w;
+      mm[0] = mv.x; mm[1] = mv.y; mm[2] = mv.z; mm[3] = mv.w;
+    }
+    if (mask) {
+      const float4 mv = ld4(mask + i * 4);
+      gg[0] *= mv.x * scale; gg[1] *= mv.y * scale; gg[2] *= mv.z * scale; gg[3] *= mv.w * scale;
+    }
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gy = gg[k] * (fmaf(aa[k], yy[k], bb[k]) > 0.f ? 1.f : slope);
+      o[k] = fmaf(aa[k], gy, -ee[k]) - ff[k] * (yy[k] - mm[k]);
+    }
+    *reinterpret_cast<float4*>(out + i * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    const float m = fmaxf(fmaxf(fabsf(o[0]), fabsf(o[1])), fmaxf(fabsf(o[2]), fabsf(o[3])));
+    if (one_obj) amax = fmaxf(amax, m);
+    else if (absmax) atomicMax(reinterpret_cast<unsigned int*>(absmax + i / per_obj4), __float_as_uint(m));
+  }
+  if (!one_obj) return;
+  __shared__ float red[8];
+  amax = warp_max(amax);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    atomicMax(reinterpret_cast<unsigned int*>(absmax + i0 / per_obj4), __float_as_uint(m));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- small row kernels
@@ -446,10 +479,11 @@ __global__ void __launch_bounds__(256) pow2_scale_kernel(const float* __restrict
 }
 
 // scale[n] = {s, 1/s}, s = 2^floor(log2(target / absmax[n])) -- the per-object scale from a maximum a producing kernel recorded
-__global__ void scale_from_absmax_kernel(const float* __restrict__ absmax, int64_t N, float target, float* __restrict__ scale) {
+__global__ void scale_from_absmax_kernel(const float* __restrict__ absmax, const float* __restrict__ absmax2, int64_t N, float target,
+                                         float* __restrict__ scale) {
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
-  const float den = absmax[n];
+  const float den = absmax[n] * (absmax2 ? fmaxf(absmax2[n], 1e-30f) : 1.f);      // as pow2_scale_kernel with (x, y)
   int ex = 0;
   if (den > 0.f && isfinite(den)) ex = (int)floorf(log2f(target / den));
   ex = max(-100, min(100, ex));
@@ -504,7 +538,26 @@ extern "C" int sga_bn_bwd_apply(const float* g, const float* y, const float* a, 
   SGA_REQUIRE((((uintptr_t)g | (uintptr_t)y | (uintptr_t)a | (uintptr_t)b | (uintptr_t)mask | (uintptr_t)e | (uintptr_t)f | (uintptr_t)out) & 15) == 0,
               "sga_bn_bwd_apply: 16-byte alignment");
   const int64_t total4 = rows * C / 4;
-  bn_bwd_apply_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, y, a, b, mask, scale, slope, e, f, mean, total4, C, out);
+  bn_bwd_apply_kernel<<<(unsigned)((total4 + 256 * kApplyPer - 1) / (256 * kApplyPer)), 256, 0, (cudaStream_t)stream>>>(g, y, a, b, mask, scale, slope, e, f, mean, total4, C, out,
+                                                                                          0, nullptr);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+// The same pass that also records absmax [rows / rows_per_object] (zeroed by the caller) = max |out| per object.
+extern "C" int sga_bn_bwd_apply_absmax(const float* g, const float* y, const float* a, const float* b, const float* mask, float scale,
+                                       float slope, const float* e, const float* f, const float* mean, int64_t rows, int C, float* out,
+                                       int64_t rows_per_object, float* absmax, void* stream) {
+  if (rows <= 0) return SGA_OK;
+  SGA_REQUIRE(g && y && a && b && out && absmax && C >= 4 && C % 4 == 0 && (e == nullptr) == (f == nullptr) && (e == nullptr) == (mean == nullptr),
+              "sga_bn_bwd_apply_absmax: bad arguments");
+  SGA_REQUIRE(rows_per_object >= 1 && rows % rows_per_object == 0, "sga_bn_bwd_apply_absmax: rows=%lld rows_per_object=%lld", (long long)rows,
+              (long long)rows_per_object);
+  SGA_REQUIRE((((uintptr_t)g | (uintptr_t)y | (uintptr_t)a | (uintptr_t)b | (uintptr_t)mask | (uintptr_t)e | (uintptr_t)f | (uintptr_t)out) & 15) == 0,
+              "sga_bn_bwd_apply_absmax: 16-byte alignment");
+  const int64_t total4 = rows * C / 4;
+  bn_bwd_apply_kernel<<<(unsigned)((total4 + 256 * kApplyPer - 1) / (256 * kApplyPer)), 256, 0, (cudaStream_t)stream>>>(g, y, a, b, mask, scale, slope, e, f, mean, total4, C, out,
+                                                                                          rows_per_object * C / 4, absmax);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }
@@ -602,7 +655,16 @@ extern "C" int sga_pct_pow2_scale(const float* x, const float* y, int64_t N, int
 extern "C" int sga_pct_scale_from_absmax(const float* absmax, int64_t N, float target, float* scale, void* stream) {
   if (N <= 0) return SGA_OK;
   SGA_REQUIRE(absmax && scale && target > 0.f, "sga_pct_scale_from_absmax: bad arguments");
-  scale_from_absmax_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(absmax, N, target, scale);
+  scale_from_absmax_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(absmax, nullptr, N, target, scale);
+  SGA_LAUNCH_CHECK();
+  return SGA_OK;
+}
+
+extern "C" int sga_pct_scale_from_absmax_pair(const float* absmax_x, const float* absmax_y, int64_t N, float target, float* scale,
+                                              void* stream) {
+  if (N <= 0) return SGA_OK;
+  SGA_REQUIRE(absmax_x && absmax_y && scale && target > 0.f, "sga_pct_scale_from_absmax_pair: bad arguments");
+  scale_from_absmax_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(absmax_x, absmax_y, N, target, scale);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }

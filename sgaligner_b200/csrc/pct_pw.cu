@@ -45,6 +45,7 @@ struct PwArgs {
   const float* W; const float* bias; int Cout; int c0;
   float* out_x; float* out0; float* out1; double* stats;
   const float* scale;                                                 // backward: [N,2] per-object {s, 1/s}: X is multiplied by s on the way in, Y by 1/s on the way out
+  float* absmax;                                                      // or NULL: [N] (zeroed) per-object max |main output| (second-generation kernel only)
 };
 
 template <bool kEmbed, bool kScaled>
@@ -566,7 +567,7 @@ __global__ void __launch_bounds__(kThreads, 2) pct_pw2_kernel(const PwArgs A) {
       ptx::mbar_wait(&bars[p2::BAR_D_FULL], it & 1);
       ptx::tc_fence_after();
       const float osc = kScaled ? __ldg(A.scale + 2 * n + 1) : 1.f;
-      float s = 0.f, sq = 0.f;
+      float s = 0.f, sq = 0.f, amax = 0.f;
 #pragma unroll 1
       for (int h = 0; h < 4; ++h) {           // 16 points at a time: the prefetched rows of the next tile stay in registers
         uint32_t v[16];
@@ -579,12 +580,17 @@ __global__ void __launch_bounds__(kThreads, 2) pct_pw2_kernel(const PwArgs A) {
           if (p0 + e < valid) {
             const float y = kScaled ? __uint_as_float(v[e]) * osc : __uint_as_float(v[e]) + bias;
             dst[(int64_t)e * 128] = y;
+            amax = fmaxf(amax, fabsf(y));
             if (want_stats) {
               s += y;
               sq = fmaf(y, y, sq);
             }
           }
         }
+      }
+      if (A.absmax) {             // the object's largest |output|: the operand scale of a later product comes from it
+        amax = warp_max(amax);
+        if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(A.absmax + n), __float_as_uint(amax));
       }
       if (kKV) {                  // k: this thread's point (lane 32 q + lane), 16 of the 32 channels
         uint32_t v[16];
@@ -637,6 +643,7 @@ int pw_launch(const PwArgs& a, cudaStream_t st) {
   static const bool v1 = [] { const char* e = getenv("SGA_PCT_PW"); return e && e[0] == 'v' && e[1] == '1'; }();
   const bool plain = !a.pts && a.Cout == 128 && a.c0 == 128;
   const bool kv = !a.pts && a.Cout == 160 && a.c0 == 32 && !a.scale && !a.stats;
+  SGA_REQUIRE(!a.absmax || ((plain || kv) && !v1), "sga_pct_pointwise: the per-object maximum is recorded by the second-generation kernel only");
   if ((plain || kv) && !v1) {       // second generation: channels on lanes, two CTAs per SM
     static bool attr2 = false;
     if (!attr2) {
@@ -674,7 +681,7 @@ static int check_pw_common(const char* who, int64_t N, int P, const float* W, in
 
 static int pct_pointwise_impl(const float* src1, const float* a1, const float* b1, const float* src2, const float* a2,
                               const float* b2, int64_t N, int P, const float* W, const float* bias, int Cout, int c0,
-                              float* out_x, float* out0, float* out1, double* stats, const float* scale, void* stream) {
+                              float* out_x, float* out0, float* out1, double* stats, const float* scale, float* absmax, void* stream) {
   if (N <= 0) return SGA_OK;
   int rc = check_pw_common("sga_pct_pointwise", N, P, W, Cout);
   if (rc) return rc;
@@ -688,14 +695,22 @@ static int pct_pointwise_impl(const float* src1, const float* a1, const float* b
   a.src2 = src2; a.a2 = a2; a.b2 = b2; a.mode2 = src2 ? (a2 ? 2 : 1) : 0;
   a.pts = nullptr; a.w1 = nullptr;
   a.N = N; a.P = P; a.W = W; a.bias = bias; a.Cout = Cout; a.c0 = c0;
-  a.out_x = out_x; a.out0 = out0; a.out1 = out1; a.stats = stats; a.scale = scale;
+  a.out_x = out_x; a.out0 = out0; a.out1 = out1; a.stats = stats; a.scale = scale; a.absmax = absmax;
   return sga::pct::pw_launch(a, (cudaStream_t)stream);
 }
 
 extern "C" int sga_pct_pointwise(const float* src1, const float* a1, const float* b1, const float* src2, const float* a2,
                                  const float* b2, int64_t N, int P, const float* W, const float* bias, int Cout, int c0,
                                  float* out_x, float* out0, float* out1, double* stats, void* stream) {
-  return pct_pointwise_impl(src1, a1, b1, src2, a2, b2, N, P, W, bias, Cout, c0, out_x, out0, out1, stats, nullptr, stream);
+  return pct_pointwise_impl(src1, a1, b1, src2, a2, b2, N, P, W, bias, Cout, c0, out_x, out0, out1, stats, nullptr, nullptr, stream);
+}
+
+// The fused k | v convolution of an SA layer (Cout = 32 + 128, no statistics) that also records max |v| per object
+// (v_absmax [N], zeroed by the caller): the backward's operand scale needs it and would otherwise re-read v.
+extern "C" int sga_pct_pointwise_kv(const float* src1, const float* a1, const float* b1, const float* src2, const float* a2,
+                                    const float* b2, int64_t N, int P, const float* W, const float* bias, float* out_x, float* k,
+                                    float* v, float* v_absmax, void* stream) {
+  return pct_pointwise_impl(src1, a1, b1, src2, a2, b2, N, P, W, bias, 160, 32, out_x, k, v, nullptr, nullptr, v_absmax, stream);
 }
 
 // The same kernel for the input-gradient products of the backward (dX = dY W: pass W^T as the weight): the operand is a
@@ -704,7 +719,15 @@ extern "C" int sga_pct_pointwise(const float* src1, const float* a1, const float
 extern "C" int sga_pct_pointwise_scaled(const float* src, const float* scale, int64_t N, int P, const float* Wt, float* out, void* stream) {
   SGA_REQUIRE(scale, "sga_pct_pointwise_scaled: null scale");
   return pct_pointwise_impl(src, nullptr, nullptr, nullptr, nullptr, nullptr, N, P, Wt, nullptr, 128, 128, nullptr, out, nullptr,
-                            nullptr, scale, stream);
+                            nullptr, scale, nullptr, stream);
+}
+
+// ... and with max |out| per object recorded on the way out (out_absmax [N], zeroed by the caller)
+extern "C" int sga_pct_pointwise_scaled_absmax(const float* src, const float* scale, int64_t N, int P, const float* Wt, float* out,
+                                               float* out_absmax, void* stream) {
+  SGA_REQUIRE(scale && out_absmax, "sga_pct_pointwise_scaled_absmax: null pointer");
+  return pct_pointwise_impl(src, nullptr, nullptr, nullptr, nullptr, nullptr, N, P, Wt, nullptr, 128, 128, nullptr, out, nullptr,
+                            nullptr, scale, out_absmax, stream);
 }
 
 extern "C" int sga_pct_embed(const float* pts, int64_t N, int P, const float* W1, const float* a1, const float* b1,

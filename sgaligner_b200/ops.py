@@ -346,6 +346,24 @@ def pct_pointwise(src1, ab1, src2, ab2, W, bias, c0: int, want_x: bool, want_sta
     return out0, out1, out_x, stats
 
 
+def pct_pointwise_kv(src1, ab1, src2, ab2, W, bias, want_x: bool):
+    """The fused k | v convolution of an SA layer (W [160,128]) that also records max |v| per object for the backward.
+    -> (k [N,P,32], v [N,P,128], X or None, v_absmax [N])."""
+    N, P, _ = src1.shape
+    dev = src1.device
+    k = torch.empty((N, P, 32), device=dev, dtype=torch.float32)
+    v = torch.empty((N, P, 128), device=dev, dtype=torch.float32)
+    out_x = torch.empty((N, P, 128), device=dev, dtype=torch.float32) if want_x else None
+    v_absmax = torch.zeros(N, device=dev, dtype=torch.float32)
+    a1, b1 = ab1 if ab1 is not None else (None, None)
+    a2, b2 = ab2 if ab2 is not None else (None, None)
+    with _timed('pct_pointwise'):
+        check(get_lib().sga_pct_pointwise_kv(_ptr(src1), _ptr(a1), _ptr(b1), _ptr(src2), _ptr(a2), _ptr(b2), N, P, _ptr(W), _ptr(bias),
+                                             _ptr(out_x), _ptr(k), _ptr(v), _ptr(v_absmax), _stream()), 'sga_pct_pointwise_kv')
+    _count(1)
+    return k, v, out_x, v_absmax
+
+
 def pct_attention(k, v, want_c2: bool = False):
     """x_s = torch.bmm(x_v, softmax(x_k^T x_k / sqrt(32), -1)) for every object (pct.py:217-224), [N,P,128]."""
     N, P, _ = k.shape
@@ -401,10 +419,11 @@ def pct_pool_act(zmax, zmin, a, b, P: int, imax=None, imin=None):
 
 # ---- NaivePCT backward building blocks (csrc/pct_bwd.cu, pct_attn.cu, pct_cat.cu)
 def bn_backward(g, y, ab, bn, stats, cnt: float, training: bool, mask=None, scale: float = 1.0, slope: float = 0.0, lin_bias=None,
-                want_dy: bool = True):
+                want_dy: bool = True, want_absmax: bool = False):
     """Backward of  act(BN(y + lin_bias)) (* mask * scale)  for the STORED y [rows, C]: (dy or None, dgamma, dbeta, (e, f, mean))
     with dy = a gy - e - f (y - mean).
-    act = ReLU (slope 0) or LeakyReLU(slope); ``stats`` = the forward's batch statistics {sum y, sum y^2} (training)."""
+    act = ReLU (slope 0) or LeakyReLU(slope); ``stats`` = the forward's batch statistics {sum y, sum y^2} (training).
+    ``want_absmax`` (y [N, P, C]): the last element becomes (e, f, mean, max |dy| per object [N])."""
     C = y.shape[-1]
     rows = y.numel() // C
     dev = y.device
@@ -421,6 +440,13 @@ def bn_backward(g, y, ab, bn, stats, cnt: float, training: bool, mask=None, scal
                               _ptr(bn.running_var), 1 if training else 0, float(bn.eps), C, _ptr(e), _ptr(f), _ptr(mean), _ptr(dgamma),
                               _ptr(dbeta), _stream()), 'sga_bn_bwd_coef')
     dy = None
+    if want_dy and want_absmax:
+        dy = torch.empty_like(y)
+        amax = torch.zeros(y.shape[0], device=dev, dtype=torch.float32)
+        check(lib.sga_bn_bwd_apply_absmax(_ptr(g), _ptr(y), _ptr(ab[0]), _ptr(ab[1]), _ptr(mask), float(scale), float(slope), _ptr(e), _ptr(f),
+                                          _ptr(mean), rows, C, _ptr(dy), rows // y.shape[0], _ptr(amax), _stream()), 'sga_bn_bwd_apply_absmax')
+        _count(3)
+        return dy, dgamma, dbeta, (e, f, mean, amax)
     if want_dy:
         dy = torch.empty_like(y)
         check(lib.sga_bn_bwd_apply(_ptr(g), _ptr(y), _ptr(ab[0]), _ptr(ab[1]), _ptr(mask), float(scale), float(slope), _ptr(e), _ptr(f),
@@ -449,12 +475,19 @@ def pct_pow2_scale(x, y=None, target: float = 4096.0, per_object: bool = True):
     return scale
 
 
-def pct_attention_backward(k, v, c2, dxs):
-    """(dk_row, dk_col [N,P,32] -- their sum is d k --, dv [N,P,128]) of x_s = bmm(x_v, softmax(k^T k / sqrt(32)))."""
+def pct_attention_backward(k, v, c2, dxs, dxs_absmax=None, v_absmax=None):
+    """(dk_row, dk_col [N,P,32] -- their sum is d k --, dv [N,P,128]) of x_s = bmm(x_v, softmax(k^T k / sqrt(32))).
+    ``dxs_absmax`` / ``v_absmax`` [N]: the per-object maxima if the producing kernels recorded them (saves a pass over both)."""
     N, P, _ = k.shape
     lib = get_lib()
     # |v_i . dxs_j| <= 128 max|v| max|dxs|: the scaled products (and T = E (dA - delta)) stay below 2^15 < 65504
-    scale = pct_pow2_scale(dxs, v, target=16384.0 / 128.0)
+    if dxs_absmax is not None and v_absmax is not None:
+        scale = torch.empty((N, 2), device=k.device, dtype=torch.float32)
+        check(lib.sga_pct_scale_from_absmax_pair(_ptr(dxs_absmax), _ptr(v_absmax), N, 16384.0 / 128.0, _ptr(scale), _stream()),
+              'sga_pct_scale_from_absmax_pair')
+        _count(1)
+    else:
+        scale = pct_pow2_scale(dxs, v, target=16384.0 / 128.0)
     dv = torch.empty_like(v)
     fused = os.environ.get('SGA_PCT_ATTN', '') != 'v1'      # the two-CTA kernel also records sum_rows dv and max |dv| per object
     dv_colsum = _f64z(128, k.device) if fused else None
@@ -481,10 +514,15 @@ def pct_attention_backward(k, v, c2, dxs):
     return dk1, dk2, dv, dv_colsum, dv_absmax
 
 
-def pct_pointwise_grad(src, Wt, absmax=None):
+def pw2_records_absmax() -> bool:
+    """The per-object maxima come from the second-generation pointwise kernel (``SGA_PCT_PW=v1`` selects the first)."""
+    return os.environ.get('SGA_PCT_PW', '') != 'v1'
+
+
+def pct_pointwise_grad(src, Wt, absmax=None, want_absmax: bool = False):
     """src [N,P,128] @ Wt^T (Wt [128,128] contiguous): the input-gradient products; src is scaled per object into the fp16
     range on the way in, the result scaled back.  ``absmax`` [N]: max |src| per object if the producer recorded it (saves
-    the reduction pass)."""
+    the reduction pass).  ``want_absmax``: -> (out, max |out| per object [N] or None)."""
     N, P, _ = src.shape
     out = torch.empty_like(src)
     if absmax is not None:
@@ -493,10 +531,15 @@ def pct_pointwise_grad(src, Wt, absmax=None):
         _count(1)
     else:
         scale = pct_pow2_scale(src)
+    out_absmax = torch.zeros(N, device=src.device, dtype=torch.float32) if (want_absmax and pw2_records_absmax()) else None
     with _timed('pct_pointwise_bwd'):
-        check(get_lib().sga_pct_pointwise_scaled(_ptr(src), _ptr(scale), N, P, _ptr(Wt), _ptr(out), _stream()), 'sga_pct_pointwise_scaled')
+        if out_absmax is not None:
+            check(get_lib().sga_pct_pointwise_scaled_absmax(_ptr(src), _ptr(scale), N, P, _ptr(Wt), _ptr(out), _ptr(out_absmax), _stream()),
+                  'sga_pct_pointwise_scaled_absmax')
+        else:
+            check(get_lib().sga_pct_pointwise_scaled(_ptr(src), _ptr(scale), N, P, _ptr(Wt), _ptr(out), _stream()), 'sga_pct_pointwise_scaled')
     _count(1)
-    return out
+    return (out, out_absmax) if want_absmax else out
 
 
 def pct_sa_input_grad(gx, gcat, dxv, dk1, dk2, Wk):

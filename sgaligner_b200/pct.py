@@ -132,7 +132,11 @@ class NaivePCT(nn.Module):
         for li, sa in enumerate((self.sa1, self.sa2, self.sa3, self.sa4)):
             Wkv = torch.cat([sa.k_conv.weight.reshape(32, 128), sa.v_conv.weight.reshape(128, 128)])
             bkv = torch.cat([torch.zeros(32, device=pts.device), sa.v_conv.bias])
-            k, v, x_in, _ = ops.pct_pointwise(src1, g1, src2, g2, Wkv, bkv, 32, want_x=(li > 0 or save), want_stats=False)
+            v_absmax = None
+            if save and ops.pw2_records_absmax():      # training: the backward's operand scale needs max |v| per object
+                k, v, x_in, v_absmax = ops.pct_pointwise_kv(src1, g1, src2, g2, Wkv, bkv, want_x=True)
+            else:
+                k, v, x_in, _ = ops.pct_pointwise(src1, g1, src2, g2, Wkv, bkv, 32, want_x=(li > 0 or save), want_stats=False)
             if li > 0:
                 xs_saved.append(x_in)      # x1, x2, x3
             x_s, c2 = ops.pct_attention(k, v, want_c2=True)
@@ -140,7 +144,7 @@ class NaivePCT(nn.Module):
                                              want_x=False, want_stats=tr)
             abt = ops.bn_fold(sa.after_norm, stt, cnt, tr)
             if save:
-                S['layers'].append(dict(x_in=x_in, k=k, v=v, c2=c2, x_s=x_s, t=t, stt=stt, abt=abt))
+                S['layers'].append(dict(x_in=x_in, k=k, v=v, c2=c2, x_s=x_s, t=t, stt=stt, abt=abt, v_absmax=v_absmax))
             if li == 0:
                 src2, g2 = t, abt          # x1 = relu(bn2(z2)) + relu(after_norm(t1))
             else:
@@ -242,14 +246,14 @@ class NaivePCT(nn.Module):
         for li in (3, 2, 1, 0):
             sa = (self.sa1, self.sa2, self.sa3, self.sa4)[li]
             Lr = L[li]
-            dt, dga, dbe, _ = ops.bn_backward(gx, Lr['t'], Lr['abt'], sa.after_norm, Lr['stt'], cnt, tr)
+            dt, dga, dbe, ex = ops.bn_backward(gx, Lr['t'], Lr['abt'], sa.after_norm, Lr['stt'], cnt, tr, want_absmax=True)
             put(sa.after_norm.weight, dga); put(sa.after_norm.bias, dbe)
             # a bias in front of a batch-statistics BatchNorm has gradient sum_r dt = 0 identically (the reference's autograd
             # returns rounding noise of 1e-7 of the largest gradient there): no pass over dt in train()
             put(sa.trans_conv.bias, torch.zeros(128, device=dev) if tr else colsum(dt, 128))
             Wt = sa.trans_conv.weight.reshape(128, 128)
-            dxs = ops.pct_pointwise_grad(dt, Wt.t().contiguous())
-            dk1, dk2, dv, dv_colsum, dv_absmax = ops.pct_attention_backward(Lr['k'], Lr['v'], Lr['c2'], dxs)
+            dxs, dxs_absmax = ops.pct_pointwise_grad(dt, Wt.t().contiguous(), absmax=ex[3], want_absmax=True)
+            dk1, dk2, dv, dv_colsum, dv_absmax = ops.pct_attention_backward(Lr['k'], Lr['v'], Lr['c2'], dxs, dxs_absmax, Lr.get('v_absmax'))
             del dxs
             Wv = sa.v_conv.weight.reshape(128, 128)
             Wk = ops._f32c(sa.k_conv.weight.reshape(32, 128))
@@ -267,7 +271,7 @@ class NaivePCT(nn.Module):
             del dt, dv, dk1
         # ---- Embedding (pct.py:120-125): gx = d/d x0, x0 = relu(bn2(conv2(a1))), a1 = relu(bn1(conv1(points)))
         emb = self.embedding
-        dz2, dga, dbe, _ = ops.bn_backward(gx, S['z2'], S['ab2'], emb.bn2, S['st2'], cnt, tr)
+        dz2, dga, dbe, ex = ops.bn_backward(gx, S['z2'], S['ab2'], emb.bn2, S['st2'], cnt, tr, want_absmax=True)
         put(emb.bn2.weight, dga); put(emb.bn2.bias, dbe)
         W1 = ops._f32c(emb.conv1.weight.reshape(128, 3))
         a1 = ops.pct_embed_a1(pts, W1, S['ab1'])
@@ -275,7 +279,7 @@ class NaivePCT(nn.Module):
         ops.pct_wgrad(dz2.reshape(-1, 128), [a1.reshape(-1, 128)], [dW2])
         put(emb.conv2.weight, dW2)
         del a1
-        da1 = ops.pct_pointwise_grad(dz2, emb.conv2.weight.reshape(128, 128).t().contiguous())
+        da1 = ops.pct_pointwise_grad(dz2, emb.conv2.weight.reshape(128, 128).t().contiguous(), absmax=ex[3])
         dW1, dga, dbe = ops.pct_embed1_backward(da1, pts, W1, S['ab1'], emb.bn1, S['st1'], S['mom'], cnt, tr)
         put(emb.bn1.weight, dga); put(emb.bn1.bias, dbe)
         put(emb.conv1.weight, dW1)

@@ -56,6 +56,14 @@ def test_pointwise_conv_prologues_and_stats(N, P, dev):
     Y3 = s1.double() @ W.double().t()
     torch.cuda.synchronize()
     assert rel_inf(k3, Y3[..., :32]) < 2e-5 and rel_inf(v3, Y3[..., 32:]) < 2e-5
+    # ... and with the per-object maxima the backward's operand scales are derived from (recorded in the epilogues)
+    k4, v4, x4, vmax = ops.pct_pointwise_kv(s1, (a1, b1), s2, (a2, b2), W, bias, want_x=True)
+    gsrc = _rand((N, P, 128), dev, 77, 1e-3)
+    dx, dxmax = ops.pct_pointwise_grad(gsrc, W[32:].t().contiguous(), want_absmax=True)
+    torch.cuda.synchronize()
+    assert torch.equal(k4, k2) and torch.equal(v4, v2) and torch.equal(x4, x2)
+    assert torch.equal(vmax, v4.abs().amax(dim=(1, 2))) and torch.equal(dxmax, dx.abs().amax(dim=(1, 2)))
+    assert rel_inf(dx, gsrc.double() @ W[32:].double()) < 2e-5
     # identity prologue, one source, Cout = 128
     W2 = W[:128].contiguous()
     y, _, _, st2 = ops.pct_pointwise(s1, None, None, None, W2, bias[:128].contiguous(), 128, want_x=False, want_stats=True)

@@ -61,6 +61,26 @@ def test_bn_backward_vs_autograd(rows, C, masked, slope, training, dev):
     assert rel_inf(dga, w.grad) < 2e-5 and rel_inf(dbe, b.grad) < 2e-5
 
 
+@pytest.mark.parametrize('N,P', [(5, 128), (7, 333), (3, 7), (64, 512)])
+def test_bn_backward_records_per_object_maximum(N, P, dev):
+    """The variant that hands the next tensor-core product its operand scale: max |dy| per object, bit-identical dy; P * 128 / 4
+    is not always a multiple of the CTA's 256 float4 (a CTA may straddle two objects)."""
+    from sgaligner_b200 import ops
+    C = 128
+    y, g = _rand((N, P, C), dev, 1), _rand((N, P, C), dev, 2)
+    bn = torch.nn.BatchNorm1d(C).to(dev)
+    with torch.no_grad():
+        bn.weight.copy_(_rand((C,), dev, 3, 0.3) + 1)
+        bn.bias.copy_(_rand((C,), dev, 4, 0.2))
+    stats = ops.col_stats(y.reshape(-1, C))
+    ab = ops.bn_fold(bn, stats, float(N * P), True)
+    dy0, _, _, _ = ops.bn_backward(g, y, ab, bn, stats, float(N * P), True)
+    dy1, _, _, ex = ops.bn_backward(g, y, ab, bn, stats, float(N * P), True, want_absmax=True)
+    torch.cuda.synchronize()
+    assert torch.equal(dy0, dy1)
+    assert torch.equal(ex[3], dy1.abs().amax(dim=(1, 2)))
+
+
 @pytest.mark.parametrize('N,P', [(3, 96), (5, 128), (4, 300), (20, 512), (7, 40), (6, 200), (400, 512)])
 def test_attention_backward_vs_autograd(N, P, dev):
     from sgaligner_b200 import ops
