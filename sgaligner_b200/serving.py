@@ -546,6 +546,13 @@ class PipelinedServing:
         passes each; 2 only if it wins by more than 10 %)."""
         if not self.big_keys:
             return 1
+        # the measurement copies staging -> static buffers: make staging a mirror of what the slot holds first, so the slot
+        # still contains the example batch afterwards
+        if c.arena_bytes:
+            c.p_arena.copy_(c.arena)
+        for k_ in self.big_keys:
+            c.p_in[k_].copy_(c.static[k_])
+        torch.cuda.synchronize(self.dev)
         best = {}
         for split in (1, 2):
             self.copy_split = split

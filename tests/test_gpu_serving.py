@@ -101,7 +101,15 @@ def test_pipelined_serving_overlaps_slots_and_matches_eager(dev):
         _, res, pos = _eager(model, to_cuda(dict(h), dev), 6)
         want.append((res['topk_idx'].cpu(), pos.cpu()))
     pipe = PipelinedServing(model, to_cuda(dict(hosts[0]), dev), k=6, n_slots=3)
-    assert pipe.h2d_bytes > 0 and pipe.d2h_bytes > 0
+    assert pipe.h2d_bytes > 0 and pipe.d2h_bytes > 0 and pipe.copy_split in (1, 2)
+    # every slot (also slot 0, whose buffers the copy-stream measurement of the constructor went through) still holds the
+    # example batch, and the staging of slot 0 mirrors it: submitting it untouched serves the example
+    pipe.submit(0)
+    got = pipe.wait(0)
+    assert torch.equal(got['topk_idx'], want[0][0]) and torch.equal(got['anchor_pos'], want[0][1])
+    # the small tensors and the anchor indices are views of ONE pinned arena (a single H2D copy per step)
+    st = pipe.staging(0)
+    assert st['e1i'].is_pinned() and st['e1i'].untyped_storage().data_ptr() == pipe.slots[0].p_arena.untyped_storage().data_ptr()
     order = [0, 1, 2, 3, 4, 2, 0, 4, 1, 3, 3, 0]
     pending = {}
     for step, b in enumerate(order):
