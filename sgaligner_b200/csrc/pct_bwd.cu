@@ -172,8 +172,8 @@ __global__ void __launch_bounds__(256) rowdot_scaled_kernel(const float* __restr
   if (lane == 0) out[r] = s * __ldg(scale + 2 * (r / P));
 }
 
-// out = gx (+ gcat) + dxv + (dk1 + dk2) Wk; dk1 <- dk1 + dk2.  One warp per row PAIR, lane = 4 output channels; the loads of
-// both rows are issued before the first use (the 32-step shuffle / FMA chain of one row runs under the other's loads).
+// out = gx (+ gcat) + dxv + (dk1 + dk2) Wk; dk1 <- dk1 + dk2.  One warp per group of four rows, lane = 4 output channels; the loads of
+// all rows are issued before the first use (the 32-step shuffle / FMA chain of one row runs under the other's loads).
 __global__ void __launch_bounds__(256) sa_input_grad_kernel(const float* __restrict__ gx, const float* __restrict__ gcat,
                                                             const float* __restrict__ dxv, float* __restrict__ dk1,
                                                             const float* __restrict__ dk2, const float* __restrict__ Wk, int64_t rows,
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(256) sa_input_grad_kernel(const float* __restr
   for (int i = threadIdx.x; i < 32 * 32; i += 256) ws[i >> 5][i & 31] = ld4(Wk + (int64_t)i * 4);
   __syncthreads();
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  constexpr int R = 2;
+  constexpr int R = 4;
   for (int64_t r0 = ((int64_t)blockIdx.x * 8 + wrp) * R; r0 < rows; r0 += (int64_t)gridDim.x * 8 * R) {
     float dks[R];
     float4 acc[R], dv[R], gc[R];
@@ -575,7 +575,7 @@ extern "C" int sga_pct_sa_input_grad(const float* gx, const float* gcat, const f
                                      const float* Wk, int64_t rows, float* out, void* stream) {
   if (rows <= 0) return SGA_OK;
   SGA_REQUIRE(gx && dxv && dk1 && dk2 && Wk && out, "sga_pct_sa_input_grad: null pointer");
-  sa_input_grad_kernel<<<grid_for(rows, 64), 256, 0, (cudaStream_t)stream>>>(gx, gcat, dxv, dk1, dk2, Wk, rows, out);
+  sa_input_grad_kernel<<<grid_for(rows, 128), 256, 0, (cudaStream_t)stream>>>(gx, gcat, dxv, dk1, dk2, Wk, rows, out);
   SGA_LAUNCH_CHECK();
   return SGA_OK;
 }
